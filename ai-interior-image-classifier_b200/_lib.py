@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI declared in include/iic.h (the in-tree `_lib/libiic_b200.so`).
+
+There is no fallback: if the shared library is missing, or it is there but no B200 is, the error is raised to the
+caller.  `load()` only dlopen()s (works on a CPU-only box, which is how the symbol-export test runs); every compute
+entry point needs a device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libiic_b200.so")
+
+IIC_OK = 0
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1
+LORA_IN_PROJ, LORA_OUT_PROJ, LORA_C_FC, LORA_C_PROJ = 0, 1, 2, 3
+OUT_PATCHES_BF16, OUT_CHW_F32, OUT_CHW_BF16 = 0, 1, 2
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RES_F32, EPI_POS_F32, EPI_GELU_ERF_BF16 = 0, 1, 2, 3, 4
+
+
+class IicConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "image_size", "patch_size", "width", "layers", "heads", "mlp_dim", "embed_dim", "activation", "device",
+        "gemm_ctas")]
+
+
+class IicDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("tokens", "grid", "patch_k", "patch_kpad", "lora_pad")]
+
+
+class IicHeadOut(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("probs", C.c_void_p), ("topk_val", C.c_void_p), ("topk_idx", C.c_void_p),
+                ("split_sum", C.c_void_p)]
+
+
+# name -> (restype, argtypes); this table IS the list of symbols include/iic.h declares (tests check both ways)
+PROTOTYPES = {
+    "iic_version": (C.c_char_p, []),
+    "iic_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(IicConfig)]),
+    "iic_destroy": (None, [C.c_void_p]),
+    "iic_last_error": (C.c_char_p, [C.c_void_p]),
+    "iic_get_dims": (C.c_int, [C.c_void_p, C.POINTER(IicDims)]),
+    "iic_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "iic_set_lora": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "iic_set_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                 C.c_int, C.c_float]),
+    "iic_preprocess": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p]),
+    "iic_preprocess_same_size": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "iic_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "iic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "iic_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "iic_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(IicHeadOut), C.c_void_p]),
+    "iic_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                               C.POINTER(IicHeadOut), C.c_void_p]),
+    "iic_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "iic_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "iic_op_lora_down": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p]),
+    "iic_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run `python -c 'import __graft_entry__ as "
+            f"g; g.build()'` or `python ai-interior-image-classifier_b200/build.py`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(handle, rc: int, what: str) -> None:
+    if rc != IIC_OK:
+        msg = load().iic_last_error(handle)
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,138 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding and launch dispatch.
+#include "gemm_sm100.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+#include "kernels.h"
+
+namespace iic {
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved at run time through the runtime so the library has no link-time dependency on libcuda.so
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128-byte swizzle.
+bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {uint32_t(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int kCtas, int kBlockN, int kEpi>
+int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
+               const GemmArgs& args, int num_sms, cudaStream_t stream) {
+  using S = GemmSmem<kCtas, kBlockN>;
+  auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return -2;
+    attr_done = true;
+  }
+  const int tile_m = kBlockM * kCtas;
+  const int m_tiles = (args.M + tile_m - 1) / tile_m;
+  const int n_tiles = (args.N + kBlockN - 1) / kBlockN;
+  const int total = m_tiles * n_tiles;
+  int clusters = num_sms / kCtas;
+  if (clusters > total) clusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(clusters * kCtas));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, tbl, args);
+  return e == cudaSuccess ? 0 : -2;
+}
+
+template <int kCtas>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
+                 const GemmArgs& args, int num_sms, cudaStream_t stream) {
+  switch (epi) {
+    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16>(ta, tb, tal, tbl, args, num_sms, stream);
+    default: return -1;
+  }
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes(int ctas) { return ctas == 2 ? GemmSmem<2, 256>::kTotal : GemmSmem<1, 256>::kTotal; }
+
+int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err) {
+  static const char* e_shape = "gemm: unsupported shape (need M,N,K > 0, N % 32 == 0, pitches % 8 == 0)";
+  static const char* e_map = "gemm: cuTensorMapEncodeTiled failed (driver entry point missing or bad pointer/pitch)";
+  static const char* e_launch = "gemm: kernel launch failed";
+  static const char* e_lora = "gemm: LoRA rank pad must be a multiple of 16 and <= 64";
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.N % 32 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldc % 4 != 0) {
+    if (err) *err = e_shape;
+    return -1;
+  }
+  const bool lora = p.lora_p != nullptr && p.lora_bt != nullptr && p.r_pad > 0;
+  if (lora && (p.r_pad % 16 != 0 || p.r_pad > 64)) {
+    if (err) *err = e_lora;
+    return -1;
+  }
+  const uint32_t box_b = uint32_t(256 / ctas);
+  CUtensorMap ta, tb, tal, tbl;
+  bool ok = make_tile_map(&ta, p.a, uint64_t(p.M), uint64_t(p.K), uint64_t(p.lda), kBlockM) &&
+            make_tile_map(&tb, p.w, uint64_t(p.N), uint64_t(p.K), uint64_t(p.ldw), box_b);
+  if (ok && lora) {
+    // [rows, r_pad] operands: columns beyond r_pad are out of bounds for TMA and arrive as zeros
+    const uint64_t ld = p.lora_ld > 0 ? uint64_t(p.lora_ld) : uint64_t(p.r_pad);
+    const uint64_t cols = ld < uint64_t(kBlockK) ? ld : uint64_t(kBlockK);
+    ok = make_tile_map(&tal, p.lora_p, uint64_t(p.M), cols, ld, kBlockM) &&
+         make_tile_map(&tbl, p.lora_bt, uint64_t(p.N), cols, ld, box_b);
+  } else {
+    tal = ta;
+    tbl = tb;
+  }
+  if (!ok) {
+    if (err) *err = e_map;
+    return -1;
+  }
+  GemmArgs args;
+  args.M = p.M;
+  args.N = p.N;
+  args.num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  args.lora_ksteps = lora ? p.r_pad / 16 : 0;
+  args.bias = p.bias;
+  args.residual = p.residual;
+  args.out = p.out;
+  args.ldc = p.ldc;
+  args.group = p.group > 0 ? p.group : 1;
+  int rc = ctas == 2 ? dispatch_epi<2>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
+                     : dispatch_epi<1>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
+  if (rc != 0 && err) *err = rc == -1 ? e_shape : e_launch;
+  return rc;
+}
+
+}  // namespace iic

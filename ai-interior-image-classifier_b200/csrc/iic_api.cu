@@ -1,0 +1,470 @@
+// C ABI (include/iic.h): engine handle, weight table, forward orchestration.  Host-only logic; every kernel is
+// launched through kernels.h.  One handle = one GPU = one CUDA stream user at a time.
+#include "../../include/iic.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemm_sm100.cuh"
+#include "kernels.h"
+
+using namespace iic;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Tensor {
+  const void* ptr = nullptr;
+};
+
+struct LoraSlot {
+  const float* a = nullptr;          // f32 [in, r4]
+  const __nv_bfloat16* bt = nullptr; // bf16 [out, lora_pad]
+  int rank = 0, r4 = 0, r_pad = 0;
+};
+
+struct Block {
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  const __nv_bfloat16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+  const float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+  LoraSlot lora[4];
+};
+
+struct Workspace {
+  __nv_bfloat16 *xln, *qkv, *attn, *hid, *p_a, *p_b;
+  float *x, *xpre;
+  size_t total;
+};
+
+}  // namespace
+
+struct iic_handle {
+  iic_config cfg;
+  int T, g, patch_k, patch_kpad, lora_pad;
+  int num_sms = 0;
+  int ctas = 2;
+  std::string err;
+  const __nv_bfloat16* conv_w = nullptr;
+  const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
+              *lnpost_b = nullptr, *proj = nullptr;
+  std::vector<Block> blocks;
+  // labels
+  const float* text = nullptr;
+  int L = 0, G = 0, topk = 0;
+  float logit_scale = 100.f;
+  int *d_group_off = nullptr, *d_group_split = nullptr;
+  bool has_split = false;
+  PreprocessPlan* pre = nullptr;
+};
+
+namespace {
+
+int fail(iic_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Workspace carve(const iic_handle* h, int B, void* base) {
+  const size_t M = size_t(B) * h->T;
+  const size_t d = h->cfg.width, mlp = h->cfg.mlp_dim;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  Workspace w;
+  w.x = static_cast<float*>(take(M * d * 4));
+  w.xln = static_cast<__nv_bfloat16*>(take(M * d * 2));
+  w.qkv = static_cast<__nv_bfloat16*>(take(M * 3 * d * 2));
+  w.attn = static_cast<__nv_bfloat16*>(take(M * d * 2));
+  w.hid = static_cast<__nv_bfloat16*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
+  w.p_a = static_cast<__nv_bfloat16*>(take(M * h->lora_pad * 2 + 4096));
+  w.p_b = static_cast<__nv_bfloat16*>(take(M * h->lora_pad * 2 + 4096));
+  w.xpre = reinterpret_cast<float*>(w.hid);
+  w.total = off;
+  return w;
+}
+
+bool check_ready(iic_handle* h) {
+  if (!h->conv_w || !h->cls || !h->pos || !h->lnpre_g || !h->lnpre_b || !h->lnpost_g || !h->lnpost_b || !h->proj)
+    return false;
+  for (const Block& b : h->blocks)
+    if (!b.ln1_g || !b.ln1_b || !b.ln2_g || !b.ln2_b || !b.w_qkv || !b.w_out || !b.w_fc || !b.w_proj || !b.b_qkv ||
+        !b.b_out || !b.b_fc || !b.b_proj)
+      return false;
+  return true;
+}
+
+int run_gemm(iic_handle* h, const __nv_bfloat16* a, int lda, const __nv_bfloat16* w, int M, int N, int K,
+             const LoraSlot* lora, const __nv_bfloat16* p, int epi, const float* bias, const float* residual, void* out,
+             int ldc, int group, cudaStream_t s) {
+  GemmProblem g;
+  g.a = a; g.lda = lda; g.w = w; g.ldw = K; g.M = M; g.N = N; g.K = K;
+  const bool use_lora = lora != nullptr && lora->rank > 0;
+  g.lora_p = use_lora ? p : nullptr;
+  g.lora_bt = use_lora ? lora->bt : nullptr;
+  g.r_pad = use_lora ? lora->r_pad : 0;
+  g.lora_ld = h->lora_pad;
+  g.epilogue = epi; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
+  const char* e = nullptr;
+  int rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
+  return 0;
+}
+
+#define IIC_TRY(expr)                                                  \
+  do {                                                                 \
+    int _rc = (expr);                                                  \
+    if (_rc != 0) {                                                    \
+      if (h->err.empty()) h->err = std::string("failed: ") + #expr;    \
+      return _rc < -2 ? _rc : (_rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA); \
+    }                                                                  \
+  } while (0)
+
+// patches -> residual stream after the last block (x f32 [M, d] in the workspace)
+int run_encoder(iic_handle* h, const __nv_bfloat16* patches, int B, const Workspace& w, cudaStream_t s) {
+  const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  const int gg = h->g * h->g;
+  const float eps = 1e-5f;
+  h->err.clear();
+  // conv1 as GEMM; epilogue adds positional_embedding[1 + p] and scatters to token rows 1..g*g of each image
+  IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
+                   nullptr, h->pos, w.xpre, d, gg, s));
+  IIC_TRY(launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s));
+  IIC_TRY(launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, s));
+  const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
+  for (Block& b : h->blocks) {
+    const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
+    const LoraSlot& l_out = b.lora[IIC_LORA_OUT_PROJ];
+    const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
+    const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
+    // x = x + attn(ln_1(x))
+    IIC_TRY(launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, l_in.rank ? l_in.a : nullptr,
+                             l_in.r4, w.p_a, h->lora_pad, s));
+    IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
+    IIC_TRY(launch_attention(w.qkv, w.attn, B, T, H, d / H, s));
+    if (l_out.rank) IIC_TRY(launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, s));
+    IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
+    // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
+    IIC_TRY(launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
+                             l_fc.r4, w.p_a, h->lora_pad, s));
+    IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s));
+    if (l_pr.rank) IIC_TRY(launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, s));
+    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
+  }
+  return 0;
+}
+
+int run_head(iic_handle* h, const float* x_cls, long long x_img_stride, const float* emb_in, int B, float* emb_out,
+             const iic_head_out* out, cudaStream_t s) {
+  const bool scores = out != nullptr;
+  if (scores && (h->text == nullptr || h->G <= 0)) return fail(h, IIC_ERR_STATE, "iic_set_labels has not been called");
+  if (scores && (out->topk_val == nullptr || out->topk_idx == nullptr))
+    return fail(h, IIC_ERR_ARG, "iic_head_out.topk_val / topk_idx are required");
+  int rc = launch_head(x_cls, x_img_stride, h->lnpost_g, h->lnpost_b, 1e-5f, h->proj, h->cfg.width, h->cfg.embed_dim,
+                       scores ? h->text : nullptr, scores ? h->L : 0, h->d_group_off,
+                       h->has_split ? h->d_group_split : nullptr, scores ? h->G : 0, h->topk, h->logit_scale, B, emb_out,
+                       scores ? out->logits : nullptr, scores ? out->probs : nullptr, scores ? out->topk_val : nullptr,
+                       scores ? out->topk_idx : nullptr, scores ? out->split_sum : nullptr, emb_in, s);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "head kernel launch failed");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* iic_version(void) { return "iic-b200 0.1 (sm_100a; tcgen05 + TMA)"; }
+
+int iic_create(iic_handle** out, const iic_config* cfg) {
+  if (out == nullptr || cfg == nullptr) { g_create_error = "iic_create: null argument"; return IIC_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->image_size <= 0 || cfg->patch_size <= 0 || cfg->image_size % cfg->patch_size != 0 || cfg->width <= 0 ||
+      cfg->width % 128 != 0 || cfg->heads <= 0 || cfg->width != cfg->heads * 64 || cfg->layers <= 0 ||
+      cfg->mlp_dim % 256 != 0 || cfg->mlp_dim * 2 < cfg->width * 4 || cfg->embed_dim <= 0 || cfg->width % 256 != 0) {
+    g_create_error = "iic_create: unsupported architecture (need head_dim 64, width % 256 == 0, mlp % 256 == 0)";
+    return IIC_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    g_create_error = "iic_create: no CUDA device (this library has no CPU path)";
+    return IIC_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "iic_create: bad device ordinal"; return IIC_ERR_ARG; }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+    g_create_error = "iic_create: cudaSetDevice failed";
+    return IIC_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "iic_create: device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+    return IIC_ERR_CUDA;
+  }
+  iic_handle* h = new iic_handle();
+  h->cfg = *cfg;
+  h->g = cfg->image_size / cfg->patch_size;
+  h->T = h->g * h->g + 1;
+  h->patch_k = 3 * cfg->patch_size * cfg->patch_size;
+  h->patch_kpad = (h->patch_k + 7) / 8 * 8;
+  h->lora_pad = 16;
+  h->num_sms = prop.multiProcessorCount;
+  h->ctas = cfg->gemm_ctas == 1 ? 1 : 2;
+  if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
+  h->blocks.resize(cfg->layers);
+  h->pre = preprocess_plan_create();
+  if (h->pre == nullptr) { delete h; g_create_error = "iic_create: preprocess plan allocation failed"; return IIC_ERR_CUDA; }
+  *out = h;
+  return IIC_OK;
+}
+
+void iic_destroy(iic_handle* h) {
+  if (h == nullptr) return;
+  if (h->d_group_off) cudaFree(h->d_group_off);
+  if (h->d_group_split) cudaFree(h->d_group_split);
+  preprocess_plan_destroy(h->pre);
+  delete h;
+}
+
+const char* iic_last_error(const iic_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int iic_get_dims(const iic_handle* h, iic_dims* out) {
+  if (!h || !out) return IIC_ERR_ARG;
+  out->tokens = h->T; out->grid = h->g; out->patch_k = h->patch_k; out->patch_kpad = h->patch_kpad;
+  out->lora_pad = h->lora_pad;
+  return IIC_OK;
+}
+
+int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dtype, int ndim, const int64_t* shape) {
+  if (!h || !name || !dev_ptr || !shape) return fail(h, IIC_ERR_ARG, "iic_load_weight: null argument");
+  const int d = h->cfg.width, mlp = h->cfg.mlp_dim, E = h->cfg.embed_dim;
+  auto want = [&](int dt, int nd, int64_t s0, int64_t s1) -> bool {
+    if (dtype != dt || ndim != nd || shape[0] != s0 || (nd == 2 && shape[1] != s1)) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "iic_load_weight(%s): expected dtype %d shape [%lld%s%lld], got dtype %d ndim %d [%lld,..]",
+               name, dt, (long long)s0, nd == 2 ? "," : "", nd == 2 ? (long long)s1 : 0ll, dtype, ndim,
+               (long long)shape[0]);
+      h->err = buf;
+      return false;
+    }
+    if ((reinterpret_cast<uintptr_t>(dev_ptr) & 15) != 0) { h->err = std::string(name) + ": pointer must be 16-byte aligned"; return false; }
+    return true;
+  };
+  const std::string n(name);
+#define IIC_SET(field, type, dt, nd, s0, s1)                              \
+  do {                                                                    \
+    if (!want(dt, nd, s0, s1)) return IIC_ERR_ARG;                        \
+    field = static_cast<type>(dev_ptr);                                   \
+    return IIC_OK;                                                        \
+  } while (0)
+  if (n == "conv1.weight") IIC_SET(h->conv_w, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, h->patch_kpad);
+  if (n == "class_embedding") IIC_SET(h->cls, const float*, IIC_DTYPE_F32, 1, d, 0);
+  if (n == "positional_embedding") IIC_SET(h->pos, const float*, IIC_DTYPE_F32, 2, h->T, d);
+  if (n == "ln_pre.weight") IIC_SET(h->lnpre_g, const float*, IIC_DTYPE_F32, 1, d, 0);
+  if (n == "ln_pre.bias") IIC_SET(h->lnpre_b, const float*, IIC_DTYPE_F32, 1, d, 0);
+  if (n == "ln_post.weight") IIC_SET(h->lnpost_g, const float*, IIC_DTYPE_F32, 1, d, 0);
+  if (n == "ln_post.bias") IIC_SET(h->lnpost_b, const float*, IIC_DTYPE_F32, 1, d, 0);
+  if (n == "proj") IIC_SET(h->proj, const float*, IIC_DTYPE_F32, 2, d, E);
+  const std::string pre = "transformer.resblocks.";
+  if (n.compare(0, pre.size(), pre) == 0) {
+    const size_t dot = n.find('.', pre.size());
+    if (dot != std::string::npos) {
+      const int li = atoi(n.substr(pre.size(), dot - pre.size()).c_str());
+      if (li >= 0 && li < int(h->blocks.size())) {
+        Block& b = h->blocks[li];
+        const std::string r = n.substr(dot + 1);
+        if (r == "ln_1.weight") IIC_SET(b.ln1_g, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "ln_1.bias") IIC_SET(b.ln1_b, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "ln_2.weight") IIC_SET(b.ln2_g, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "ln_2.bias") IIC_SET(b.ln2_b, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "attn.in_proj_weight") IIC_SET(b.w_qkv, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, 3 * d, d);
+        if (r == "attn.in_proj_bias") IIC_SET(b.b_qkv, const float*, IIC_DTYPE_F32, 1, 3 * d, 0);
+        if (r == "attn.out_proj.weight") IIC_SET(b.w_out, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, d);
+        if (r == "attn.out_proj.bias") IIC_SET(b.b_out, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "mlp.c_fc.weight") IIC_SET(b.w_fc, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, mlp, d);
+        if (r == "mlp.c_fc.bias") IIC_SET(b.b_fc, const float*, IIC_DTYPE_F32, 1, mlp, 0);
+        if (r == "mlp.c_proj.weight") IIC_SET(b.w_proj, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, mlp);
+        if (r == "mlp.c_proj.bias") IIC_SET(b.b_proj, const float*, IIC_DTYPE_F32, 1, d, 0);
+      }
+    }
+  }
+#undef IIC_SET
+  return fail(h, IIC_ERR_ARG, std::string("iic_load_weight: unknown weight name ") + name);
+}
+
+int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, const void* b_t, int rank) {
+  if (!h) return IIC_ERR_ARG;
+  if (layer < 0 || layer >= int(h->blocks.size()) || which < 0 || which > 3)
+    return fail(h, IIC_ERR_ARG, "iic_set_lora: bad layer / projection id");
+  LoraSlot& s = h->blocks[layer].lora[which];
+  if (rank <= 0) { s = LoraSlot(); return IIC_OK; }
+  if (rank > h->lora_pad) return fail(h, IIC_ERR_ARG, "iic_set_lora: rank exceeds iic_dims.lora_pad (16)");
+  if (!a_scaled || !b_t || (reinterpret_cast<uintptr_t>(a_scaled) & 15) || (reinterpret_cast<uintptr_t>(b_t) & 15))
+    return fail(h, IIC_ERR_ARG, "iic_set_lora: null or unaligned pointer");
+  s.a = a_scaled;
+  s.bt = static_cast<const __nv_bfloat16*>(b_t);
+  s.rank = rank;
+  s.r4 = (rank + 3) / 4 * 4;
+  s.r_pad = (rank + 15) / 16 * 16;
+  return IIC_OK;
+}
+
+int iic_set_labels(iic_handle* h, const float* text, int num_labels, const int* group_offsets, const int* group_split,
+                   int num_groups, int topk, float logit_scale) {
+  if (!h) return IIC_ERR_ARG;
+  if (!text || num_labels <= 0 || !group_offsets || num_groups <= 0 || topk <= 0 || topk > 8)
+    return fail(h, IIC_ERR_ARG, "iic_set_labels: bad argument (need L > 0, G > 0, 1 <= topk <= 8)");
+  if (group_offsets[0] != 0 || group_offsets[num_groups] != num_labels)
+    return fail(h, IIC_ERR_ARG, "iic_set_labels: group_offsets must start at 0 and end at num_labels");
+  for (int g = 0; g < num_groups; ++g)
+    if (group_offsets[g + 1] <= group_offsets[g]) return fail(h, IIC_ERR_ARG, "iic_set_labels: empty or unordered group");
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "cudaSetDevice failed");
+  if (h->d_group_off) cudaFree(h->d_group_off);
+  if (h->d_group_split) cudaFree(h->d_group_split);
+  h->d_group_off = h->d_group_split = nullptr;
+  std::vector<int> split(num_groups, 0);
+  if (group_split) split.assign(group_split, group_split + num_groups);
+  if (cudaMalloc(&h->d_group_off, sizeof(int) * (num_groups + 1)) != cudaSuccess ||
+      cudaMalloc(&h->d_group_split, sizeof(int) * num_groups) != cudaSuccess ||
+      cudaMemcpy(h->d_group_off, group_offsets, sizeof(int) * (num_groups + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->d_group_split, split.data(), sizeof(int) * num_groups, cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(h, IIC_ERR_CUDA, "iic_set_labels: device allocation/copy failed");
+  h->has_split = group_split != nullptr;
+  h->text = text; h->L = num_labels; h->G = num_groups; h->topk = topk; h->logit_scale = logit_scale;
+  return IIC_OK;
+}
+
+int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int B, void* out, int out_layout,
+                   void* stream) {
+  if (!h || !imgs || !hw || !out || B < 0 || out_layout < 0 || out_layout > 2)
+    return fail(h, IIC_ERR_ARG, "iic_preprocess: bad argument");
+  const char* e = nullptr;
+  int rc = launch_preprocess(h->pre, imgs, hw, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
+                             static_cast<cudaStream_t>(stream), &e);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "preprocess failed");
+  return IIC_OK;
+}
+
+int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* out, int out_layout, void* stream) {
+  if (!h || !imgs || !out || B < 0 || out_layout < 0 || out_layout > 2)
+    return fail(h, IIC_ERR_ARG, "iic_preprocess_same_size: bad argument");
+  int rc = launch_preprocess_fast(h->pre, imgs, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
+                                  static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "preprocess_same_size launch failed");
+  return IIC_OK;
+}
+
+int iic_patchify(iic_handle* h, const void* chw, int dtype, int B, void* patches_out, void* stream) {
+  if (!h || !chw || !patches_out || B < 0) return fail(h, IIC_ERR_ARG, "iic_patchify: bad argument");
+  if (h->patch_kpad != h->patch_k) {
+    // padded tail columns must be zero for the GEMM
+    if (cudaMemsetAsync(patches_out, 0, size_t(B) * h->g * h->g * h->patch_kpad * 2, static_cast<cudaStream_t>(stream)) !=
+        cudaSuccess)
+      return fail(h, IIC_ERR_CUDA, "iic_patchify: memset failed");
+  }
+  int rc = launch_chw_to_patches(chw, dtype, static_cast<__nv_bfloat16*>(patches_out), B, h->cfg.image_size,
+                                 h->cfg.patch_size, h->patch_kpad, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "patchify launch failed");
+  return IIC_OK;
+}
+
+size_t iic_workspace_bytes(const iic_handle* h, int B) {
+  if (!h || B <= 0) return 0;
+  return carve(h, B, nullptr).total + 1024;
+}
+
+static int check_ws(iic_handle* h, int B, void* workspace, size_t bytes, Workspace* w) {
+  if (B <= 0 || !workspace) return fail(h, IIC_ERR_ARG, "workspace / batch: bad argument");
+  if (!check_ready(h)) return fail(h, IIC_ERR_STATE, "not all weights have been loaded (iic_load_weight)");
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  *w = carve(h, B, base);
+  if (size_t(base - static_cast<uint8_t*>(workspace)) + w->total > bytes)
+    return fail(h, IIC_ERR_ARG, "workspace too small: see iic_workspace_bytes");
+  return 0;
+}
+
+int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
+               void* stream) {
+  if (!h || !patches || !emb_out) return fail(h, IIC_ERR_ARG, "iic_encode: null argument");
+  Workspace w;
+  int rc = check_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = run_encoder(h, static_cast<const __nv_bfloat16*>(patches), B, w, s);
+  if (rc) return rc;
+  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, nullptr, s);
+}
+
+int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, void* stream) {
+  if (!h || !emb || !out || B <= 0) return fail(h, IIC_ERR_ARG, "iic_head: bad argument");
+  return run_head(h, nullptr, 0, emb, B, nullptr, out, static_cast<cudaStream_t>(stream));
+}
+
+int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
+                 const iic_head_out* out, void* stream) {
+  if (!h || !patches || !out) return fail(h, IIC_ERR_ARG, "iic_classify: null argument");
+  Workspace w;
+  int rc = check_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = run_encoder(h, static_cast<const __nv_bfloat16*>(patches), B, w, s);
+  if (rc) return rc;
+  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, out, s);
+}
+
+// ---- single operators ----
+int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
+                const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
+                void* out, int ldc, int group, int ctas, void* stream) {
+  if (!h || !a || !w || !out) return fail(h, IIC_ERR_ARG, "iic_op_gemm: null argument");
+  GemmProblem g;
+  g.a = static_cast<const __nv_bfloat16*>(a); g.lda = lda;
+  g.w = static_cast<const __nv_bfloat16*>(w); g.ldw = ldw;
+  g.M = M; g.N = N; g.K = K;
+  g.lora_p = static_cast<const __nv_bfloat16*>(lora_p);
+  g.lora_bt = static_cast<const __nv_bfloat16*>(lora_bt);
+  g.r_pad = r_pad; g.lora_ld = lora_ld;
+  g.epilogue = epilogue; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
+  const char* e = nullptr;
+  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
+  return IIC_OK;
+}
+
+int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const float* beta, void* out_bf16,
+                     float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
+                     void* stream) {
+  if (!h || !x || !gamma || !beta) return fail(h, IIC_ERR_ARG, "iic_op_layernorm: null argument");
+  int rc = launch_layernorm(x, D, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), out_f32, D, rows, D, 1e-5f,
+                            lora_a_scaled, r4, static_cast<__nv_bfloat16*>(p_out), p_ld, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "layernorm: unsupported width or launch failure");
+  return IIC_OK;
+}
+
+int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const float* lora_a_scaled, int r4, void* p_out,
+                     int p_ld, void* stream) {
+  if (!h || !x_bf16 || !lora_a_scaled || !p_out) return fail(h, IIC_ERR_ARG, "iic_op_lora_down: null argument");
+  int rc = launch_lora_down_bf16(static_cast<const __nv_bfloat16*>(x_bf16), K, rows, lora_a_scaled, r4,
+                                 static_cast<__nv_bfloat16*>(p_out), p_ld, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "lora_down launch failed");
+  return IIC_OK;
+}
+
+int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream) {
+  if (!h || !qkv_bf16 || !out_bf16) return fail(h, IIC_ERR_ARG, "iic_op_attention: null argument");
+  int rc = launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, T,
+                            heads, 64, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention launch failed");
+  return IIC_OK;
+}
+
+}  // extern "C"

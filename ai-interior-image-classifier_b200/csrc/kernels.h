@@ -1,0 +1,68 @@
+// Internal launcher interface between the C-ABI engine (iic_api.cu) and the kernel translation units.
+// Every launcher returns 0 on success, -1 for an unsupported shape/argument, -2 for a CUDA launch error.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iic {
+
+// ---- rowwise.cu ----
+int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta,
+                     __nv_bfloat16* out_bf16, float* out_f32, long long out_row_stride, int rows, int D, float eps,
+                     const float* lora_a, int r4, __nv_bfloat16* p_out, int p_ld, cudaStream_t stream);
+int launch_lora_down_bf16(const __nv_bfloat16* x, int K, int rows, const float* lora_a, int r4, __nv_bfloat16* p_out,
+                          int p_ld, cudaStream_t stream);
+int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
+// dtype: 0 = f32, 1 = bf16, 2 = f16
+int launch_chw_to_patches(const void* img, int dtype, __nv_bfloat16* patches, int B, int R, int P, int k_pad,
+                          cudaStream_t stream);
+
+// ---- attention.cu ----
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int head_dim,
+                     cudaStream_t stream);
+
+// ---- head.cu ----
+int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,
+                const float* proj, int W, int E, const float* text, int L, const int* group_off,
+                const int* group_split, int G, int topk, float logit_scale, int B, float* emb_out, float* logits_out,
+                float* probs_out, float* topk_val, int* topk_idx, float* split_sum, const float* emb_in,
+                cudaStream_t stream);
+
+// ---- preprocess.cu ----
+struct PreprocessPlan;  // opaque: host-side coefficient tables + device scratch, owned by the engine handle
+PreprocessPlan* preprocess_plan_create();
+void preprocess_plan_destroy(PreprocessPlan*);
+// imgs: HOST array of B DEVICE pointers to uint8 HWC RGB images; hw: HOST array [B][2] = (height, width).
+// out_mode 0: bf16 patch matrix [B*g*g, k_pad];  out_mode 1: f32 CHW [B,3,R,R];  out_mode 2: bf16 CHW.
+int launch_preprocess(PreprocessPlan* plan, const uint8_t* const* imgs, const int* hw, int B, int R, int P, int k_pad,
+                      void* out, int out_mode, cudaStream_t stream, const char** err);
+// same-size fast path: one contiguous uint8 [B,R,R,3] device buffer, no resampling.
+int launch_preprocess_fast(PreprocessPlan* plan, const uint8_t* imgs, int B, int R, int P, int k_pad, void* out,
+                           int out_mode, cudaStream_t stream);
+
+// ---- gemm_sm100.cu ----
+struct GemmProblem {
+  const __nv_bfloat16* a;   // [M, lda]   (lda = row pitch in elements, multiple of 8)
+  int lda;
+  const __nv_bfloat16* w;   // [N, ldw]
+  int ldw;
+  int M, N, K;
+  const __nv_bfloat16* lora_p;  // [M, r_pad] (row pitch r_pad) or null
+  const __nv_bfloat16* lora_bt; // [N, r_pad]
+  int r_pad;                    // multiple of 16, <= 64: columns the MMA consumes
+  int lora_ld;                  // row pitch (elements) of lora_p / lora_bt; 0 -> r_pad.  Columns [r_pad, 64) of the
+                                // TMA box fall outside the tensor and are zero-filled (never consumed anyway).
+  int epilogue;                 // GemmEpilogue
+  const float* bias;
+  const float* residual;        // residual [M, ldc] or pos table [G+1, N]
+  void* out;
+  int ldc;
+  int group;
+};
+// ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
+int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);
+size_t gemm_smem_bytes(int ctas);
+
+}  // namespace iic

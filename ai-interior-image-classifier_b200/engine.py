@@ -1,0 +1,342 @@
+"""Host-side driver of the CUDA engine: owns an `iic_handle`, keeps the device copies of the weights in the
+layouts include/iic.h documents, and exposes the hot path as tensor-in / tensor-out calls.
+
+PyTorch is used for device memory, streams and the one-off weight layout conversion only; every FLOP of the
+image path runs in the kernels behind the C ABI.  There is no CPU path: constructing an engine without a CUDA
+device, or without the built extension, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass(frozen=True)
+class VisionArch:
+    image_size: int = 224
+    patch_size: int = 16
+    width: int = 768
+    layers: int = 12
+    heads: int = 12
+    embed_dim: int = 512
+    activation: int = L.ACT_QUICK_GELU
+
+    @property
+    def mlp_dim(self) -> int:
+        return 4 * self.width
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch_size
+
+    @property
+    def tokens(self) -> int:
+        return self.grid * self.grid + 1
+
+
+VIT_B_16 = VisionArch()
+VIT_L_14_336 = VisionArch(image_size=336, patch_size=14, width=1024, layers=24, heads=16, embed_dim=768)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+@dataclass
+class HeadResult:
+    """Device tensors produced by the fused head kernel."""
+    embedding: Optional[torch.Tensor]  # [B, E] fp32, un-normalised (== encode_image output)
+    logits: torch.Tensor               # [B, L] fp32 = logit_scale * cos
+    probs: torch.Tensor                # [B, L] fp32, softmax inside each label group
+    topk_val: torch.Tensor             # [B, G, k] fp32
+    topk_idx: torch.Tensor             # [B, G, k] int32, index inside the group (-1 = padding)
+    split_sum: torch.Tensor            # [B, G] fp32
+
+
+class Engine:
+    """One engine = one GPU.  Calls are serialised by an internal lock (the reference calls its detector from a
+    4-thread pool, /root/reference/main.py:345-346)."""
+
+    def __init__(self, arch: VisionArch = VIT_B_16, device: "torch.device | str | int" = "cuda", gemm_ctas: int = 0):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("iic-b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise RuntimeError(f"iic-b200 engine cannot run on device {self.device}: CUDA only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.arch = arch
+        cfg = L.IicConfig(arch.image_size, arch.patch_size, arch.width, arch.layers, arch.heads, arch.mlp_dim,
+                          arch.embed_dim, arch.activation, self.device.index, gemm_ctas)
+        h = C.c_void_p()
+        rc = self.lib.iic_create(C.byref(h), C.byref(cfg))
+        if rc != L.IIC_OK:
+            msg = self.lib.iic_last_error(None)
+            raise RuntimeError(f"iic_create failed (code {rc}): {msg.decode() if msg else '?'}")
+        self.h = h
+        dims = L.IicDims()
+        L.check(self.h, self.lib.iic_get_dims(self.h, C.byref(dims)), "iic_get_dims")
+        self.dims = dims
+        self._lock = threading.RLock()
+        self._weights: Dict[str, torch.Tensor] = {}    # keeps borrowed buffers alive
+        self._lora: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._labels: Optional[Tuple[torch.Tensor, List[int], int]] = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._patches: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.iic_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_weight(self, name: str, tensor: torch.Tensor) -> None:
+        """`tensor` must already have the dtype/shape include/iic.h lists for `name`."""
+        t = tensor.detach().to(self.device).contiguous()
+        dt = {torch.float32: L.DTYPE_F32, torch.bfloat16: L.DTYPE_BF16, torch.float16: L.DTYPE_F16}[t.dtype]
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        with self._lock:
+            L.check(self.h, self.lib.iic_load_weight(self.h, name.encode(), t.data_ptr(), dt, t.dim(), shape),
+                    f"iic_load_weight({name})")
+            self._weights[name] = t
+
+    def load_visual_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """`sd`: OpenAI-CLIP `visual.*` tensors keyed WITHOUT the `visual.` prefix (fp32, any device).
+        Linear / conv weights are rounded to bf16 here (the compute dtype), everything else stays fp32."""
+        a = self.arch
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        bf16 = lambda t: t.detach().to(self.device, torch.float32).to(torch.bfloat16).contiguous()
+        conv = sd["conv1.weight"].detach().to(self.device, torch.float32).reshape(a.width, -1)
+        if conv.shape[1] != self.dims.patch_kpad:
+            conv = torch.nn.functional.pad(conv, (0, self.dims.patch_kpad - conv.shape[1]))
+        self.load_weight("conv1.weight", conv.to(torch.bfloat16))
+        for n in ("class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight",
+                  "ln_post.bias", "proj"):
+            self.load_weight(n, f32(sd[n]))
+        for i in range(a.layers):
+            p = f"transformer.resblocks.{i}."
+            for n in ("ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_bias", "attn.out_proj.bias",
+                      "mlp.c_fc.bias", "mlp.c_proj.bias"):
+                self.load_weight(p + n, f32(sd[p + n]))
+            for n in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
+                self.load_weight(p + n, bf16(sd[p + n]))
+
+    def set_lora(self, layer: int, which: int, lora_a: Optional[torch.Tensor], lora_b: Optional[torch.Tensor],
+                 scaling: float = 1.0) -> None:
+        """lora_a [in, r], lora_b [r, out] exactly as the reference stores them (main.py:26-27); `scaling` is
+        alpha / rank (main.py:28).  None clears the slot."""
+        with self._lock:
+            if lora_a is None or lora_b is None:
+                L.check(self.h, self.lib.iic_set_lora(self.h, layer, which, None, None, 0), "iic_set_lora")
+                self._lora.pop((layer, which), None)
+                return
+            r = lora_a.shape[1]
+            r4 = (r + 3) // 4 * 4
+            pad = self.dims.lora_pad
+            a = torch.zeros(lora_a.shape[0], r4, device=self.device, dtype=torch.float32)
+            a[:, :r] = lora_a.detach().to(self.device, torch.float32) * float(scaling)
+            bt = torch.zeros(lora_b.shape[1], pad, device=self.device, dtype=torch.bfloat16)
+            bt[:, :r] = lora_b.detach().to(self.device, torch.float32).t().to(torch.bfloat16)
+            L.check(self.h, self.lib.iic_set_lora(self.h, layer, which, a.data_ptr(), bt.data_ptr(), r), "iic_set_lora")
+            self._lora[(layer, which)] = (a, bt)
+
+    def set_labels(self, text_features: torch.Tensor, group_sizes: Sequence[int],
+                   group_split: Optional[Sequence[int]] = None, topk: int = 5, logit_scale: float = 100.0) -> None:
+        """text_features [L, E]: L2-normalised label embeddings, groups concatenated in order."""
+        t = text_features.detach().to(self.device, torch.float32).contiguous()
+        offs = [0]
+        for s in group_sizes:
+            offs.append(offs[-1] + int(s))
+        if offs[-1] != t.shape[0]:
+            raise ValueError("group sizes do not add up to the number of label rows")
+        G = len(group_sizes)
+        c_off = (C.c_int * (G + 1))(*offs)
+        c_split = (C.c_int * G)(*[int(x) for x in group_split]) if group_split is not None else None
+        with self._lock:
+            L.check(self.h, self.lib.iic_set_labels(self.h, t.data_ptr(), t.shape[0], c_off, c_split, G, int(topk),
+                                                    float(logit_scale)), "iic_set_labels")
+            self._labels = (t, offs, int(topk))
+
+    # ------------------------------------------------------------------ buffers
+    def _ws(self, B: int) -> torch.Tensor:
+        need = int(self.lib.iic_workspace_bytes(self.h, B))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def patch_buffer(self, B: int) -> torch.Tensor:
+        rows = B * self.arch.grid * self.arch.grid
+        if self._patches is None or self._patches.shape[0] < rows:
+            self._patches = None
+            self._patches = torch.zeros(rows, self.dims.patch_kpad, dtype=torch.bfloat16, device=self.device)
+        return self._patches[:rows]
+
+    # ------------------------------------------------------------------ preprocessing
+    def preprocess_same_size(self, images_u8: torch.Tensor, out: Optional[torch.Tensor] = None,
+                             layout: int = L.OUT_PATCHES_BF16) -> torch.Tensor:
+        """uint8 [B, R, R, 3] on the device -> patch matrix (default) or CHW tensor."""
+        a = self.arch
+        assert images_u8.dtype == torch.uint8 and images_u8.is_cuda and images_u8.is_contiguous()
+        B = images_u8.shape[0]
+        assert tuple(images_u8.shape[1:]) == (a.image_size, a.image_size, 3), images_u8.shape
+        if out is None:
+            out = self._alloc_pre_out(B, layout)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_preprocess_same_size(self.h, images_u8.data_ptr(), B, out.data_ptr(), layout,
+                                                              _stream_ptr(self.device)), "iic_preprocess_same_size")
+        return out
+
+    def _alloc_pre_out(self, B: int, layout: int) -> torch.Tensor:
+        a = self.arch
+        if layout == L.OUT_PATCHES_BF16:
+            return self.patch_buffer(B)
+        dt = torch.float32 if layout == L.OUT_CHW_F32 else torch.bfloat16
+        return torch.empty(B, 3, a.image_size, a.image_size, dtype=dt, device=self.device)
+
+    def preprocess(self, images_u8: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
+                   layout: int = L.OUT_PATCHES_BF16) -> torch.Tensor:
+        """List of uint8 [H, W, 3] device tensors of any size -> PIL-compatible resize + crop + normalise."""
+        B = len(images_u8)
+        for t in images_u8:
+            assert t.dtype == torch.uint8 and t.is_cuda and t.is_contiguous() and t.dim() == 3 and t.shape[2] == 3
+        ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in images_u8])
+        hw = (C.c_int * (2 * B))(*[v for t in images_u8 for v in (t.shape[0], t.shape[1])])
+        if out is None:
+            out = self._alloc_pre_out(B, layout)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_preprocess(self.h, ptrs, hw, B, out.data_ptr(), layout,
+                                                    _stream_ptr(self.device)), "iic_preprocess")
+        return out
+
+    def patchify(self, chw: torch.Tensor) -> torch.Tensor:
+        a = self.arch
+        assert chw.is_cuda and chw.dim() == 4 and tuple(chw.shape[1:]) == (3, a.image_size, a.image_size), chw.shape
+        chw = chw.contiguous()
+        dt = {torch.float32: L.DTYPE_F32, torch.bfloat16: L.DTYPE_BF16, torch.float16: L.DTYPE_F16}[chw.dtype]
+        out = self.patch_buffer(chw.shape[0])
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_patchify(self.h, chw.data_ptr(), dt, chw.shape[0], out.data_ptr(),
+                                                  _stream_ptr(self.device)), "iic_patchify")
+        return out
+
+    # ------------------------------------------------------------------ encoder / head
+    def encode_patches(self, patches: torch.Tensor, B: int) -> torch.Tensor:
+        emb = torch.empty(B, self.arch.embed_dim, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._ws(B)
+            L.check(self.h, self.lib.iic_encode(self.h, patches.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                                                emb.data_ptr(), _stream_ptr(self.device)), "iic_encode")
+        return emb
+
+    def encode_image(self, chw: torch.Tensor) -> torch.Tensor:
+        """[B,3,R,R] float tensor -> [B,E] fp32 (un-normalised): the engine behind model.encode_image."""
+        with self._lock:
+            return self.encode_patches(self.patchify(chw), chw.shape[0])
+
+    def _head_out(self, B: int, want_logits: bool = True):
+        if self._labels is None:
+            raise RuntimeError("set_labels() has not been called")
+        t, offs, k = self._labels
+        Lc, G = t.shape[0], len(offs) - 1
+        dev = self.device
+        logits = torch.empty(B, Lc, dtype=torch.float32, device=dev)
+        probs = torch.empty(B, Lc, dtype=torch.float32, device=dev)
+        tv = torch.empty(B, G, k, dtype=torch.float32, device=dev)
+        ti = torch.empty(B, G, k, dtype=torch.int32, device=dev)
+        ss = torch.empty(B, G, dtype=torch.float32, device=dev)
+        out = L.IicHeadOut(logits.data_ptr(), probs.data_ptr(), tv.data_ptr(), ti.data_ptr(), ss.data_ptr())
+        return out, logits, probs, tv, ti, ss
+
+    def head(self, emb: torch.Tensor) -> HeadResult:
+        emb = emb.detach().to(self.device, torch.float32).contiguous()
+        B = emb.shape[0]
+        with self._lock, torch.cuda.device(self.device):
+            out, logits, probs, tv, ti, ss = self._head_out(B)
+            L.check(self.h, self.lib.iic_head(self.h, emb.data_ptr(), B, C.byref(out), _stream_ptr(self.device)),
+                    "iic_head")
+        return HeadResult(emb, logits, probs, tv, ti, ss)
+
+    def classify_patches(self, patches: torch.Tensor, B: int, want_embedding: bool = True) -> HeadResult:
+        with self._lock, torch.cuda.device(self.device):
+            out, logits, probs, tv, ti, ss = self._head_out(B)
+            emb = torch.empty(B, self.arch.embed_dim, dtype=torch.float32, device=self.device) if want_embedding else None
+            ws = self._ws(B)
+            L.check(self.h, self.lib.iic_classify(self.h, patches.data_ptr(), B, ws.data_ptr(), ws.numel(), _ptr(emb),
+                                                  C.byref(out), _stream_ptr(self.device)), "iic_classify")
+        return HeadResult(emb, logits, probs, tv, ti, ss)
+
+    def classify_same_size(self, images_u8: torch.Tensor, want_embedding: bool = True) -> HeadResult:
+        """uint8 [B,R,R,3] device tensor -> preprocess + encoder + head."""
+        with self._lock:
+            return self.classify_patches(self.preprocess_same_size(images_u8), images_u8.shape[0], want_embedding)
+
+    def classify(self, images_u8: Sequence[torch.Tensor], want_embedding: bool = True) -> HeadResult:
+        """list of uint8 [H,W,3] device tensors (any size) -> preprocess + encoder + head."""
+        with self._lock:
+            return self.classify_patches(self.preprocess(images_u8), len(images_u8), want_embedding)
+
+    # ------------------------------------------------------------------ single operators (tests / profiling)
+    def op_gemm(self, a: torch.Tensor, w: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                lora_p: Optional[torch.Tensor] = None, lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0,
+                group: int = 1, ctas: int = 0, out_rows: Optional[int] = None) -> torch.Tensor:
+        M, K = a.shape
+        N = w.shape[0]
+        f32_out = epilogue in (L.EPI_BIAS_RES_F32, L.EPI_POS_F32)
+        if out is None:
+            out = torch.empty(out_rows or M, N, dtype=torch.float32 if f32_out else torch.bfloat16, device=self.device)
+        lora_ld = lora_p.stride(0) if lora_p is not None else 0
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_gemm(self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                                 _ptr(lora_p), _ptr(lora_bt), r_pad, lora_ld, epilogue, _ptr(bias),
+                                                 _ptr(residual), out.data_ptr(), out.stride(0), group, ctas,
+                                                 _stream_ptr(self.device)), "iic_op_gemm")
+        return out
+
+    def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=torch.bfloat16,
+                     lora_a_scaled: Optional[torch.Tensor] = None, p_ld: int = 16):
+        rows, D = x.shape
+        out = torch.empty(rows, D, dtype=out_dtype, device=self.device)
+        p = None
+        r4 = 0
+        if lora_a_scaled is not None:
+            r4 = lora_a_scaled.shape[1]
+            p = torch.zeros(rows, p_ld, dtype=torch.bfloat16, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_layernorm(
+                self.h, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                out.data_ptr() if out_dtype == torch.bfloat16 else None,
+                out.data_ptr() if out_dtype == torch.float32 else None, rows, D, _ptr(lora_a_scaled), r4, _ptr(p), p_ld,
+                _stream_ptr(self.device)), "iic_op_layernorm")
+        return (out, p) if lora_a_scaled is not None else out
+
+    def op_lora_down(self, x: torch.Tensor, lora_a_scaled: torch.Tensor, p_ld: int = 16) -> torch.Tensor:
+        rows, K = x.shape
+        p = torch.zeros(rows, p_ld, dtype=torch.bfloat16, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_lora_down(self.h, x.data_ptr(), K, rows, lora_a_scaled.data_ptr(),
+                                                      lora_a_scaled.shape[1], p.data_ptr(), p_ld,
+                                                      _stream_ptr(self.device)), "iic_op_lora_down")
+        return p
+
+    def op_attention(self, qkv: torch.Tensor, B: int, T: int, heads: int) -> torch.Tensor:
+        out = torch.empty(B * T, heads * 64, dtype=torch.bfloat16, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_attention(self.h, qkv.data_ptr(), out.data_ptr(), B, T, heads,
+                                                      _stream_ptr(self.device)), "iic_op_attention")
+        return out

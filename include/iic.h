@@ -1,0 +1,159 @@
+/* iic.h -- C ABI of the B200-native LoRA-ViT image encoder + label-scoring head.
+ *
+ * The reference (M1A5TO/AI-interior-image-classifier) has no FFI of its own: its seam is the Python duck type
+ * returned by `clip.load(...)` and used at
+ *     /root/reference/main.py:152,241          model, preprocess = clip.load("ViT-B/16", device)
+ *     /root/reference/main.py:201,438,489      preprocess(PIL.Image)            -> iic_preprocess*
+ *     /root/reference/main.py:204,444,503      model.encode_image(batch)        -> iic_patchify + iic_encode
+ *     /root/reference/main.py:205-211,445-459,504-509   L2-norm, 100*cos, softmax, topk -> iic_head / iic_classify
+ *     /root/reference/main.py:30-31,42-43      LoRALinear / LoRALayer forward   -> iic_set_lora (fused in the GEMM)
+ * Every entry point below is what a ctypes / cffi binding on the reference side would bind; INTEGRATION.md shows
+ * that binding.  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless a parameter says "host".
+ *   - The caller owns every input / output / workspace buffer and keeps weight buffers alive for the life of
+ *     the handle (weights are borrowed, not copied).  The library owns only a few KB of descriptors plus the
+ *     grow-only resampling scratch used by iic_preprocess.
+ *   - All work is enqueued on the caller's stream (cudaStream_t passed as void*); calls are asynchronous.
+ *   - Return value: 0 = IIC_OK, negative = error; iic_last_error(h) describes the last failure.
+ *   - A handle is not re-entrant: serialise calls per handle (one handle per GPU per process for data parallel).
+ *   - There is no CPU path.  Without a CUDA device every compute entry point fails.
+ */
+#ifndef IIC_H_
+#define IIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIC_OK 0
+#define IIC_ERR_ARG (-1)    /* bad argument / unsupported shape */
+#define IIC_ERR_CUDA (-2)   /* CUDA runtime / launch failure    */
+#define IIC_ERR_STATE (-3)  /* weights / labels missing         */
+
+#define IIC_DTYPE_F32 0
+#define IIC_DTYPE_BF16 1
+#define IIC_DTYPE_F16 2
+
+#define IIC_ACT_QUICK_GELU 0 /* OpenAI CLIP: x * sigmoid(1.702 x) */
+#define IIC_ACT_GELU_ERF 1
+
+/* which projection of a residual block a LoRA pair attaches to */
+#define IIC_LORA_IN_PROJ 0  /* not reachable from the reference (F3): generic slot */
+#define IIC_LORA_OUT_PROJ 1 /* reference wraps it but nn.MultiheadAttention never calls it (F4): off by default */
+#define IIC_LORA_C_FC 2
+#define IIC_LORA_C_PROJ 3
+
+/* preprocess output layouts */
+#define IIC_OUT_PATCHES_BF16 0 /* [B*g*g, k_pad] patch matrix, column = c*P*P + ky*P + kx (what iic_encode eats) */
+#define IIC_OUT_CHW_F32 1      /* [B,3,R,R] float32: exactly what the reference's preprocess returns              */
+#define IIC_OUT_CHW_BF16 2
+
+typedef struct iic_handle iic_handle;
+
+typedef struct iic_config {
+  int image_size; /* R: 224 (ViT-B/16) or 336 (ViT-L/14@336px) */
+  int patch_size; /* P: 16 or 14                               */
+  int width;      /* 768 / 1024                                */
+  int layers;     /* 12 / 24                                   */
+  int heads;      /* width / 64                                */
+  int mlp_dim;    /* 4 * width                                 */
+  int embed_dim;  /* 512 / 768                                 */
+  int activation; /* IIC_ACT_*                                 */
+  int device;     /* CUDA ordinal                              */
+  int gemm_ctas;  /* 0 = default, 1 = single-SM tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
+} iic_config;
+
+typedef struct iic_dims {
+  int tokens;     /* T = g*g + 1                   */
+  int grid;       /* g = R / P                     */
+  int patch_k;    /* 3*P*P                         */
+  int patch_kpad; /* patch_k rounded up to 8       */
+  int lora_pad;   /* row pitch of LoRA operands    */
+} iic_dims;
+
+int iic_create(iic_handle** out, const iic_config* cfg);
+void iic_destroy(iic_handle* h);
+const char* iic_last_error(const iic_handle* h); /* h may be NULL: last create error */
+int iic_get_dims(const iic_handle* h, iic_dims* out);
+const char* iic_version(void);
+
+/* ---- weights (borrowed device pointers; names are OpenAI-CLIP `visual.` state-dict names without the prefix) --
+ *   conv1.weight                      bf16 [width, patch_kpad]   (conv weight flattened (c,ky,kx), zero padded)
+ *   class_embedding                   f32  [width]
+ *   positional_embedding              f32  [T, width]
+ *   ln_pre.weight|bias, ln_post.weight|bias                      f32 [width]
+ *   proj                              f32  [width, embed_dim]
+ *   transformer.resblocks.{i}.ln_1.weight|bias, .ln_2.weight|bias           f32 [width]
+ *   transformer.resblocks.{i}.attn.in_proj_weight   bf16 [3*width, width];  .attn.in_proj_bias   f32 [3*width]
+ *   transformer.resblocks.{i}.attn.out_proj.weight  bf16 [width, width];    .attn.out_proj.bias  f32 [width]
+ *   transformer.resblocks.{i}.mlp.c_fc.weight       bf16 [mlp, width];      .mlp.c_fc.bias       f32 [mlp]
+ *   transformer.resblocks.{i}.mlp.c_proj.weight     bf16 [width, mlp];      .mlp.c_proj.bias     f32 [width]
+ */
+int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dtype, int ndim, const int64_t* shape);
+
+/* LoRA pair for one projection (reference: LoRALayer, /root/reference/main.py:19-31):
+ *   a_scaled f32 [in, r4]   = lora_A * (alpha/rank), columns zero padded to r4 = round_up(rank, 4)
+ *   b_t      bf16 [out, ld] = lora_B^T, columns zero padded to ld = iic_dims.lora_pad (16 for rank <= 16, ...)
+ * Passing rank == 0 clears the slot.  A cleared slot costs nothing. */
+int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, const void* b_t, int rank);
+
+/* Label text embeddings the head scores against (reference: text_features_cache, main.py:296-311 and
+ * detector text_features, main.py:179-182): text f32 [L, embed_dim], rows L2-normalised by the caller exactly as
+ * the reference does.  group_offsets (host, G+1 ints) partitions the L labels into softmax groups;
+ * group_split (host, G ints or NULL): for each group the number of leading labels whose probabilities are summed
+ * into split_sum (detector: 11).  topk <= 8.  logit_scale = 100.0 in the reference. */
+int iic_set_labels(iic_handle* h, const float* text, int num_labels, const int* group_offsets, const int* group_split,
+                   int num_groups, int topk, float logit_scale);
+
+/* ---- preprocessing ------------------------------------------------------------------------------------------ */
+/* General path: B images of arbitrary size.  imgs = HOST array of B device pointers to uint8 HWC RGB;
+ * hw = HOST array [B][2] = (height, width).  PIL-compatible antialiased bicubic + centre crop + normalise. */
+int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int B, void* out, int out_layout,
+                   void* stream);
+/* Fast path: one contiguous uint8 [B, R, R, 3] buffer already at the model resolution (no resampling). */
+int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* out, int out_layout, void* stream);
+/* [B,3,R,R] float tensor (what reference code feeds encode_image) -> patch matrix. */
+int iic_patchify(iic_handle* h, const void* chw, int dtype, int B, void* patches_out, void* stream);
+
+/* ---- encoder + head ----------------------------------------------------------------------------------------- */
+size_t iic_workspace_bytes(const iic_handle* h, int B);
+/* patches bf16 [B*g*g, patch_kpad] -> emb f32 [B, embed_dim] (un-normalised, == model.encode_image output) */
+int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
+               void* stream);
+
+typedef struct iic_head_out {
+  float* logits;    /* [B, L]      logit_scale * cos            (nullable) */
+  float* probs;     /* [B, L]      per-group softmax            (nullable) */
+  float* topk_val;  /* [B, G, k]   descending                   (required) */
+  int32_t* topk_idx;/* [B, G, k]   index inside the group, -1 pad (required) */
+  float* split_sum; /* [B, G]      sum of the first group_split[g] probabilities (nullable) */
+} iic_head_out;
+
+/* emb f32 [B, embed_dim] (un-normalised) -> scores */
+int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, void* stream);
+/* fused: patches -> encoder -> head; emb_out nullable */
+int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
+                 const iic_head_out* out, void* stream);
+
+/* ---- single operators (exported for parity tests and profiling; same kernels the encoder runs) -------------- */
+/* D = epilogue(A[M,K] . W[N,K]^T (+ P[M,r] . Bt[N,r]^T));  epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16,
+ * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16.  lora_p/lora_bt nullable. */
+int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
+                const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
+                void* out, int ldc, int group, int ctas, void* stream);
+int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const float* beta, void* out_bf16,
+                     float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
+                     void* stream);
+int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const float* lora_a_scaled, int r4, void* p_out,
+                     int p_ld, void* stream);
+int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIC_H_ */

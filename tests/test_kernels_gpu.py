@@ -1,0 +1,190 @@
+"""Per-kernel numerics on a B200, through the C ABI (`iic_op_*`), against plain PyTorch fp32 references of the same
+op computed from the SAME bf16-rounded operands (so the only differences are accumulation order and the final
+rounding).  Tolerances are written next to each check.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+L = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _consts(iic):
+    global L
+    L = iic._lib
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16)
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+GEMM_SHAPES = [
+    # (M, N, K): one full tile; ragged M; multi-tile persistent; encoder shapes at a small batch
+    (128, 256, 64),
+    (256, 256, 768),
+    (197 * 3, 768, 768),
+    (197 * 16, 2304, 768),
+    (197 * 16, 3072, 768),
+    (197 * 16, 768, 3072),
+    (197 * 40 + 5, 768, 768),
+]
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_bias_bf16(engine, shape, ctas):
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = engine.op_gemm(a, w, L.EPI_BIAS_BF16, bias=bias, ctas=ctas)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    # bf16 output rounding: 2^-9 relative per element; fp32 accumulation order differences are far below that
+    assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=2e-2), (out.float() - ref).abs().max()
+    assert _rel(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+def test_gemm_quickgelu(engine, ctas):
+    M, N, K = 197 * 8, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = engine.op_gemm(a, w, L.EPI_BIAS_GELU_BF16, bias=bias, ctas=ctas)
+    ref = quick_gelu(a.float() @ w.float().t() + bias)
+    assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=1e-2), (out.float() - ref).abs().max()
+    out2 = engine.op_gemm(a, w, L.EPI_GELU_ERF_BF16, bias=bias, ctas=ctas)
+    ref2 = torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    assert torch.allclose(out2.float(), ref2, rtol=2 ** -7, atol=1e-2), (out2.float() - ref2).abs().max()
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+def test_gemm_residual_f32_inplace(engine, ctas):
+    M, N, K = 197 * 8 + 3, 768, 3072
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + a.float() @ w.float().t() + bias
+    engine.op_gemm(a, w, L.EPI_BIAS_RES_F32, bias=bias, residual=x, out=x, ctas=ctas)  # in place on the stream
+    # fp32 in, fp32 out: only the accumulation order differs
+    assert torch.allclose(x, ref, rtol=1e-4, atol=2e-4), (x - ref).abs().max()
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+def test_gemm_patch_embed_scatter(engine, ctas):
+    B, G, N, K = 5, 196, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = _bf16(torch.randn(B * G, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    pos = torch.randn(G + 1, N, device="cuda", generator=g)
+    out = torch.full((B * (G + 1), N), 7.0, device="cuda")
+    engine.op_gemm(a, w, L.EPI_POS_F32, residual=pos, out=out, group=G, ctas=ctas)
+    ref = (a.float() @ w.float().t()).view(B, G, N) + pos[1:]
+    got = out.view(B, G + 1, N)
+    assert torch.allclose(got[:, 1:], ref, rtol=1e-4, atol=2e-4)
+    assert (got[:, 0] == 7.0).all()  # class-token rows are not touched by the GEMM
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+@pytest.mark.parametrize("rank", [4, 16])
+def test_gemm_lora_fused(engine, ctas, rank):
+    """reference semantic: linear(x) + (x @ A @ B) * scaling  (/root/reference/main.py:30-31, 42-43)"""
+    M, N, K = 197 * 6, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(4 + rank)
+    x = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    A = torch.randn(K, rank, device="cuda", generator=g) * 0.02
+    Bm = torch.randn(rank, N, device="cuda", generator=g) * 0.3   # large on purpose: the delta must be visible
+    scaling = 2.0
+    r4 = (rank + 3) // 4 * 4
+    a_scaled = torch.zeros(K, r4, device="cuda")
+    a_scaled[:, :rank] = A * scaling
+    p = engine.op_lora_down(x, a_scaled)
+    p_ref = (x.float() @ A) * scaling
+    assert torch.allclose(p[:, :rank].float(), p_ref, rtol=2 ** -7, atol=1e-3)
+    assert (p[:, rank:] == 0).all()
+    bt = torch.zeros(N, 16, device="cuda", dtype=torch.bfloat16)
+    bt[:, :rank] = _bf16(Bm.t())
+    out = engine.op_gemm(x, w, L.EPI_BIAS_BF16, bias=bias, lora_p=p, lora_bt=bt, r_pad=16, ctas=ctas)
+    base = x.float() @ w.float().t() + bias
+    ref = base + p[:, :rank].float() @ bt[:, :rank].float().t()
+    assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=2e-2), (out.float() - ref).abs().max()
+    # and the delta is really there (a skipped LoRA block would fail this)
+    assert (out.float() - base).abs().mean() > 10 * (out.float() - ref).abs().mean()
+    # against the un-rounded reference formula
+    full = base + (x.float() @ A @ Bm) * scaling
+    assert _rel(out.float(), full) < 6e-3
+
+
+@pytest.mark.parametrize("D", [768, 1024])
+def test_layernorm(engine, D):
+    rows = 197 * 4 + 1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 0.5
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-5)
+    out32 = engine.op_layernorm(x, gamma, beta, out_dtype=torch.float32)
+    assert torch.allclose(out32, ref, rtol=1e-5, atol=1e-5), (out32 - ref).abs().max()
+    out16 = engine.op_layernorm(x, gamma, beta, out_dtype=torch.bfloat16)
+    assert torch.allclose(out16.float(), ref, rtol=2 ** -8, atol=1e-6)
+    A = torch.randn(D, 4, device="cuda", generator=g) * 0.04
+    out16b, p = engine.op_layernorm(x, gamma, beta, out_dtype=torch.bfloat16, lora_a_scaled=A)
+    assert torch.equal(out16b, out16)
+    assert torch.allclose(p[:, :4].float(), ref @ A, rtol=2 ** -7, atol=1e-3)
+
+
+@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12)])
+def test_attention(engine, T, B, H):
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(6)
+    qkv = _bf16(torch.randn(B * T, 3 * d, device="cuda", generator=g))
+    out = engine.op_attention(qkv, B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v)  # fp32 math
+    ref = ref.permute(0, 2, 1, 3).reshape(B * T, d)
+    # P is rounded to bf16 before the PV product and the output is bf16: 2^-8 relative on values O(1)
+    assert torch.allclose(out.float(), ref, rtol=2 ** -6, atol=2e-2), (out.float() - ref).abs().max()
+    assert _rel(out.float(), ref) < 8e-3
+
+
+def test_head_from_embeddings(engine):
+    E, groups, split = 512, [40, 20, 12, 299, 36, 30], [11, 0, 0, 0, 0, 0]
+    Lc = sum(groups)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    text = torch.nn.functional.normalize(torch.randn(Lc, E, device="cuda", generator=g), dim=-1)
+    engine.set_labels(text, groups, split, topk=5, logit_scale=100.0)
+    for B in (1, 4, 7):
+        emb = torch.randn(B, E, device="cuda", generator=g) * 3
+        r = engine.head(emb)
+        f = emb / emb.norm(dim=-1, keepdim=True)
+        logits = 100.0 * f @ text.t()
+        assert torch.allclose(r.logits, logits, rtol=1e-5, atol=2e-4), (r.logits - logits).abs().max()
+        off = 0
+        for gi, n in enumerate(groups):
+            p = logits[:, off:off + n].softmax(dim=-1)
+            assert torch.allclose(r.probs[:, off:off + n], p, rtol=1e-4, atol=1e-6)
+            vals, inds = p.topk(min(5, n), dim=-1)
+            assert torch.allclose(r.topk_val[:, gi], vals, rtol=1e-4, atol=1e-6)
+            assert torch.equal(r.topk_idx[:, gi].long(), inds)
+            if split[gi]:
+                assert torch.allclose(r.split_sum[:, gi], p[:, :split[gi]].sum(-1), rtol=1e-4, atol=1e-6)
+            off += n
