@@ -23,7 +23,7 @@ EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RES_F32, EPI_POS_F32, EPI_GELU_ERF_B
 class IicConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "image_size", "patch_size", "width", "layers", "heads", "mlp_dim", "embed_dim", "activation", "device",
-        "gemm_ctas")]
+        "gemm_ctas", "operand_dtype")]
 
 
 class IicDims(C.Structure):

@@ -1,0 +1,385 @@
+"""The reference's analyzer entry points, re-hosted on the CUDA engine.
+
+Same class names, constructor arguments, method names and return shapes as /root/reference/main.py:
+    InteriorImageDetector(device).is_interior_image(image, confidence_threshold) -> (bool, float, str)   main.py:149-226
+    CachedInteriorAnalyzer(use_lora, lora_weights_path, lora_rank, lora_alpha, device)                     main.py:232-262
+        .analyze_images_batch(image_paths, batch_size, filter_interiors, confidence_threshold) -> dict    main.py:371-469
+        .analyze_image_from_url(url, filter_interiors)                                                     main.py:472-498
+        ._analyze_image_tensor_fast(image_input)                                                           main.py:500-510
+        .filter_interior_images(image_paths, confidence_threshold)                                         main.py:313-369
+and the intended shape of python-worker/main_API.py's DatabaseStyleRoomAnalyzer._analyze_styles_batch (its body is
+`pass` in the reference, main_API.py:268-271; the consumer at main_API.py:219-236 fixes the contract).
+
+What changes underneath: one engine and ONE encode per image feeds both the detector head
+and the five attribute heads - the reference encodes every interior image twice with two copies of the same
+frozen ViT (main.py:333 and 444) - the 6 label groups (40 detector prompts + styles, characteristics, materials,
+colors, room_types) are scored by one fused head kernel, and results come back in one device-to-host copy instead
+of ~28 `.item()` syncs per image.  JSON label schema, prompt templates (main.py:302-305), top-5 per group, the
+detector rule (main.py:216-220) and the result dict layout are unchanged.
+"""
+from __future__ import annotations
+
+import json
+import os
+from concurrent.futures import ThreadPoolExecutor
+from io import BytesIO
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import clip_compat as clip
+from .lora import load_lora_weights_to_model, replace_linears_with_lora
+
+DETECTOR_CATEGORIES = [
+    # interiors (positive) - first 11, main.py:155-160, 185
+    "interior of a room", "living room", "bedroom", "kitchen", "bathroom",
+    "dining room", "office interior", "apartment interior", "house interior",
+    "interior design", "home decor",
+    # exteriors
+    "building exterior", "outside of building", "street view", "garden",
+    "landscape", "cityscape", "outdoor",
+    # plans and diagrams
+    "floor plan", "blueprint", "architectural plan", "diagram",
+    "map", "technical drawing",
+    # logos and graphics
+    "company logo", "brand logo", "text", "signature",
+    "advertisement", "brochure", "flyer",
+    # other unwanted
+    "person", "people", "animal", "pet", "car", "vehicle",
+    "close-up of object", "product photo", "furniture close-up",
+]
+N_INTERIOR = 11
+GROUP_ORDER = ("styles", "characteristics", "materials", "colors", "room_types")  # main.py:289-295
+
+
+def load_image(path_or_url: str, timeout: int = 30):
+    """main.py:119-128 / 325-327: URL -> requests, else local file; RGB PIL image or None."""
+    from PIL import Image
+    try:
+        if path_or_url.startswith("http"):
+            import requests
+            r = requests.get(path_or_url, timeout=timeout)
+            r.raise_for_status()
+            return Image.open(BytesIO(r.content)).convert("RGB")
+        return Image.open(path_or_url).convert("RGB")
+    except Exception as e:  # noqa: BLE001 - the reference prints and skips
+        print(f"Błąd ładowania {path_or_url}: {e}")
+        return None
+
+
+def _encode_labels(model, texts: Sequence[str], device) -> torch.Tensor:
+    with torch.no_grad():
+        tok = clip.tokenize(list(texts)).to(device)
+        f = model.encode_text(tok).float()
+        return f / f.norm(dim=-1, keepdim=True)
+
+
+class InteriorImageDetector:
+    def __init__(self, device=None, model=None, preprocess=None):
+        self.device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        if model is None:
+            model, preprocess = clip.load("ViT-B/16", device=self.device)
+        self.model, self.preprocess = model, preprocess
+        self.categories = list(DETECTOR_CATEGORIES)
+        self.text_features = _encode_labels(self.model, self.categories, self.device)
+        self.interior_indices = list(range(0, N_INTERIOR))
+        self.non_interior_indices = list(range(N_INTERIOR, len(self.categories)))
+        self._labels_key = None
+        print(f"Detektor wnętrz zainicjalizowany. Kategorie wnętrz: {len(self.interior_indices)}, "
+              f"inne: {len(self.non_interior_indices)}")
+
+    def _engine(self):
+        # the reference's detector is a separate, un-LoRA'd copy of the ViT (main.py:152 vs 241/247)
+        eng = self.model.visual.sync_engine(use_lora=False)
+        key = (id(eng), "detector")
+        if getattr(eng, "_labels_owner", None) != key:
+            eng.set_labels(self.text_features, [len(self.categories)], [N_INTERIOR], topk=1, logit_scale=100.0)
+            eng._labels_owner = key
+        return eng
+
+    def detect_batch(self, images, confidence_threshold: float = 0.3, batch_size: int = 64):
+        """List of PIL images -> [(is_interior, interior_confidence, top_category)], one encode per image, one
+        device-to-host copy per batch.  Decision rule: main.py:208-222."""
+        out = []
+        for i in range(0, len(images), batch_size):
+            eng = self._engine()
+            with eng._lock:
+                eng = self._engine()
+                u8 = [clip.Preprocess._to_u8(im, eng.device) for im in images[i:i + batch_size]]
+                r = eng.classify(u8, want_embedding=False)
+                top_conf, top_idx = r.topk_val[:, 0, 0].cpu(), r.topk_idx[:, 0, 0].cpu()
+                interior = r.split_sum[:, 0].cpu()
+                non_interior = r.probs[:, N_INTERIOR:].sum(-1).cpu()
+            for j in range(len(u8)):
+                ok = bool(interior[j] > non_interior[j] and top_conf[j] > confidence_threshold)
+                out.append((ok, float(interior[j]), self.categories[int(top_idx[j])]))
+        return out
+
+    def is_interior_image(self, image, confidence_threshold: float = 0.3):
+        if image is None:
+            return False, 0.0, "invalid image"
+        try:
+            return self.detect_batch([image], confidence_threshold)[0]
+        except Exception as e:  # noqa: BLE001 - reference behaviour, main.py:224-226
+            print(f"Błąd podczas detekcji wnętrza: {e}")
+            return False, 0.0, f"error: {str(e)}"
+
+
+class CachedInteriorAnalyzer:
+    def __init__(self, use_lora: bool = False, lora_weights_path: Optional[str] = None, lora_rank: int = 4,
+                 lora_alpha: float = 8, device=None, json_path: str = "interior_dataset.json", model=None,
+                 preprocess=None, share_detector_encoder: Optional[bool] = None):
+        self.device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        print(f"Urządzenie: {self.device}")
+        if model is None:
+            model, preprocess = clip.load("ViT-B/16", device=self.device)
+        self.model, self.preprocess = model, preprocess
+        # The reference gives the detector its own, un-LoRA'd ViT (main.py:238).  Text features of the detector must
+        # therefore come from the BASE text tower: encode them before LoRA is applied to the shared model.
+        self.detector = InteriorImageDetector(device=self.device, model=self.model, preprocess=self.preprocess)
+        self.use_lora = False
+        if use_lora:
+            print("Aplikuję LoRA do modelu...")
+            replaced = replace_linears_with_lora(self.model, rank=lora_rank, alpha=lora_alpha)
+            print(f"Zastąpiono warstwy Linear: {len(replaced)}")
+            if lora_weights_path and os.path.exists(lora_weights_path):
+                print("Wczytywanie wag LoRA...")
+                load_lora_weights_to_model(self.model, lora_weights_path, strict_match=False)
+            else:
+                print("Brak ścieżki do wag LoRA -> używam losowych LoRA")
+            self.use_lora = True
+        else:
+            print("Nie używam LoRA - model bez modyfikacji")
+        # One encode can serve both heads only while the LoRA'd vision tower equals the base tower (always true for
+        # the shipped checkpoints: they hold text-tower tensors only and lora_B initialises to zero - SURVEY F7).
+        self._vision_lora_is_zero = self._check_vision_lora_zero()
+        self.share_detector_encoder = (self._vision_lora_is_zero if share_detector_encoder is None
+                                       else share_detector_encoder)
+        self.training_data = self._load_training_data(json_path)
+        self.all_categories = self._extract_all_categories()
+        self.text_features_cache: Dict[str, torch.Tensor] = {}
+        self._precompute_text_features_optimized()
+
+    # -- reference-shaped helpers ---------------------------------------------------------------------------
+    def _check_vision_lora_zero(self) -> bool:
+        for n, p in self.model.visual.named_parameters():
+            if n.endswith("lora.lora_B") and ".attn.out_proj." not in n and bool((p != 0).any()):
+                return False
+        return True
+
+    def _load_training_data(self, json_path: str = "interior_dataset.json"):
+        try:
+            with open(json_path, "r", encoding="utf-8") as f:
+                return json.load(f).get("training_data", [])
+        except Exception as e:  # noqa: BLE001
+            print(f"Nie udało się wczytać training data: {e}")
+            return []
+
+    def _extract_all_categories(self) -> Dict[str, List[str]]:
+        """interior_dataset.json schema (main.py:273-295).  Label order inside a group is sorted here; the
+        reference's order comes from set iteration and is not stable between runs - results are keyed
+        by label string either way."""
+        groups = {k: set() for k in GROUP_ORDER}
+        for item in self.training_data:
+            groups["styles"].add(item.get("style", ""))
+            groups["room_types"].add(item.get("room_type", ""))
+            for key in ("characteristics", "materials", "colors"):
+                groups[key].update(item.get(key, []))
+        return {k: sorted(v for v in groups[k] if v) for k in GROUP_ORDER}
+
+    def _precompute_text_features_optimized(self):
+        print("Prekomputowanie cech tekstowych...")
+        for category, attributes in self.all_categories.items():
+            if not attributes:
+                continue
+            texts = [f"{a}" for a in attributes] if category == "room_types" else [f"wnętrze z {a}" for a in attributes]
+            self.text_features_cache[category] = _encode_labels(self.model, texts, self.device)
+        print("Prekomputowanie zakończone.")
+
+    # -- fused scoring ---------------------------------------------------------------------------------------
+    def _group_names(self) -> List[str]:
+        return [g for g in GROUP_ORDER if g in self.text_features_cache]
+
+    def _engine(self, with_detector: bool):
+        eng = self.model.visual.sync_engine()
+        names = self._group_names()
+        key = (id(eng), "analyzer", with_detector, tuple(names))
+        if getattr(eng, "_labels_owner", None) != key:
+            mats = [self.text_features_cache[g] for g in names]
+            sizes = [m.shape[0] for m in mats]
+            split = [0] * len(names)
+            if with_detector:
+                mats = [self.detector.text_features] + mats
+                sizes = [len(self.detector.categories)] + sizes
+                split = [N_INTERIOR] + split
+            eng.set_labels(torch.cat(mats, 0), sizes, split, topk=5, logit_scale=100.0)
+            eng._labels_owner = key
+        return eng, names
+
+    def _analysis_from_head(self, tv, ti, row: int, names: List[str], g0: int) -> Dict[str, list]:
+        out = {}
+        for gi, g in enumerate(names):
+            attrs = self.all_categories[g]
+            k = min(5, len(attrs))
+            out[g] = [(attrs[int(ti[row, g0 + gi, j])], float(tv[row, g0 + gi, j])) for j in range(k)]
+        return out
+
+    def _classify_pil(self, images, with_detector: bool, batch_size: int):
+        """PIL list -> (topk_val, topk_idx, split_sum, probs-of-detector) on the host, one D2H per batch."""
+        tvs, tis, sss, nons = [], [], [], []
+        for i in range(0, len(images), batch_size):
+            eng, names = self._engine(with_detector)
+            with eng._lock:
+                eng, names = self._engine(with_detector)
+                u8 = [clip.Preprocess._to_u8(im, eng.device) for im in images[i:i + batch_size]]
+                r = eng.classify(u8, want_embedding=False)
+                tvs.append(r.topk_val.cpu())
+                tis.append(r.topk_idx.cpu())
+                sss.append(r.split_sum.cpu())
+                if with_detector:
+                    nons.append(r.probs[:, N_INTERIOR:len(self.detector.categories)].sum(-1).cpu())
+        cat = lambda xs: torch.cat(xs, 0) if xs else None
+        return cat(tvs), cat(tis), cat(sss), cat(nons), names
+
+    # -- public API (reference signatures) -------------------------------------------------------------------
+    def filter_interior_images(self, image_paths, confidence_threshold: float = 0.3):
+        print(f" Filtrowanie {len(image_paths)} obrazów - wykrywanie wnętrz...")
+        with ThreadPoolExecutor(max_workers=4) as ex:  # host-side fetch/decode only; GPU work is batched below
+            imgs = list(ex.map(load_image, image_paths))
+        ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
+        interior_images, non_interior_info = [], []
+        for p, im in zip(image_paths, imgs):
+            if im is None:
+                non_interior_info.append({"path": p, "confidence": 0.0, "category": "load error",
+                                          "reason": "Nie wnętrze: load error (confidence: 0.000)"})
+        dets = self.detector.detect_batch([im for _, im in ok], confidence_threshold) if ok else []
+        for (p, im), (is_interior, confidence, category) in zip(ok, dets):
+            if is_interior:
+                interior_images.append((p, im, confidence))
+            else:
+                non_interior_info.append({"path": p, "confidence": confidence, "category": category,
+                                          "reason": f"Nie wnętrze: {category} (confidence: {confidence:.3f})"})
+        print(f" Znaleziono {len(interior_images)} obrazów wnętrz")
+        print(f" Odrzucono {len(non_interior_info)} obrazów nie-wnętrz")
+        return interior_images, non_interior_info
+
+    def _analyze_shared(self, image_paths, batch_size: int, confidence_threshold: float):
+        """filter + analyse in ONE encode per image (valid while the vision LoRA delta is zero)."""
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            imgs = list(ex.map(load_image, image_paths))
+        results = {}
+        ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
+        for p, im in zip(image_paths, imgs):
+            if im is None:
+                results[p] = {"is_interior": False, "interior_confidence": 0.0, "detected_category": "load error",
+                              "analysis": {}, "reason": "Nie wnętrze: load error (confidence: 0.000)"}
+        if not ok:
+            return results
+        tv, ti, ss, non, names = self._classify_pil([im for _, im in ok], True, max(batch_size, 64))
+        for r, (p, _) in enumerate(ok):
+            interior, top_conf = float(ss[r, 0]), float(tv[r, 0, 0])
+            category = self.detector.categories[int(ti[r, 0, 0])]
+            if interior > float(non[r]) and top_conf > confidence_threshold:
+                results[p] = {"is_interior": True, "interior_confidence": interior, "detected_category": "interior",
+                              "analysis": self._analysis_from_head(tv, ti, r, names, 1),
+                              "reason": "Success - interior image analyzed"}
+            else:
+                results[p] = {"is_interior": False, "interior_confidence": interior, "detected_category": category,
+                              "analysis": {}, "reason": f"Nie wnętrze: {category} (confidence: {interior:.3f})"}
+        return results
+
+    def analyze_images_batch(self, image_paths, batch_size: int = 16, filter_interiors: bool = True,
+                             confidence_threshold: float = 0.3):
+        results, valid_images, image_metadata = {}, [], []
+        if filter_interiors and self.share_detector_encoder:
+            return self._analyze_shared(image_paths, batch_size, confidence_threshold)
+        if filter_interiors:
+            interior_images, non_interior_info = self.filter_interior_images(image_paths, confidence_threshold)
+            for info in non_interior_info:
+                results[info["path"]] = {"is_interior": False, "interior_confidence": info["confidence"],
+                                         "detected_category": info["category"], "analysis": {}, "reason": info["reason"]}
+            for path, img, confidence in interior_images:
+                valid_images.append(img)
+                image_metadata.append({"path": path, "interior_confidence": confidence, "is_interior": True})
+        else:
+            print("  Pomijam filtrowanie wnętrz - przetwarzam wszystkie obrazy")
+            for path in image_paths:
+                img = load_image(path)
+                if img is not None:
+                    valid_images.append(img)
+                    image_metadata.append({"path": path, "interior_confidence": 1.0, "is_interior": True})
+                else:
+                    results[path] = {"is_interior": False, "interior_confidence": 0.0, "detected_category": "load error",
+                                     "analysis": {}, "reason": "Błąd ładowania"}
+        if not valid_images:
+            print("Brak obrazów do analizy")
+            return results
+        print(f"  Przetwarzam {len(valid_images)} obrazów w batchach po {batch_size}...")
+        tv, ti, _, _, names = self._classify_pil(valid_images, False, max(batch_size, 1))
+        for idx, meta in enumerate(image_metadata):
+            results[meta["path"]] = {"is_interior": True, "interior_confidence": meta["interior_confidence"],
+                                     "detected_category": "interior",
+                                     "analysis": self._analysis_from_head(tv, ti, idx, names, 0),
+                                     "reason": "Success - interior image analyzed"}
+        return results
+
+    def analyze_image_from_url(self, url, filter_interiors: bool = True):
+        img = load_image(url)
+        if img is None:
+            return {"is_interior": False, "reason": "Failed to load image"}
+        confidence = 1.0
+        if filter_interiors:
+            is_interior, confidence, category = self.detector.is_interior_image(img)
+            if not is_interior:
+                return {"is_interior": False, "interior_confidence": confidence, "detected_category": category,
+                        "analysis": {}, "reason": f"Not an interior image: {category}"}
+        tv, ti, _, _, names = self._classify_pil([img], False, 1)
+        return {"is_interior": True, "interior_confidence": confidence if filter_interiors else 1.0,
+                "detected_category": "interior", "analysis": self._analysis_from_head(tv, ti, 0, names, 0),
+                "reason": "Success - interior image analyzed"}
+
+    def _analyze_image_tensor_fast(self, image_input: torch.Tensor):
+        """image_input: preprocessed float tensor [1,3,R,R] (what the reference passes, main.py:489, 500)."""
+        eng, names = self._engine(False)
+        with eng._lock:
+            eng, names = self._engine(False)
+            r = eng.classify_patches(eng.patchify(image_input.to(eng.device)), image_input.shape[0], want_embedding=False)
+            tv, ti = r.topk_val.cpu(), r.topk_idx.cpu()
+        return self._analysis_from_head(tv, ti, 0, names, 0)
+
+
+class DatabaseStyleRoomAnalyzer:
+    """Compute half of python-worker/main_API.py:130-281 (the Mongo plumbing stays where it is): ten fixed Polish
+    style prompts `wnętrze w stylu {style}` -> per image {'style': argmax label, 'confidence': max prob}."""
+
+    STYLES = ["nowoczesny", "tradycyjny", "skandynawski", "industrialny", "minimalistyczny", "rustykalny", "glamour",
+              "boho", "klasyczny", "loft"]
+
+    def __init__(self, use_lora: bool = False, lora_weights_path: Optional[str] = None, device=None, styles=None,
+                 model=None, preprocess=None):
+        self.device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+        if model is None:
+            model, preprocess = clip.load("ViT-B/16", device=self.device)
+        self.model, self.preprocess = model, preprocess
+        self.detector = InteriorImageDetector(device=self.device, model=self.model, preprocess=self.preprocess)
+        if use_lora:
+            replace_linears_with_lora(self.model, rank=4, alpha=8)  # main_API.py:143
+            if lora_weights_path and os.path.exists(lora_weights_path):
+                load_lora_weights_to_model(self.model, lora_weights_path, strict_match=False)
+        self.styles = list(styles) if styles is not None else list(self.STYLES)
+        self.style_features = _encode_labels(self.model, [f"wnętrze w stylu {s}" for s in self.styles], self.device)
+
+    def _analyze_styles_batch(self, images, batch_size: int = 16):
+        out = []
+        for i in range(0, len(images), batch_size):
+            eng = self.model.visual.sync_engine()
+            with eng._lock:
+                eng = self.model.visual.sync_engine()
+                eng.set_labels(self.style_features, [len(self.styles)], None, topk=1, logit_scale=100.0)
+                eng._labels_owner = None
+                u8 = [clip.Preprocess._to_u8(im, eng.device) for im in images[i:i + batch_size]]
+                r = eng.classify(u8, want_embedding=False)
+                tv, ti = r.topk_val.cpu(), r.topk_idx.cpu()
+            out += [{"style": self.styles[int(ti[j, 0, 0])], "confidence": float(tv[j, 0, 0])} for j in range(tv.shape[0])]
+        return out

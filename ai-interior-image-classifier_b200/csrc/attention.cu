@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "act_types.cuh"
 #include "kernels.h"
 
 namespace iic {
@@ -43,23 +44,28 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+template <bool kF16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (kF16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 // byte offset of (row, 16-byte chunk) inside a [rows][64] bf16 tile with 128-byte rows, XOR swizzled
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 }  // namespace
 
+template <bool kF16>
 __global__ void __launch_bounds__(kWarps * 32, 4)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int TP, int H,
+attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int T, int TP, int H,
                  float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int d = H * kHd;
@@ -70,13 +76,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
   const uint32_t ks = smem_u32(smem);
   const uint32_t vs = ks + uint32_t(TP) * 128u;
-  const __nv_bfloat16* base = qkv + size_t(b) * T * (3 * d) + h * kHd;
+  const uint16_t* base = qkv + size_t(b) * T * (3 * d) + h * kHd;
 
   // ---- stage K and V of this (image, head) ----
   for (int i = threadIdx.x; i < TP * 8; i += kWarps * 32) {
     const int row = i >> 3, ch = i & 7;
     if (row < T) {
-      const __nv_bfloat16* src = base + size_t(row) * (3 * d) + ch * 8;
+      const uint16_t* src = base + size_t(row) * (3 * d) + ch * 8;
       cp_async16(ks + swz(row, ch), src + d);
       cp_async16(vs + swz(row, ch), src + 2 * d);
     } else {
@@ -97,8 +103,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     uint32_t qf[4][4];
     {
       const int r0 = q0 + g, r1 = q0 + g + 8;
-      const __nv_bfloat16* p0 = base + size_t(r0) * (3 * d);
-      const __nv_bfloat16* p1 = base + size_t(r1) * (3 * d);
+      const uint16_t* p0 = base + size_t(r0) * (3 * d);
+      const uint16_t* p1 = base + size_t(r1) * (3 * d);
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         const int c = kt * 16 + 2 * t;
@@ -129,8 +135,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
           for (int kp = 0; kp < 2; ++kp) {  // two pairs of 16-wide k-tiles
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4(ks + swz(krow, kp * 4 + (lane >> 3)), b0, b1, b2, b3);
-            mma_bf16(s[nt], qf[kp * 2], b0, b1);
-            mma_bf16(s[nt], qf[kp * 2 + 1], b2, b3);
+            mma_16816<kF16>(s[nt], qf[kp * 2], b0, b1);
+            mma_16816<kF16>(s[nt], qf[kp * 2 + 1], b2, b3);
           }
         }
       }
@@ -175,17 +181,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       for (int kt = 0; kt < 4; ++kt) {
         if (2 * kt < n_nt) {
           uint32_t pf[4];
-          pf[0] = pack2(s[2 * kt][0], s[2 * kt][1]);
-          pf[1] = pack2(s[2 * kt][2], s[2 * kt][3]);
-          pf[2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-          pf[3] = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+          pf[0] = Act<kF16>::pack(s[2 * kt][0], s[2 * kt][1]);
+          pf[1] = Act<kF16>::pack(s[2 * kt][2], s[2 * kt][3]);
+          pf[2] = Act<kF16>::pack(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+          pf[3] = Act<kF16>::pack(s[2 * kt + 1][2], s[2 * kt + 1][3]);
           const int vrow = key0 + kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
           for (int np = 0; np < 4; ++np) {  // pairs of 8-wide head-dim n-tiles
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4_trans(vs + swz(vrow, np * 2 + (lane >> 4)), b0, b1, b2, b3);
-            mma_bf16(o[np * 2], pf, b0, b1);
-            mma_bf16(o[np * 2 + 1], pf, b2, b3);
+            mma_16816<kF16>(o[np * 2], pf, b0, b1);
+            mma_16816<kF16>(o[np * 2 + 1], pf, b2, b3);
           }
         }
       }
@@ -197,18 +203,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     const int r0 = q0 + g, r1 = q0 + g + 8;
-    __nv_bfloat16* ob = out + size_t(b) * T * d + h * kHd;
+    uint16_t* ob = out + size_t(b) * T * d + h * kHd;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = nt * 8 + 2 * t;
-      if (r0 < T) *reinterpret_cast<uint32_t*>(ob + size_t(r0) * d + c) = pack2(o[nt][0] * i0, o[nt][1] * i0);
-      if (r1 < T) *reinterpret_cast<uint32_t*>(ob + size_t(r1) * d + c) = pack2(o[nt][2] * i1, o[nt][3] * i1);
+      if (r0 < T) *reinterpret_cast<uint32_t*>(ob + size_t(r0) * d + c) = Act<kF16>::pack(o[nt][0] * i0, o[nt][1] * i0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(ob + size_t(r1) * d + c) = Act<kF16>::pack(o[nt][2] * i1, o[nt][3] * i1);
     }
   }
 }
 
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int head_dim,
-                     cudaStream_t stream) {
+int launch_attention(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16, cudaStream_t stream) {
   if (B <= 0) return 0;
   if (head_dim != kHd) return -1;
   const int TP = (T + 15) / 16 * 16;
@@ -216,12 +221,20 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T,
   if (smem > 227 * 1024) return -1;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return -2;
     attr_done = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
-  attention_kernel<<<B * H, kWarps * 32, smem, stream>>>(qkv, out, T, TP, H, scale_log2e);
+  const uint16_t* q = static_cast<const uint16_t*>(qkv);
+  uint16_t* o = static_cast<uint16_t*>(out);
+  if (f16)
+    attention_kernel<true><<<B * H, kWarps * 32, smem, stream>>>(q, o, T, TP, H, scale_log2e);
+  else
+    attention_kernel<false><<<B * H, kWarps * 32, smem, stream>>>(q, o, T, TP, H, scale_log2e);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

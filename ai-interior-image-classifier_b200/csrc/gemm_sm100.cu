@@ -25,24 +25,25 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128-byte swizzle.
-bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   bool f16) {
   auto fn = get_encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint64_t gstride[1] = {ld * 2};
   cuuint32_t box[2] = {uint32_t(kBlockK), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int kCtas, int kBlockN, int kEpi>
+template <int kCtas, int kBlockN, int kEpi, bool kF16>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
                const GemmArgs& args, int num_sms, cudaStream_t stream) {
   using S = GemmSmem<kCtas, kBlockN>;
-  auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi>;
+  auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi, kF16>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return -2;
@@ -70,15 +71,15 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   return e == cudaSuccess ? 0 : -2;
 }
 
-template <int kCtas>
+template <int kCtas, bool kF16>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
                  const GemmArgs& args, int num_sms, cudaStream_t stream) {
   switch (epi) {
-    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
     default: return -1;
   }
 }
@@ -103,14 +104,15 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   }
   const uint32_t box_b = uint32_t(256 / ctas);
   CUtensorMap ta, tb, tal, tbl;
-  bool ok = make_tile_map(&ta, p.a, uint64_t(p.M), uint64_t(p.K), uint64_t(p.lda), kBlockM) &&
-            make_tile_map(&tb, p.w, uint64_t(p.N), uint64_t(p.K), uint64_t(p.ldw), box_b);
+  const bool f16 = p.f16 != 0;
+  bool ok = make_tile_map(&ta, p.a, uint64_t(p.M), uint64_t(p.K), uint64_t(p.lda), kBlockM, f16) &&
+            make_tile_map(&tb, p.w, uint64_t(p.N), uint64_t(p.K), uint64_t(p.ldw), box_b, f16);
   if (ok && lora) {
     // [rows, r_pad] operands: columns beyond r_pad are out of bounds for TMA and arrive as zeros
     const uint64_t ld = p.lora_ld > 0 ? uint64_t(p.lora_ld) : uint64_t(p.r_pad);
     const uint64_t cols = ld < uint64_t(kBlockK) ? ld : uint64_t(kBlockK);
-    ok = make_tile_map(&tal, p.lora_p, uint64_t(p.M), cols, ld, kBlockM) &&
-         make_tile_map(&tbl, p.lora_bt, uint64_t(p.N), cols, ld, box_b);
+    ok = make_tile_map(&tal, p.lora_p, uint64_t(p.M), cols, ld, kBlockM, f16) &&
+         make_tile_map(&tbl, p.lora_bt, uint64_t(p.N), cols, ld, box_b, f16);
   } else {
     tal = ta;
     tbl = tb;
@@ -129,8 +131,13 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   args.out = p.out;
   args.ldc = p.ldc;
   args.group = p.group > 0 ? p.group : 1;
-  int rc = ctas == 2 ? dispatch_epi<2>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
-                     : dispatch_epi<1>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
+  int rc;
+  if (f16)
+    rc = ctas == 2 ? dispatch_epi<2, true>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
+                   : dispatch_epi<1, true>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
+  else
+    rc = ctas == 2 ? dispatch_epi<2, false>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
+                   : dispatch_epi<1, false>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
   if (rc != 0 && err) *err = rc == -1 ? e_shape : e_launch;
   return rc;
 }

@@ -1,6 +1,6 @@
 // Persistent, warp-specialised tcgen05 GEMM for the ViT encoder:   D[M,N] = epilogue( A[M,K] . W[N,K]^T  (+ P[M,r] . Bl[N,r]^T) )
 //
-//   A  : activations, bf16, row-major (K contiguous)           -> "K-major" UMMA operand A
+//   A  : activations, bf16 (or fp16: template switch kF16), row-major (K contiguous)           -> "K-major" UMMA operand A
 //   W  : nn.Linear weight [out,in] exactly as PyTorch stores it -> "K-major" UMMA operand B (no transpose needed)
 //   P  : s * (x . lora_A), bf16 [M, r_pad] produced upstream;  Bl = lora_B^T, bf16 [N, r_pad].
 //        The LoRA update is one extra (short) k-block accumulated into the SAME TMEM tile as the frozen W.x
@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "act_types.cuh"
 #include "ptx_sm100.cuh"
 
 namespace iic {
@@ -73,12 +74,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-template <int kCtas, int kBlockN, int kEpi>
+template <int kCtas, int kBlockN, int kEpi, bool kF16>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bl,
@@ -170,10 +166,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
       }
     }
+    __syncwarp();  // reconverge before the (.aligned) teardown barriers
   } else if (warp == 1) {
     // ======================= MMA issuer (leader CTA) =======================
     if (leader && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, kBlockN);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kBlockN, kF16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -200,6 +197,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ======================= epilogue =======================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
@@ -285,14 +283,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
           }
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + size_t(out_row) * args.ldc + col;
+          uint16_t* o = reinterpret_cast<uint16_t*>(args.out) + size_t(out_row) * args.ldc + col;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 pk;
-            pk.x = pack_bf16x2(f[i], f[i + 1]);
-            pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
-            pk.z = pack_bf16x2(f[i + 4], f[i + 5]);
-            pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            pk.x = Act<kF16>::pack(f[i], f[i + 1]);
+            pk.y = Act<kF16>::pack(f[i + 2], f[i + 3]);
+            pk.z = Act<kF16>::pack(f[i + 4], f[i + 5]);
+            pk.w = Act<kF16>::pack(f[i + 6], f[i + 7]);
             *reinterpret_cast<uint4*>(o + i) = pk;
           }
         }

@@ -25,19 +25,19 @@ struct Tensor {
 
 struct LoraSlot {
   const float* a = nullptr;          // f32 [in, r4]
-  const __nv_bfloat16* bt = nullptr; // bf16 [out, lora_pad]
+  const void* bt = nullptr;          // 16-bit [out, lora_pad]
   int rank = 0, r4 = 0, r_pad = 0;
 };
 
 struct Block {
   const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-  const __nv_bfloat16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+  const void *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
   const float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
   LoraSlot lora[4];
 };
 
 struct Workspace {
-  __nv_bfloat16 *xln, *qkv, *attn, *hid, *p_a, *p_b;
+  uint16_t *xln, *qkv, *attn, *hid, *p_a, *p_b;
   float *x, *xpre;
   size_t total;
 };
@@ -50,7 +50,8 @@ struct iic_handle {
   int num_sms = 0;
   int ctas = 2;
   std::string err;
-  const __nv_bfloat16* conv_w = nullptr;
+  const void* conv_w = nullptr;
+  int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
   std::vector<Block> blocks;
@@ -84,12 +85,12 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   };
   Workspace w;
   w.x = static_cast<float*>(take(M * d * 4));
-  w.xln = static_cast<__nv_bfloat16*>(take(M * d * 2));
-  w.qkv = static_cast<__nv_bfloat16*>(take(M * 3 * d * 2));
-  w.attn = static_cast<__nv_bfloat16*>(take(M * d * 2));
-  w.hid = static_cast<__nv_bfloat16*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
-  w.p_a = static_cast<__nv_bfloat16*>(take(M * h->lora_pad * 2 + 4096));
-  w.p_b = static_cast<__nv_bfloat16*>(take(M * h->lora_pad * 2 + 4096));
+  w.xln = static_cast<uint16_t*>(take(M * d * 2));
+  w.qkv = static_cast<uint16_t*>(take(M * 3 * d * 2));
+  w.attn = static_cast<uint16_t*>(take(M * d * 2));
+  w.hid = static_cast<uint16_t*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
+  w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+  w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.total = off;
   return w;
@@ -105,8 +106,8 @@ bool check_ready(iic_handle* h) {
   return true;
 }
 
-int run_gemm(iic_handle* h, const __nv_bfloat16* a, int lda, const __nv_bfloat16* w, int M, int N, int K,
-             const LoraSlot* lora, const __nv_bfloat16* p, int epi, const float* bias, const float* residual, void* out,
+int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
+             const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
              int ldc, int group, cudaStream_t s) {
   GemmProblem g;
   g.a = a; g.lda = lda; g.w = w; g.ldw = K; g.M = M; g.N = N; g.K = K;
@@ -116,6 +117,7 @@ int run_gemm(iic_handle* h, const __nv_bfloat16* a, int lda, const __nv_bfloat16
   g.r_pad = use_lora ? lora->r_pad : 0;
   g.lora_ld = h->lora_pad;
   g.epilogue = epi; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
+  g.f16 = h->f16;
   const char* e = nullptr;
   int rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
@@ -132,7 +134,7 @@ int run_gemm(iic_handle* h, const __nv_bfloat16* a, int lda, const __nv_bfloat16
   } while (0)
 
 // patches -> residual stream after the last block (x f32 [M, d] in the workspace)
-int run_encoder(iic_handle* h, const __nv_bfloat16* patches, int B, const Workspace& w, cudaStream_t s) {
+int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const int gg = h->g * h->g;
   const float eps = 1e-5f;
@@ -141,7 +143,7 @@ int run_encoder(iic_handle* h, const __nv_bfloat16* patches, int B, const Worksp
   IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
                    nullptr, h->pos, w.xpre, d, gg, s));
   IIC_TRY(launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s));
-  IIC_TRY(launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, s));
+  IIC_TRY(launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s));
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
   for (Block& b : h->blocks) {
     const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
@@ -150,16 +152,16 @@ int run_encoder(iic_handle* h, const __nv_bfloat16* patches, int B, const Worksp
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     // x = x + attn(ln_1(x))
     IIC_TRY(launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, l_in.rank ? l_in.a : nullptr,
-                             l_in.r4, w.p_a, h->lora_pad, s));
+                             l_in.r4, w.p_a, h->lora_pad, h->f16, s));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
-    IIC_TRY(launch_attention(w.qkv, w.attn, B, T, H, d / H, s));
-    if (l_out.rank) IIC_TRY(launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, s));
+    IIC_TRY(launch_attention(w.qkv, w.attn, B, T, H, d / H, h->f16, s));
+    if (l_out.rank) IIC_TRY(launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s));
     IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
     IIC_TRY(launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
-                             l_fc.r4, w.p_a, h->lora_pad, s));
+                             l_fc.r4, w.p_a, h->lora_pad, h->f16, s));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s));
-    if (l_pr.rank) IIC_TRY(launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, s));
+    if (l_pr.rank) IIC_TRY(launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, h->f16, s));
     IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
   }
   return 0;
@@ -191,7 +193,8 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   *out = nullptr;
   if (cfg->image_size <= 0 || cfg->patch_size <= 0 || cfg->image_size % cfg->patch_size != 0 || cfg->width <= 0 ||
       cfg->width % 128 != 0 || cfg->heads <= 0 || cfg->width != cfg->heads * 64 || cfg->layers <= 0 ||
-      cfg->mlp_dim % 256 != 0 || cfg->mlp_dim * 2 < cfg->width * 4 || cfg->embed_dim <= 0 || cfg->width % 256 != 0) {
+      cfg->mlp_dim % 256 != 0 || cfg->mlp_dim * 2 < cfg->width * 4 || cfg->embed_dim <= 0 || cfg->width % 256 != 0 ||
+      (cfg->operand_dtype != IIC_DTYPE_BF16 && cfg->operand_dtype != IIC_DTYPE_F16 && cfg->operand_dtype != 0)) {
     g_create_error = "iic_create: unsupported architecture (need head_dim 64, width % 256 == 0, mlp % 256 == 0)";
     return IIC_ERR_ARG;
   }
@@ -219,6 +222,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->lora_pad = 16;
   h->num_sms = prop.multiProcessorCount;
   h->ctas = cfg->gemm_ctas == 1 ? 1 : 2;
+  h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -260,13 +264,14 @@ int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dt
     return true;
   };
   const std::string n(name);
+  const int wdt = h->f16 ? IIC_DTYPE_F16 : IIC_DTYPE_BF16;  // matmul weights share the activation operand format
 #define IIC_SET(field, type, dt, nd, s0, s1)                              \
   do {                                                                    \
     if (!want(dt, nd, s0, s1)) return IIC_ERR_ARG;                        \
     field = static_cast<type>(dev_ptr);                                   \
     return IIC_OK;                                                        \
   } while (0)
-  if (n == "conv1.weight") IIC_SET(h->conv_w, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, h->patch_kpad);
+  if (n == "conv1.weight") IIC_SET(h->conv_w, const void*, wdt, 2, d, h->patch_kpad);
   if (n == "class_embedding") IIC_SET(h->cls, const float*, IIC_DTYPE_F32, 1, d, 0);
   if (n == "positional_embedding") IIC_SET(h->pos, const float*, IIC_DTYPE_F32, 2, h->T, d);
   if (n == "ln_pre.weight") IIC_SET(h->lnpre_g, const float*, IIC_DTYPE_F32, 1, d, 0);
@@ -286,13 +291,13 @@ int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dt
         if (r == "ln_1.bias") IIC_SET(b.ln1_b, const float*, IIC_DTYPE_F32, 1, d, 0);
         if (r == "ln_2.weight") IIC_SET(b.ln2_g, const float*, IIC_DTYPE_F32, 1, d, 0);
         if (r == "ln_2.bias") IIC_SET(b.ln2_b, const float*, IIC_DTYPE_F32, 1, d, 0);
-        if (r == "attn.in_proj_weight") IIC_SET(b.w_qkv, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, 3 * d, d);
+        if (r == "attn.in_proj_weight") IIC_SET(b.w_qkv, const void*, wdt, 2, 3 * d, d);
         if (r == "attn.in_proj_bias") IIC_SET(b.b_qkv, const float*, IIC_DTYPE_F32, 1, 3 * d, 0);
-        if (r == "attn.out_proj.weight") IIC_SET(b.w_out, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, d);
+        if (r == "attn.out_proj.weight") IIC_SET(b.w_out, const void*, wdt, 2, d, d);
         if (r == "attn.out_proj.bias") IIC_SET(b.b_out, const float*, IIC_DTYPE_F32, 1, d, 0);
-        if (r == "mlp.c_fc.weight") IIC_SET(b.w_fc, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, mlp, d);
+        if (r == "mlp.c_fc.weight") IIC_SET(b.w_fc, const void*, wdt, 2, mlp, d);
         if (r == "mlp.c_fc.bias") IIC_SET(b.b_fc, const float*, IIC_DTYPE_F32, 1, mlp, 0);
-        if (r == "mlp.c_proj.weight") IIC_SET(b.w_proj, const __nv_bfloat16*, IIC_DTYPE_BF16, 2, d, mlp);
+        if (r == "mlp.c_proj.weight") IIC_SET(b.w_proj, const void*, wdt, 2, d, mlp);
         if (r == "mlp.c_proj.bias") IIC_SET(b.b_proj, const float*, IIC_DTYPE_F32, 1, d, 0);
       }
     }
@@ -311,7 +316,7 @@ int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, con
   if (!a_scaled || !b_t || (reinterpret_cast<uintptr_t>(a_scaled) & 15) || (reinterpret_cast<uintptr_t>(b_t) & 15))
     return fail(h, IIC_ERR_ARG, "iic_set_lora: null or unaligned pointer");
   s.a = a_scaled;
-  s.bt = static_cast<const __nv_bfloat16*>(b_t);
+  s.bt = b_t;
   s.rank = rank;
   s.r4 = (rank + 3) / 4 * 4;
   s.r_pad = (rank + 15) / 16 * 16;
@@ -349,7 +354,7 @@ int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int
     return fail(h, IIC_ERR_ARG, "iic_preprocess: bad argument");
   const char* e = nullptr;
   int rc = launch_preprocess(h->pre, imgs, hw, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
-                             static_cast<cudaStream_t>(stream), &e);
+                             h->f16, static_cast<cudaStream_t>(stream), &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "preprocess failed");
   return IIC_OK;
 }
@@ -358,7 +363,7 @@ int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* ou
   if (!h || !imgs || !out || B < 0 || out_layout < 0 || out_layout > 2)
     return fail(h, IIC_ERR_ARG, "iic_preprocess_same_size: bad argument");
   int rc = launch_preprocess_fast(h->pre, imgs, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
-                                  static_cast<cudaStream_t>(stream));
+                                  h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "preprocess_same_size launch failed");
   return IIC_OK;
 }
@@ -371,8 +376,8 @@ int iic_patchify(iic_handle* h, const void* chw, int dtype, int B, void* patches
         cudaSuccess)
       return fail(h, IIC_ERR_CUDA, "iic_patchify: memset failed");
   }
-  int rc = launch_chw_to_patches(chw, dtype, static_cast<__nv_bfloat16*>(patches_out), B, h->cfg.image_size,
-                                 h->cfg.patch_size, h->patch_kpad, static_cast<cudaStream_t>(stream));
+  int rc = launch_chw_to_patches(chw, dtype, patches_out, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad,
+                                 h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "patchify launch failed");
   return IIC_OK;
 }
@@ -399,7 +404,7 @@ int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_
   int rc = check_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = run_encoder(h, static_cast<const __nv_bfloat16*>(patches), B, w, s);
+  rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
   return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, nullptr, s);
 }
@@ -416,7 +421,7 @@ int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, siz
   int rc = check_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = run_encoder(h, static_cast<const __nv_bfloat16*>(patches), B, w, s);
+  rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
   return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, out, s);
 }
@@ -427,11 +432,12 @@ int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, i
                 void* out, int ldc, int group, int ctas, void* stream) {
   if (!h || !a || !w || !out) return fail(h, IIC_ERR_ARG, "iic_op_gemm: null argument");
   GemmProblem g;
-  g.a = static_cast<const __nv_bfloat16*>(a); g.lda = lda;
-  g.w = static_cast<const __nv_bfloat16*>(w); g.ldw = ldw;
+  g.a = a; g.lda = lda;
+  g.w = w; g.ldw = ldw;
   g.M = M; g.N = N; g.K = K;
-  g.lora_p = static_cast<const __nv_bfloat16*>(lora_p);
-  g.lora_bt = static_cast<const __nv_bfloat16*>(lora_bt);
+  g.lora_p = lora_p;
+  g.lora_bt = lora_bt;
+  g.f16 = h->f16;
   g.r_pad = r_pad; g.lora_ld = lora_ld;
   g.epilogue = epilogue; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
   const char* e = nullptr;
@@ -444,8 +450,8 @@ int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const fl
                      float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
                      void* stream) {
   if (!h || !x || !gamma || !beta) return fail(h, IIC_ERR_ARG, "iic_op_layernorm: null argument");
-  int rc = launch_layernorm(x, D, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), out_f32, D, rows, D, 1e-5f,
-                            lora_a_scaled, r4, static_cast<__nv_bfloat16*>(p_out), p_ld, static_cast<cudaStream_t>(stream));
+  int rc = launch_layernorm(x, D, gamma, beta, out_bf16, out_f32, D, rows, D, 1e-5f, lora_a_scaled, r4, p_out, p_ld,
+                            h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "layernorm: unsupported width or launch failure");
   return IIC_OK;
 }
@@ -453,16 +459,15 @@ int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const fl
 int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const float* lora_a_scaled, int r4, void* p_out,
                      int p_ld, void* stream) {
   if (!h || !x_bf16 || !lora_a_scaled || !p_out) return fail(h, IIC_ERR_ARG, "iic_op_lora_down: null argument");
-  int rc = launch_lora_down_bf16(static_cast<const __nv_bfloat16*>(x_bf16), K, rows, lora_a_scaled, r4,
-                                 static_cast<__nv_bfloat16*>(p_out), p_ld, static_cast<cudaStream_t>(stream));
+  int rc = launch_lora_down_bf16(x_bf16, K, rows, lora_a_scaled, r4, p_out, p_ld, h->f16,
+                                 static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "lora_down launch failed");
   return IIC_OK;
 }
 
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream) {
   if (!h || !qkv_bf16 || !out_bf16) return fail(h, IIC_ERR_ARG, "iic_op_attention: null argument");
-  int rc = launch_attention(static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), B, T,
-                            heads, 64, static_cast<cudaStream_t>(stream));
+  int rc = launch_attention(qkv_bf16, out_bf16, B, T, heads, 64, h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention launch failed");
   return IIC_OK;
 }

@@ -10,17 +10,17 @@ namespace iic {
 
 // ---- rowwise.cu ----
 int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta,
-                     __nv_bfloat16* out_bf16, float* out_f32, long long out_row_stride, int rows, int D, float eps,
-                     const float* lora_a, int r4, __nv_bfloat16* p_out, int p_ld, cudaStream_t stream);
-int launch_lora_down_bf16(const __nv_bfloat16* x, int K, int rows, const float* lora_a, int r4, __nv_bfloat16* p_out,
-                          int p_ld, cudaStream_t stream);
+                     void* out_bf16, float* out_f32, long long out_row_stride, int rows, int D, float eps,
+                     const float* lora_a, int r4, void* p_out, int p_ld, int f16, cudaStream_t stream);
+int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, int r4, void* p_out,
+                          int p_ld, int f16, cudaStream_t stream);
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 // dtype: 0 = f32, 1 = bf16, 2 = f16
-int launch_chw_to_patches(const void* img, int dtype, __nv_bfloat16* patches, int B, int R, int P, int k_pad,
+int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int f16,
                           cudaStream_t stream);
 
 // ---- attention.cu ----
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int head_dim,
+int launch_attention(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16,
                      cudaStream_t stream);
 
 // ---- head.cu ----
@@ -35,22 +35,23 @@ struct PreprocessPlan;  // opaque: host-side coefficient tables + device scratch
 PreprocessPlan* preprocess_plan_create();
 void preprocess_plan_destroy(PreprocessPlan*);
 // imgs: HOST array of B DEVICE pointers to uint8 HWC RGB images; hw: HOST array [B][2] = (height, width).
-// out_mode 0: bf16 patch matrix [B*g*g, k_pad];  out_mode 1: f32 CHW [B,3,R,R];  out_mode 2: bf16 CHW.
+// out_mode 0: 16-bit patch matrix [B*g*g, k_pad];  out_mode 1: f32 CHW [B,3,R,R];  out_mode 2: 16-bit CHW.
+// f16: 16-bit outputs are fp16 instead of bf16.
 int launch_preprocess(PreprocessPlan* plan, const uint8_t* const* imgs, const int* hw, int B, int R, int P, int k_pad,
-                      void* out, int out_mode, cudaStream_t stream, const char** err);
+                      void* out, int out_mode, int f16, cudaStream_t stream, const char** err);
 // same-size fast path: one contiguous uint8 [B,R,R,3] device buffer, no resampling.
 int launch_preprocess_fast(PreprocessPlan* plan, const uint8_t* imgs, int B, int R, int P, int k_pad, void* out,
-                           int out_mode, cudaStream_t stream);
+                           int out_mode, int f16, cudaStream_t stream);
 
 // ---- gemm_sm100.cu ----
 struct GemmProblem {
-  const __nv_bfloat16* a;   // [M, lda]   (lda = row pitch in elements, multiple of 8)
+  const void* a;   // [M, lda]   (lda = row pitch in elements, multiple of 8)
   int lda;
-  const __nv_bfloat16* w;   // [N, ldw]
+  const void* w;   // [N, ldw]
   int ldw;
   int M, N, K;
-  const __nv_bfloat16* lora_p;  // [M, r_pad] (row pitch r_pad) or null
-  const __nv_bfloat16* lora_bt; // [N, r_pad]
+  const void* lora_p;  // [M, r_pad] (row pitch r_pad) or null
+  const void* lora_bt; // [N, r_pad]
   int r_pad;                    // multiple of 16, <= 64: columns the MMA consumes
   int lora_ld;                  // row pitch (elements) of lora_p / lora_bt; 0 -> r_pad.  Columns [r_pad, 64) of the
                                 // TMA box fall outside the tensor and are zero-filled (never consumed anyway).
@@ -60,6 +61,7 @@ struct GemmProblem {
   void* out;
   int ldc;
   int group;
+  int f16;  // 16-bit operand format: 0 = bf16, 1 = fp16
 };
 // ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);

@@ -24,6 +24,7 @@
 #include <tuple>
 #include <vector>
 
+#include "act_types.cuh"
 #include "kernels.h"
 
 namespace iic {
@@ -142,16 +143,22 @@ resize_h_kernel(const ImgDesc* __restrict__ descs, const int32_t* __restrict__ t
   o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
 }
 
-__device__ __forceinline__ void store_px(void* out, int out_mode, int b, int c, int yy, int xx, int R, int P, int k_pad,
-                                         float v) {
+__device__ __forceinline__ uint16_t to16(float v, int f16) {
+  if (f16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__device__ __forceinline__ void store_px(void* out, int out_mode, int f16, int b, int c, int yy, int xx, int R, int P,
+                                         int k_pad, float v) {
   if (out_mode == 0) {
     const int g = R / P;
     const size_t row = size_t(b) * g * g + (yy / P) * g + xx / P;
-    reinterpret_cast<__nv_bfloat16*>(out)[row * k_pad + c * P * P + (yy % P) * P + xx % P] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(out)[row * k_pad + c * P * P + (yy % P) * P + xx % P] = to16(v, f16);
   } else if (out_mode == 1) {
     reinterpret_cast<float*>(out)[((size_t(b) * 3 + c) * R + yy) * R + xx] = v;
   } else {
-    reinterpret_cast<__nv_bfloat16*>(out)[((size_t(b) * 3 + c) * R + yy) * R + xx] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(out)[((size_t(b) * 3 + c) * R + yy) * R + xx] = to16(v, f16);
   }
 }
 
@@ -159,7 +166,7 @@ __device__ __forceinline__ void store_px(void* out, int out_mode, int b, int c, 
 __global__ void __launch_bounds__(256)
 resize_v_kernel(const ImgDesc* __restrict__ descs, const int32_t* __restrict__ tables,
                 const uint8_t* __restrict__ scratch, const float* __restrict__ lut, int R, int P, int k_pad, void* out,
-                int out_mode) {
+                int out_mode, int f16) {
   const ImgDesc d = descs[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * R) return;
@@ -176,16 +183,17 @@ resize_v_kernel(const ImgDesc* __restrict__ descs, const int32_t* __restrict__ t
     a2 += int(p[2]) * c;
   }
   const int b = blockIdx.y;
-  store_px(out, out_mode, b, 0, yy, xx, R, P, k_pad, lut[clip8(a0)]);
-  store_px(out, out_mode, b, 1, yy, xx, R, P, k_pad, lut[256 + clip8(a1)]);
-  store_px(out, out_mode, b, 2, yy, xx, R, P, k_pad, lut[512 + clip8(a2)]);
+  store_px(out, out_mode, f16, b, 0, yy, xx, R, P, k_pad, lut[clip8(a0)]);
+  store_px(out, out_mode, f16, b, 1, yy, xx, R, P, k_pad, lut[256 + clip8(a1)]);
+  store_px(out, out_mode, f16, b, 2, yy, xx, R, P, k_pad, lut[512 + clip8(a2)]);
 }
 
 // Same-size fast path, patch-matrix output, P == 16: one thread per (image, row, patch-x) moves 16 pixels:
 // 48 contiguous input bytes -> three 32-byte bf16 runs.
+template <bool kF16>
 __global__ void __launch_bounds__(256)
 preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut,
-                           __nv_bfloat16* __restrict__ out, int B, int R, int k_pad) {
+                           uint16_t* __restrict__ out, int B, int R, int k_pad) {
   __shared__ float s_lut[768];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
   __syncthreads();
@@ -207,7 +215,7 @@ preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restr
   }
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(w);
   const int py = y >> 4, ky = y & 15;
-  __nv_bfloat16* dst = out + (size_t(b) * g * g + py * g + px) * k_pad + ky * 16;
+  uint16_t* dst = out + (size_t(b) * g * g + py * g + px) * k_pad + ky * 16;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     uint32_t pk[8];
@@ -215,8 +223,7 @@ preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restr
     for (int j = 0; j < 8; ++j) {
       const float lo = s_lut[c * 256 + bytes[(2 * j) * 3 + c]];
       const float hi = s_lut[c * 256 + bytes[(2 * j + 1) * 3 + c]];
-      __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-      pk[j] = *reinterpret_cast<uint32_t*>(&v);
+      pk[j] = Act<kF16>::pack(lo, hi);
     }
     uint4* o = reinterpret_cast<uint4*>(dst + c * 256);
     o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -226,8 +233,8 @@ preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restr
 
 // generic same-size path (any P / output mode): thread per pixel
 __global__ void __launch_bounds__(256)
-preprocess_same_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut, void* out, int out_mode, int B,
-                       int R, int P, int k_pad) {
+preprocess_same_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut, void* out, int out_mode, int f16,
+                       int B, int R, int P, int k_pad) {
   const long long total = (long long)B * R * R;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -236,9 +243,9 @@ preprocess_same_kernel(const uint8_t* __restrict__ img, const float* __restrict_
   const int yy = int(t % R);
   const int b = int(t / R);
   const uint8_t* p = img + size_t(i) * 3;
-  store_px(out, out_mode, b, 0, yy, xx, R, P, k_pad, lut[p[0]]);
-  store_px(out, out_mode, b, 1, yy, xx, R, P, k_pad, lut[256 + p[1]]);
-  store_px(out, out_mode, b, 2, yy, xx, R, P, k_pad, lut[512 + p[2]]);
+  store_px(out, out_mode, f16, b, 0, yy, xx, R, P, k_pad, lut[p[0]]);
+  store_px(out, out_mode, f16, b, 1, yy, xx, R, P, k_pad, lut[256 + p[1]]);
+  store_px(out, out_mode, f16, b, 2, yy, xx, R, P, k_pad, lut[512 + p[2]]);
 }
 
 }  // namespace
@@ -299,23 +306,27 @@ bool grow(T*& ptr, size_t& cap, size_t need) {
 }  // namespace
 
 int launch_preprocess_fast(PreprocessPlan* plan, const uint8_t* imgs, int B, int R, int P, int k_pad, void* out,
-                           int out_mode, cudaStream_t stream) {
+                           int out_mode, int f16, cudaStream_t stream) {
   if (B <= 0) return 0;
   if (plan == nullptr || R % P != 0) return -1;
   if (out_mode == 0 && P == 16 && (reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && k_pad % 8 == 0) {
     const long long total = (long long)B * R * (R / 16);
-    preprocess_fast_p16_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-        imgs, plan->d_lut, reinterpret_cast<__nv_bfloat16*>(out), B, R, k_pad);
+    if (f16)
+      preprocess_fast_p16_kernel<true><<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+          imgs, plan->d_lut, reinterpret_cast<uint16_t*>(out), B, R, k_pad);
+    else
+      preprocess_fast_p16_kernel<false><<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+          imgs, plan->d_lut, reinterpret_cast<uint16_t*>(out), B, R, k_pad);
   } else {
     const long long total = (long long)B * R * R;
-    preprocess_same_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(imgs, plan->d_lut, out, out_mode, B, R, P,
-                                                                            k_pad);
+    preprocess_same_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(imgs, plan->d_lut, out, out_mode, f16, B,
+                                                                            R, P, k_pad);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int launch_preprocess(PreprocessPlan* plan, const uint8_t* const* imgs, const int* hw, int B, int R, int P, int k_pad,
-                      void* out, int out_mode, cudaStream_t stream, const char** err) {
+                      void* out, int out_mode, int f16, cudaStream_t stream, const char** err) {
   static const char* e_arg = "preprocess: bad argument (null image, non-positive size, or R % patch != 0)";
   static const char* e_mem = "preprocess: device/pinned allocation failed";
   static const char* e_launch = "preprocess: CUDA launch/copy failed";
@@ -407,7 +418,7 @@ int launch_preprocess(PreprocessPlan* plan, const uint8_t* const* imgs, const in
     resize_h_kernel<<<gh, 256, 0, stream>>>(plan->d_descs, plan->d_tables, plan->d_scratch, R);
     dim3 gv(unsigned((size_t(R) * R + 255) / 256), unsigned(B));
     resize_v_kernel<<<gv, 256, 0, stream>>>(plan->d_descs, plan->d_tables, plan->d_scratch, plan->d_lut, R, P, k_pad, out,
-                                            out_mode);
+                                            out_mode, f16);
     ok = cudaGetLastError() == cudaSuccess;
   }
   if (!ok) { if (err) *err = e_launch; return -2; }

@@ -258,11 +258,12 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;
   return d;
 }
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, no negate/saturate/sparsity.
+// Instruction descriptor, kind::f16: D fp32, A/B bf16 or f16, both K-major, no negate/saturate/sparsity.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)  [15] A major (0=K)  [16] B major (0=K)
 //   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+//   A/B format field: 0 = f16, 1 = bf16
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "act_types.cuh"
 #include "kernels.h"
 
 namespace iic {
@@ -23,12 +24,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One warp per row.  kVec = D / 128 float4 chunks per lane (D = 768 -> 6, 1024 -> 8).
 // out_bf16 / out_f32 may each be null.  If lora_a != null also emits P[row, 0..r_pad) = xln . lora_a
 // (lora_a is [D, r4] fp32 with the LoRA scaling already folded in, r4 = rank rounded up to 4; P row pitch = p_ld).
-template <int kVec>
+template <int kVec, bool kF16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                 const float* __restrict__ beta, uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32,
                  long long out_row_stride, int rows, float eps, const float* __restrict__ lora_a, int r4,
-                 __nv_bfloat16* __restrict__ p_out, int p_ld) {
+                 uint16_t* __restrict__ p_out, int p_ld) {
   constexpr int D = kVec * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -67,10 +68,9 @@ layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const floa
     uint2* o = reinterpret_cast<uint2*>(out_bf16 + size_t(warp) * out_row_stride);
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[j].x, v[j].y), hi = __floats2bfloat162_rn(v[j].z, v[j].w);
       uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      pk.x = Act<kF16>::pack(v[j].x, v[j].y);
+      pk.y = Act<kF16>::pack(v[j].z, v[j].w);
       o[lane + 32 * j] = pk;
     }
   }
@@ -92,10 +92,9 @@ layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const floa
       }
       a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
       if (lane == 0) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        pk.x = Act<kF16>::pack(a0, a1);
+        pk.y = Act<kF16>::pack(a2, a3);
         *reinterpret_cast<uint2*>(p_out + size_t(warp) * p_ld + c0) = pk;
       }
     }
@@ -103,9 +102,10 @@ layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const floa
 }
 
 // P[row, 0..r4) = X[row, :] . A   for bf16 X [rows, K] (K % 256 == 0).  One warp per row, fp32 accumulate.
+template <bool kF16>
 __global__ void __launch_bounds__(256)
-lora_down_bf16_kernel(const __nv_bfloat16* __restrict__ x, int K, int rows, const float* __restrict__ lora_a, int r4,
-                      __nv_bfloat16* __restrict__ p_out, int p_ld) {
+lora_down_bf16_kernel(const uint16_t* __restrict__ x, int K, int rows, const float* __restrict__ lora_a, int r4,
+                      uint16_t* __restrict__ p_out, int p_ld) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -114,10 +114,10 @@ lora_down_bf16_kernel(const __nv_bfloat16* __restrict__ x, int K, int rows, cons
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int ch = lane; ch < K / 8; ch += 32) {
       const uint4 raw = xr[ch];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 xv = __bfloat1622float2(h[e]);
+        const float2 xv = Act<kF16>::unpack(h[e]);
         const int k = ch * 8 + 2 * e;
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k) * r4 + c0));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 1) * r4 + c0));
@@ -129,10 +129,9 @@ lora_down_bf16_kernel(const __nv_bfloat16* __restrict__ x, int K, int rows, cons
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     if (lane == 0) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
       uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      pk.x = Act<kF16>::pack(a0, a1);
+      pk.y = Act<kF16>::pack(a2, a3);
       *reinterpret_cast<uint2*>(p_out + size_t(warp) * p_ld + c0) = pk;
     }
   }
@@ -149,9 +148,10 @@ __global__ void fill_cls_kernel(float* __restrict__ x_pre, const float* __restri
 
 // float/bf16 CHW image batch [B,3,R,R] -> bf16 patch matrix [B*g*g, k_pad], column = c*P*P + ky*P + kx
 // (the im2col of a stride==kernel conv is a pure re-index).  One thread per (b, c, y, patch-x) handles P pixels.
-template <typename T>
+template <typename T, bool kF16>
 __global__ void __launch_bounds__(256)
-chw_to_patches_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ patches, int B, int R, int P, int k_pad) {
+chw_to_patches_kernel(const T* __restrict__ img, typename Act<kF16>::T* __restrict__ patches, int B, int R, int P,
+                      int k_pad) {
   const int g = R / P;
   const long long total = (long long)B * 3 * R * g;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,49 +163,53 @@ chw_to_patches_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ pat
   const int b = int(t / 3);
   const int py = y / P, ky = y - py * P;
   const T* src = img + ((size_t(b) * 3 + c) * R + y) * R + px * P;
-  __nv_bfloat16* dst = patches + (size_t(b) * g * g + py * g + px) * k_pad + c * P * P + ky * P;
-  for (int kx = 0; kx < P; ++kx) dst[kx] = __float2bfloat16(float(src[kx]));
+  typename Act<kF16>::T* dst = patches + (size_t(b) * g * g + py * g + px) * k_pad + c * P * P + ky * P;
+  for (int kx = 0; kx < P; ++kx) dst[kx] = Act<kF16>::from_float(float(src[kx]));
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
-int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta,
-                     __nv_bfloat16* out_bf16, float* out_f32, long long out_row_stride, int rows, int D, float eps,
-                     const float* lora_a, int r4, __nv_bfloat16* p_out, int p_ld, cudaStream_t stream) {
-  if (rows <= 0) return 0;
+template <bool kF16>
+static int layernorm_dispatch(const float* x, long long x_row_stride, const float* gamma, const float* beta, uint16_t* ob,
+                              float* of, long long ors, int rows, int D, float eps, const float* la, int r4, uint16_t* po,
+                              int pld, cudaStream_t stream) {
   const int threads = 256;
   const int blocks = (rows + (threads / 32) - 1) / (threads / 32);
   switch (D) {
-    case 512:
-      layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, out_bf16, out_f32,
-                                                          out_row_stride, rows, eps, lora_a, r4, p_out, p_ld);
-      break;
-    case 768:
-      layernorm_kernel<6><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, out_bf16, out_f32,
-                                                          out_row_stride, rows, eps, lora_a, r4, p_out, p_ld);
-      break;
-    case 1024:
-      layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, out_bf16, out_f32,
-                                                          out_row_stride, rows, eps, lora_a, r4, p_out, p_ld);
-      break;
-    case 1280:
-      layernorm_kernel<10><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, out_bf16, out_f32,
-                                                           out_row_stride, rows, eps, lora_a, r4, p_out, p_ld);
-      break;
-    default:
-      return -1;
+    case 512: layernorm_kernel<4, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
+    case 768: layernorm_kernel<6, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
+    case 1024: layernorm_kernel<8, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
+    case 1280: layernorm_kernel<10, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
+    default: return -1;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int launch_lora_down_bf16(const __nv_bfloat16* x, int K, int rows, const float* lora_a, int r4, __nv_bfloat16* p_out,
-                          int p_ld, cudaStream_t stream) {
+int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta, void* out_bf16,
+                     float* out_f32, long long out_row_stride, int rows, int D, float eps, const float* lora_a, int r4,
+                     void* p_out, int p_ld, int f16, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  uint16_t* ob = static_cast<uint16_t*>(out_bf16);
+  uint16_t* po = static_cast<uint16_t*>(p_out);
+  return f16 ? layernorm_dispatch<true>(x, x_row_stride, gamma, beta, ob, out_f32, out_row_stride, rows, D, eps, lora_a,
+                                        r4, po, p_ld, stream)
+             : layernorm_dispatch<false>(x, x_row_stride, gamma, beta, ob, out_f32, out_row_stride, rows, D, eps, lora_a,
+                                         r4, po, p_ld, stream);
+}
+
+int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, int r4, void* p_out, int p_ld, int f16,
+                          cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (K % 8 != 0) return -1;
   const int threads = 256;
   const int blocks = (rows + 7) / 8;
-  lora_down_bf16_kernel<<<blocks, threads, 0, stream>>>(x, K, rows, lora_a, r4, p_out, p_ld);
+  if (f16)
+    lora_down_bf16_kernel<true><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a, r4,
+                                                                static_cast<uint16_t*>(p_out), p_ld);
+  else
+    lora_down_bf16_kernel<false><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a, r4,
+                                                                 static_cast<uint16_t*>(p_out), p_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -216,21 +220,28 @@ int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int launch_chw_to_patches(const void* img, int dtype, __nv_bfloat16* patches, int B, int R, int P, int k_pad,
+template <bool kF16>
+static int patches_dispatch(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int blocks,
+                            cudaStream_t stream) {
+  using OT = typename Act<kF16>::T;
+  if (dtype == 0)
+    chw_to_patches_kernel<float, kF16><<<blocks, 256, 0, stream>>>(static_cast<const float*>(img), static_cast<OT*>(patches), B, R, P, k_pad);
+  else if (dtype == 1)
+    chw_to_patches_kernel<__nv_bfloat16, kF16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(img), static_cast<OT*>(patches), B, R, P, k_pad);
+  else if (dtype == 2)
+    chw_to_patches_kernel<__half, kF16><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(img), static_cast<OT*>(patches), B, R, P, k_pad);
+  else
+    return -1;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int f16,
                           cudaStream_t stream) {
   const long long total = (long long)B * 3 * R * (R / P);
   if (total <= 0) return 0;
   const int blocks = int((total + 255) / 256);
-  if (dtype == 0)
-    chw_to_patches_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(img), patches, B, R, P, k_pad);
-  else if (dtype == 1)
-    chw_to_patches_kernel<__nv_bfloat16>
-        <<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(img), patches, B, R, P, k_pad);
-  else if (dtype == 2)
-    chw_to_patches_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(img), patches, B, R, P, k_pad);
-  else
-    return -1;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  return f16 ? patches_dispatch<true>(img, dtype, patches, B, R, P, k_pad, blocks, stream)
+             : patches_dispatch<false>(img, dtype, patches, B, R, P, k_pad, blocks, stream);
 }
 
 }  // namespace iic

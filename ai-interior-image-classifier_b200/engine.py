@@ -8,6 +8,7 @@ device, or without the built extension, raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -67,7 +68,8 @@ class Engine:
     """One engine = one GPU.  Calls are serialised by an internal lock (the reference calls its detector from a
     4-thread pool, /root/reference/main.py:345-346)."""
 
-    def __init__(self, arch: VisionArch = VIT_B_16, device: "torch.device | str | int" = "cuda", gemm_ctas: int = 0):
+    def __init__(self, arch: VisionArch = VIT_B_16, device: "torch.device | str | int" = "cuda", gemm_ctas: int = 0,
+                 operand_dtype: "torch.dtype | str | None" = None):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise RuntimeError("iic-b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -77,8 +79,17 @@ class Engine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.arch = arch
+        if operand_dtype is None:
+            operand_dtype = os.environ.get("IIC_OPERAND_DTYPE", "bf16")
+        if isinstance(operand_dtype, str):
+            operand_dtype = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "f16": torch.float16,
+                             "fp16": torch.float16, "float16": torch.float16}[operand_dtype.lower()]
+        if operand_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
+        self.op_dtype = operand_dtype
         cfg = L.IicConfig(arch.image_size, arch.patch_size, arch.width, arch.layers, arch.heads, arch.mlp_dim,
-                          arch.embed_dim, arch.activation, self.device.index, gemm_ctas)
+                          arch.embed_dim, arch.activation, self.device.index, gemm_ctas,
+                          L.DTYPE_F16 if operand_dtype == torch.float16 else L.DTYPE_BF16)
         h = C.c_void_p()
         rc = self.lib.iic_create(C.byref(h), C.byref(cfg))
         if rc != L.IIC_OK:
@@ -119,11 +130,11 @@ class Engine:
         Linear / conv weights are rounded to bf16 here (the compute dtype), everything else stays fp32."""
         a = self.arch
         f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
-        bf16 = lambda t: t.detach().to(self.device, torch.float32).to(torch.bfloat16).contiguous()
+        bf16 = lambda t: t.detach().to(self.device, torch.float32).to(self.op_dtype).contiguous()
         conv = sd["conv1.weight"].detach().to(self.device, torch.float32).reshape(a.width, -1)
         if conv.shape[1] != self.dims.patch_kpad:
             conv = torch.nn.functional.pad(conv, (0, self.dims.patch_kpad - conv.shape[1]))
-        self.load_weight("conv1.weight", conv.to(torch.bfloat16))
+        self.load_weight("conv1.weight", conv.to(self.op_dtype))
         for n in ("class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight",
                   "ln_post.bias", "proj"):
             self.load_weight(n, f32(sd[n]))
@@ -145,12 +156,20 @@ class Engine:
                 self._lora.pop((layer, which), None)
                 return
             r = lora_a.shape[1]
+            d, mlp = self.arch.width, self.arch.mlp_dim
+            want_in, want_out = {L.LORA_IN_PROJ: (d, 3 * d), L.LORA_OUT_PROJ: (d, d), L.LORA_C_FC: (d, mlp),
+                                 L.LORA_C_PROJ: (mlp, d)}[which]
+            if tuple(lora_a.shape) != (want_in, r) or tuple(lora_b.shape) != (r, want_out):
+                raise ValueError(
+                    f"LoRA pair for layer {layer} slot {which} has shapes {tuple(lora_a.shape)} / {tuple(lora_b.shape)}, "
+                    f"expected ({want_in}, r) / (r, {want_out}) - a text-tower checkpoint suffix-matched onto the vision "
+                    f"tower? (SURVEY appendix B hazard)")
             r4 = (r + 3) // 4 * 4
             pad = self.dims.lora_pad
             a = torch.zeros(lora_a.shape[0], r4, device=self.device, dtype=torch.float32)
             a[:, :r] = lora_a.detach().to(self.device, torch.float32) * float(scaling)
-            bt = torch.zeros(lora_b.shape[1], pad, device=self.device, dtype=torch.bfloat16)
-            bt[:, :r] = lora_b.detach().to(self.device, torch.float32).t().to(torch.bfloat16)
+            bt = torch.zeros(lora_b.shape[1], pad, device=self.device, dtype=self.op_dtype)
+            bt[:, :r] = lora_b.detach().to(self.device, torch.float32).t().to(self.op_dtype)
             L.check(self.h, self.lib.iic_set_lora(self.h, layer, which, a.data_ptr(), bt.data_ptr(), r), "iic_set_lora")
             self._lora[(layer, which)] = (a, bt)
 
@@ -183,7 +202,7 @@ class Engine:
         rows = B * self.arch.grid * self.arch.grid
         if self._patches is None or self._patches.shape[0] < rows:
             self._patches = None
-            self._patches = torch.zeros(rows, self.dims.patch_kpad, dtype=torch.bfloat16, device=self.device)
+            self._patches = torch.zeros(rows, self.dims.patch_kpad, dtype=self.op_dtype, device=self.device)
         return self._patches[:rows]
 
     # ------------------------------------------------------------------ preprocessing
@@ -205,7 +224,7 @@ class Engine:
         a = self.arch
         if layout == L.OUT_PATCHES_BF16:
             return self.patch_buffer(B)
-        dt = torch.float32 if layout == L.OUT_CHW_F32 else torch.bfloat16
+        dt = torch.float32 if layout == L.OUT_CHW_F32 else self.op_dtype
         return torch.empty(B, 3, a.image_size, a.image_size, dtype=dt, device=self.device)
 
     def preprocess(self, images_u8: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
@@ -299,7 +318,7 @@ class Engine:
         N = w.shape[0]
         f32_out = epilogue in (L.EPI_BIAS_RES_F32, L.EPI_POS_F32)
         if out is None:
-            out = torch.empty(out_rows or M, N, dtype=torch.float32 if f32_out else torch.bfloat16, device=self.device)
+            out = torch.empty(out_rows or M, N, dtype=torch.float32 if f32_out else self.op_dtype, device=self.device)
         lora_ld = lora_p.stride(0) if lora_p is not None else 0
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_gemm(self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
@@ -308,26 +327,27 @@ class Engine:
                                                  _stream_ptr(self.device)), "iic_op_gemm")
         return out
 
-    def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=torch.bfloat16,
+    def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=None,
                      lora_a_scaled: Optional[torch.Tensor] = None, p_ld: int = 16):
         rows, D = x.shape
+        out_dtype = out_dtype or self.op_dtype
         out = torch.empty(rows, D, dtype=out_dtype, device=self.device)
         p = None
         r4 = 0
         if lora_a_scaled is not None:
             r4 = lora_a_scaled.shape[1]
-            p = torch.zeros(rows, p_ld, dtype=torch.bfloat16, device=self.device)
+            p = torch.zeros(rows, p_ld, dtype=self.op_dtype, device=self.device)
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_layernorm(
                 self.h, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                out.data_ptr() if out_dtype == torch.bfloat16 else None,
+                out.data_ptr() if out_dtype != torch.float32 else None,
                 out.data_ptr() if out_dtype == torch.float32 else None, rows, D, _ptr(lora_a_scaled), r4, _ptr(p), p_ld,
                 _stream_ptr(self.device)), "iic_op_layernorm")
         return (out, p) if lora_a_scaled is not None else out
 
     def op_lora_down(self, x: torch.Tensor, lora_a_scaled: torch.Tensor, p_ld: int = 16) -> torch.Tensor:
         rows, K = x.shape
-        p = torch.zeros(rows, p_ld, dtype=torch.bfloat16, device=self.device)
+        p = torch.zeros(rows, p_ld, dtype=self.op_dtype, device=self.device)
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_lora_down(self.h, x.data_ptr(), K, rows, lora_a_scaled.data_ptr(),
                                                       lora_a_scaled.shape[1], p.data_ptr(), p_ld,
@@ -335,7 +355,7 @@ class Engine:
         return p
 
     def op_attention(self, qkv: torch.Tensor, B: int, T: int, heads: int) -> torch.Tensor:
-        out = torch.empty(B * T, heads * 64, dtype=torch.bfloat16, device=self.device)
+        out = torch.empty(B * T, heads * 64, dtype=self.op_dtype, device=self.device)
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_attention(self.h, qkv.data_ptr(), out.data_ptr(), B, T, heads,
                                                       _stream_ptr(self.device)), "iic_op_attention")

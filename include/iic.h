@@ -66,6 +66,9 @@ typedef struct iic_config {
   int activation; /* IIC_ACT_*                                 */
   int device;     /* CUDA ordinal                              */
   int gemm_ctas;  /* 0 = default, 1 = single-SM tiles, 2 = CTA pairs (tcgen05 cta_group::2) */
+  int operand_dtype; /* 16-bit format of activations and matmul weights: IIC_DTYPE_BF16 (default, also for 0) or
+                        IIC_DTYPE_F16 (OpenAI CLIP's own GPU dtype; same tensor-core rate, 3 more mantissa bits).
+                        Accumulation, LayerNorm, softmax, the residual stream and the head are fp32 in both. */
 } iic_config;
 
 typedef struct iic_dims {
@@ -83,6 +86,7 @@ int iic_get_dims(const iic_handle* h, iic_dims* out);
 const char* iic_version(void);
 
 /* ---- weights (borrowed device pointers; names are OpenAI-CLIP `visual.` state-dict names without the prefix) --
+ *   ("bf16" below means the handle's operand_dtype: bf16 or fp16)
  *   conv1.weight                      bf16 [width, patch_kpad]   (conv weight flattened (c,ky,kx), zero padded)
  *   class_embedding                   f32  [width]
  *   positional_embedding              f32  [T, width]

@@ -23,4 +23,12 @@ def engine(iic):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    return iic.Engine(iic.VIT_B_16, "cuda:0")
+    return iic.Engine(iic.VIT_B_16, "cuda:0", operand_dtype="bf16")
+
+
+@pytest.fixture(scope="session")
+def engine_f16(iic):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return iic.Engine(iic.VIT_B_16, "cuda:0", operand_dtype="f16")

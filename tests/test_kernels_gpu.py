@@ -188,3 +188,47 @@ def test_head_from_embeddings(engine):
             if split[gi]:
                 assert torch.allclose(r.split_sum[:, gi], p[:, :split[gi]].sum(-1), rtol=1e-4, atol=1e-6)
             off += n
+
+
+# ---------------------------------------------------------------------------------------------- fp16 operand mode
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+def test_f16_gemm_lora_gelu(engine_f16, ctas):
+    """same kernels instantiated for fp16 operands (instruction descriptor, TMA dtype, packers)"""
+    eng = engine_f16
+    M, N, K, rank = 197 * 5 + 7, 3072, 768, 4
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    A = torch.randn(K, rank, device="cuda", generator=g) * 0.04
+    Bm = (torch.randn(rank, N, device="cuda", generator=g) * 0.3)
+    p = eng.op_lora_down(x, A.contiguous())
+    assert p.dtype == torch.float16
+    bt = torch.zeros(N, 16, device="cuda", dtype=torch.float16)
+    bt[:, :rank] = Bm.t().half()
+    out = eng.op_gemm(x, w, L.EPI_BIAS_GELU_BF16, bias=bias, lora_p=p, lora_bt=bt, r_pad=16, ctas=ctas)
+    assert out.dtype == torch.float16
+    ref = quick_gelu(x.float() @ w.float().t() + bias + p[:, :rank].float() @ bt[:, :rank].float().t())
+    # fp16 output rounding: 2^-11 relative
+    assert torch.allclose(out.float(), ref, rtol=2 ** -9, atol=3e-3), (out.float() - ref).abs().max()
+    x32 = torch.randn(M, 768, device="cuda", generator=g)
+    w2 = (torch.randn(768, N, device="cuda", generator=g) * N ** -0.5).half()
+    ref2 = x32 + out.float() @ w2.float().t()
+    eng.op_gemm(out, w2, L.EPI_BIAS_RES_F32, residual=x32, out=x32, ctas=ctas)
+    assert torch.allclose(x32, ref2, rtol=1e-4, atol=3e-4), (x32 - ref2).abs().max()
+
+
+def test_f16_layernorm_attention(engine_f16):
+    eng = engine_f16
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(197 * 2, 768, device="cuda", generator=g) * 2
+    gamma, beta = torch.randn(768, device="cuda", generator=g), torch.randn(768, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (768,), gamma, beta, 1e-5)
+    out = eng.op_layernorm(x, gamma, beta)
+    assert out.dtype == torch.float16 and torch.allclose(out.float(), ref, rtol=2 ** -10, atol=1e-6)
+    B, T, H = 2, 197, 12
+    qkv = torch.randn(B * T, 3 * H * 64, device="cuda", generator=g).half()
+    o = eng.op_attention(qkv, B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    r = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
+    assert torch.allclose(o.float(), r, rtol=2 ** -8, atol=3e-3), (o.float() - r).abs().max()
