@@ -318,6 +318,29 @@ def build_model(name: str = "ViT-B/16", state_dict: Optional[Dict[str, torch.Ten
     return model.eval()
 
 
+def build_visual(name: str = "ViT-B/16", seed: int = 0) -> VisionTransformer:
+    """Vision tower only (what the image hot path needs), seeded random weights with the upstream init scales:
+    attn_std = width^-0.5, proj_std = width^-0.5 * (2*layers)^-0.5, fc_std = (2*width)^-0.5."""
+    cfg = _MODELS[name]
+    rng = torch.random.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        w, layers = cfg["vision_width"], cfg["vision_layers"]
+        v = VisionTransformer(cfg["image_resolution"], cfg["vision_patch_size"], w, layers, w // 64, cfg["embed_dim"])
+        attn_std, fc_std = w ** -0.5, (2 * w) ** -0.5
+        proj_std = attn_std * (2 * layers) ** -0.5
+        for b in v.transformer.resblocks:
+            nn.init.normal_(b.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(b.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(b.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(b.mlp.c_proj.weight, std=proj_std)
+            for t in (b.attn.in_proj_bias, b.attn.out_proj.bias, b.mlp.c_fc.bias, b.mlp.c_proj.bias):
+                nn.init.normal_(t, std=0.02)
+    finally:
+        torch.random.set_rng_state(rng)
+    return v.eval()
+
+
 def _checkpoint_state_dict(path: str) -> Optional[Dict[str, torch.Tensor]]:
     try:
         try:

@@ -44,7 +44,40 @@ struct Workspace {
 
 }  // namespace
 
+namespace {
+// Optional per-kernel-class CUDA-event timing on the caller's stream (bench.py's roofline line) + launch counter.
+enum KClass { kGemm = 0, kLayerNorm = 1, kAttention = 2, kLoraDown = 3, kHead = 4, kPreprocess = 5, kMisc = 6, kNumClasses = 7 };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t used = 0;
+  long long launches[kNumClasses] = {0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+struct Scope {  // brackets one launch
+  Profiler& p; int cls; cudaStream_t s; cudaEvent_t a = nullptr;
+  Scope(Profiler& p_, int cls_, cudaStream_t s_) : p(p_), cls(cls_), s(s_) {
+    p.launches[cls]++;
+    if (p.on) { a = p.get(); cudaEventRecord(a, s); }
+  }
+  ~Scope() {
+    if (p.on) { cudaEvent_t b = p.get(); cudaEventRecord(b, s); p.spans.push_back({cls, a, b}); }
+  }
+};
+}  // namespace
+
 struct iic_handle {
+  Profiler prof;
   iic_config cfg;
   int T, g, patch_k, patch_kpad, lora_pad;
   int num_sms = 0;
@@ -119,9 +152,16 @@ int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N,
   g.epilogue = epi; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
   g.f16 = h->f16;
   const char* e = nullptr;
+  Scope sc(h->prof, kGemm, s);
   int rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
   return 0;
+}
+
+template <class F>
+int timed(iic_handle* h, int cls, cudaStream_t s, F&& f) {
+  Scope sc(h->prof, cls, s);
+  return f();
 }
 
 #define IIC_TRY(expr)                                                  \
@@ -142,8 +182,10 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
   // conv1 as GEMM; epilogue adds positional_embedding[1 + p] and scatters to token rows 1..g*g of each image
   IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
                    nullptr, h->pos, w.xpre, d, gg, s));
-  IIC_TRY(launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s));
-  IIC_TRY(launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s));
+  IIC_TRY(timed(h, kMisc, s, [&] { return launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s); }));
+  IIC_TRY(timed(h, kLayerNorm, s, [&] {
+    return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+  }));
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
   for (Block& b : h->blocks) {
     const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
@@ -151,17 +193,27 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
     const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     // x = x + attn(ln_1(x))
-    IIC_TRY(launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, l_in.rank ? l_in.a : nullptr,
-                             l_in.r4, w.p_a, h->lora_pad, h->f16, s));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, l_in.rank ? l_in.a : nullptr,
+                              l_in.r4, w.p_a, h->lora_pad, h->f16, s);
+    }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
-    IIC_TRY(launch_attention(w.qkv, w.attn, B, T, H, d / H, h->f16, s));
-    if (l_out.rank) IIC_TRY(launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s));
+    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(w.qkv, w.attn, B, T, H, d / H, h->f16, s); }));
+    if (l_out.rank)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s);
+      }));
     IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
-    IIC_TRY(launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
-                             l_fc.r4, w.p_a, h->lora_pad, h->f16, s));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
+                              l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
+    }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s));
-    if (l_pr.rank) IIC_TRY(launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, h->f16, s));
+    if (l_pr.rank)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, h->f16, s);
+      }));
     IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
   }
   return 0;
@@ -173,6 +225,7 @@ int run_head(iic_handle* h, const float* x_cls, long long x_img_stride, const fl
   if (scores && (h->text == nullptr || h->G <= 0)) return fail(h, IIC_ERR_STATE, "iic_set_labels has not been called");
   if (scores && (out->topk_val == nullptr || out->topk_idx == nullptr))
     return fail(h, IIC_ERR_ARG, "iic_head_out.topk_val / topk_idx are required");
+  Scope sc(h->prof, kHead, s);
   int rc = launch_head(x_cls, x_img_stride, h->lnpost_g, h->lnpost_b, 1e-5f, h->proj, h->cfg.width, h->cfg.embed_dim,
                        scores ? h->text : nullptr, scores ? h->L : 0, h->d_group_off,
                        h->has_split ? h->d_group_split : nullptr, scores ? h->G : 0, h->topk, h->logit_scale, B, emb_out,
@@ -353,6 +406,8 @@ int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int
   if (!h || !imgs || !hw || !out || B < 0 || out_layout < 0 || out_layout > 2)
     return fail(h, IIC_ERR_ARG, "iic_preprocess: bad argument");
   const char* e = nullptr;
+  Scope sc(h->prof, kPreprocess, static_cast<cudaStream_t>(stream));
+  h->prof.launches[kPreprocess]++;  // two kernels (horizontal + vertical pass)
   int rc = launch_preprocess(h->pre, imgs, hw, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
                              h->f16, static_cast<cudaStream_t>(stream), &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "preprocess failed");
@@ -362,6 +417,7 @@ int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int
 int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* out, int out_layout, void* stream) {
   if (!h || !imgs || !out || B < 0 || out_layout < 0 || out_layout > 2)
     return fail(h, IIC_ERR_ARG, "iic_preprocess_same_size: bad argument");
+  Scope sc(h->prof, kPreprocess, static_cast<cudaStream_t>(stream));
   int rc = launch_preprocess_fast(h->pre, imgs, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
                                   h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "preprocess_same_size launch failed");
@@ -376,6 +432,7 @@ int iic_patchify(iic_handle* h, const void* chw, int dtype, int B, void* patches
         cudaSuccess)
       return fail(h, IIC_ERR_CUDA, "iic_patchify: memset failed");
   }
+  Scope sc(h->prof, kMisc, static_cast<cudaStream_t>(stream));
   int rc = launch_chw_to_patches(chw, dtype, patches_out, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad,
                                  h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "patchify launch failed");
@@ -424,6 +481,35 @@ int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, siz
   rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
   return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, out, s);
+}
+
+int iic_profile(iic_handle* h, int enable) {
+  if (!h) return IIC_ERR_ARG;
+  h->prof.on = enable != 0;
+  h->prof.spans.clear();
+  h->prof.used = 0;
+  for (long long& l : h->prof.launches) l = 0;
+  return IIC_OK;
+}
+
+int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_class, int n) {
+  if (!h || n < kNumClasses) return fail(h, IIC_ERR_ARG, "iic_profile_read: need room for 7 classes");
+  for (int i = 0; i < kNumClasses; ++i) {
+    if (ms_by_class) ms_by_class[i] = 0.0;
+    if (launches_by_class) launches_by_class[i] = h->prof.launches[i];
+  }
+  if (!h->prof.spans.empty()) {
+    if (cudaEventSynchronize(h->prof.spans.back().b) != cudaSuccess)
+      return fail(h, IIC_ERR_CUDA, "iic_profile_read: event synchronize failed (a kernel faulted?)");
+    for (const Profiler::Span& sp : h->prof.spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && ms_by_class) ms_by_class[sp.cls] += ms;
+    }
+  }
+  h->prof.spans.clear();
+  h->prof.used = 0;
+  for (long long& l : h->prof.launches) l = 0;
+  return IIC_OK;
 }
 
 // ---- single operators ----

@@ -309,6 +309,27 @@ class Engine:
         with self._lock:
             return self.classify_patches(self.preprocess(images_u8), len(images_u8), want_embedding)
 
+    # ------------------------------------------------------------------ measurement
+    def profile(self, enable: bool = True) -> None:
+        L.check(self.h, self.lib.iic_profile(self.h, 1 if enable else 0), "iic_profile")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        """{kernel class: {"ms": summed CUDA-event time, "launches": count}} since the last read."""
+        n = len(L.KERNEL_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_longlong * n)()
+        L.check(self.h, self.lib.iic_profile_read(self.h, ms, cnt, n), "iic_profile_read")
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(L.KERNEL_CLASSES)}
+
+    def classify_host_u8(self, images_u8_pinned: torch.Tensor, staging: Optional[torch.Tensor] = None):
+        """End-to-end call with HOST buffers: uint8 [B,R,R,3] (pinned) -> H2D copy -> preprocess + encoder + head ->
+        top-k values / indices / detector sums copied back to the host.  Returns host tensors."""
+        with self._lock, torch.cuda.device(self.device):
+            dev = images_u8_pinned.to(self.device, non_blocking=True) if staging is None else staging.copy_(
+                images_u8_pinned, non_blocking=True)
+            r = self.classify_same_size(dev, want_embedding=False)
+            out = (r.topk_val.cpu(), r.topk_idx.cpu(), r.split_sum.cpu())
+        return out
+
     # ------------------------------------------------------------------ single operators (tests / profiling)
     def op_gemm(self, a: torch.Tensor, w: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,

@@ -144,6 +144,14 @@ int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, vo
 int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
                  const iic_head_out* out, void* stream);
 
+/* ---- measurement ----------------------------------------------------------------------------------------------
+ * Kernel classes: 0 tcgen05 GEMM, 1 LayerNorm, 2 attention, 3 LoRA down-projection, 4 head, 5 preprocess, 6 misc.
+ * iic_profile(h, 1) starts counting launches and bracketing every launch with CUDA events on the caller's stream;
+ * iic_profile_read sums the elapsed milliseconds and launch counts per class since the last read and resets them
+ * (it synchronises on the last recorded event).  iic_profile(h, 0) keeps counting launches but records no events. */
+int iic_profile(iic_handle* h, int enable);
+int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_class, int n);
+
 /* ---- single operators (exported for parity tests and profiling; same kernels the encoder runs) -------------- */
 /* D = epilogue(A[M,K] . W[N,K]^T (+ P[M,r] . Bt[N,r]^T));  epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16,
  * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16.  lora_p/lora_bt nullable. */
