@@ -24,25 +24,33 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128-byte swizzle.
-bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                   bool f16) {
+// row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 128 bytes of columns], 128-byte swizzle.
+// kind: 0 = bf16, 1 = fp16 (64-column boxes), 2 = fp32 (32-column boxes).
+bool make_tile_map_kind(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                        int kind) {
   auto fn = get_encode_fn();
   if (fn == nullptr) return false;
+  const uint64_t esz = kind == 2 ? 4 : 2;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {uint32_t(kBlockK), box_rows};
+  cuuint64_t gstride[1] = {ld * esz};
+  cuuint32_t box[2] = {uint32_t(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  const CUtensorMapDataType dt = kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   bool f16) {
+  return make_tile_map_kind(map, ptr, rows, cols, ld, box_rows, f16 ? 1 : 0);
+}
 
 template <int kCtas, int kBlockN, int kEpi, bool kF16>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
-               const GemmArgs& args, int num_sms, cudaStream_t stream) {
-  using S = GemmSmem<kCtas, kBlockN>;
+               const CUtensorMap& tout, const CUtensorMap& tres, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+  using S = GemmSmem<kCtas, kBlockN, kEpi>;
   auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi, kF16>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -67,33 +75,37 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, tbl, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, tbl, tout, tres, args);
   return e == cudaSuccess ? 0 : -2;
 }
 
 template <int kCtas, bool kF16>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
-                 const GemmArgs& args, int num_sms, cudaStream_t stream) {
+                 const CUtensorMap& tout, const CUtensorMap& tres, const GemmArgs& args, int num_sms,
+                 cudaStream_t stream) {
   switch (epi) {
-    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
-    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, args, num_sms, stream);
+    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
     default: return -1;
   }
 }
 
 }  // namespace
 
-size_t gemm_smem_bytes(int ctas) { return ctas == 2 ? GemmSmem<2, 256>::kTotal : GemmSmem<1, 256>::kTotal; }
+size_t gemm_smem_bytes(int ctas) {
+  return ctas == 2 ? GemmSmem<2, 256, kEpiBiasBf16>::kTotal : GemmSmem<1, 256, kEpiBiasBf16>::kTotal;
+}
 
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err) {
   static const char* e_shape = "gemm: unsupported shape (need M,N,K > 0, N % 32 == 0, pitches % 8 == 0)";
   static const char* e_map = "gemm: cuTensorMapEncodeTiled failed (driver entry point missing or bad pointer/pitch)";
   static const char* e_launch = "gemm: kernel launch failed";
   static const char* e_lora = "gemm: LoRA rank pad must be a multiple of 16 and <= 64";
-  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.N % 32 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldc % 4 != 0) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.N % 32 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldc % 8 != 0 ||
+      (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) {
     if (err) *err = e_shape;
     return -1;
   }
@@ -117,6 +129,16 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     tal = ta;
     tbl = tb;
   }
+  // output (and residual) maps for the TMA-store epilogue; the patch-embedding epilogue stores directly
+  CUtensorMap tout = ta, tres = ta;
+  if (ok && p.epilogue != kEpiPosF32) {
+    const bool f32_out = p.epilogue == kEpiBiasResF32;
+    ok = make_tile_map_kind(&tout, p.out, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f32_out ? 2 : (f16 ? 1 : 0));
+    if (ok && f32_out) {
+      if (p.residual == nullptr) ok = false;
+      else ok = make_tile_map_kind(&tres, p.residual, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, 2);
+    }
+  }
   if (!ok) {
     if (err) *err = e_map;
     return -1;
@@ -131,13 +153,15 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   args.out = p.out;
   args.ldc = p.ldc;
   args.group = p.group > 0 ? p.group : 1;
+  args.down_a = p.down_a;
+  args.down_part = p.down_part;
   int rc;
   if (f16)
-    rc = ctas == 2 ? dispatch_epi<2, true>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
-                   : dispatch_epi<1, true>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, true>(p.epilogue, ta, tb, tal, tbl, tout, tres, args, num_sms, stream)
+                   : dispatch_epi<1, true>(p.epilogue, ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
   else
-    rc = ctas == 2 ? dispatch_epi<2, false>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream)
-                   : dispatch_epi<1, false>(p.epilogue, ta, tb, tal, tbl, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, false>(p.epilogue, ta, tb, tal, tbl, tout, tres, args, num_sms, stream)
+                   : dispatch_epi<1, false>(p.epilogue, ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
   if (rc != 0 && err) *err = rc == -1 ? e_shape : e_launch;
   return rc;
 }

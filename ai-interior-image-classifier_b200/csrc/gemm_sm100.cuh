@@ -1,8 +1,8 @@
 // Persistent, warp-specialised tcgen05 GEMM for the ViT encoder:   D[M,N] = epilogue( A[M,K] . W[N,K]^T  (+ P[M,r] . Bl[N,r]^T) )
 //
-//   A  : activations, bf16 (or fp16: template switch kF16), row-major (K contiguous)           -> "K-major" UMMA operand A
+//   A  : activations, bf16 (or fp16: template switch kF16), row-major (K contiguous) -> "K-major" UMMA operand A
 //   W  : nn.Linear weight [out,in] exactly as PyTorch stores it -> "K-major" UMMA operand B (no transpose needed)
-//   P  : s * (x . lora_A), bf16 [M, r_pad] produced upstream;  Bl = lora_B^T, bf16 [N, r_pad].
+//   P  : s * (x . lora_A), 16-bit [M, r_pad] produced upstream;  Bl = lora_B^T, 16-bit [N, r_pad].
 //        The LoRA update is one extra (short) k-block accumulated into the SAME TMEM tile as the frozen W.x
 //        product, i.e. reference main.py:42-43 `linear(x) + lora(x)` happens inside the accumulator.
 //
@@ -10,14 +10,21 @@
 // (`LoRALinear.forward`, /root/reference/main.py:42-43, `LoRALayer.forward` main.py:30-31) and visual.conv1.
 //
 // Structure (one CTA per SM, 256 threads):
-//   warp 0      TMA producer      (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
+//   warp 0      TMA producer of the A/W ring (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
 //   warp 1      MMA issuer        (one elected thread; tcgen05.mma, fp32 accumulators in TMEM; leader CTA only)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue          (tcgen05.ld -> bias / QuickGELU / residual / pos-emb -> global)
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue), static
-// persistent tile schedule (n fastest so the CTAs working at the same time share A rows in L2).
+//   warp 3      residual producer (fp32-residual epilogue only): TMA-loads 128x32 fp32 slabs of the residual stream
+//               into the epilogue staging ring ahead of the epilogue
+//   warps 4..7  epilogue: tcgen05.ld -> bias / QuickGELU / residual -> swizzled smem slab -> TMA store
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue), staging ring
+// (residual TMA load -> epilogue threads -> TMA store), static persistent tile schedule (n fastest so the CTAs working
+// at the same time share A rows in L2).
 // kCtas == 2 pairs two SMs on one 256 x kBlockN tile (tcgen05 cta_group::2): each CTA loads its own 128 rows of
 // A and half of the W tile, the leader issues the MMAs for both, commits are multicast to both CTAs.
+//
+// Why the epilogue goes through shared memory + TMA: with one thread per accumulator row, direct global stores touch
+// 32 different 128-byte lines per warp instruction (and the fp32 residual read does the same with a dependent load);
+// ncu on the first version showed the tensor pipe only 21-54 % active with the tile time set by the epilogue.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,11 +36,11 @@
 namespace iic {
 
 enum GemmEpilogue : int {
-  kEpiBiasBf16 = 0,      // out bf16 = acc + bias                          (attn in_proj)
-  kEpiBiasGeluBf16 = 1,  // out bf16 = quick_gelu(acc + bias)              (mlp.c_fc)
+  kEpiBiasBf16 = 0,      // out 16-bit = acc + bias                        (attn in_proj)
+  kEpiBiasGeluBf16 = 1,  // out 16-bit = quick_gelu(acc + bias)            (mlp.c_fc)
   kEpiBiasResF32 = 2,    // out f32  = acc + bias + residual (in place ok) (attn.out_proj, mlp.c_proj)
   kEpiPosF32 = 3,        // out f32[row + row/G + 1] = acc + pos[row%G + 1] (visual.conv1 patch embedding)
-  kEpiGeluExactBf16 = 4, // out bf16 = gelu_erf(acc + bias)                (non-OpenAI checkpoints)
+  kEpiGeluExactBf16 = 4, // out 16-bit = gelu_erf(acc + bias)              (non-OpenAI checkpoints)
 };
 
 struct GemmArgs {
@@ -42,27 +49,39 @@ struct GemmArgs {
   int num_k_blocks;  // ceil(K / 64) of the frozen product
   int lora_ksteps;   // 0: no LoRA block; else r_pad/16 (1..4) UMMA K-steps from the (P, Bl) tile pair
   const float* bias;      // [N] or nullptr
-  const float* residual;  // kEpiBiasResF32: f32 [M, ldc];  kEpiPosF32: pos table f32 [G+1, N]
-  void* out;              // bf16 or f32, leading dimension ldc
+  const float* residual;  // kEpiPosF32: pos table f32 [G+1, N] (kEpiBiasResF32 reads the residual through tm_res)
+  void* out;              // kEpiPosF32 only: f32 base pointer, leading dimension ldc (other modes store through tm_out)
   int ldc;
   int group;  // kEpiPosF32: G = patches per image
+  // activation epilogues: per-tile partial of the consumer's LoRA down-projection, part[n_blk][row][0..3] (see kernels.h)
+  const float* down_a;
+  float* down_part;
 };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
 constexpr int kBlockK = 64;   // one 128-byte swizzle span of bf16
 constexpr int kUmmaK = 16;
+constexpr int kSlabBytes = kBlockM * 128;  // epilogue staging slab: 128 rows x 128 bytes (64 x 16-bit or 32 x fp32)
 
-template <int kCtas, int kBlockN>
+template <int kCtas, int kBlockN, int kEpi>
 struct GemmSmem {
+  static constexpr bool kResidual = kEpi == kEpiBiasResF32;
+  static constexpr bool kDirect = kEpi == kEpiPosF32;  // old direct-store epilogue, no staging ring
   static constexpr int kLoadN = kBlockN / kCtas;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = kLoadN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes;  // 4 x 48 KB (1 CTA) or 6 x 32 KB (2 CTA)
+  static constexpr int kSlabs = kDirect ? 0 : (kResidual ? 4 : 2);  // staging ring depth
+  static constexpr int kRingBudget = 192 * 1024 - kSlabs * kSlabBytes;
+  static constexpr int kStages = kRingBudget / kStageBytes;  // 2 CTA: 6 / 5 / 4;  1 CTA: 4 / 3 / 2 ... see static_assert
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * kBlockN;  // 512 when kBlockN = 256
   static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+  static constexpr int kDownBytes = kBlockN * 16;  // consumer LoRA-A slice of the current tile: [kBlockN][4] fp32
+  static constexpr int kTotal =
+      kStages * kStageBytes + kSlabs * kSlabBytes + kBarBytes + kDownBytes + 1024 /*alignment slack*/;
+  static_assert(kStages >= 2, "smem ring too shallow");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static_assert(kTmemCols == 32 || kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512,
                 "TMEM allocation must be a power of two >= 32 columns");
 };
@@ -74,29 +93,44 @@ __device__ __forceinline__ float quick_gelu(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int kCtas, int kBlockN, int kEpi, bool kF16>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bl,
+                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                     const GemmArgs args) {
-  using S = GemmSmem<kCtas, kBlockN>;
+  using S = GemmSmem<kCtas, kBlockN, kEpi>;
   constexpr int kStages = S::kStages;
+  constexpr int kSlabs = S::kSlabs;
   constexpr int kTileM = kBlockM * kCtas;
+  constexpr bool kResidual = S::kResidual;
+  constexpr bool kDirect = S::kDirect;
+  constexpr bool kAct = kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16;
+  constexpr int kSlabCols = kResidual ? 32 : 64;           // columns per staging slab
+  constexpr int kSlabsPerTile = kBlockN / kSlabCols;       // 8 (fp32) or 4 (16-bit)
 
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * S::kStageBytes;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t slab_base = smem_base + kStages * S::kStageBytes;
+  const uint32_t bar_base = slab_base + kSlabs * kSlabBytes;
   auto smem_a = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + S::kAccStages + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * S::kAccStages);
-  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + 8 * (2 * kStages + 2 * S::kAccStages));
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + b); };
+  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 4 + b); };
+  constexpr int kTmemSlotOff = 8 * (2 * kStages + 2 * S::kAccStages + 8);
+  const uint32_t tmem_slot = bar_base + kTmemSlotOff;
+  uint8_t* bar_gen = smem_gen + kStages * S::kStageBytes + kSlabs * kSlabBytes;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_gen + kTmemSlotOff);
+  float4* down_s = reinterpret_cast<float4*>(bar_gen + S::kBarBytes);
+  uint8_t* slab_gen = smem_gen + kStages * S::kStageBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +144,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       ptx::prefetch_tensormap(&tm_al);
       ptx::prefetch_tensormap(&tm_bl);
     }
+    if constexpr (!kDirect) ptx::prefetch_tensormap(&tm_out);
+    if constexpr (kResidual) ptx::prefetch_tensormap(&tm_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -119,6 +155,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     for (int a = 0; a < S::kAccStages; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);             // one tcgen05.commit
       ptx::mbar_init(tempty_bar(a), kCtas * 128);  // every epilogue thread of the pair
+    }
+    for (int b = 0; b < 4; ++b) {
+      ptx::mbar_init(rfull_bar(b), 1);   // residual producer's arrive.expect_tx
+      ptx::mbar_init(rempty_bar(b), 1);  // the storing epilogue thread, once the TMA store has read the slab
     }
     ptx::fence_mbar_init();
   }
@@ -198,103 +238,206 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ======================= residual producer (fp32-residual epilogue) =======================
+    if constexpr (kResidual) {
+      if (ptx::elect_one()) {
+        int slab = 0;  // running slab counter of this CTA
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+          const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+          const int row0 = m_blk * kTileM + int(cta_rank) * kBlockM;
+          const int col0 = n_blk * kBlockN;
+          for (int s = 0; s < kSlabsPerTile; ++s, ++slab) {
+            const int b = slab % kSlabs;
+            const uint32_t ph = uint32_t(slab / kSlabs) & 1u;
+            ptx::mbar_wait(rempty_bar(b), ph ^ 1u);
+            ptx::mbar_arrive_expect_tx(rfull_bar(b), kSlabBytes);
+            ptx::tma_load_2d(&tm_res, rfull_bar(b), slab_base + b * kSlabBytes, col0 + s * kSlabCols, row0,
+                             ptx::kEvictFirst);
+          }
+        }
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ======================= epilogue =======================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r_in_tile = quad * 32 + lane;
+    const bool storer = threadIdx.x == 128;  // issues every TMA store of this CTA (bulk groups are per thread)
     int it = 0;
+    int slab = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row = m_blk * kTileM + int(cta_rank) * kBlockM + quad * 32 + lane;
+      const int row0 = m_blk * kTileM + int(cta_rank) * kBlockM;
+      const int row = row0 + r_in_tile;
       const int col0 = n_blk * kBlockN;
       const bool row_ok = row < args.M;
 
-      long long out_row = row;
-      const float* addend = nullptr;  // residual row or pos-emb row
-      if constexpr (kEpi == kEpiBiasResF32) {
-        addend = args.residual + size_t(row) * args.ldc;
-      } else if constexpr (kEpi == kEpiPosF32) {
-        const int img = row / args.group;
-        out_row = row + img + 1;
-        addend = args.residual + size_t(row - img * args.group + 1) * args.N;
-      }
-      if constexpr (kEpi == kEpiBiasResF32) {
-        // The residual tile of the NEXT tile of this CTA: pull it into L2 while this tile's math runs so the
-        // epilogue's dependent loads see L2 latency, not HBM latency.
-        const int nt = tile + num_clusters;
-        if (nt < total_tiles) {
-          const int nm = nt / n_tiles, nn = nt - nm * n_tiles;
-          const int nrow = nm * kTileM + int(cta_rank) * kBlockM + quad * 32 + lane;
-          if (nrow < args.M) {
-            const char* pr = reinterpret_cast<const char*>(args.residual + size_t(nrow) * args.ldc + nn * kBlockN);
-#pragma unroll
-            for (int i = 0; i < kBlockN * 4 / 128; ++i)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i * 128));
-          }
+      if constexpr (kAct) {
+        if (args.down_a != nullptr) {
+          // stage this tile's slice of the consumer's LoRA-A while the MMAs of the tile are still running
+          const int t = threadIdx.x - 128;  // 0..127
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (col0 + 2 * t < args.N) v0 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + 2 * t);
+          if (col0 + 2 * t + 1 < args.N) v1 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + 2 * t + 1);
+          epi_bar_sync();  // previous tile's readers are done with the buffer
+          down_s[2 * t] = v0;
+          down_s[2 * t + 1] = v1;
+          epi_bar_sync();
         }
       }
-
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * kBlockN);
 
+      if constexpr (kDirect) {
+        // ---- patch embedding: rows are scattered (image boundaries), direct global stores ----
+        const int img = row / args.group;
+        const long long out_row = (long long)row + img + 1;
+        const float* addend = args.residual + size_t(row - img * args.group + 1) * args.N;
 #pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
-        ptx::tmem_ld_wait();
-        if (c == kBlockN / 32 - 1) {
-          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
-          ptx::tcgen05_fence_before();
-          if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
-          else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
+          ptx::tmem_ld_wait();
+          if (c == kBlockN / 32 - 1) {
+            ptx::tcgen05_fence_before();
+            if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
+            else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+          }
+          const int col = col0 + c * 32;
+          if (!row_ok || col >= args.N) continue;
+          float* o = reinterpret_cast<float*>(args.out) + size_t(out_row) * args.ldc + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 r = *reinterpret_cast<const float4*>(addend + col + i);
+            *reinterpret_cast<float4*>(o + i) =
+                make_float4(__uint_as_float(v[i]) + r.x, __uint_as_float(v[i + 1]) + r.y,
+                            __uint_as_float(v[i + 2]) + r.z, __uint_as_float(v[i + 3]) + r.w);
+          }
         }
-        const int col = col0 + c * 32;
-        if (!row_ok || col >= args.N) continue;
-        float f[32];
+      } else {
+        float dacc0 = 0.f, dacc1 = 0.f, dacc2 = 0.f, dacc3 = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < kSlabsPerTile; ++s, ++slab) {
+          const int b = slab % kSlabs;
+          const int col = col0 + s * kSlabCols;
+          uint8_t* my_row = slab_gen + b * kSlabBytes + r_in_tile * 128;  // this thread's 128-byte row of the slab
+          const int sw = r_in_tile & 7;                                    // 128B swizzle: 16B chunk j -> j ^ (row & 7)
+          if constexpr (kResidual) {
+            // ---- out = acc + bias + residual: the slab already holds the residual (TMA-loaded by warp 3) ----
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 32), v);
+            ptx::mbar_wait(rfull_bar(b), uint32_t(slab / kSlabs) & 1u);
+            ptx::tmem_ld_wait();
+            if (s == kSlabsPerTile - 1) {
+              ptx::tcgen05_fence_before();
+              if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
+              else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+            }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if constexpr (kEpi != kEpiPosF32) {
-          if (args.bias != nullptr) {
+            for (int j = 0; j < 8; ++j) {
+              float4* p = reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4));
+              float4 r = *p;
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (args.bias != nullptr && col + 4 * j < args.N) bb = __ldg(reinterpret_cast<const float4*>(args.bias + col + 4 * j));
+              r.x += __uint_as_float(v[4 * j]) + bb.x;
+              r.y += __uint_as_float(v[4 * j + 1]) + bb.y;
+              r.z += __uint_as_float(v[4 * j + 2]) + bb.z;
+              r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
+              *p = r;
+            }
+            ptx::fence_proxy_async_smem();
+            epi_bar_sync();
+            if (storer) {
+              ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
+              ptx::tma_store_commit();
+              // the slab stored one step ago has been read by now (at most 1 group still in flight): hand it back
+              if (slab >= 1) {
+                ptx::tma_store_wait_read<1>();
+                ptx::mbar_arrive(rempty_bar((slab - 1) % kSlabs));
+              }
+            }
+          } else {
+            // ---- 16-bit outputs: 64 columns per slab ----
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64), v0);
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64 + 32), v1);
+            ptx::tmem_ld_wait();
+            if (s == kSlabsPerTile - 1) {
+              ptx::tcgen05_fence_before();
+              if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
+              else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+            }
+            uint4 pk[8];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(args.bias + col + i));
-              f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            for (int half = 0; half < 2; ++half) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(half == 0 ? v0[i] : v1[i]);
+              const int c = col + half * 32;
+              if (args.bias != nullptr && c < args.N) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(args.bias + c + i));
+                  f[i] += bb.x; f[i + 1] += bb.y; f[i + 2] += bb.z; f[i + 3] += bb.w;
+                }
+              }
+              if constexpr (kEpi == kEpiBiasGeluBf16) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+              } else if constexpr (kEpi == kEpiGeluExactBf16) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+              }
+              if constexpr (kAct) {
+                if (args.down_a != nullptr) {
+                  // warp-uniform shared-memory address: one broadcast wavefront per column
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float4 a = down_s[s * 64 + half * 32 + i];
+                    dacc0 = fmaf(f[i], a.x, dacc0);
+                    dacc1 = fmaf(f[i], a.y, dacc1);
+                    dacc2 = fmaf(f[i], a.z, dacc2);
+                    dacc3 = fmaf(f[i], a.w, dacc3);
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 q;
+                q.x = Act<kF16>::pack(f[i], f[i + 1]);
+                q.y = Act<kF16>::pack(f[i + 2], f[i + 3]);
+                q.z = Act<kF16>::pack(f[i + 4], f[i + 5]);
+                q.w = Act<kF16>::pack(f[i + 6], f[i + 7]);
+                pk[half * 4 + i / 8] = q;
+              }
+            }
+            // the slab written kSlabs steps ago must have been read by its TMA store before it is overwritten
+            if (storer) ptx::tma_store_wait_read<kSlabs - 1>();
+            epi_bar_sync();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = pk[j];
+            ptx::fence_proxy_async_smem();
+            epi_bar_sync();
+            if (storer) {
+              ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
+              ptx::tma_store_commit();
             }
           }
         }
-        if constexpr (kEpi == kEpiBiasResF32 || kEpi == kEpiPosF32) {
-          const float* ad = addend + (kEpi == kEpiBiasResF32 ? col : col);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 r = *reinterpret_cast<const float4*>(ad + i);
-            f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
-          }
-          float* o = reinterpret_cast<float*>(args.out) + size_t(out_row) * args.ldc + col;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-        } else {
-          if constexpr (kEpi == kEpiBiasGeluBf16) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
-          } else if constexpr (kEpi == kEpiGeluExactBf16) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-          }
-          uint16_t* o = reinterpret_cast<uint16_t*>(args.out) + size_t(out_row) * args.ldc + col;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 pk;
-            pk.x = Act<kF16>::pack(f[i], f[i + 1]);
-            pk.y = Act<kF16>::pack(f[i + 2], f[i + 3]);
-            pk.z = Act<kF16>::pack(f[i + 4], f[i + 5]);
-            pk.w = Act<kF16>::pack(f[i + 6], f[i + 7]);
-            *reinterpret_cast<uint4*>(o + i) = pk;
-          }
+        if constexpr (kAct) {
+          if (args.down_a != nullptr && row_ok)
+            *reinterpret_cast<float4*>(args.down_part + (size_t(n_blk) * args.M + row) * 4) =
+                make_float4(dacc0, dacc1, dacc2, dacc3);
         }
       }
+    }
+    // all global writes of this CTA's TMA stores must be complete before the kernel ends
+    if constexpr (!kDirect) {
+      if (storer) ptx::tma_store_wait<0>();
     }
   }
 

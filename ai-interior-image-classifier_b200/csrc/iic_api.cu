@@ -38,7 +38,7 @@ struct Block {
 
 struct Workspace {
   uint16_t *xln, *qkv, *attn, *hid, *p_a, *p_b;
-  float *x, *xpre;
+  float *x, *xpre, *down_part;
   size_t total;
 };
 
@@ -124,6 +124,7 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   w.hid = static_cast<uint16_t*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
   w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+  w.down_part = static_cast<float*>(take(size_t((mlp + 255) / 256) * M * 16));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.total = off;
   return w;
@@ -141,8 +142,10 @@ bool check_ready(iic_handle* h) {
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
              const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
-             int ldc, int group, cudaStream_t s) {
+             int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr) {
   GemmProblem g;
+  g.down_a = down_a;
+  g.down_part = down_part;
   g.a = a; g.lda = lda; g.w = w; g.ldw = K; g.M = M; g.N = N; g.K = K;
   const bool use_lora = lora != nullptr && lora->rank > 0;
   g.lora_p = use_lora ? p : nullptr;
@@ -209,8 +212,15 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
       return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
                               l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
-    IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s));
-    if (l_pr.rank)
+    // c_proj's LoRA down-projection (h . A2) rides in the c_fc epilogue while h is still in registers (rank <= 4)
+    const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
+    IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
+                     fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
+    if (fuse_down)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_reduce(w.down_part, (mlp + 255) / 256, M, w.p_b, h->lora_pad, h->f16, s);
+      }));
+    else if (l_pr.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, h->f16, s);
       }));

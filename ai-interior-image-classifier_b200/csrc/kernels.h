@@ -14,6 +14,8 @@ int launch_layernorm(const float* x, long long x_row_stride, const float* gamma,
                      const float* lora_a, int r4, void* p_out, int p_ld, int f16, cudaStream_t stream);
 int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, int r4, void* p_out,
                           int p_ld, int f16, cudaStream_t stream);
+// sums the per-column-tile partials written by the c_fc GEMM epilogue (GemmProblem::down_*) into the 16-bit P matrix
+int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, int p_ld, int f16, cudaStream_t stream);
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 // dtype: 0 = f32, 1 = bf16, 2 = f16
 int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int f16,
@@ -62,6 +64,10 @@ struct GemmProblem {
   int ldc;
   int group;
   int f16;  // 16-bit operand format: 0 = bf16, 1 = fp16
+  // optional, activation epilogues only: fuse the NEXT projection's LoRA down-projection (rank <= 4) into this epilogue.
+  // down_a f32 [N, 4] = scaling * lora_A of the consumer; down_part f32 [ceil(N/256)][M][4] receives per-tile partials.
+  const float* down_a = nullptr;
+  float* down_part = nullptr;
 };
 // ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);

@@ -21,120 +21,200 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// One warp per row.  kVec = D / 128 float4 chunks per lane (D = 768 -> 6, 1024 -> 8).
-// out_bf16 / out_f32 may each be null.  If lora_a != null also emits P[row, 0..r_pad) = xln . lora_a
-// (lora_a is [D, r4] fp32 with the LoRA scaling already folded in, r4 = rank rounded up to 4; P row pitch = p_ld).
-template <int kVec, bool kF16>
-__global__ void __launch_bounds__(256)
+// LayerNorm rows (fp32 in, fp32 stats) -> 16-bit GEMM operand and/or fp32, optionally fused with the LoRA
+// down-projection P[row, :] = xln[row, :] . (scaling * lora_A) for the projection that consumes the normalised row.
+//   kVec  = D / 128 float4 chunks per lane (D = 768 -> 6, 1024 -> 8)
+//   kMode = 0: no LoRA;  1: r4 == 4 with the lane's slice of A held in registers (96 floats at D = 768), amortised
+//           over every row the warp processes;  2: any r4 (multiple of 4), A re-read through L1 per row.
+// Each warp walks rows warp_id, warp_id + n_warps, ... and prefetches the next row while it works on the current one.
+// P rows are written full width (p_ld columns, zeros beyond r4): the GEMM's LoRA k-step reads 16 columns.
+template <int kVec, bool kF16, int kMode>
+__global__ void __launch_bounds__(256, kMode == 1 ? 1 : 2)
 layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32,
                  long long out_row_stride, int rows, float eps, const float* __restrict__ lora_a, int r4,
                  uint16_t* __restrict__ p_out, int p_ld) {
   constexpr int D = kVec * 128;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + size_t(warp) * x_row_stride);
-  float4 v[kVec];
-#pragma unroll
-  for (int j = 0; j < kVec; ++j) v[j] = xr[lane + 32 * j];
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < kVec; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int j = 0; j < kVec; ++j) {
-    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+
+  float4 areg[kMode == 1 ? kVec * 4 : 1];
+  if constexpr (kMode == 1) {
 #pragma unroll
-  for (int j = 0; j < kVec; ++j) {
-    const float4 g = __ldg(g4 + lane + 32 * j), b = __ldg(b4 + lane + 32 * j);
-    v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
-    v[j].y = (v[j].y - mean) * rstd * g.y + b.y;
-    v[j].z = (v[j].z - mean) * rstd * g.z + b.z;
-    v[j].w = (v[j].w - mean) * rstd * g.w + b.w;
-  }
-  if (out_f32 != nullptr) {
-    float4* o = reinterpret_cast<float4*>(out_f32 + size_t(warp) * out_row_stride);
+    for (int j = 0; j < kVec; ++j)
 #pragma unroll
-    for (int j = 0; j < kVec; ++j) o[lane + 32 * j] = v[j];
+      for (int q = 0; q < 4; ++q)
+        areg[j * 4 + q] = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(4 * (lane + 32 * j) + q) * 4));
   }
-  if (out_bf16 != nullptr) {
-    uint2* o = reinterpret_cast<uint2*>(out_bf16 + size_t(warp) * out_row_stride);
+
+  float4 nxt[kVec];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + size_t(row) * x_row_stride);
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) nxt[j] = xr[lane + 32 * j];
+  }
+  for (; row < rows; row += n_warps) {
+    float4 v[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) v[j] = nxt[j];
+    if (row + n_warps < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + size_t(row + n_warps) * x_row_stride);
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) nxt[j] = xr[lane + 32 * j];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-      uint2 pk;
-      pk.x = Act<kF16>::pack(v[j].x, v[j].y);
-      pk.y = Act<kF16>::pack(v[j].z, v[j].w);
-      o[lane + 32 * j] = pk;
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
     }
-  }
-  if (lora_a != nullptr) {
-    // P[row, c] = sum_k xln[k] * A[k, c];  4 columns at a time, A rows read as float4 (L1/L2 resident)
-    for (int c0 = 0; c0 < r4; c0 += 4) {
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const float4 g = __ldg(g4 + lane + 32 * j), b = __ldg(b4 + lane + 32 * j);
+      v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
+      v[j].y = (v[j].y - mean) * rstd * g.y + b.y;
+      v[j].z = (v[j].z - mean) * rstd * g.z + b.z;
+      v[j].w = (v[j].w - mean) * rstd * g.w + b.w;
+    }
+    if (out_f32 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + size_t(row) * out_row_stride);
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) o[lane + 32 * j] = v[j];
+    }
+    if (out_bf16 != nullptr) {
+      uint2* o = reinterpret_cast<uint2*>(out_bf16 + size_t(row) * out_row_stride);
+#pragma unroll
+      for (int j = 0; j < kVec; ++j) {
+        uint2 pk;
+        pk.x = Act<kF16>::pack(v[j].x, v[j].y);
+        pk.y = Act<kF16>::pack(v[j].z, v[j].w);
+        o[lane + 32 * j] = pk;
+      }
+    }
+    if constexpr (kMode == 1) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int j = 0; j < kVec; ++j) {
-        const int k = 4 * (lane + 32 * j);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k) * r4 + c0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 1) * r4 + c0));
-        const float4 w2 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 2) * r4 + c0));
-        const float4 w3 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 3) * r4 + c0));
+        const float4 w0 = areg[j * 4], w1 = areg[j * 4 + 1], w2 = areg[j * 4 + 2], w3 = areg[j * 4 + 3];
         a0 += v[j].x * w0.x + v[j].y * w1.x + v[j].z * w2.x + v[j].w * w3.x;
         a1 += v[j].x * w0.y + v[j].y * w1.y + v[j].z * w2.y + v[j].w * w3.y;
         a2 += v[j].x * w0.z + v[j].y * w1.z + v[j].z * w2.z + v[j].w * w3.z;
         a3 += v[j].x * w0.w + v[j].y * w1.w + v[j].z * w2.w + v[j].w * w3.w;
       }
       a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
-      if (lane == 0) {
-        uint2 pk;
-        pk.x = Act<kF16>::pack(a0, a1);
-        pk.y = Act<kF16>::pack(a2, a3);
-        *reinterpret_cast<uint2*>(p_out + size_t(warp) * p_ld + c0) = pk;
+      // lanes 0 .. p_ld/4-1 each write one 4-column group: group 0 carries the values, the rest are zeros
+      if (lane * 4 < p_ld) {
+        uint2 pk = make_uint2(0u, 0u);
+        if (lane == 0) { pk.x = Act<kF16>::pack(a0, a1); pk.y = Act<kF16>::pack(a2, a3); }
+        *reinterpret_cast<uint2*>(p_out + size_t(row) * p_ld + lane * 4) = pk;
+      }
+    } else if constexpr (kMode == 2) {
+      for (int c0 = 0; c0 < p_ld; c0 += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (c0 < r4) {
+#pragma unroll
+          for (int j = 0; j < kVec; ++j) {
+            const int k = 4 * (lane + 32 * j);
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k) * r4 + c0));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 1) * r4 + c0));
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 2) * r4 + c0));
+            const float4 w3 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 3) * r4 + c0));
+            a0 += v[j].x * w0.x + v[j].y * w1.x + v[j].z * w2.x + v[j].w * w3.x;
+            a1 += v[j].x * w0.y + v[j].y * w1.y + v[j].z * w2.y + v[j].w * w3.y;
+            a2 += v[j].x * w0.z + v[j].y * w1.z + v[j].z * w2.z + v[j].w * w3.z;
+            a3 += v[j].x * w0.w + v[j].y * w1.w + v[j].z * w2.w + v[j].w * w3.w;
+          }
+          a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        }
+        if (lane == 0) {
+          uint2 pk;
+          pk.x = Act<kF16>::pack(a0, a1);
+          pk.y = Act<kF16>::pack(a2, a3);
+          *reinterpret_cast<uint2*>(p_out + size_t(row) * p_ld + c0) = pk;
+        }
       }
     }
   }
 }
 
-// P[row, 0..r4) = X[row, :] . A   for bf16 X [rows, K] (K % 256 == 0).  One warp per row, fp32 accumulate.
-template <bool kF16>
+// P[row, 0..p_ld) = X[row, :] . A (zeros beyond r4) for 16-bit X [rows, K] (K % 8 == 0).  Stand-alone fallback used
+// where the down-projection cannot ride in a producer kernel (attn.out_proj slot, ranks other than 4): one warp per
+// kRows rows so every A row fetched from L1 is used kRows times; fp32 accumulate.
+template <bool kF16, int kRows>
 __global__ void __launch_bounds__(256)
 lora_down_bf16_kernel(const uint16_t* __restrict__ x, int K, int rows, const float* __restrict__ lora_a, int r4,
                       uint16_t* __restrict__ p_out, int p_ld) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + size_t(warp) * K);
-  for (int c0 = 0; c0 < r4; c0 += 4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int ch = lane; ch < K / 8; ch += 32) {
-      const uint4 raw = xr[ch];
-      const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
+  const int row0 = warp * kRows;
+  if (row0 >= rows) return;
+  for (int c0 = 0; c0 < p_ld; c0 += 4) {
+    float acc[kRows][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 xv = Act<kF16>::unpack(h[e]);
-        const int k = ch * 8 + 2 * e;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k) * r4 + c0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(k + 1) * r4 + c0));
-        a0 += xv.x * w0.x + xv.y * w1.x;
-        a1 += xv.x * w0.y + xv.y * w1.y;
-        a2 += xv.x * w0.z + xv.y * w1.z;
-        a3 += xv.x * w0.w + xv.y * w1.w;
+    for (int r = 0; r < kRows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    if (c0 < r4) {
+      for (int ch = lane; ch < K / 8; ch += 32) {
+        float4 w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = __ldg(reinterpret_cast<const float4*>(lora_a + size_t(ch * 8 + e) * r4 + c0));
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (row0 + r < rows) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(x + size_t(row0 + r) * K + ch * 8);
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 xv = Act<kF16>::unpack(h[e]);
+              acc[r][0] += xv.x * w[2 * e].x + xv.y * w[2 * e + 1].x;
+              acc[r][1] += xv.x * w[2 * e].y + xv.y * w[2 * e + 1].y;
+              acc[r][2] += xv.x * w[2 * e].z + xv.y * w[2 * e + 1].z;
+              acc[r][3] += xv.x * w[2 * e].w + xv.y * w[2 * e + 1].w;
+            }
+          }
+        }
       }
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
-    if (lane == 0) {
-      uint2 pk;
-      pk.x = Act<kF16>::pack(a0, a1);
-      pk.y = Act<kF16>::pack(a2, a3);
-      *reinterpret_cast<uint2*>(p_out + size_t(warp) * p_ld + c0) = pk;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float a0 = warp_sum(acc[r][0]), a1 = warp_sum(acc[r][1]), a2 = warp_sum(acc[r][2]), a3 = warp_sum(acc[r][3]);
+      if (lane == 0 && row0 + r < rows) {
+        uint2 pk;
+        pk.x = Act<kF16>::pack(a0, a1);
+        pk.y = Act<kF16>::pack(a2, a3);
+        *reinterpret_cast<uint2*>(p_out + size_t(row0 + r) * p_ld + c0) = pk;
+      }
     }
   }
+}
+
+// Finishes the down-projection the c_fc GEMM epilogue started: part[n_tile][row][4] fp32 partial dot products
+// (one per 256-column tile of the hidden activation) -> P[row, 0..p_ld) 16-bit, zeros beyond column 4.
+// Deterministic (fixed summation order), unlike an atomic accumulation.
+template <bool kF16>
+__global__ void __launch_bounds__(256)
+lora_reduce_kernel(const float* __restrict__ part, int n_tiles, int rows, uint16_t* __restrict__ p_out, int p_ld) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < n_tiles; ++t) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (size_t(t) * rows + row) * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  uint2 pk;
+  pk.x = Act<kF16>::pack(s.x, s.y);
+  pk.y = Act<kF16>::pack(s.z, s.w);
+  uint2* o = reinterpret_cast<uint2*>(p_out + size_t(row) * p_ld);
+  o[0] = pk;
+  for (int c = 1; c < p_ld / 4; ++c) o[c] = make_uint2(0u, 0u);
 }
 
 // x_pre[b*T + 0, :] = class_embedding + positional_embedding[0]
@@ -170,26 +250,46 @@ chw_to_patches_kernel(const T* __restrict__ img, typename Act<kF16>::T* __restri
 // ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
-template <bool kF16>
-static int layernorm_dispatch(const float* x, long long x_row_stride, const float* gamma, const float* beta, uint16_t* ob,
-                              float* of, long long ors, int rows, int D, float eps, const float* la, int r4, uint16_t* po,
-                              int pld, cudaStream_t stream) {
-  const int threads = 256;
-  const int blocks = (rows + (threads / 32) - 1) / (threads / 32);
-  switch (D) {
-    case 512: layernorm_kernel<4, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
-    case 768: layernorm_kernel<6, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
-    case 1024: layernorm_kernel<8, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
-    case 1280: layernorm_kernel<10, kF16><<<blocks, threads, 0, stream>>>(x, x_row_stride, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld); break;
-    default: return -1;
+template <int kVec, bool kF16>
+static int layernorm_launch(const float* x, long long xs, const float* gamma, const float* beta, uint16_t* ob, float* of,
+                            long long ors, int rows, float eps, const float* la, int r4, uint16_t* po, int pld,
+                            cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = 256, wpb = threads / 32;
+  const int need = (rows + wpb - 1) / wpb;
+  if (la == nullptr) {
+    const int blocks = need < sms * 8 ? need : sms * 8;   // <= 8 resident CTAs/SM worth of warps, grid-stride beyond
+    layernorm_kernel<kVec, kF16, 0><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
+  } else if (r4 == 4) {
+    const int blocks = need < sms ? need : sms;           // A slice lives in registers (1 CTA/SM): few, long-lived warps
+    layernorm_kernel<kVec, kF16, 1><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
+  } else {
+    const int blocks = need < sms * 8 ? need : sms * 8;
+    layernorm_kernel<kVec, kF16, 2><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+template <bool kF16>
+static int layernorm_dispatch(const float* x, long long xs, const float* gamma, const float* beta, uint16_t* ob,
+                              float* of, long long ors, int rows, int D, float eps, const float* la, int r4, uint16_t* po,
+                              int pld, cudaStream_t stream) {
+  switch (D) {
+    case 512: return layernorm_launch<4, kF16>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld, stream);
+    case 768: return layernorm_launch<6, kF16>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld, stream);
+    case 1024: return layernorm_launch<8, kF16>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld, stream);
+    case 1280: return layernorm_launch<10, kF16>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld, stream);
+    default: return -1;
+  }
 }
 
 int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta, void* out_bf16,
                      float* out_f32, long long out_row_stride, int rows, int D, float eps, const float* lora_a, int r4,
                      void* p_out, int p_ld, int f16, cudaStream_t stream) {
   if (rows <= 0) return 0;
+  if (lora_a != nullptr && (r4 % 4 != 0 || p_ld % 4 != 0 || r4 > p_ld || p_ld > 128)) return -1;
   uint16_t* ob = static_cast<uint16_t*>(out_bf16);
   uint16_t* po = static_cast<uint16_t*>(p_out);
   return f16 ? layernorm_dispatch<true>(x, x_row_stride, gamma, beta, ob, out_f32, out_row_stride, rows, D, eps, lora_a,
@@ -201,15 +301,28 @@ int launch_layernorm(const float* x, long long x_row_stride, const float* gamma,
 int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, int r4, void* p_out, int p_ld, int f16,
                           cudaStream_t stream) {
   if (rows <= 0) return 0;
-  if (K % 8 != 0) return -1;
+  if (K % 8 != 0 || r4 % 4 != 0 || p_ld % 4 != 0 || r4 > p_ld) return -1;
+  constexpr int kRows = 4;
   const int threads = 256;
-  const int blocks = (rows + 7) / 8;
+  const int warps = (rows + kRows - 1) / kRows;
+  const int blocks = (warps + 7) / 8;
   if (f16)
-    lora_down_bf16_kernel<true><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a, r4,
-                                                                static_cast<uint16_t*>(p_out), p_ld);
+    lora_down_bf16_kernel<true, kRows><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a, r4,
+                                                                       static_cast<uint16_t*>(p_out), p_ld);
   else
-    lora_down_bf16_kernel<false><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a, r4,
-                                                                 static_cast<uint16_t*>(p_out), p_ld);
+    lora_down_bf16_kernel<false, kRows><<<blocks, threads, 0, stream>>>(static_cast<const uint16_t*>(x), K, rows, lora_a,
+                                                                        r4, static_cast<uint16_t*>(p_out), p_ld);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, int p_ld, int f16, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (p_ld % 4 != 0 || p_ld < 4) return -1;
+  const int blocks = (rows + 255) / 256;
+  if (f16)
+    lora_reduce_kernel<true><<<blocks, 256, 0, stream>>>(part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
+  else
+    lora_reduce_kernel<false><<<blocks, 256, 0, stream>>>(part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

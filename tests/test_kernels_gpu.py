@@ -150,6 +150,10 @@ def test_layernorm(engine, D):
     out16b, p = engine.op_layernorm(x, gamma, beta, out_dtype=torch.bfloat16, lora_a_scaled=A)
     assert torch.equal(out16b, out16)
     assert torch.allclose(p[:, :4].float(), ref @ A, rtol=2 ** -7, atol=1e-3)
+    assert (p[:, 4:] == 0).all()
+    A8 = torch.randn(D, 8, device="cuda", generator=g) * 0.04          # generic-rank path
+    _, p8 = engine.op_layernorm(x, gamma, beta, out_dtype=torch.bfloat16, lora_a_scaled=A8)
+    assert torch.allclose(p8[:, :8].float(), ref @ A8, rtol=2 ** -7, atol=1e-3) and (p8[:, 8:] == 0).all()
 
 
 @pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12)])
