@@ -245,10 +245,10 @@ class Preprocess:
         import numpy as np
         if hasattr(img, "convert"):
             img = img.convert("RGB")
-        arr = np.asarray(img, dtype=np.uint8)
+        arr = np.array(img, dtype=np.uint8, order="C")  # owning, writable copy of the decoded pixels
         if arr.ndim != 3 or arr.shape[2] != 3:
             raise ValueError(f"expected an RGB image, got array of shape {arr.shape}")
-        return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=False)
+        return torch.from_numpy(arr).to(device, non_blocking=False)
 
     def batch(self, images, layout: int = L.OUT_CHW_F32) -> torch.Tensor:
         eng = self._visual.engine()

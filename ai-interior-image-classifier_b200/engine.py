@@ -237,6 +237,8 @@ class Engine:
         hw = (C.c_int * (2 * B))(*[v for t in images_u8 for v in (t.shape[0], t.shape[1])])
         if out is None:
             out = self._alloc_pre_out(B, layout)
+        if B == 0:
+            return out
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_preprocess(self.h, ptrs, hw, B, out.data_ptr(), layout,
                                                     _stream_ptr(self.device)), "iic_preprocess")

@@ -1,0 +1,109 @@
+"""The reference's public entry points, re-hosted (analyzer.py), against the outputs of the reference's own
+`CachedInteriorAnalyzer.analyze_images_batch` / `is_interior_image` (tests/golden/ref_batch12.json, ref_shipped.npz)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _common import GOLDEN, golden_json, golden_npz, oracle_model, oracle_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def analyzer(iic, tmp_path_factory):
+    """Same construction sequence as main.py:232-262 but with the oracle's tensors: base model -> detector text
+    features -> LoRA wrap -> text-LoRA state from the golden run (the shipped checkpoint is not on the GPU box, so the
+    label matrix the reference computed with it is injected instead)."""
+    from PIL import Image
+    root = tmp_path_factory.mktemp("dataset")
+    crops = golden_npz("crops_u8.npz")
+    files = [str(f) for f in crops["files"]]
+    os.makedirs(root / "dataset_images", exist_ok=True)
+    for f, c in zip(files, crops["crops"]):
+        Image.fromarray(c).save(root / (os.path.splitext(f)[0] + ".png"))   # lossless 224x224: resize is the identity
+    model, pre = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="f16")
+    a = iic.CachedInteriorAnalyzer(use_lora=True, lora_weights_path=None, lora_rank=4, lora_alpha=8, device="cuda",
+                                   json_path=os.path.join(GOLDEN, "interior_dataset_fixture.json"), model=model,
+                                   preprocess=pre)
+    lab = golden_json("labels.json")
+    text = torch.from_numpy(golden_npz("text_features.npz")["text"]).cuda()
+    # label schema known answers
+    assert [len(a.all_categories[g]) for g in ("styles", "room_types", "characteristics", "materials", "colors")] == \
+        [20, 12, 299, 36, 30]
+    for g in lab["group_order"]:
+        assert a.all_categories[g] == lab["groups"][g]
+    off = 40
+    a.detector.text_features = text[:40].clone()
+    for g in lab["group_order"]:
+        n = len(lab["groups"][g])
+        a.text_features_cache[g] = text[off:off + n].clone()
+        off += n
+    a.root = root
+    a.files = files
+    return a
+
+
+def _png(a, f):
+    return str(a.root / (os.path.splitext(f)[0] + ".png"))
+
+
+def _same_analysis(got, want, tol=5e-3):
+    for g, pairs in want.items():
+        assert [l for l, _ in got[g]] == [l for l, _ in pairs], (g, got[g], pairs)
+        assert np.allclose([p for _, p in got[g]], [p for _, p in pairs], atol=tol)
+
+
+def test_analyze_images_batch_matches_reference(analyzer):
+    ref = golden_json("ref_batch12.json")
+    files = analyzer.files[:12]
+    paths = [_png(analyzer, f) for f in files]
+    for key, flt in (("filter", True), ("nofilter", False)):
+        res = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=flt)
+        assert set(res) == set(paths)
+        for f, p in zip(files, paths):
+            want, got = ref[key][f], res[p]
+            assert got["is_interior"] == want["is_interior"] and got["detected_category"] == want["detected_category"]
+            assert got["reason"] == want["reason"]
+            assert abs(got["interior_confidence"] - want["interior_confidence"]) < 5e-3
+            _same_analysis(got["analysis"], want["analysis"])
+
+
+def test_detector_matches_reference_on_all_images(analyzer):
+    from PIL import Image
+    ref = golden_npz("ref_shipped.npz")
+    imgs = [Image.open(_png(analyzer, f)) for f in analyzer.files]
+    det = analyzer.detector.detect_batch(imgs, 0.3)
+    same = sum(int(d[0] == bool(ref["det_is"][i]) and d[2] == str(ref["det_cat"][i]) and
+                   abs(d[1] - float(ref["det_conf"][i])) < 5e-3) for i, d in enumerate(det))
+    assert same / len(det) >= 0.99, same
+    one = analyzer.detector.is_interior_image(imgs[0], 0.3)
+    assert one[0] == bool(ref["det_is"][0]) and one[2] == str(ref["det_cat"][0])
+    assert analyzer.detector.is_interior_image(None) == (False, 0.0, "invalid image")
+
+
+def test_single_image_paths(analyzer):
+    ref_top5 = json.loads(str(golden_npz("ref_shipped.npz")["top5"]))
+    f = analyzer.files[-1]
+    assert f == "interior_sample.jpg"            # BASELINE config 1
+    from PIL import Image
+    x = analyzer.preprocess(Image.open(_png(analyzer, f))).unsqueeze(0)
+    assert x.shape == (1, 3, 224, 224) and x.dtype == torch.float32
+    got = analyzer._analyze_image_tensor_fast(x)
+    _same_analysis(got, ref_top5[-1])
+    res = analyzer.analyze_image_from_url(_png(analyzer, f), filter_interiors=False)
+    assert res["is_interior"] and res["detected_category"] == "interior"
+    _same_analysis(res["analysis"], ref_top5[-1])
+    assert analyzer.analyze_image_from_url(str(analyzer.root / "missing.png")) == \
+        {"is_interior": False, "reason": "Failed to load image"}
+
+
+def test_style_worker_shape(iic, analyzer):
+    """DatabaseStyleRoomAnalyzer._analyze_styles_batch contract (main_API.py:219-236): [{'style', 'confidence'}]"""
+    from PIL import Image
+    w = iic.DatabaseStyleRoomAnalyzer(device="cuda", model=analyzer.model, preprocess=analyzer.preprocess)
+    imgs = [Image.open(_png(analyzer, f)) for f in analyzer.files[:5]]
+    out = w._analyze_styles_batch(imgs, batch_size=2)
+    assert len(out) == 5 and all(o["style"] in w.styles and 0.0 < o["confidence"] <= 1.0 for o in out)
