@@ -1,0 +1,30 @@
+"""Data-parallel helpers for the image path: images are independent, so inference shards the batch
+across ranks with NO data-path collective - one process per GPU, weights replicated, results gathered by the caller.
+(The only collective of the whole design is the all-reduce of the tiny LoRA gradients in training.)"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of `n_items` for `rank`; sizes differ by at most one, order is preserved."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard(items: Sequence, rank: int, world: int) -> Sequence:
+    lo, hi = shard_bounds(len(items), rank, world)
+    return items[lo:hi]
+
+
+def gather_in_order(local_results: List, group=None) -> List:
+    """all_gather_object of per-rank result lists, concatenated in rank order (host-side result plumbing only)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return list(local_results)
+    bucket = [None] * dist.get_world_size(group)
+    dist.all_gather_object(bucket, list(local_results), group=group)
+    return [r for part in bucket for r in part]

@@ -1,0 +1,170 @@
+"""Host-side mirrors of the reference interface (no GPU): LoRA API + checkpoint layout, text tower, tokenizer, label
+schema, no-CPU-fallback behaviour, the C-ABI symbol table, data-parallel sharding (gloo, world_size 2)."""
+import copy
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from _common import GOLDEN, ROOT, golden_json, golden_npz, oracle_model, oracle_state_dict
+
+
+@pytest.fixture(scope="module")
+def product_cpu(iic):
+    model, pre = iic.load("ViT-B/16", device="cpu", state_dict=oracle_state_dict())
+    return model, pre
+
+
+def _shipped_layout_checkpoint(seed=3):
+    """A checkpoint with exactly the key set / shapes / dtype of lora_models/comprehensive_lora.pth."""
+    g = torch.Generator().manual_seed(seed)
+    ck = {}
+    for i in range(12):
+        p = f"clip_model.transformer.resblocks.{i}.mlp."
+        ck[p + "c_fc.lora.lora_A"] = torch.randn(512, 4, generator=g) * 0.02
+        ck[p + "c_fc.lora.lora_B"] = torch.randn(4, 2048, generator=g) * 0.005
+        ck[p + "c_proj.lora.lora_A"] = torch.randn(2048, 4, generator=g) * 0.02
+        ck[p + "c_proj.lora.lora_B"] = torch.randn(4, 512, generator=g) * 0.005
+    return ck
+
+
+def test_lora_wrap_names_and_checkpoint_layout(iic, product_cpu, tmp_path):
+    from oracle import ref_semantics as RS
+    model = copy.deepcopy(product_cpu[0])
+    names = iic.replace_linears_with_lora(model, rank=4, alpha=8)
+    omodel = copy.deepcopy(oracle_model())
+    assert names == RS.replace_linears_with_lora(omodel, rank=4, alpha=8) and len(names) == 72
+    assert [n for n, _ in model.named_parameters()] == [n for n, _ in omodel.named_parameters()]
+    lora_names = [n for n, _ in model.named_parameters() if "lora" in n]
+    assert len(lora_names) == 144 and "visual.transformer.resblocks.0.mlp.c_fc.lora.lora_A" in lora_names
+    ck = _shipped_layout_checkpoint()
+    path = tmp_path / "comprehensive_lora.pth"
+    torch.save(ck, path)
+    loaded, missing = iic.load_lora_weights_to_model(model, str(path), strict_match=False)
+    assert (loaded, len(missing)) == (48, 96)                      # SURVEY F7 known answer
+    assert (loaded, missing) == RS.load_lora_state(omodel, ck)
+    assert all(bool((p == 0).all()) for n, p in model.named_parameters() if n.startswith("visual.") and n.endswith("lora_B"))
+    with pytest.raises(RuntimeError):
+        iic.load_lora_weights_to_model(copy.deepcopy(product_cpu[0]) and model, str(path), strict_match=True)
+    with pytest.raises(FileNotFoundError):
+        iic.load_lora_weights_to_model(model, str(tmp_path / "nope.pth"))
+    # save: {name: fp32 cpu tensor} for every 'lora' parameter, torch.save, loadable by the reference-style reader
+    out = tmp_path / "saved.pth"
+    iic.save_lora_weights(model, str(out))
+    sd = torch.load(out, map_location="cpu")
+    assert sorted(sd) == sorted(lora_names) and all(v.dtype == torch.float32 and v.device.type == "cpu" for v in sd.values())
+    again = copy.deepcopy(product_cpu[0])
+    iic.replace_linears_with_lora(again, rank=4, alpha=8)
+    assert iic.load_lora_weights_to_model(again, str(out))[0] == 144
+    # text tower with the LoRA live == oracle text tower with the same LoRA (this is what makes the label matrix)
+    tok = iic.tokenize(["wnętrze z drewno", "salon"])
+    with torch.no_grad():
+        assert torch.allclose(model.encode_text(tok), omodel.encode_text(tok), rtol=1e-4, atol=1e-5)
+
+
+def test_text_tower_and_tokenizer_match_oracle(iic, product_cpu):
+    from oracle import clip_ref
+    texts = ["interior of a room", "wnętrze z żółty", "  Pokój   dziecięcy ", ""]
+    assert torch.equal(iic.tokenize(texts), clip_ref.tokenize(texts))
+    tok = iic.tokenize(texts)
+    assert tok.shape == (4, 77) and tok.dtype == torch.long and (tok.argmax(-1) == (tok == 49407).float().argmax(-1)).all()
+    with pytest.raises(RuntimeError):
+        iic.tokenize("x" * 200)
+    with torch.no_grad():
+        a, b = product_cpu[0].encode_text(tok), oracle_model().encode_text(tok)
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert abs(product_cpu[0].logit_scale.exp().item() - 100.0) < 1e-3
+
+
+def test_label_schema_known_answers(iic):
+    """interior_dataset.json schema: 151 entries / 150 files, group sizes 20/12/299/36/30."""
+    data = golden_json("interior_dataset_fixture.json")["training_data"]
+    assert len(data) == 151 and len({d["image_path"] for d in data}) == 150
+    a = iic.CachedInteriorAnalyzer.__new__(iic.CachedInteriorAnalyzer)
+    a.training_data = a._load_training_data(os.path.join(GOLDEN, "interior_dataset_fixture.json"))
+    cats = a._extract_all_categories()
+    assert [len(cats[k]) for k in ("styles", "room_types", "characteristics", "materials", "colors")] == [20, 12, 299, 36, 30]
+    assert cats == golden_json("labels.json")["groups"]
+    from importlib import import_module
+    an = import_module("ai-interior-image-classifier_b200.analyzer")
+    assert len(an.DETECTOR_CATEGORIES) == 40 and an.N_INTERIOR == 11 and an.DETECTOR_CATEGORIES == golden_json("labels.json")["detector"]
+    assert a._load_training_data("/nonexistent.json") == []
+
+
+def test_no_cpu_fallback(iic, product_cpu):
+    model, pre = product_cpu
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.encode_image(torch.zeros(1, 3, 224, 224))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            iic.Engine(iic.VIT_B_16, "cuda")
+        from PIL import Image
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pre(Image.new("RGB", (300, 260)))
+
+
+def test_c_abi_header_library_and_binding_agree(iic):
+    """every function include/iic.h declares is exported by the shared library and bound in _lib.PROTOTYPES (and v.v.)"""
+    hdr = open(os.path.join(ROOT, "include", "iic.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(iic_[a-z0-9_]+)\s*\(", hdr))
+    lib = iic._lib.load()
+    assert declared == set(iic._lib.PROTOTYPES), declared ^ set(iic._lib.PROTOTYPES)
+    nm = subprocess.run(["nm", "-D", "--defined-only", iic._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (iic_[a-z0-9_]+)\b", nm))
+    assert declared <= exported, declared - exported
+    assert b"sm_100a" in lib.iic_version()
+    assert lib.iic_last_error(None) is not None
+    # library is self-contained: no libcuda / libcudart link-time dependency (driver entry points resolved at run time)
+    ldd = subprocess.run(["ldd", iic._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in ldd and "libcudart" not in ldd
+
+
+def test_shard_bounds_partition():
+    from importlib import import_module
+    dp = import_module("ai-interior-image-classifier_b200.dp")
+    for n in (0, 1, 7, 150, 151, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [dp.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        dp.shard_bounds(4, 2, 2)
+
+
+_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from importlib import import_module
+dp = import_module("ai-interior-image-classifier_b200.dp")
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+items = [f"interior{{i}}.jpg" for i in range(151)]
+mine = dp.shard(items, rank, world)
+local = [(p, len(p) * 7 % 13) for p in mine]                  # stand-in for per-image results
+allr = dp.gather_in_order(local)
+t = torch.tensor([10.0 + rank], dtype=torch.float64)          # bench.py: max over ranks of the step time
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+ok = [p for p, _ in allr] == items and t.item() == 11.0 and len(mine) in (75, 76)
+dist.barrier(); dist.destroy_process_group()
+print(json.dumps({{"rank": rank, "ok": bool(ok), "n": len(mine)}}))
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_data_parallel_sharding_gloo_world2(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert sum(eval(o[0].strip().splitlines()[-1].replace("true", "True"))["n"] for o in outs) == 151
