@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libiic_b200.so")
-SOURCES = ["gemm_sm100.cu", "rowwise.cu", "attention.cu", "head.cu", "preprocess.cu", "iic_api.cu"]
+SOURCES = ["gemm_sm100.cu", "rowwise.cu", "attention.cu", "attention_bwd.cu", "train_ops.cu", "head.cu", "preprocess.cu",
+           "iic_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off",
@@ -61,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, srcs))
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -127,7 +127,7 @@ class VisionTransformer(nn.Module):
             self._sig = None
         return self._engine
 
-    def _tensors(self) -> Tuple[Dict[str, torch.Tensor], Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, float]]]:
+    def _tensors(self, keep_zero_lora: bool = False) -> Tuple[Dict[str, torch.Tensor], Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, float]]]:
         sd: Dict[str, torch.Tensor] = {
             "conv1.weight": self.conv1.weight, "class_embedding": self.class_embedding,
             "positional_embedding": self.positional_embedding, "ln_pre.weight": self.ln_pre.weight,
@@ -145,15 +145,15 @@ class VisionTransformer(nn.Module):
                 sd[p + name + ".weight"], sd[p + name + ".bias"] = mod.weight, mod.bias  # proxies on a LoRALinear
                 if _is_lora_wrapped(mod) and (which != L.LORA_OUT_PROJ or self.apply_out_proj_lora):
                     scaling = float(getattr(mod.lora, "scaling", 1.0))
-                    if bool((mod.lora.lora_B != 0).any()):  # B == 0 (fresh / missing in the checkpoint): delta is exactly 0
+                    if keep_zero_lora or bool((mod.lora.lora_B != 0).any()):  # B == 0 (fresh / missing in ckpt): delta is exactly 0
                         lora[(i, which)] = (mod.lora.lora_A, mod.lora.lora_B, scaling)
         return sd, lora
 
-    def sync_engine(self, force: bool = False, use_lora: bool = True) -> Engine:
+    def sync_engine(self, force: bool = False, use_lora: bool = True, keep_zero_lora: bool = False) -> Engine:
         """(Re)upload whatever changed since the last call (optimizer step, checkpoint load, `.data` swap).
         use_lora=False runs the frozen base tower (the reference's detector owns an un-LoRA'd copy, main.py:238)."""
         eng = self.engine()
-        sd, lora = self._tensors()
+        sd, lora = self._tensors(keep_zero_lora)
         if not use_lora:
             lora = {}
         sig_w = tuple((k, t.data_ptr(), t._version, t.device.type) for k, t in sd.items())

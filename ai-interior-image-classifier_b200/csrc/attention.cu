@@ -65,8 +65,8 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return uint32_t(ro
 
 template <bool kF16>
 __global__ void __launch_bounds__(kWarps * 32, 4)
-attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int T, int TP, int H,
-                 float scale_log2e) {
+attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, float* __restrict__ lse, int T, int TP,
+                 int H, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int d = H * kHd;
   const int bh = blockIdx.x;
@@ -203,6 +203,11 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     const int r0 = q0 + g, r1 = q0 + g + 8;
+    if (lse != nullptr && t == 0) {
+      // training: log2-domain log-sum-exp of the scaled scores, so the backward recomputes P = exp2(s*c - lse)
+      if (r0 < T) lse[size_t(bh) * T + r0] = m0 + log2f(l0);
+      if (r1 < T) lse[size_t(bh) * T + r1] = m1 + log2f(l1);
+    }
     uint16_t* ob = out + size_t(b) * T * d + h * kHd;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -213,7 +218,8 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
   }
 }
 
-int launch_attention(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16, cudaStream_t stream) {
+int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16,
+                     cudaStream_t stream) {
   if (B <= 0) return 0;
   if (head_dim != kHd) return -1;
   const int TP = (T + 15) / 16 * 16;
@@ -232,9 +238,9 @@ int launch_attention(const void* qkv, void* out, int B, int T, int H, int head_d
   const uint16_t* q = static_cast<const uint16_t*>(qkv);
   uint16_t* o = static_cast<uint16_t*>(out);
   if (f16)
-    attention_kernel<true><<<B * H, kWarps * 32, smem, stream>>>(q, o, T, TP, H, scale_log2e);
+    attention_kernel<true><<<B * H, kWarps * 32, smem, stream>>>(q, o, lse, T, TP, H, scale_log2e);
   else
-    attention_kernel<false><<<B * H, kWarps * 32, smem, stream>>>(q, o, T, TP, H, scale_log2e);
+    attention_kernel<false><<<B * H, kWarps * 32, smem, stream>>>(q, o, lse, T, TP, H, scale_log2e);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -24,14 +24,22 @@ struct Tensor {
 };
 
 struct LoraSlot {
-  const float* a = nullptr;          // f32 [in, r4]
-  const void* bt = nullptr;          // 16-bit [out, lora_pad]
+  const float* a = nullptr;          // f32 [in, r4]   = scaling * lora_A
+  const void* bt = nullptr;          // 16-bit [out, lora_pad] = lora_B^T
   int rank = 0, r4 = 0, r_pad = 0;
+  // training only
+  const void* a16 = nullptr;         // 16-bit [in, lora_pad]  = scaling * lora_A (operand of the dX LoRA k-step)
+  const float* bt32 = nullptr;       // f32 [out, r4]          = lora_B^T (operand of dP = dY . B^T)
+  float scaling = 1.f;
+  float* grad_a = nullptr;           // f32 [in, rank]   d(loss)/d(lora_A)
+  float* grad_b = nullptr;           // f32 [rank, out]  d(loss)/d(lora_B)
 };
 
 struct Block {
   const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   const void *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+  // transposed copies [in, out] for the dX GEMMs of the backward pass (training only)
+  const void *w_qkv_t = nullptr, *w_out_t = nullptr, *w_fc_t = nullptr, *w_proj_t = nullptr;
   const float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
   LoraSlot lora[4];
 };
@@ -85,6 +93,7 @@ struct iic_handle {
   std::string err;
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
+  float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
   std::vector<Block> blocks;
@@ -201,7 +210,7 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
                               l_in.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
-    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(w.qkv, w.attn, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(w.qkv, w.attn, nullptr, B, T, H, d / H, h->f16, s); }));
     if (l_out.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s);
@@ -242,6 +251,190 @@ int run_head(iic_handle* h, const float* x_cls, long long x_img_stride, const fl
                        scores ? out->logits : nullptr, scores ? out->probs : nullptr, scores ? out->topk_val : nullptr,
                        scores ? out->topk_idx : nullptr, scores ? out->split_sum : nullptr, emb_in, s);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "head kernel launch failed");
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// training step (LoRA-only gradients): forward that keeps what the backward needs, backward through the frozen blocks
+// ------------------------------------------------------------------------------------------------------------------
+struct TrainLayer {
+  float *x_in, *x_mid;            // f32 [M, d]: inputs of ln_1 / ln_2
+  uint16_t *qkv, *attn, *y2;      // 16-bit [M, 3d], [M, d], [M, d] (ln_2 output = c_fc operand)
+  uint16_t *p1, *p2;              // 16-bit [M, lora_pad]: s1*(y2.A1), s2*(h.A2)
+  float* lse;                     // f32 [B*H, T]
+};
+struct TrainWorkspace {
+  std::vector<TrainLayer> layers;
+  float *x, *xpre, *dx, *down_part, *outer_scratch;
+  uint16_t *xln, *hid, *u, *dh, *g16, *dy, *dqkv, *da, *dp1, *dp2;
+  size_t total;
+};
+constexpr int kOuterSplits = 32;
+
+TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
+  const size_t M = size_t(B) * h->T;
+  const size_t d = h->cfg.width, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  TrainWorkspace w;
+  w.x = static_cast<float*>(take(M * d * 4));
+  w.dx = static_cast<float*>(take(M * d * 4));
+  w.xln = static_cast<uint16_t*>(take(M * d * 2));
+  w.hid = static_cast<uint16_t*>(take(M * mlp * 2));
+  w.u = static_cast<uint16_t*>(take(M * mlp * 2));
+  w.dh = static_cast<uint16_t*>(take(M * mlp * 2));
+  w.g16 = static_cast<uint16_t*>(take(M * d * 2));
+  w.dy = static_cast<uint16_t*>(take(M * d * 2));
+  w.dqkv = static_cast<uint16_t*>(take(M * 3 * d * 2));
+  w.da = static_cast<uint16_t*>(take(M * d * 2));
+  w.dp1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+  w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+  w.down_part = static_cast<float*>(take(size_t((mlp + 255) / 256) * M * 16));
+  w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), kOuterSplits)));
+  w.xpre = reinterpret_cast<float*>(w.hid);
+  w.layers.resize(h->blocks.size());
+  for (TrainLayer& l : w.layers) {
+    l.x_in = static_cast<float*>(take(M * d * 4));
+    l.x_mid = static_cast<float*>(take(M * d * 4));
+    l.qkv = static_cast<uint16_t*>(take(M * 3 * d * 2));
+    l.attn = static_cast<uint16_t*>(take(M * d * 2));
+    l.y2 = static_cast<uint16_t*>(take(M * d * 2));
+    l.p1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+    l.p2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
+    l.lse = static_cast<float*>(take(size_t(B) * H * h->T * 4));
+  }
+  w.total = off;
+  return w;
+}
+
+bool check_train_ready(iic_handle* h) {
+  for (const Block& b : h->blocks) {
+    if (!b.w_qkv_t || !b.w_out_t || !b.w_fc_t || !b.w_proj_t) return false;
+    for (int w : {IIC_LORA_C_FC, IIC_LORA_C_PROJ})
+      if (b.lora[w].rank > 0 && (!b.lora[w].a16 || !b.lora[w].bt32 || !b.lora[w].grad_a || !b.lora[w].grad_b)) return false;
+  }
+  return true;
+}
+
+int copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows, cudaStream_t s) {
+  return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -2;
+}
+
+// forward in training mode: same kernels as inference, per-layer activations kept
+int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace& w, float* x_cls_out, cudaStream_t s) {
+  const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  const int gg = h->g * h->g;
+  const float eps = 1e-5f;
+  const size_t xbytes = size_t(M) * d * 4;
+  h->err.clear();
+  IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
+                   nullptr, h->pos, w.xpre, d, gg, s));
+  IIC_TRY(timed(h, kMisc, s, [&] { return launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s); }));
+  IIC_TRY(timed(h, kLayerNorm, s, [&] {
+    return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+  }));
+  const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
+  for (size_t li = 0; li < h->blocks.size(); ++li) {
+    Block& b = h->blocks[li];
+    TrainLayer& t = w.layers[li];
+    const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
+    const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
+    if (b.lora[IIC_LORA_IN_PROJ].rank || b.lora[IIC_LORA_OUT_PROJ].rank)
+      return fail(h, IIC_ERR_ARG, "training supports LoRA on mlp.c_fc / mlp.c_proj (what the reference's wrap makes effective)");
+    if (cudaMemcpyAsync(t.x_in, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+    }));
+    IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, nullptr, nullptr, kEpiBiasBf16, b.b_qkv, nullptr, t.qkv, 3 * d, 1, s));
+    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(t.qkv, t.attn, t.lse, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(run_gemm(h, t.attn, d, b.w_out, M, d, d, nullptr, nullptr, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
+    if (cudaMemcpyAsync(t.x_mid, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, t.y2, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr, l_fc.r4,
+                              t.p1, h->lora_pad, h->f16, s);
+    }));
+    const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
+    IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
+                     fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
+    if (fuse_down)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_reduce(w.down_part, (mlp + 255) / 256, M, t.p2, h->lora_pad, h->f16, s);
+      }));
+    else if (l_pr.rank)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, t.p2, h->lora_pad, h->f16, s);
+      }));
+    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, t.p2, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
+  }
+  // class-token rows of the final residual stream (input of ln_post), [B, d] contiguous
+  return copy_rows_async(x_cls_out, size_t(d) * 4, w.x, size_t(T) * d * 4, size_t(d) * 4, size_t(B), s) ? fail(h, IIC_ERR_CUDA, "copy failed") : 0;
+}
+
+int run_train_backward_begin(iic_handle* h, int B, TrainWorkspace& w, const float* dx_cls, cudaStream_t s) {
+  const int d = h->cfg.width, T = h->T, M = B * T;
+  h->err.clear();
+  // dx = 0 except the class-token rows
+  if (cudaMemsetAsync(w.dx, 0, size_t(M) * d * 4, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "memset failed");
+  if (copy_rows_async(w.dx, size_t(T) * d * 4, dx_cls, size_t(d) * 4, size_t(d) * 4, size_t(B), s)) return fail(h, IIC_ERR_CUDA, "copy failed");
+  IIC_TRY(timed(h, kMisc, s, [&] { return launch_cast16(w.dx, w.g16, (long long)M * d, h->f16, s); }));
+  return 0;
+}
+
+// backward through block `li` (call for li = layers-1 ... 0 after run_train_backward_begin); its LoRA gradients are final on return
+int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cudaStream_t s) {
+  const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  const float eps = 1e-5f;
+  const int act = h->cfg.activation == IIC_ACT_GELU_ERF ? 2 : 1;
+  LoraSlot none;
+  {
+    Block& b = h->blocks[li];
+    TrainLayer& t = w.layers[li];
+    const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
+    const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
+    // ---- c_proj:  x_out = x_mid + h W2^T + b2 + P2 B2   (P2 = s2 h A2) ----
+    LoraSlot bw_pr;   // LoRA k-step of the dX GEMM: dh += dP2 . (s2 A2)^T
+    if (l_pr.rank) {
+      IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.g16, d, M, l_pr.bt32, l_pr.r4, w.dp2, h->lora_pad, h->f16, s); }));
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, kOuterSplits, h->f16, s);
+      }));
+      bw_pr.rank = l_pr.rank; bw_pr.r4 = l_pr.r4; bw_pr.r_pad = l_pr.r_pad; bw_pr.bt = l_pr.a16;
+    }
+    // recompute the pre-activation u = y2 W1^T + b1 + P1 B1 (cheaper than keeping [M, 4d] per layer)
+    IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasBf16, b.b_fc, nullptr, w.u, mlp, 1, s));
+    if (l_pr.rank)
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_outer(w.dp2, h->lora_pad, w.u, mlp, M, act, l_pr.rank, l_pr.scaling * h->grad_unscale, 1, l_pr.grad_a, w.outer_scratch, kOuterSplits, h->f16, s);
+      }));
+    IIC_TRY(run_gemm(h, w.g16, d, b.w_proj_t, M, mlp, d, &bw_pr, w.dp2, kEpiBiasBf16, nullptr, nullptr, w.dh, mlp, 1, s));
+    IIC_TRY(timed(h, kMisc, s, [&] { return launch_act_bwd(w.dh, w.u, (long long)M * mlp, act, h->f16, s); }));   // dh := du
+    // ---- c_fc:  u = y2 W1^T + b1 + P1 B1   (P1 = s1 y2 A1) ----
+    LoraSlot bw_fc;
+    if (l_fc.rank) {
+      IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.dh, mlp, M, l_fc.bt32, l_fc.r4, w.dp1, h->lora_pad, h->f16, s); }));
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, kOuterSplits, h->f16, s);
+      }));
+      IIC_TRY(timed(h, kLoraDown, s, [&] {
+        return launch_lora_outer(w.dp1, h->lora_pad, t.y2, d, M, 0, l_fc.rank, l_fc.scaling * h->grad_unscale, 1, l_fc.grad_a, w.outer_scratch, kOuterSplits, h->f16, s);
+      }));
+      bw_fc.rank = l_fc.rank; bw_fc.r4 = l_fc.r4; bw_fc.r_pad = l_fc.r_pad; bw_fc.bt = l_fc.a16;
+    }
+    IIC_TRY(run_gemm(h, w.dh, mlp, b.w_fc_t, M, d, mlp, &bw_fc, w.dp1, kEpiBiasBf16, nullptr, nullptr, w.dy, d, 1, s));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] { return launch_layernorm_bwd(w.dy, t.x_mid, b.ln2_g, w.dx, w.g16, M, d, eps, h->f16, s); }));
+    if (li == 0) return 0;   // nothing below the first block's MLP carries a LoRA parameter
+    // ---- attention block:  x_mid = x_in + attn(ln_1(x_in)) W_o^T + b_o ----
+    IIC_TRY(run_gemm(h, w.g16, d, b.w_out_t, M, d, d, &none, nullptr, kEpiBiasBf16, nullptr, nullptr, w.da, d, 1, s));
+    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention_bwd(t.qkv, t.attn, w.da, t.lse, w.dqkv, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(run_gemm(h, w.dqkv, 3 * d, b.w_qkv_t, M, d, 3 * d, &none, nullptr, kEpiBiasBf16, nullptr, nullptr, w.dy, d, 1, s));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] { return launch_layernorm_bwd(w.dy, t.x_in, b.ln1_g, w.dx, w.g16, M, d, eps, h->f16, s); }));
+  }
   return 0;
 }
 
@@ -362,6 +555,10 @@ int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dt
         if (r == "mlp.c_fc.bias") IIC_SET(b.b_fc, const float*, IIC_DTYPE_F32, 1, mlp, 0);
         if (r == "mlp.c_proj.weight") IIC_SET(b.w_proj, const void*, wdt, 2, d, mlp);
         if (r == "mlp.c_proj.bias") IIC_SET(b.b_proj, const float*, IIC_DTYPE_F32, 1, d, 0);
+        if (r == "attn.in_proj_weight_t") IIC_SET(b.w_qkv_t, const void*, wdt, 2, d, 3 * d);
+        if (r == "attn.out_proj.weight_t") IIC_SET(b.w_out_t, const void*, wdt, 2, d, d);
+        if (r == "mlp.c_fc.weight_t") IIC_SET(b.w_fc_t, const void*, wdt, 2, d, mlp);
+        if (r == "mlp.c_proj.weight_t") IIC_SET(b.w_proj_t, const void*, wdt, 2, mlp, d);
       }
     }
   }
@@ -522,6 +719,117 @@ int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_
   return IIC_OK;
 }
 
+
+// ---- training ----
+int iic_set_lora_train(iic_handle* h, int layer, int which, const void* a16, const float* bt32, float scaling,
+                       float* grad_a, float* grad_b) {
+  if (!h) return IIC_ERR_ARG;
+  if (layer < 0 || layer >= int(h->blocks.size()) || which < 0 || which > 3)
+    return fail(h, IIC_ERR_ARG, "iic_set_lora_train: bad layer / projection id");
+  LoraSlot& s = h->blocks[layer].lora[which];
+  if (s.rank <= 0) return fail(h, IIC_ERR_STATE, "iic_set_lora_train: call iic_set_lora for this slot first");
+  if (!a16 || !bt32 || !grad_a || !grad_b) return fail(h, IIC_ERR_ARG, "iic_set_lora_train: null pointer");
+  s.a16 = a16; s.bt32 = bt32; s.scaling = scaling; s.grad_a = grad_a; s.grad_b = grad_b;
+  return IIC_OK;
+}
+
+int iic_train_set_loss_scale(iic_handle* h, float loss_scale) {
+  if (!h || !(loss_scale > 0.f)) return fail(h, IIC_ERR_ARG, "iic_train_set_loss_scale: scale must be positive");
+  h->grad_unscale = 1.0f / loss_scale;
+  return IIC_OK;
+}
+
+size_t iic_train_workspace_bytes(const iic_handle* h, int B) {
+  if (!h || B <= 0) return 0;
+  return carve_train(h, B, nullptr).total + 1024;
+}
+
+static int check_train_ws(iic_handle* h, int B, void* workspace, size_t bytes, TrainWorkspace* w) {
+  if (B <= 0 || !workspace) return fail(h, IIC_ERR_ARG, "workspace / batch: bad argument");
+  if (!check_ready(h)) return fail(h, IIC_ERR_STATE, "not all weights have been loaded (iic_load_weight)");
+  if (!check_train_ready(h)) return fail(h, IIC_ERR_STATE, "training needs the transposed weights (*_t) and iic_set_lora_train for every LoRA slot");
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  *w = carve_train(h, B, base);
+  if (size_t(base - static_cast<uint8_t*>(workspace)) + w->total > bytes)
+    return fail(h, IIC_ERR_ARG, "training workspace too small: see iic_train_workspace_bytes");
+  return 0;
+}
+
+int iic_train_forward(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* x_cls_out,
+                      void* stream) {
+  if (!h || !patches || !x_cls_out) return fail(h, IIC_ERR_ARG, "iic_train_forward: null argument");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  return run_train_forward(h, patches, B, w, x_cls_out, static_cast<cudaStream_t>(stream));
+}
+
+int iic_train_backward(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream) {
+  if (!h || !dx_cls) return fail(h, IIC_ERR_ARG, "iic_train_backward: null argument");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  rc = run_train_backward_begin(h, B, w, dx_cls, static_cast<cudaStream_t>(stream));
+  for (int li = int(h->blocks.size()) - 1; li >= 0 && rc == 0; --li)
+    rc = run_train_backward_layer(h, B, w, li, static_cast<cudaStream_t>(stream));
+  return rc;
+}
+
+int iic_train_backward_begin(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream) {
+  if (!h || !dx_cls) return fail(h, IIC_ERR_ARG, "iic_train_backward_begin: null argument");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  return run_train_backward_begin(h, B, w, dx_cls, static_cast<cudaStream_t>(stream));
+}
+
+int iic_train_backward_layer(iic_handle* h, int B, void* workspace, size_t workspace_bytes, int layer, void* stream) {
+  if (!h || layer < 0 || layer >= int(h->blocks.size())) return fail(h, IIC_ERR_ARG, "iic_train_backward_layer: bad argument");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  return run_train_backward_layer(h, B, w, layer, static_cast<cudaStream_t>(stream));
+}
+
+int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* d_out, void* dqkv, float* lse_scratch,
+                         int B, int T, int heads, void* stream) {
+  if (!h || !qkv || !out || !d_out || !dqkv || !lse_scratch) return fail(h, IIC_ERR_ARG, "iic_op_attention_bwd: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // recompute the forward into `out`'s twin to obtain the log-sum-exp (op-level test helper)
+  int rc = launch_attention(qkv, out, lse_scratch, B, T, heads, 64, h->f16, s);
+  if (rc == 0) rc = launch_attention_bwd(qkv, out, d_out, lse_scratch, dqkv, B, T, heads, 64, h->f16, s);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention backward: unsupported shape (T <= 432) or launch failure");
+  return IIC_OK;
+}
+
+int iic_op_layernorm_bwd(iic_handle* h, const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows,
+                         int D, void* stream) {
+  if (!h || !dy || !x || !gamma || !dx) return fail(h, IIC_ERR_ARG, "iic_op_layernorm_bwd: null argument");
+  int rc = launch_layernorm_bwd(dy, x, gamma, dx, dx16, rows, D, 1e-5f, h->f16, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "layernorm backward failed");
+  return IIC_OK;
+}
+
+int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act, void* stream) {
+  if (!h || !dh || !u) return fail(h, IIC_ERR_ARG, "iic_op_act_bwd: null argument");
+  int rc = launch_act_bwd(dh, u, n, act, h->f16, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "activation backward failed");
+  return IIC_OK;
+}
+
+int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale,
+                      int transpose, float* out, void* stream) {
+  if (!h || !P || !Y || !out) return fail(h, IIC_ERR_ARG, "iic_op_lora_outer: null argument");
+  float* scratch = nullptr;
+  const int splits = 16;
+  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, splits)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
+  int rc = launch_lora_outer(P, p_ld, Y, N, M, act, rank, scale, transpose, out, scratch, splits, h->f16, static_cast<cudaStream_t>(stream));
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(scratch);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "lora_outer failed");
+  return IIC_OK;
+}
+
 // ---- single operators ----
 int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                 const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
@@ -563,7 +871,7 @@ int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const f
 
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream) {
   if (!h || !qkv_bf16 || !out_bf16) return fail(h, IIC_ERR_ARG, "iic_op_attention: null argument");
-  int rc = launch_attention(qkv_bf16, out_bf16, B, T, heads, 64, h->f16, static_cast<cudaStream_t>(stream));
+  int rc = launch_attention(qkv_bf16, out_bf16, nullptr, B, T, heads, 64, h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention launch failed");
   return IIC_OK;
 }

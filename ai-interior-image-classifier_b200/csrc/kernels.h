@@ -22,8 +22,23 @@ int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int 
                           cudaStream_t stream);
 
 // ---- attention.cu ----
-int launch_attention(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16,
+// lse (nullable): f32 [B*H, T] log2-domain log-sum-exp of the scaled scores, saved for the backward pass
+int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16,
                      cudaStream_t stream);
+// dqkv[M, 3d] (16-bit) from d_out[M, d], the saved qkv / out / lse.  T <= 432 (everything of one head lives in smem).
+int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int T,
+                         int H, int head_dim, int f16, cudaStream_t stream);
+
+// ---- train_ops.cu ----
+int launch_layernorm_bwd(const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows, int D,
+                         float eps, int f16, cudaStream_t stream);
+int launch_cast16(const float* in, void* out, long long n, int f16, cudaStream_t stream);
+// act: 0 identity, 1 QuickGELU, 2 GELU(erf)
+int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaStream_t stream);
+size_t lora_outer_scratch_bytes(int N, int splits);
+// out = scale * P[:, :rank]^T . act(Y)  ->  [rank, N] (transpose = 0: dB) or [N, rank] (transpose = 1: dA); deterministic
+int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
+                      float* out, float* scratch, int splits, int f16, cudaStream_t stream);
 
 // ---- head.cu ----
 int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,

@@ -1,0 +1,241 @@
+// Backward-pass kernels of the LoRA fine-tuning step (everything that is not a GEMM or attention):
+//   LayerNorm backward, QuickGELU / GELU backward, the skinny LoRA gradient reductions dB = P^T dY and
+//   dA = s * act(X)^T dP, fp32 -> 16-bit casts.
+//
+// Reference semantics: torch.autograd through OpenAI CLIP's ResidualAttentionBlock with /root/reference/main.py's
+// LoRALinear on mlp.c_fc / mlp.c_proj (main.py:30-31, 42-43) and the training loop of train_lora.py:231-252
+// (only parameters whose name contains 'lora' receive gradients; the frozen weights only propagate dX).
+// Activation gradients travel in the 16-bit operand format (they are GEMM operands), every reduction is fp32,
+// the residual-stream gradient is fp32.  All reductions are deterministic (fixed partial order, no float atomics).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "act_types.cuh"
+#include "kernels.h"
+
+namespace iic {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float act_fwd(float u, int act) {
+  if (act == 1) return u / (1.0f + __expf(-1.702f * u));                       // QuickGELU
+  if (act == 2) return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f));     // GELU (erf)
+  return u;
+}
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == 1) {
+    const float s = 1.0f / (1.0f + __expf(-1.702f * u));
+    return s * (1.0f + 1.702f * u * (1.0f - s));
+  }
+  if (act == 2) {
+    const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+    return cdf + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+  }
+  return 1.0f;
+}
+
+// dx[row,:] += LN'(dy[row,:]; x[row,:], gamma);  optional 16-bit copy of the updated dx (next GEMM operand).
+// One warp per row, grid-stride.  kVec = D / 128.
+template <int kVec, bool kF16>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     float* __restrict__ dx, uint16_t* __restrict__ dx16, int rows, float eps) {
+  constexpr int D = kVec * 128;
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += n_warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + size_t(row) * D);
+    const uint2* dr = reinterpret_cast<const uint2*>(dy + size_t(row) * D);
+    float4 xv[kVec], gv[kVec];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      xv[j] = xr[lane + 32 * j];
+      s += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      xv[j].x -= mean; xv[j].y -= mean; xv[j].z -= mean; xv[j].w -= mean;
+      q += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const uint2 raw = dr[lane + 32 * j];
+      const float2 d01 = Act<kF16>::unpack(raw.x), d23 = Act<kF16>::unpack(raw.y);
+      const float4 g = __ldg(g4 + lane + 32 * j);
+      xv[j].x *= rstd; xv[j].y *= rstd; xv[j].z *= rstd; xv[j].w *= rstd;   // xhat
+      gv[j] = make_float4(d01.x * g.x, d01.y * g.y, d23.x * g.z, d23.y * g.w);
+      c1 += (gv[j].x + gv[j].y) + (gv[j].z + gv[j].w);
+      c2 += (gv[j].x * xv[j].x + gv[j].y * xv[j].y) + (gv[j].z * xv[j].z + gv[j].w * xv[j].w);
+    }
+    c1 = warp_sum(c1) * (1.0f / D);
+    c2 = warp_sum(c2) * (1.0f / D);
+    float4* o = reinterpret_cast<float4*>(dx + size_t(row) * D);
+    uint2* o16 = dx16 ? reinterpret_cast<uint2*>(dx16 + size_t(row) * D) : nullptr;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      float4 r = o[lane + 32 * j];
+      r.x += rstd * (gv[j].x - c1 - xv[j].x * c2);
+      r.y += rstd * (gv[j].y - c1 - xv[j].y * c2);
+      r.z += rstd * (gv[j].z - c1 - xv[j].z * c2);
+      r.w += rstd * (gv[j].w - c1 - xv[j].w * c2);
+      o[lane + 32 * j] = r;
+      if (o16) {
+        uint2 pk;
+        pk.x = Act<kF16>::pack(r.x, r.y);
+        pk.y = Act<kF16>::pack(r.z, r.w);
+        o16[lane + 32 * j] = pk;
+      }
+    }
+  }
+}
+
+template <bool kF16>
+__global__ void __launch_bounds__(256)
+cast16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(in)[i];
+  uint2 pk;
+  pk.x = Act<kF16>::pack(v.x, v.y);
+  pk.y = Act<kF16>::pack(v.z, v.w);
+  reinterpret_cast<uint2*>(out)[i] = pk;
+}
+
+// dh <- dh * act'(u), elementwise, 8 elements per thread
+template <bool kF16>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ u, long long n8, int act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 a = reinterpret_cast<uint4*>(dh)[i];
+  const uint4 b = reinterpret_cast<const uint4*>(u)[i];
+  uint32_t* pa = reinterpret_cast<uint32_t*>(&a);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 g = Act<kF16>::unpack(pa[e]), uu = Act<kF16>::unpack(pb[e]);
+    pa[e] = Act<kF16>::pack(g.x * act_grad(uu.x, act), g.y * act_grad(uu.y, act));
+  }
+  reinterpret_cast<uint4*>(dh)[i] = a;
+}
+
+// part[split][c][n] = sum over the split's rows of P[m, c] * f(Y[m, n]),  c < 4, f = act_fwd (act = 0: identity).
+// P 16-bit [M, p_ld], Y 16-bit [M, N].  Thread = 2 adjacent columns of Y; CTA = 256 columns x one row split.
+template <bool kF16>
+__global__ void __launch_bounds__(128)
+lora_outer_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int rows_per_split,
+                  int act, float* __restrict__ part) {  // P already offset to the 4-column group
+  const int n = blockIdx.x * 256 + threadIdx.x * 2;
+  const int split = blockIdx.y;
+  const int m0 = split * rows_per_split;
+  const int m1 = min(M, m0 + rows_per_split);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (n < N) {
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) {
+      const uint2 praw = *reinterpret_cast<const uint2*>(P + size_t(m) * p_ld);   // warp-uniform: broadcast
+      const float2 p01 = Act<kF16>::unpack(praw.x), p23 = Act<kF16>::unpack(praw.y);
+      float2 y = Act<kF16>::unpack(*reinterpret_cast<const uint32_t*>(Y + size_t(m) * N + n));
+      if (act != 0) { y.x = act_fwd(y.x, act); y.y = act_fwd(y.y, act); }
+      acc[0][0] = fmaf(p01.x, y.x, acc[0][0]); acc[0][1] = fmaf(p01.y, y.x, acc[0][1]);
+      acc[0][2] = fmaf(p23.x, y.x, acc[0][2]); acc[0][3] = fmaf(p23.y, y.x, acc[0][3]);
+      acc[1][0] = fmaf(p01.x, y.y, acc[1][0]); acc[1][1] = fmaf(p01.y, y.y, acc[1][1]);
+      acc[1][2] = fmaf(p23.x, y.y, acc[1][2]); acc[1][3] = fmaf(p23.y, y.y, acc[1][3]);
+    }
+    float* o = part + (size_t(split) * 4) * N + n;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<float2*>(o + size_t(c) * N) = make_float2(acc[0][c], acc[1][c]);
+  }
+}
+
+// out = scale * sum_split part[split][c][n]   written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r))
+__global__ void __launch_bounds__(256)
+lora_outer_reduce_kernel(const float* __restrict__ part, int splits, int N, int rank, int c0, float scale, int transpose,
+                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * N) return;
+  const int c = i / N, n = i - c * N;
+  if (c0 + c >= rank) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += part[(size_t(sp) * 4 + c) * N + n];
+  s *= scale;
+  if (transpose) out[size_t(n) * rank + c0 + c] = s;
+  else out[size_t(c0 + c) * N + n] = s;
+}
+
+}  // namespace
+
+int launch_layernorm_bwd(const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows, int D,
+                         float eps, int f16, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  const int threads = 256;
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const uint16_t* d = static_cast<const uint16_t*>(dy);
+  uint16_t* o = static_cast<uint16_t*>(dx16);
+#define IIC_LNB(KV)                                                                                          \
+  if (f16) layernorm_bwd_kernel<KV, true><<<blocks, threads, 0, stream>>>(d, x, gamma, dx, o, rows, eps);    \
+  else layernorm_bwd_kernel<KV, false><<<blocks, threads, 0, stream>>>(d, x, gamma, dx, o, rows, eps);
+  switch (D) {
+    case 512: IIC_LNB(4) break;
+    case 768: IIC_LNB(6) break;
+    case 1024: IIC_LNB(8) break;
+    case 1280: IIC_LNB(10) break;
+    default: return -1;
+  }
+#undef IIC_LNB
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_cast16(const float* in, void* out, long long n, int f16, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 4 != 0) return -1;
+  const long long n4 = n / 4;
+  const unsigned blocks = unsigned((n4 + 255) / 256);
+  if (f16) cast16_kernel<true><<<blocks, 256, 0, stream>>>(in, static_cast<uint16_t*>(out), n4);
+  else cast16_kernel<false><<<blocks, 256, 0, stream>>>(in, static_cast<uint16_t*>(out), n4);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8 != 0) return -1;
+  const long long n8 = n / 8;
+  const unsigned blocks = unsigned((n8 + 255) / 256);
+  if (f16) act_bwd_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<uint16_t*>(dh), static_cast<const uint16_t*>(u), n8, act);
+  else act_bwd_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<uint16_t*>(dh), static_cast<const uint16_t*>(u), n8, act);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+size_t lora_outer_scratch_bytes(int N, int splits) { return size_t(splits) * 4 * N * sizeof(float); }
+
+int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
+                      float* out, float* scratch, int splits, int f16, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (rank < 1 || (rank + 3) / 4 * 4 > p_ld || N % 2 != 0 || splits < 1) return -1;
+  const int rps = (M + splits - 1) / splits;
+  dim3 grid(unsigned((N + 255) / 256), unsigned(splits));
+  const uint16_t* p = static_cast<const uint16_t*>(P);
+  const uint16_t* y = static_cast<const uint16_t*>(Y);
+  for (int c0 = 0; c0 < rank; c0 += 4) {   // 4 LoRA columns per pass over Y (rank 4: one pass)
+    if (f16) lora_outer_kernel<true><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
+    else lora_outer_kernel<false><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
+    lora_outer_reduce_kernel<<<(4 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, c0, scale, transpose, out);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace iic

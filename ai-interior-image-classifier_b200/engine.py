@@ -8,6 +8,7 @@ device, or without the built extension, raises.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import threading
 from dataclasses import dataclass
@@ -310,6 +311,109 @@ class Engine:
         """list of uint8 [H,W,3] device tensors (any size) -> preprocess + encoder + head."""
         with self._lock:
             return self.classify_patches(self.preprocess(images_u8), len(images_u8), want_embedding)
+
+    # ------------------------------------------------------------------ training (LoRA-only gradients)
+    def enable_training(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Upload the transposed projection weights the dX GEMMs need (`sd` as in load_visual_state_dict)."""
+        for i in range(self.arch.layers):
+            p = f"transformer.resblocks.{i}."
+            for n in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
+                w = sd[p + n].detach().to(self.device, torch.float32).to(self.op_dtype)
+                self.load_weight(p + n + "_t", w.t().contiguous())
+
+    def set_lora_train(self, layer: int, which: int, lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float,
+                       grad_a: torch.Tensor, grad_b: torch.Tensor) -> None:
+        """Extra operands + gradient destinations for one LoRA slot (after set_lora).  grad_a [in, r] and grad_b [r, out]
+        are fp32 device tensors (typically views of the parameters' .grad) that train_backward overwrites."""
+        r = lora_a.shape[1]
+        r4 = (r + 3) // 4 * 4
+        a16 = torch.zeros(lora_a.shape[0], self.dims.lora_pad, device=self.device, dtype=self.op_dtype)
+        a16[:, :r] = (lora_a.detach().to(self.device, torch.float32) * float(scaling)).to(self.op_dtype)
+        bt32 = torch.zeros(lora_b.shape[1], r4, device=self.device, dtype=torch.float32)
+        bt32[:, :r] = lora_b.detach().to(self.device, torch.float32).t()
+        for g, shape in ((grad_a, tuple(lora_a.shape)), (grad_b, tuple(lora_b.shape))):
+            assert g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == shape
+        with self._lock:
+            L.check(self.h, self.lib.iic_set_lora_train(self.h, layer, which, a16.data_ptr(), bt32.data_ptr(), float(scaling),
+                                                        grad_a.data_ptr(), grad_b.data_ptr()), "iic_set_lora_train")
+            self._lora[(layer, which, "train")] = (a16, bt32, grad_a, grad_b)
+
+    def _train_ws(self, B: int) -> torch.Tensor:
+        need = int(self.lib.iic_train_workspace_bytes(self.h, B))
+        ws = getattr(self, "_train_workspace", None)
+        if ws is None or ws.numel() < need:
+            self._train_workspace = None
+            self._train_workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._train_workspace
+
+    def train_forward(self, patches: torch.Tensor, B: int) -> torch.Tensor:
+        """-> x_cls f32 [B, width]: class-token rows of the final residual stream (input of ln_post)."""
+        x_cls = torch.empty(B, self.arch.width, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._train_ws(B)
+            L.check(self.h, self.lib.iic_train_forward(self.h, patches.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                                                       x_cls.data_ptr(), _stream_ptr(self.device)), "iic_train_forward")
+        return x_cls
+
+    def train_backward(self, dx_cls: torch.Tensor, layer_done=None, loss_scale: "float | str" = "auto") -> None:
+        """dx_cls f32 [B, width].  `layer_done(layer)` (optional) is called right after block `layer`'s backward has been
+        enqueued - its LoRA gradients are final once the stream reaches that point (hook for the gradient all-reduce).
+        loss_scale: power of two applied to the activation gradients and divided out of the LoRA gradients ("auto": chosen
+        so that max |dx_cls| maps to 2^8, which keeps fp16 operands clear of both underflow and overflow)."""
+        dx_cls = dx_cls.detach().to(self.device, torch.float32).contiguous()
+        B = dx_cls.shape[0]
+        if loss_scale == "auto":
+            amax = float(dx_cls.abs().max())
+            loss_scale = 2.0 ** math.floor(math.log2(256.0 / amax)) if amax > 0 and math.isfinite(amax) else 1.0
+        loss_scale = float(loss_scale)
+        if loss_scale != 1.0:
+            dx_cls = dx_cls * loss_scale
+        L.check(self.h, self.lib.iic_train_set_loss_scale(self.h, loss_scale), "iic_train_set_loss_scale")
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._train_ws(B)
+            s = _stream_ptr(self.device)
+            if layer_done is None:
+                L.check(self.h, self.lib.iic_train_backward(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(), s),
+                        "iic_train_backward")
+                return
+            L.check(self.h, self.lib.iic_train_backward_begin(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(), s),
+                    "iic_train_backward_begin")
+            for layer in range(self.arch.layers - 1, -1, -1):
+                L.check(self.h, self.lib.iic_train_backward_layer(self.h, B, ws.data_ptr(), ws.numel(), layer, s),
+                        "iic_train_backward_layer")
+                layer_done(layer)
+
+    def op_attention_bwd(self, qkv: torch.Tensor, d_out: torch.Tensor, B: int, T: int, heads: int):
+        out = torch.empty(B * T, heads * 64, dtype=self.op_dtype, device=self.device)
+        dqkv = torch.empty_like(qkv)
+        lse = torch.empty(B * heads * T, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_attention_bwd(self.h, qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(),
+                                                          lse.data_ptr(), B, T, heads, _stream_ptr(self.device)), "iic_op_attention_bwd")
+        return out, dqkv, lse
+
+    def op_layernorm_bwd(self, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: torch.Tensor):
+        rows, D = x.shape
+        dx16 = torch.empty(rows, D, dtype=self.op_dtype, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_layernorm_bwd(self.h, dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
+                                                          dx16.data_ptr(), rows, D, _stream_ptr(self.device)), "iic_op_layernorm_bwd")
+        return dx16
+
+    def op_act_bwd(self, dh: torch.Tensor, u: torch.Tensor, act: int = 1) -> None:
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_act_bwd(self.h, dh.data_ptr(), u.data_ptr(), dh.numel(), act,
+                                                    _stream_ptr(self.device)), "iic_op_act_bwd")
+
+    def op_lora_outer(self, P: torch.Tensor, Y: torch.Tensor, rank: int, act: int = 0, scale: float = 1.0,
+                      transpose: bool = False) -> torch.Tensor:
+        M, N = Y.shape
+        out = torch.zeros((N, rank) if transpose else (rank, N), dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_lora_outer(self.h, P.data_ptr(), P.stride(0), Y.data_ptr(), N, M, act, rank, float(scale),
+                                                       1 if transpose else 0, out.data_ptr(), _stream_ptr(self.device)),
+                    "iic_op_lora_outer")
+        return out
 
     # ------------------------------------------------------------------ measurement
     def profile(self, enable: bool = True) -> None:

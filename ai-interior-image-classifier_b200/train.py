@@ -1,0 +1,139 @@
+"""LoRA fine-tuning step of the vision tower on the CUDA engine.
+
+Mirrors the step of /root/reference/train_lora.py:227-252 - symmetric InfoNCE between L2-normalised image and text
+features scaled by `logit_scale.exp()`, labels = arange(batch), `loss.backward()`, `clip_grad_norm_(max_norm=1.0)`,
+AdamW(lr=1e-4, weight_decay=0.01) over the parameters whose name contains 'lora' - with the LoRA sitting on the
+vision MLPs (`mlp.c_fc`, `mlp.c_proj`: what main.py's wrap makes effective) and the text side supplying
+fixed target embeddings (BASELINE config 4).  The reference itself fine-tunes the text tower and keeps the vision tower
+under no_grad; this is the vision-side counterpart the north star asks for.
+
+Split of work: the engine runs the encoder forward (keeping activations) and the whole backward through the frozen
+blocks (dX GEMMs on tcgen05, attention / LayerNorm / GELU backward, LoRA dA/dB reductions); the O(B x width) head + loss
+(ln_post, proj, L2-norm, cross-entropy) and the optimizer are ordinary PyTorch, exactly the reference's code path.
+Data parallel: per-rank local loss (labels = arange(local batch)), then ONE collective per block - an NCCL all-reduce
+(average) of that block's four LoRA gradient tensors (1.47 MB in total at rank 4), issued on a side stream as soon as the
+block's backward has been enqueued, so it overlaps the backward of the blocks below.  The gradient-norm clip uses the
+averaged (global) gradients.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from .clip_compat import CLIP, VisionTransformer, _is_lora_wrapped
+
+
+class VisionLoRATrainer:
+    def __init__(self, model: "CLIP | VisionTransformer", lr: float = 1e-4, weight_decay: float = 0.01,
+                 max_grad_norm: float = 1.0, logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
+        self.visual: VisionTransformer = model.visual if hasattr(model, "visual") else model
+        self.logit_scale = float(logit_scale) if logit_scale is not None else (
+            float(model.logit_scale.exp()) if hasattr(model, "logit_scale") else 100.0)
+        self.max_grad_norm = max_grad_norm
+        self.pg = process_group
+        self.overlap = overlap
+        self.eng = self.visual.engine()
+        dev = self.eng.device
+        # trainable = LoRA pairs the forward actually uses; an attn.out_proj LoRA never receives a gradient (F4)
+        self.slots: List[Tuple[int, int, torch.nn.Module]] = []
+        for i, blk in enumerate(self.visual.transformer.resblocks):
+            for which, mod in ((L.LORA_C_FC, blk.mlp.c_fc), (L.LORA_C_PROJ, blk.mlp.c_proj)):
+                if _is_lora_wrapped(mod):
+                    self.slots.append((i, which, mod))
+        if not self.slots:
+            raise RuntimeError("no LoRA-wrapped mlp.c_fc / mlp.c_proj found: call replace_linears_with_lora(model) first")
+        for p in self.visual.parameters():
+            p.requires_grad_(False)
+        # one flat fp32 gradient bucket per block; each parameter's .grad is a view into it
+        self.buckets: Dict[int, torch.Tensor] = {}
+        self.params: List[torch.nn.Parameter] = []
+        per_layer: Dict[int, List[torch.nn.Parameter]] = {}
+        for i, which, mod in self.slots:
+            for p in (mod.lora.lora_A, mod.lora.lora_B):
+                if p.device != dev or p.dtype != torch.float32:
+                    p.data = p.data.to(dev, torch.float32)
+                p.requires_grad_(True)
+                per_layer.setdefault(i, []).append(p)
+                self.params.append(p)
+        for i, ps in per_layer.items():
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.buckets[i] = flat
+        self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)   # train_lora.py:212
+        self.comm_stream = torch.cuda.Stream(device=dev) if process_group is not None or self._dist_on() else None
+        self._training_weights_sig = None
+
+    @staticmethod
+    def _dist_on() -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _sync(self) -> None:
+        v = self.visual
+        eng = v.sync_engine(keep_zero_lora=True)
+        sd, _ = v._tensors()
+        sig = tuple((k, t.data_ptr(), t._version) for k, t in sd.items() if k.endswith(".weight") and "ln_" not in k)
+        if sig != self._training_weights_sig:
+            eng.enable_training(sd)
+            self._training_weights_sig = sig
+        for i, which, mod in self.slots:
+            lo = mod.lora
+            eng.set_lora_train(i, which, lo.lora_A, lo.lora_B, float(lo.scaling), lo.lora_A.grad, lo.lora_B.grad)
+
+    def head_and_loss(self, x_cls: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
+        """ln_post -> proj -> L2 -> symmetric InfoNCE (train_lora.py:241-246), fp32."""
+        v = self.visual
+        f = F.layer_norm(x_cls, (x_cls.shape[-1],), v.ln_post.weight.detach().float(), v.ln_post.bias.detach().float(), 1e-5)
+        f = f @ v.proj.detach().float()
+        f = f / f.norm(dim=-1, keepdim=True)
+        logits_per_image = (f @ text_features.t()) * self.logit_scale
+        labels = torch.arange(x_cls.shape[0], device=x_cls.device)
+        return (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_image.t(), labels)) / 2
+
+    def forward_backward(self, images: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
+        """One forward + backward; LoRA gradients land in the parameters' .grad (averaged over ranks when distributed)."""
+        import torch.distributed as dist
+        eng = self.eng
+        self._sync()
+        if images.dtype == torch.uint8:
+            patches, B = eng.preprocess_same_size(images.to(eng.device)), images.shape[0]
+        else:
+            patches, B = eng.patchify(images.to(eng.device)), images.shape[0]
+        x_cls = eng.train_forward(patches, B).requires_grad_(True)
+        loss = self.head_and_loss(x_cls, text_features.detach().to(eng.device, torch.float32))
+        (dx_cls,) = torch.autograd.grad(loss, x_cls)
+        works = []
+        distributed = self._dist_on()
+
+        def layer_done(layer: int) -> None:
+            if not distributed or layer not in self.buckets:
+                return
+            if self.overlap:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(eng.device))
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    works.append(dist.all_reduce(self.buckets[layer], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            else:
+                works.append(dist.all_reduce(self.buckets[layer], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+
+        eng.train_backward(dx_cls, layer_done=layer_done)
+        for w in works:
+            w.wait()
+        if distributed and self.overlap:
+            torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
+        return loss.detach()
+
+    def step(self, images: torch.Tensor, text_features: torch.Tensor) -> float:
+        """train_lora.py:249-252: backward, clip_grad_norm_(1.0), optimizer.step()."""
+        loss = self.forward_backward(images, text_features)
+        torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm)
+        self.optimizer.step()
+        return float(loss)

@@ -144,6 +144,32 @@ int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, vo
 int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
                  const iic_head_out* out, void* stream);
 
+/* ---- training step (reference: train_lora.py:231-252; LoRA on the vision MLPs) ------------------
+ * Only LoRA parameters receive gradients; frozen weights only carry dX.  Needs, in addition to the inference state:
+ *   - transposed copies of the four projection weights of every block, loaded with iic_load_weight under the names
+ *     `...attn.in_proj_weight_t` [width, 3*width], `...attn.out_proj.weight_t` [width, width],
+ *     `...mlp.c_fc.weight_t` [width, mlp], `...mlp.c_proj.weight_t` [mlp, width]   (operand dtype);
+ *   - per LoRA slot (after iic_set_lora): a16 = scaling*lora_A in the operand dtype [in, lora_pad] (zero padded),
+ *     bt32 = lora_B^T f32 [out, r4], scaling = alpha/rank, and where the gradients go:
+ *     grad_a f32 [in, rank] (d loss / d lora_A), grad_b f32 [rank, out] (d loss / d lora_B) - the reference's layouts.
+ * iic_train_forward keeps the activations the backward needs inside the (larger) training workspace and returns the
+ * class-token rows of the final residual stream, x_cls f32 [B, width] (the input of ln_post): the head and the loss
+ * (ln_post, proj, L2-norm, InfoNCE - O(B*width) work) stay with the caller, who hands back dx_cls = d loss / d x_cls.
+ * iic_train_backward overwrites every registered grad_a / grad_b.  LoRA rank <= 16 on mlp.c_fc / mlp.c_proj. */
+int iic_set_lora_train(iic_handle* h, int layer, int which, const void* a16, const float* bt32, float scaling,
+                       float* grad_a, float* grad_b);
+/* Loss scaling for the 16-bit gradient operands (needed with fp16: activation gradients underflow otherwise): the caller
+ * multiplies dx_cls by `loss_scale` (a power of two), the engine divides the LoRA gradients by it.  Default 1. */
+int iic_train_set_loss_scale(iic_handle* h, float loss_scale);
+size_t iic_train_workspace_bytes(const iic_handle* h, int B);
+int iic_train_forward(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* x_cls_out,
+                      void* stream);
+int iic_train_backward(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream);
+/* The same backward, one residual block at a time (layer = layers-1 ... 0 after _begin): block `layer`'s LoRA gradients
+ * are final when the call's work completes, so the caller can all-reduce them while the blocks below are still running. */
+int iic_train_backward_begin(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream);
+int iic_train_backward_layer(iic_handle* h, int B, void* workspace, size_t workspace_bytes, int layer, void* stream);
+
 /* ---- measurement ----------------------------------------------------------------------------------------------
  * Kernel classes: 0 tcgen05 GEMM, 1 LayerNorm, 2 attention, 3 LoRA down-projection, 4 head, 5 preprocess, 6 misc.
  * iic_profile(h, 1) starts counting launches and bracketing every launch with CUDA events on the caller's stream;
@@ -164,6 +190,15 @@ int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const fl
 int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const float* lora_a_scaled, int r4, void* p_out,
                      int p_ld, void* stream);
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream);
+/* backward operators (same kernels iic_train_backward runs).  iic_op_attention_bwd recomputes the forward into `out`
+ * (to obtain the log-sum-exp, lse_scratch f32 [B*heads*T]) and then writes dqkv [M, 3*d]. */
+int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* d_out, void* dqkv, float* lse_scratch,
+                         int B, int T, int heads, void* stream);
+int iic_op_layernorm_bwd(iic_handle* h, const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows,
+                         int D, void* stream);
+int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act, void* stream);
+int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale,
+                      int transpose, float* out, void* stream);
 
 #ifdef __cplusplus
 }
