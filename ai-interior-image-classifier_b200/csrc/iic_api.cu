@@ -270,7 +270,6 @@ struct TrainWorkspace {
   uint16_t *xln, *hid, *u, *dh, *g16, *dy, *dqkv, *da, *dp1, *dp2;
   size_t total;
 };
-constexpr int kOuterSplits = 32;
 
 TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   const size_t M = size_t(B) * h->T;
@@ -296,7 +295,7 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   w.dp1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.down_part = static_cast<float*>(take(size_t((mlp + 255) / 256) * M * 16));
-  w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), kOuterSplits)));
+  w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), int(M))));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.layers.resize(h->blocks.size());
   for (TrainLayer& l : w.layers) {
@@ -402,7 +401,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     if (l_pr.rank) {
       IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.g16, d, M, l_pr.bt32, l_pr.r4, w.dp2, h->lora_pad, h->f16, s); }));
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, kOuterSplits, h->f16, s);
+        return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, h->f16, s);
       }));
       bw_pr.rank = l_pr.rank; bw_pr.r4 = l_pr.r4; bw_pr.r_pad = l_pr.r_pad; bw_pr.bt = l_pr.a16;
     }
@@ -410,7 +409,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasBf16, b.b_fc, nullptr, w.u, mlp, 1, s));
     if (l_pr.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(w.dp2, h->lora_pad, w.u, mlp, M, act, l_pr.rank, l_pr.scaling * h->grad_unscale, 1, l_pr.grad_a, w.outer_scratch, kOuterSplits, h->f16, s);
+        return launch_lora_outer(w.dp2, h->lora_pad, w.u, mlp, M, act, l_pr.rank, l_pr.scaling * h->grad_unscale, 1, l_pr.grad_a, w.outer_scratch, h->f16, s);
       }));
     IIC_TRY(run_gemm(h, w.g16, d, b.w_proj_t, M, mlp, d, &bw_pr, w.dp2, kEpiBiasBf16, nullptr, nullptr, w.dh, mlp, 1, s));
     IIC_TRY(timed(h, kMisc, s, [&] { return launch_act_bwd(w.dh, w.u, (long long)M * mlp, act, h->f16, s); }));   // dh := du
@@ -419,10 +418,10 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     if (l_fc.rank) {
       IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.dh, mlp, M, l_fc.bt32, l_fc.r4, w.dp1, h->lora_pad, h->f16, s); }));
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, kOuterSplits, h->f16, s);
+        return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, h->f16, s);
       }));
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(w.dp1, h->lora_pad, t.y2, d, M, 0, l_fc.rank, l_fc.scaling * h->grad_unscale, 1, l_fc.grad_a, w.outer_scratch, kOuterSplits, h->f16, s);
+        return launch_lora_outer(w.dp1, h->lora_pad, t.y2, d, M, 0, l_fc.rank, l_fc.scaling * h->grad_unscale, 1, l_fc.grad_a, w.outer_scratch, h->f16, s);
       }));
       bw_fc.rank = l_fc.rank; bw_fc.r4 = l_fc.r4; bw_fc.r_pad = l_fc.r_pad; bw_fc.bt = l_fc.a16;
     }
@@ -821,9 +820,8 @@ int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int
                       int transpose, float* out, void* stream) {
   if (!h || !P || !Y || !out) return fail(h, IIC_ERR_ARG, "iic_op_lora_outer: null argument");
   float* scratch = nullptr;
-  const int splits = 16;
-  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, splits)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
-  int rc = launch_lora_outer(P, p_ld, Y, N, M, act, rank, scale, transpose, out, scratch, splits, h->f16, static_cast<cudaStream_t>(stream));
+  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, M)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
+  int rc = launch_lora_outer(P, p_ld, Y, N, M, act, rank, scale, transpose, out, scratch, h->f16, static_cast<cudaStream_t>(stream));
   cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   cudaFree(scratch);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "lora_outer failed");

@@ -35,10 +35,10 @@ int launch_layernorm_bwd(const void* dy, const float* x, const float* gamma, flo
 int launch_cast16(const float* in, void* out, long long n, int f16, cudaStream_t stream);
 // act: 0 identity, 1 QuickGELU, 2 GELU(erf)
 int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaStream_t stream);
-size_t lora_outer_scratch_bytes(int N, int splits);
+size_t lora_outer_scratch_bytes(int N, int M);
 // out = scale * P[:, :rank]^T . act(Y)  ->  [rank, N] (transpose = 0: dB) or [N, rank] (transpose = 1: dA); deterministic
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
-                      float* out, float* scratch, int splits, int f16, cudaStream_t stream);
+                      float* out, float* scratch, int f16, cudaStream_t stream);
 
 // ---- head.cu ----
 int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,

@@ -133,31 +133,42 @@ act_bwd_kernel(uint16_t* __restrict__ dh, const uint16_t* __restrict__ u, long l
 }
 
 // part[split][c][n] = sum over the split's rows of P[m, c] * f(Y[m, n]),  c < 4, f = act_fwd (act = 0: identity).
-// P 16-bit [M, p_ld], Y 16-bit [M, N].  Thread = 2 adjacent columns of Y; CTA = 256 columns x one row split.
+// P 16-bit [M, p_ld] (already offset to the 4-column group), Y 16-bit [M, N] (N % 8 == 0).
+// Thread = 8 adjacent columns of Y (one 16-byte load per row, 8 rows in flight); CTA = 128 threads = 1024 columns x
+// one split of `rows_per_split` rows.  Many short splits keep >100k threads busy: the kernel is a pure stream over Y.
 template <bool kF16>
 __global__ void __launch_bounds__(128)
 lora_outer_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int rows_per_split,
-                  int act, float* __restrict__ part) {  // P already offset to the 4-column group
-  const int n = blockIdx.x * 256 + threadIdx.x * 2;
+                  int act, float* __restrict__ part) {
+  const int n = blockIdx.x * 1024 + threadIdx.x * 8;
   const int split = blockIdx.y;
   const int m0 = split * rows_per_split;
   const int m1 = min(M, m0 + rows_per_split);
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  if (n < N) {
-#pragma unroll 4
-    for (int m = m0; m < m1; ++m) {
-      const uint2 praw = *reinterpret_cast<const uint2*>(P + size_t(m) * p_ld);   // warp-uniform: broadcast
-      const float2 p01 = Act<kF16>::unpack(praw.x), p23 = Act<kF16>::unpack(praw.y);
-      float2 y = Act<kF16>::unpack(*reinterpret_cast<const uint32_t*>(Y + size_t(m) * N + n));
-      if (act != 0) { y.x = act_fwd(y.x, act); y.y = act_fwd(y.y, act); }
-      acc[0][0] = fmaf(p01.x, y.x, acc[0][0]); acc[0][1] = fmaf(p01.y, y.x, acc[0][1]);
-      acc[0][2] = fmaf(p23.x, y.x, acc[0][2]); acc[0][3] = fmaf(p23.y, y.x, acc[0][3]);
-      acc[1][0] = fmaf(p01.x, y.y, acc[1][0]); acc[1][1] = fmaf(p01.y, y.y, acc[1][1]);
-      acc[1][2] = fmaf(p23.x, y.y, acc[1][2]); acc[1][3] = fmaf(p23.y, y.y, acc[1][3]);
-    }
-    float* o = part + (size_t(split) * 4) * N + n;
+  if (n >= N) return;
+  float acc[8][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) *reinterpret_cast<float2*>(o + size_t(c) * N) = make_float2(acc[0][c], acc[1][c]);
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 8
+  for (int m = m0; m < m1; ++m) {
+    const uint2 praw = *reinterpret_cast<const uint2*>(P + size_t(m) * p_ld);   // warp-uniform: broadcast
+    const float2 p01 = Act<kF16>::unpack(praw.x), p23 = Act<kF16>::unpack(praw.y);
+    const uint4 yraw = *reinterpret_cast<const uint4*>(Y + size_t(m) * N + n);
+    const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yraw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 y = Act<kF16>::unpack(yw[e]);
+      if (act != 0) { y.x = act_fwd(y.x, act); y.y = act_fwd(y.y, act); }
+      acc[2 * e][0] = fmaf(p01.x, y.x, acc[2 * e][0]); acc[2 * e][1] = fmaf(p01.y, y.x, acc[2 * e][1]);
+      acc[2 * e][2] = fmaf(p23.x, y.x, acc[2 * e][2]); acc[2 * e][3] = fmaf(p23.y, y.x, acc[2 * e][3]);
+      acc[2 * e + 1][0] = fmaf(p01.x, y.y, acc[2 * e + 1][0]); acc[2 * e + 1][1] = fmaf(p01.y, y.y, acc[2 * e + 1][1]);
+      acc[2 * e + 1][2] = fmaf(p23.x, y.y, acc[2 * e + 1][2]); acc[2 * e + 1][3] = fmaf(p23.y, y.y, acc[2 * e + 1][3]);
+    }
+  }
+  float* o = part + (size_t(split) * 4) * N + n;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    *reinterpret_cast<float4*>(o + size_t(c) * N) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    *reinterpret_cast<float4*>(o + size_t(c) * N + 4) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
   }
 }
 
@@ -220,14 +231,16 @@ int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaS
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-size_t lora_outer_scratch_bytes(int N, int splits) { return size_t(splits) * 4 * N * sizeof(float); }
+int lora_outer_splits(int M) { return (M + 63) / 64; }   // 64 rows per split
+size_t lora_outer_scratch_bytes(int N, int M) { return size_t(lora_outer_splits(M)) * 4 * N * sizeof(float); }
 
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
-                      float* out, float* scratch, int splits, int f16, cudaStream_t stream) {
+                      float* out, float* scratch, int f16, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
-  if (rank < 1 || (rank + 3) / 4 * 4 > p_ld || N % 2 != 0 || splits < 1) return -1;
-  const int rps = (M + splits - 1) / splits;
-  dim3 grid(unsigned((N + 255) / 256), unsigned(splits));
+  if (rank < 1 || (rank + 3) / 4 * 4 > p_ld || N % 8 != 0) return -1;
+  const int splits = lora_outer_splits(M);
+  const int rps = 64;
+  dim3 grid(unsigned((N + 1023) / 1024), unsigned(splits));
   const uint16_t* p = static_cast<const uint16_t*>(P);
   const uint16_t* y = static_cast<const uint16_t*>(Y);
   for (int c0 = 0; c0 < rank; c0 += 4) {   // 4 LoRA columns per pass over Y (rank 4: one pass)

@@ -363,7 +363,11 @@ class Engine:
         dx_cls = dx_cls.detach().to(self.device, torch.float32).contiguous()
         B = dx_cls.shape[0]
         if loss_scale == "auto":
-            amax = float(dx_cls.abs().max())
+            # max |dx_cls| of the PREVIOUS step picks the scale (the value is long since on the host: no pipeline stall);
+            # the 2^8 target leaves 2^8 of headroom below fp16's maximum for step-to-step drift
+            prev = getattr(self, "_amax_prev", None)
+            amax = float(prev) if prev is not None else float(dx_cls.abs().max())
+            self._amax_prev = dx_cls.abs().max().to("cpu", non_blocking=True)
             loss_scale = 2.0 ** math.floor(math.log2(256.0 / amax)) if amax > 0 and math.isfinite(amax) else 1.0
         loss_scale = float(loss_scale)
         if loss_scale != 1.0:
