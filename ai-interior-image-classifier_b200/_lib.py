@@ -17,7 +17,8 @@ DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1
 LORA_IN_PROJ, LORA_OUT_PROJ, LORA_C_FC, LORA_C_PROJ = 0, 1, 2, 3
 OUT_PATCHES_BF16, OUT_CHW_F32, OUT_CHW_BF16 = 0, 1, 2
-KERNEL_CLASSES = ("gemm", "layernorm", "attention", "lora_down", "head", "preprocess", "misc")
+KERNEL_CLASSES = ("gemm", "layernorm", "attention", "lora_down", "head", "preprocess", "misc",
+                  "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_other")
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RES_F32, EPI_POS_F32, EPI_GELU_ERF_BF16 = 0, 1, 2, 3, 4
 
 
@@ -74,7 +75,7 @@ PROTOTYPES = {
     "iic_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "iic_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                              C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                              C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "iic_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "iic_op_lora_down": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

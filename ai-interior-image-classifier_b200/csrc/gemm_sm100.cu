@@ -65,7 +65,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(clusters * kCtas));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -9,13 +9,15 @@
 // Reference call sites this replaces: nn.MultiheadAttention in_proj/out_proj, mlp.c_fc / mlp.c_proj
 // (`LoRALinear.forward`, /root/reference/main.py:42-43, `LoRALayer.forward` main.py:30-31) and visual.conv1.
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0      TMA producer of the A/W ring (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier complete_tx)
 //   warp 1      MMA issuer        (one elected thread; tcgen05.mma, fp32 accumulators in TMEM; leader CTA only)
 //   warp 2      TMEM allocator
 //   warp 3      residual producer (fp32-residual epilogue only): TMA-loads 128x32 fp32 slabs of the residual stream
 //               into the epilogue staging ring ahead of the epilogue
-//   warps 4..7  epilogue: tcgen05.ld -> bias / QuickGELU / residual -> swizzled smem slab -> TMA store
+//   warps 4..11 epilogue, two groups of 4 warps (one warp per TMEM lane quadrant each): group g owns the slabs s with
+//               s % 2 == g of every tile: tcgen05.ld -> bias / QuickGELU / residual -> swizzled smem slab -> TMA store.
+//               Two warps per scheduler let one group's MUFU / TMEM latency hide under the other's ALU work.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue), staging ring
 // (residual TMA load -> epilogue threads -> TMA store), static persistent tile schedule (n fastest so the CTAs working
 // at the same time share A rows in L2).
@@ -71,7 +73,12 @@ struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = kLoadN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlabs = kDirect ? 0 : (kResidual ? 4 : 2);  // staging ring depth
+  // epilogue warp groups working on alternate slabs of a tile: 2 for the MUFU-heavy activation epilogues (one group's
+  // MUFU / TMEM latency hides under the other's ALU work), 1 otherwise (measured: a second group only adds contention
+  // for the bias-only and the residual epilogues)
+  static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect) ? 2 : 1;
+  static constexpr int kSlabs = kDirect ? 0 : (kResidual ? 4 : 2);  // staging ring depth (all groups together)
+  static constexpr int kBufPerGroup = kDirect ? 1 : kSlabs / kGroups;
   static constexpr int kRingBudget = 192 * 1024 - kSlabs * kSlabBytes;
   static constexpr int kStages = kRingBudget / kStageBytes;  // 2 CTA: 6 / 5 / 4;  1 CTA: 4 / 3 / 2 ... see static_assert
   static constexpr int kAccStages = 2;
@@ -87,16 +94,23 @@ struct GemmSmem {
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)  (OpenAI CLIP QuickGELU)
-  const float e = exp2f(-1.702f * 1.4426950408889634f * x);
-  return __fdividef(x, 1.0f + e);
+  // x * sigmoid(1.702 x)  (OpenAI CLIP QuickGELU) as 5 instructions: FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL.
+  // ex2.approx.ftz / rcp.approx.ftz: 2^-22 relative error, far below the 16-bit rounding of the result; for very negative x
+  // the exponential overflows to +inf and x * (1/inf) = -0, the correct limit.
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr int kGemmThreads = 384;
+// named barrier of one epilogue group (ids 1, 2) / of both groups (id 3)
+__device__ __forceinline__ void epi_bar_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
 template <int kCtas, int kBlockN, int kEpi, bool kF16>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bl,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
@@ -154,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     for (int a = 0; a < S::kAccStages; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);             // one tcgen05.commit
-      ptx::mbar_init(tempty_bar(a), kCtas * 128);  // every epilogue thread of the pair
+      ptx::mbar_init(tempty_bar(a), kCtas * 128 * S::kGroups);  // every working epilogue thread of the pair
     }
     for (int b = 0; b < 4; ++b) {
       ptx::mbar_init(rfull_bar(b), 1);   // residual producer's arrive.expect_tx
@@ -261,12 +275,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
   } else if (warp >= 4) {
     // ======================= epilogue =======================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    constexpr int kGroups = S::kGroups;
+    constexpr int kBufPG = S::kBufPerGroup;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int grp = (warp - 4) >> 2;     // epilogue group 0 / 1
     const int r_in_tile = quad * 32 + lane;
-    const bool storer = threadIdx.x == 128;  // issues every TMA store of this CTA (bulk groups are per thread)
+    const bool storer = (threadIdx.x & 127) == 0;  // first thread of each group issues that group's TMA stores
     int it = 0;
-    int slab = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+    int my_slab = grp;                   // running index (over the whole kernel) of the next slab this group handles
+    for (int tile = cluster_id; tile < total_tiles && grp < kGroups; tile += num_clusters, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -278,35 +295,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       if constexpr (kAct) {
         if (args.down_a != nullptr) {
           // stage this tile's slice of the consumer's LoRA-A while the MMAs of the tile are still running
-          const int t = threadIdx.x - 128;  // 0..127
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (col0 + 2 * t < args.N) v0 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + 2 * t);
-          if (col0 + 2 * t + 1 < args.N) v1 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + 2 * t + 1);
-          epi_bar_sync();  // previous tile's readers are done with the buffer
-          down_s[2 * t] = v0;
-          down_s[2 * t + 1] = v1;
-          epi_bar_sync();
+          static_assert(!kAct || kGroups == 2, "down-projection staging assumes both epilogue groups");
+          const int t = threadIdx.x - 128;  // 0..255
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col0 + t < args.N) v0 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + t);
+          epi_bar_sync_all();  // previous tile's readers are done with the buffer
+          down_s[t] = v0;
+          epi_bar_sync_all();
         }
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * kBlockN);
+      auto release_tmem = [&]() {
+        ptx::tcgen05_fence_before();
+        if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
+        else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+      };
 
       if constexpr (kDirect) {
-        // ---- patch embedding: rows are scattered (image boundaries), direct global stores ----
+        // ---- patch embedding: rows are scattered (image boundaries), direct global stores; group g takes chunks c % 2 == g ----
         const int img = row / args.group;
         const long long out_row = (long long)row + img + 1;
         const float* addend = args.residual + size_t(row - img * args.group + 1) * args.N;
 #pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
+        for (int c = grp; c < kBlockN / 32; c += kGroups) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
           ptx::tmem_ld_wait();
-          if (c == kBlockN / 32 - 1) {
-            ptx::tcgen05_fence_before();
-            if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
-            else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
-          }
+          if (c + kGroups >= kBlockN / 32) release_tmem();
           const int col = col0 + c * 32;
           if (!row_ok || col >= args.N) continue;
           float* o = reinterpret_cast<float*>(args.out) + size_t(out_row) * args.ldc + col;
@@ -321,8 +338,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       } else {
         float dacc0 = 0.f, dacc1 = 0.f, dacc2 = 0.f, dacc3 = 0.f;
 #pragma unroll 1
-        for (int s = 0; s < kSlabsPerTile; ++s, ++slab) {
-          const int b = slab % kSlabs;
+        for (int s = grp; s < kSlabsPerTile; s += kGroups, my_slab += kGroups) {
+          const int b = grp + kGroups * ((my_slab / kGroups) % kBufPG);   // this group's ring of kBufPG buffers
           const int col = col0 + s * kSlabCols;
           uint8_t* my_row = slab_gen + b * kSlabBytes + r_in_tile * 128;  // this thread's 128-byte row of the slab
           const int sw = r_in_tile & 7;                                    // 128B swizzle: 16B chunk j -> j ^ (row & 7)
@@ -330,13 +347,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             // ---- out = acc + bias + residual: the slab already holds the residual (TMA-loaded by warp 3) ----
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 32), v);
-            ptx::mbar_wait(rfull_bar(b), uint32_t(slab / kSlabs) & 1u);
+            ptx::mbar_wait(rfull_bar(b), uint32_t(my_slab / kSlabs) & 1u);
             ptx::tmem_ld_wait();
-            if (s == kSlabsPerTile - 1) {
-              ptx::tcgen05_fence_before();
-              if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
-              else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
-            }
+            if (s + kGroups >= kSlabsPerTile) release_tmem();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4* p = reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4));
@@ -350,14 +363,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               *p = r;
             }
             ptx::fence_proxy_async_smem();
-            epi_bar_sync();
+            epi_bar_sync(grp);
             if (storer) {
               ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
               ptx::tma_store_commit();
-              // the slab stored one step ago has been read by now (at most 1 group still in flight): hand it back
-              if (slab >= 1) {
+              // this group's previous slab has been read by its store by now (at most 1 group still in flight): hand it back
+              if (my_slab >= kGroups) {
                 ptx::tma_store_wait_read<1>();
-                ptx::mbar_arrive(rempty_bar((slab - 1) % kSlabs));
+                ptx::mbar_arrive(rempty_bar((my_slab - kGroups) % kSlabs));
               }
             }
           } else {
@@ -366,11 +379,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64), v0);
             ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64 + 32), v1);
             ptx::tmem_ld_wait();
-            if (s == kSlabsPerTile - 1) {
-              ptx::tcgen05_fence_before();
-              if constexpr (kCtas == 1) ptx::mbar_arrive(tempty_bar(acc));
-              else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
-            }
+            if (s + kGroups >= kSlabsPerTile) release_tmem();
             uint4 pk[8];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -415,13 +424,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 pk[half * 4 + i / 8] = q;
               }
             }
-            // the slab written kSlabs steps ago must have been read by its TMA store before it is overwritten
-            if (storer) ptx::tma_store_wait_read<kSlabs - 1>();
-            epi_bar_sync();
+            // the slab this group wrote kBufPG steps ago used the same buffer: its TMA store must have read it by now
+            if (storer) ptx::tma_store_wait_read<kBufPG - 1>();
+            epi_bar_sync(grp);
 #pragma unroll
             for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = pk[j];
             ptx::fence_proxy_async_smem();
-            epi_bar_sync();
+            epi_bar_sync(grp);
             if (storer) {
               ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
               ptx::tma_store_commit();
@@ -429,15 +438,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
         if constexpr (kAct) {
+          // one partial per (column tile, epilogue group): part[2 * n_blk + grp][row][0..3]
           if (args.down_a != nullptr && row_ok)
-            *reinterpret_cast<float4*>(args.down_part + (size_t(n_blk) * args.M + row) * 4) =
+            *reinterpret_cast<float4*>(args.down_part + (size_t(2 * n_blk + grp) * args.M + row) * 4) =
                 make_float4(dacc0, dacc1, dacc2, dacc3);
         }
       }
     }
     // all global writes of this CTA's TMA stores must be complete before the kernel ends
     if constexpr (!kDirect) {
-      if (storer) ptx::tma_store_wait<0>();
+      if (storer && grp < kGroups) ptx::tma_store_wait<0>();
     }
   }
 

@@ -54,14 +54,15 @@ struct Workspace {
 
 namespace {
 // Optional per-kernel-class CUDA-event timing on the caller's stream (bench.py's roofline line) + launch counter.
-enum KClass { kGemm = 0, kLayerNorm = 1, kAttention = 2, kLoraDown = 3, kHead = 4, kPreprocess = 5, kMisc = 6, kNumClasses = 7 };
+enum KClass { kGemm = 0, kLayerNorm = 1, kAttention = 2, kLoraDown = 3, kHead = 4, kPreprocess = 5, kMisc = 6,
+              kGemmQkv = 7, kGemmOut = 8, kGemmFc = 9, kGemmProj = 10, kGemmOther = 11, kNumClasses = 12 };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> pool;
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
   size_t used = 0;
-  long long launches[kNumClasses] = {0, 0, 0, 0, 0, 0, 0};
+  long long launches[kNumClasses] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t get() {
     if (used == pool.size()) {
       cudaEvent_t e;
@@ -133,7 +134,7 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   w.hid = static_cast<uint16_t*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
   w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
-  w.down_part = static_cast<float*>(take(size_t((mlp + 255) / 256) * M * 16));
+  w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.total = off;
   return w;
@@ -164,7 +165,12 @@ int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N,
   g.epilogue = epi; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
   g.f16 = h->f16;
   const char* e = nullptr;
+  // sub-class by shape (forward: qkv N=3d, out N=K=d, fc N=mlp, proj K=mlp); class 0 stays the total over all GEMMs
+  const int d_ = h->cfg.width, mlp_ = h->cfg.mlp_dim;
+  const int sub = (epi == kEpiPosF32) ? kGemmOther : (N == 3 * d_ && K == d_) ? kGemmQkv : (N == d_ && K == d_) ? kGemmOut
+                  : (N == mlp_ && K == d_) ? kGemmFc : (N == d_ && K == mlp_) ? kGemmProj : kGemmOther;
   Scope sc(h->prof, kGemm, s);
+  Scope sc2(h->prof, sub, s);
   int rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
   return 0;
@@ -227,7 +233,7 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
                      fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
     if (fuse_down)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_reduce(w.down_part, (mlp + 255) / 256, M, w.p_b, h->lora_pad, h->f16, s);
+        return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, w.p_b, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
@@ -294,7 +300,7 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   w.da = static_cast<uint16_t*>(take(M * d * 2));
   w.dp1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
-  w.down_part = static_cast<float*>(take(size_t((mlp + 255) / 256) * M * 16));
+  w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
   w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), int(M))));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.layers.resize(h->blocks.size());
@@ -363,7 +369,7 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
                      fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
     if (fuse_down)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_reduce(w.down_part, (mlp + 255) / 256, M, t.p2, h->lora_pad, h->f16, s);
+        return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, t.p2, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
@@ -699,7 +705,7 @@ int iic_profile(iic_handle* h, int enable) {
 }
 
 int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_class, int n) {
-  if (!h || n < kNumClasses) return fail(h, IIC_ERR_ARG, "iic_profile_read: need room for 7 classes");
+  if (!h || n < kNumClasses) return fail(h, IIC_ERR_ARG, "iic_profile_read: need room for 12 classes");
   for (int i = 0; i < kNumClasses; ++i) {
     if (ms_by_class) ms_by_class[i] = 0.0;
     if (launches_by_class) launches_by_class[i] = h->prof.launches[i];
@@ -831,9 +837,11 @@ int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int
 // ---- single operators ----
 int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                 const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
-                void* out, int ldc, int group, int ctas, void* stream) {
+                void* out, int ldc, int group, int ctas, const float* down_a, float* down_part, void* stream) {
   if (!h || !a || !w || !out) return fail(h, IIC_ERR_ARG, "iic_op_gemm: null argument");
   GemmProblem g;
+  g.down_a = down_a;
+  g.down_part = down_part;
   g.a = a; g.lda = lda;
   g.w = w; g.ldw = ldw;
   g.M = M; g.N = N; g.K = K;

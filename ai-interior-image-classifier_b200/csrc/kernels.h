@@ -80,7 +80,8 @@ struct GemmProblem {
   int group;
   int f16;  // 16-bit operand format: 0 = bf16, 1 = fp16
   // optional, activation epilogues only: fuse the NEXT projection's LoRA down-projection (rank <= 4) into this epilogue.
-  // down_a f32 [N, 4] = scaling * lora_A of the consumer; down_part f32 [ceil(N/256)][M][4] receives per-tile partials.
+  // down_a f32 [N, 4] = scaling * lora_A of the consumer; down_part f32 [2*ceil(N/256)][M][4] receives per-tile partials
+  // (two per column tile: one from each epilogue warp group).
   const float* down_a = nullptr;
   float* down_part = nullptr;
 };

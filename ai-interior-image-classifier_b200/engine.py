@@ -444,7 +444,8 @@ class Engine:
     def op_gemm(self, a: torch.Tensor, w: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 lora_p: Optional[torch.Tensor] = None, lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0,
-                group: int = 1, ctas: int = 0, out_rows: Optional[int] = None) -> torch.Tensor:
+                group: int = 1, ctas: int = 0, out_rows: Optional[int] = None, down_a: Optional[torch.Tensor] = None,
+                down_part: Optional[torch.Tensor] = None) -> torch.Tensor:
         M, K = a.shape
         N = w.shape[0]
         f32_out = epilogue in (L.EPI_BIAS_RES_F32, L.EPI_POS_F32)
@@ -454,8 +455,8 @@ class Engine:
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_gemm(self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
                                                  _ptr(lora_p), _ptr(lora_bt), r_pad, lora_ld, epilogue, _ptr(bias),
-                                                 _ptr(residual), out.data_ptr(), out.stride(0), group, ctas,
-                                                 _stream_ptr(self.device)), "iic_op_gemm")
+                                                 _ptr(residual), out.data_ptr(), out.stride(0), group, ctas, _ptr(down_a),
+                                                 _ptr(down_part), _stream_ptr(self.device)), "iic_op_gemm")
         return out
 
     def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=None,

@@ -279,14 +279,16 @@ def main():
             "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(images.numel()),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K,
                     "call": "Engine.classify_host_u8(pinned uint8 [B,R,R,3]) -> host top-k (C ABI: iic_preprocess_same_size + iic_classify)"},
-            "gpu_launches": int(sum(v["launches"] for v in prof.values())),
+            "gpu_launches": int(sum(v["launches"] for k, v in prof.items() if not k.startswith("gemm_"))),
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all GEMM launches of the step)",
                          "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (ach / peaks["tflops"]) if ach else None,
                          "traffic": traffic, "peak_source": peaks["source"], "launches": gemm_launches,
                          "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                          "algorithmic_gflop_per_image": gemm_f / 1e9,
                          "model_tflops_whole_step": total_f * B * K / (ms_total * 1e-3) / 1e12 / 1.0,
-                         "share_of_step": {k: v["ms"] / ms_total for k, v in prof.items()}},
+                         "share_of_step": {k: v["ms"] / ms_total for k, v in prof.items() if not k.startswith("gemm_")},
+                         "gemm_ms_per_launch_by_shape": {k[5:]: v["ms"] / max(v["launches"], 1) for k, v in prof.items()
+                                                         if k.startswith("gemm_") and v["launches"]}},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -171,7 +171,8 @@ int iic_train_backward_begin(iic_handle* h, int B, void* workspace, size_t works
 int iic_train_backward_layer(iic_handle* h, int B, void* workspace, size_t workspace_bytes, int layer, void* stream);
 
 /* ---- measurement ----------------------------------------------------------------------------------------------
- * Kernel classes: 0 tcgen05 GEMM, 1 LayerNorm, 2 attention, 3 LoRA down-projection, 4 head, 5 preprocess, 6 misc.
+ * Kernel classes: 0 tcgen05 GEMM (all), 1 LayerNorm, 2 attention, 3 LoRA down-projection, 4 head, 5 preprocess, 6 misc,
+ * 7-11 the GEMM launches again by shape (qkv, out_proj, c_fc, c_proj, other): n >= 12.
  * iic_profile(h, 1) starts counting launches and bracketing every launch with CUDA events on the caller's stream;
  * iic_profile_read sums the elapsed milliseconds and launch counts per class since the last read and resets them
  * (it synchronises on the last recorded event).  iic_profile(h, 0) keeps counting launches but records no events. */
@@ -180,10 +181,12 @@ int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_
 
 /* ---- single operators (exported for parity tests and profiling; same kernels the encoder runs) -------------- */
 /* D = epilogue(A[M,K] . W[N,K]^T (+ P[M,r] . Bt[N,r]^T));  epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16,
- * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16.  lora_p/lora_bt nullable. */
+ * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16.  lora_p/lora_bt nullable.
+ * down_a f32 [N,4] / down_part f32 [2*ceil(N/256)][M][4] (nullable, activation epilogues): the consumer's LoRA
+ * down-projection fused into this epilogue as per-column-tile partials. */
 int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                 const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
-                void* out, int ldc, int group, int ctas, void* stream);
+                void* out, int ldc, int group, int ctas, const float* down_a, float* down_part, void* stream);
 int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const float* beta, void* out_bf16,
                      float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
                      void* stream);
