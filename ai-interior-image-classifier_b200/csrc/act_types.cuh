@@ -21,6 +21,10 @@ struct Act<false> {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   }
   static __device__ __forceinline__ T from_float(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 
 template <>
@@ -32,6 +36,10 @@ struct Act<true> {
   }
   static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
   static __device__ __forceinline__ T from_float(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 
 }  // namespace iic

@@ -94,6 +94,7 @@ struct iic_handle {
   std::string err;
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
+  int attn_impl = 0;  // 0 auto (tcgen05 kernel when T <= 256), 1 mma.sync kernel, 2 tcgen05 kernel
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
@@ -148,6 +149,16 @@ bool check_ready(iic_handle* h) {
         !b.b_out || !b.b_fc || !b.b_proj)
       return false;
   return true;
+}
+
+// inference attention: tcgen05/TMEM kernel for short sequences, mma.sync kernel otherwise (and for training, which needs the LSE)
+int run_attention(iic_handle* h, const void* qkv, void* out, int B, int T, int H, int hd, int impl, cudaStream_t s) {
+  if (impl == 0) impl = h->attn_impl;
+  if (impl != 1) {
+    int rc = launch_attention_sm100(qkv, out, B, T, H, hd, h->f16, h->num_sms, s);
+    if (rc != -3 || impl == 2) return rc == -3 ? -1 : rc;
+  }
+  return launch_attention(qkv, out, nullptr, B, T, H, hd, h->f16, s);
 }
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
@@ -216,7 +227,7 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
                               l_in.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
-    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(w.qkv, w.attn, nullptr, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, w.qkv, w.attn, B, T, H, d / H, 0, s); }));
     if (l_out.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s);
@@ -484,6 +495,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->num_sms = prop.multiProcessorCount;
   h->ctas = cfg->gemm_ctas == 1 ? 1 : 2;
   h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
+  if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -875,9 +887,9 @@ int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const f
   return IIC_OK;
 }
 
-int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, void* stream) {
+int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int impl, void* stream) {
   if (!h || !qkv_bf16 || !out_bf16) return fail(h, IIC_ERR_ARG, "iic_op_attention: null argument");
-  int rc = launch_attention(qkv_bf16, out_bf16, nullptr, B, T, heads, 64, h->f16, static_cast<cudaStream_t>(stream));
+  int rc = run_attention(h, qkv_bf16, out_bf16, B, T, heads, 64, impl, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention launch failed");
   return IIC_OK;
 }

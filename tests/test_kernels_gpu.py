@@ -156,12 +156,15 @@ def test_layernorm(engine, D):
     assert torch.allclose(p8[:, :8].float(), ref @ A8, rtol=2 ** -7, atol=1e-3) and (p8[:, 8:] == 0).all()
 
 
-@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12)])
-def test_attention(engine, T, B, H):
+@pytest.mark.parametrize("impl", [1, 2], ids=["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12), (197, 40, 12), (256, 2, 12), (129, 1, 12)])
+def test_attention(engine, T, B, H, impl):
+    if impl == 2 and T > 256:
+        pytest.skip("tcgen05 attention kernel covers T <= 256 (one TMEM accumulator per query tile)")
     d = H * 64
     g = torch.Generator(device="cuda").manual_seed(6)
     qkv = _bf16(torch.randn(B * T, 3 * d, device="cuda", generator=g))
-    out = engine.op_attention(qkv, B, T, H)
+    out = engine.op_attention(qkv, B, T, H, impl=impl)
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v)  # fp32 math
     ref = ref.permute(0, 2, 1, 3).reshape(B * T, d)

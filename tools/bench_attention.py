@@ -1,0 +1,20 @@
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import iic_b200
+def timeit(fn, warmup=3, iters=10):
+    for _ in range(warmup): fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+eng = iic_b200.Engine(iic_b200.VIT_B_16, "cuda:0")
+B, T, H = 1024, 197, 12
+qkv = torch.randn(B * T, 3 * H * 64, device="cuda").bfloat16()
+for impl, name in ((1, "mma.sync"), (2, "tcgen05")):
+    try:
+        t = timeit(lambda: eng.op_attention(qkv, B, T, H, impl=impl))
+        print(f"{name:10s} {t:.3f} ms   {4.0 * T * T * 64 * B * H / t / 1e9:.0f} TFLOP/s (unpadded)")
+    except Exception as ex:
+        print(name, "FAILED", str(ex)[:200])
