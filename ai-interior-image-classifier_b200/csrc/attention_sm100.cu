@@ -1,23 +1,31 @@
-// tcgen05 attention for sequences that fit one TMEM accumulator (T <= 256: ViT-B/16 @ 224 has T = 197).
+// tcgen05 attention, head_dim 64, any ViT sequence length that fits one SM's shared memory (T <= ~760):
 //
 //   softmax(Q K^T / sqrt(64)) V   per (image, head)        [reference: nn.MultiheadAttention inside CLIP's
 //   ResidualAttentionBlock, reached through model.encode_image at /root/reference/main.py:204, 444, 503]
 //
-// One persistent CTA per SM walks (image, head) items.  Per item the 197 queries form two 128-row tiles handled
-// concurrently; everything between the two tensor-core products stays on chip:
+// One persistent CTA per SM walks (image, head) items; K and V of the item are resident in 128B-swizzled smem (two items
+// in flight when they fit).  The queries form 128-row tiles; two softmax groups (4 warps each) take alternate tiles, so
+// one group's tensor-core round trip hides under the other group's exponentials.  Per tile, with the keys cut into
+// nb blocks of Nb <= 192 (a single block of <= 256 when the whole row fits: ViT-B/16 @ 224, T = 197):
 //
-//   warp 0   producer   TMA: Q (256 rows) + K (TP rows) and V (TP rows) of the item into 128B-swizzled smem
-//   warp 1   MMA        S_g = Q_g K^T      (tcgen05.mma, M=128, N=TP, fp32 accumulator in TMEM)            g = 0, 1
-//                       O_g = P_g V        (A = P_g from smem, B = V in its natural [key][dim] layout = MN-major operand;
-//                                           the accumulator re-uses the TMEM columns of S_g)
-//   warp 2   TMEM allocator (512 columns: two 256-column regions)
-//   warps 4-7 / 8-11   softmax group g: ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b gives a thread its whole row, so
-//                       row max and row sum are thread-local: no shuffles at all): pass 1 max, pass 2 p = exp2(s*c - m*c),
-//                       row sum, P -> 16-bit -> swizzled smem (K-major UMMA operand); later O row * 1/sum -> global.
+//   pass A (nb > 1 only)   S_j = Q K_j^T -> TMEM, row maximum only.  The scores are simply computed twice (the tensor
+//                          pipe is idle most of the time) so that pass B needs no running maximum and no rescaling
+//                          of O: the numerics are those of a plain two-pass softmax for every T.
+//   pass B                 S_j = Q K_j^T -> TMEM (fp32, columns [0, Nj) of the group's 256-column region);
+//                          ONE THREAD PER QUERY ROW: tcgen05.ld 32x32b hands a thread its own row, so max and sum are
+//                          thread-local (no shuffles); p = exp2(s*c - m*c) with packed FFMA2/FADD2, converted to 16 bit
+//                          and written back IN PLACE over S (tcgen05.st, columns [0, Nj/2)): P never touches smem;
+//                          O += P_j V_j with A = P from TMEM, B = V in its natural [key][dim] layout (MN-major operand),
+//                          accumulator in columns [192, 256) of the region.
+//   epilogue               O row * 1/sum -> 16 bit -> global; optional log2-domain LSE for the backward pass.
 //
-// mbarrier pipelines: qk_full/qk_empty, v_full/v_empty (TMA <-> MMA), s_full[g] / p_full[g] / o_full[g] / s_free[g]
-// (MMA <-> softmax group g).  The loads of item i+1 start as soon as the MMAs that read Q/K (resp. V) of item i retire,
-// so they overlap the softmax of item i.  All waits are bounded (trap, never hang).
+//   warp 0  TMA producer K/V      warp 1  MMA issuer (one thread, event loop over both groups)
+//   warp 2  TMEM allocator        warp 3  TMA producer Q tiles      warps 4-7 / 8-11  softmax groups 0 / 1
+//
+// The softmax is bound by the MUFU pipe (16 ex2/clk/SM, tools/ubench_sm100.cu); everything else in the inner loop is
+// ~2 issue slots per element.  TMEM reads are not a limit (>= 700 B/clk/SM measured), which is why S is read twice
+// rather than kept in registers.  tcgen05.mma instructions of one CTA execute in issue order, which is what orders
+// "PV_j reads P_j" before "S_{j+1} overwrites it".  All waits are bounded (trap, never hang).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -36,25 +44,100 @@ namespace {
 
 constexpr int kHd = 64;
 constexpr int kThreads = 384;
-constexpr int kQBytes = 256 * 128;        // two 128-row query tiles
-constexpr int kKvBytesMax = 256 * 128;    // TP <= 256 rows of 128 bytes
-constexpr int kPBlockBytes = 128 * 128;   // [128 rows x 64 keys] 16-bit, one 128B swizzle span per row
-constexpr int kPBytes = 4 * kPBlockBytes; // up to 256 keys
-constexpr int kSmemTotal = kQBytes + 2 * kKvBytesMax + 2 * kPBytes + 1024 /*barriers*/ + 1024 /*align*/;
+constexpr int kQTileBytes = 128 * 128;   // 128 query rows x 64 dims x 2 B
+constexpr int kRegionCols = 256;         // TMEM columns per softmax group
+constexpr int kOCol = 192;               // O accumulator: columns [192, 256) of the region
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kBarBytes = 256;
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
+struct AttnParams {
+  uint16_t* out;
+  float* lse;
+  int items, T, H;
+  int nq;         // 128-row query tiles per item
+  int nb, Nb;     // key blocks per item, rows per block (multiple of 16)
+  int TP;         // keys rounded up to 16
+  int kv_stages;  // items whose K/V are resident at once (1 or 2)
+  int kv_bytes;   // bytes of one K (or V) buffer = nb * Nb * 128
+  float scale_log2e;
+};
 
-// instruction descriptor: D f32, A/B 16-bit, A K-major, B K-major (b_mn = false) or MN-major (b_mn = true)
+// instruction descriptor: D f32, A/B 16-bit, A K-major (or TMEM), B K-major (b_mn = false) or MN-major (b_mn = true)
 __host__ __device__ constexpr uint32_t idesc(uint32_t m, uint32_t n, bool f16, bool b_mn) {
   return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((b_mn ? 1u : 0u) << 16) | ((n >> 3) << 17) |
          ((m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t id, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(id), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// running maximum over the first `valid` of the 32 columns in v (valid >= 32: no masking)
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int valid, float m) {
+  if (valid >= 32) {
+    float a = m, b = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      a = max3(a, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      b = max3(b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    }
+    return fmaxf(a, b);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) m = fmaxf(m, i < valid ? __uint_as_float(v[i]) : -INFINITY);
+  return m;
 }
 
 }  // namespace
@@ -62,37 +145,40 @@ __host__ __device__ constexpr uint32_t idesc(uint32_t m, uint32_t n, bool f16, b
 template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                       uint16_t* __restrict__ out, int items, int T, int TP, int H, float scale_log2e, uint32_t v_lbo_enc,
-                       uint32_t v_sbo_enc) {
+                       const __grid_constant__ AttnParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const uint32_t q_s = base, k_s = q_s + kQBytes, v_s = k_s + kKvBytesMax, p_s = v_s + kKvBytesMax;
-  const uint32_t bar = p_s + 2 * kPBytes;
-  uint8_t* p_gen = gen + kQBytes + 2 * kKvBytesMax;
-  // barrier slots
-  const uint32_t qk_full = bar, qk_empty = bar + 8, v_full = bar + 16, v_empty = bar + 24;
-  auto s_full = [&](int g) { return bar + 32 + 8u * g; };
-  auto p_full = [&](int g) { return bar + 48 + 8u * g; };
-  auto o_full = [&](int g) { return bar + 64 + 8u * g; };
-  auto s_free = [&](int g) { return bar + 80 + 8u * g; };
-  const uint32_t tmem_slot = bar + 96;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + kQBytes + 2 * kKvBytesMax + 2 * kPBytes + 96);
+  const uint32_t q_s = base;                                    // two Q tiles (one per group)
+  const uint32_t kv_s = base + 2 * kQTileBytes;                 // stage s: K at kv_s + s*2*kv_bytes, V right behind
+  const uint32_t bar = kv_s + uint32_t(prm.kv_stages) * 2u * uint32_t(prm.kv_bytes);
+  const uint32_t bar_off = bar - base;
+  auto k_full = [&](int s) { return bar + 8u * s; };
+  auto v_full = [&](int s) { return bar + 16 + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 32 + 8u * s; };
+  auto q_full = [&](int g) { return bar + 48 + 8u * g; };
+  auto q_empty = [&](int g) { return bar + 64 + 8u * g; };
+  auto s_full = [&](int g) { return bar + 80 + 8u * g; };
+  auto sm_done = [&](int g) { return bar + 96 + 8u * g; };
+  auto o_full = [&](int g) { return bar + 112 + 8u * g; };
+  auto o_free = [&](int g) { return bar + 128 + 8u * g; };
+  const uint32_t tmem_slot = bar + 144;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + bar_off + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = prm.T, H = prm.H, nq = prm.nq, nb = prm.nb, Nb = prm.Nb, TP = prm.TP, items = prm.items;
   const int d = H * kHd;
 
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_q);
-    ptx::prefetch_tensormap(&tm_kv);
-  }
+  if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tm_kv);
+  if (warp == 3 && lane == 0) ptx::prefetch_tensormap(&tm_q);
   if (warp == 1 && lane == 0) {
-    ptx::mbar_init(qk_full, 1); ptx::mbar_init(qk_empty, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(v_empty, 1);
-    for (int g = 0; g < 2; ++g) {
-      ptx::mbar_init(s_full(g), 1);    // tcgen05.commit
-      ptx::mbar_init(p_full(g), 1);    // one thread of the group after the group barrier
-      ptx::mbar_init(o_full(g), 1);    // tcgen05.commit
-      ptx::mbar_init(s_free(g), 1);    // one thread of the group after the group barrier
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(k_full(s), 1); ptx::mbar_init(v_full(s), 1); ptx::mbar_init(kv_empty(s), 1);
+      ptx::mbar_init(q_full(s), 1); ptx::mbar_init(q_empty(s), 1);
+      ptx::mbar_init(s_full(s), 1);      // tcgen05.commit
+      ptx::mbar_init(sm_done(s), 128);   // every thread of the group
+      ptx::mbar_init(o_full(s), 1);      // tcgen05.commit
+      ptx::mbar_init(o_free(s), 128);    // every thread of the group
     }
     ptx::fence_mbar_init();
   }
@@ -102,80 +188,139 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t kv_bytes = uint32_t(TP) * 128u;
-  const int n_pblk = (TP + 63) / 64;      // 64-key P blocks
-  const int n_kstep = TP / 16;            // UMMA K-steps of the P.V product
+  const int n_items = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int first_pass = nb > 1 ? 0 : 1;
 
   if (warp == 0) {
-    // ======================= producer =======================
+    // ======================= K/V producer =======================
     if (ptx::elect_one()) {
-      uint32_t ph = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ph ^= 1u) {
+      int n = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
         const int b = item / H, h = item - b * H;
         const int row0 = b * T;
-        ptx::mbar_wait(qk_empty, ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(qk_full, kQBytes + kv_bytes);
-        ptx::tma_load_2d(&tm_q, qk_full, q_s, h * kHd, row0, ptx::kEvictFirst);
-        ptx::tma_load_2d(&tm_kv, qk_full, k_s, d + h * kHd, row0, ptx::kEvictFirst);
-        ptx::mbar_wait(v_empty, ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(v_full, kv_bytes);
-        ptx::tma_load_2d(&tm_kv, v_full, v_s, 2 * d + h * kHd, row0, ptx::kEvictFirst);
+        const int s = n % prm.kv_stages;
+        const uint32_t par = uint32_t(n / prm.kv_stages) & 1u;
+        const uint32_t ks = kv_s + uint32_t(s) * 2u * uint32_t(prm.kv_bytes), vs = ks + uint32_t(prm.kv_bytes);
+        ptx::mbar_wait(kv_empty(s), par ^ 1u);
+        ptx::mbar_arrive_expect_tx(k_full(s), uint32_t(prm.kv_bytes));
+        for (int j = 0; j < nb; ++j)
+          ptx::tma_load_2d(&tm_kv, k_full(s), ks + uint32_t(j * Nb) * 128u, d + h * kHd, row0 + j * Nb, ptx::kEvictFirst);
+        ptx::mbar_arrive_expect_tx(v_full(s), uint32_t(prm.kv_bytes));
+        for (int j = 0; j < nb; ++j)
+          ptx::tma_load_2d(&tm_kv, v_full(s), vs + uint32_t(j * Nb) * 128u, 2 * d + h * kHd, row0 + j * Nb, ptx::kEvictFirst);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ======================= Q producer: tile t of every item goes to group t & 1 =======================
+    if (ptx::elect_one()) {
+      uint32_t cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / H, h = item - b * H;
+        for (int t = 0; t < nq; ++t) {
+          const int g = t & 1;
+          ptx::mbar_wait(q_empty(g), (cnt[g] & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(q_full(g), kQTileBytes);
+          ptx::tma_load_2d(&tm_q, q_full(g), q_s + g * kQTileBytes, h * kHd, b * T + t * 128, ptx::kEvictFirst);
+          ++cnt[g];
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    // One thread serves both query-tile groups as a small event loop, so that group g's chain
-    //   S_g(i) -> softmax -> P_g V(i) -> O_g read -> S_g(i+1) ...
-    // never waits behind the other group's products (the two chains only meet at the single-buffered Q/K and V tiles).
+    // ======================= MMA issuer: one thread, a small event loop over both groups =======================
     if (ptx::elect_one()) {
-      const uint32_t idesc_s = idesc(128, uint32_t(TP), kF16, false);
       const uint32_t idesc_o = idesc(128, kHd, kF16, true);
-      const uint64_t dk = ptx::make_kmajor_sw128_desc(k_s);
-      const int n_items = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-      int it[2] = {0, 0};        // item counter per group
-      int stage[2] = {0, 0};     // 0: S_g(it) to issue, 1: P_g V(it) to issue
-      int s_issued = 0, pv_issued = 0;   // products issued so far (2 per item): drive qk_empty / v_empty
-      const long long t0 = clock64();
-      while (it[0] < n_items || it[1] < n_items) {
+      struct GState {
+        int n, t, pass, j, st;
+        uint32_t q_cnt, smd_cnt, o_cnt;
+        bool active;
+      } gs[2];
+      for (int g = 0; g < 2; ++g) gs[g] = {0, g, first_pass, 0, 0, 0u, 0u, 0u, g < nq && n_items > 0};
+      int tiles_done[2] = {0, 0};
+      long long t_last = clock64();
+      while (gs[0].active || gs[1].active) {
         bool progress = false;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (it[g] >= n_items) continue;
-          const uint32_t ph = uint32_t(it[g]) & 1u;
-          if (stage[g] == 0) {
-            // Q/K of this item landed, and group g has drained O_g of its previous item
-            if (!ptx::mbar_test_wait(qk_full, ph) || !ptx::mbar_test_wait(s_free(g), ph ^ 1u)) continue;
+          GState& s = gs[g];
+          if (!s.active) continue;
+          const int stage = s.n % prm.kv_stages;
+          const uint32_t kv_par = uint32_t(s.n / prm.kv_stages) & 1u;
+          const uint32_t ks = kv_s + uint32_t(stage) * 2u * uint32_t(prm.kv_bytes), vs = ks + uint32_t(prm.kv_bytes);
+          const uint32_t region = tmem_base + uint32_t(g * kRegionCols);
+          const int Nj = min(Nb, TP - s.j * Nb);
+          if (s.st == 0) {
+            // ---- S_j = Q K_j^T ----
+            if (s.j == 0 && s.pass == first_pass) {
+              if (!ptx::mbar_test_wait(q_full(g), s.q_cnt & 1u)) continue;
+              if (!ptx::mbar_test_wait(k_full(stage), kv_par)) continue;
+              // a single-block S wider than 192 columns overlaps the O accumulator of the previous tile
+              if (nb == 1 && TP > kOCol && s.o_cnt > 0 && !ptx::mbar_test_wait(o_free(g), (s.o_cnt - 1u) & 1u)) continue;
+            }
             ptx::tcgen05_fence_after();
-            const uint64_t dq = ptx::make_kmajor_sw128_desc(q_s + g * (128 * 128));
+            const uint64_t dq = ptx::make_kmajor_sw128_desc(q_s + g * kQTileBytes);
+            const uint64_t dk = ptx::make_kmajor_sw128_desc(ks + uint32_t(s.j * Nb) * 128u);
+            const uint32_t id = idesc(128, uint32_t(Nj), kF16, false);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_f16<1>(tmem_base + g * 256, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(region, dq + uint64_t(2 * k), dk + uint64_t(2 * k), id, k != 0 ? 1u : 0u);
             ptx::umma_commit<1>(s_full(g));
-            if ((++s_issued & 1) == 0) ptx::umma_commit<1>(qk_empty);   // both S products of the item issued: Q/K reusable
-            stage[g] = 1;
+            if (s.pass == 1 && s.j == nb - 1) {   // last product that reads this Q tile
+              ptx::umma_commit<1>(q_empty(g));
+              ++s.q_cnt;
+            }
+            s.st = 1;
             progress = true;
           } else {
-            if (!ptx::mbar_test_wait(v_full, ph) || !ptx::mbar_test_wait(p_full(g), ph)) continue;
+            if (!ptx::mbar_test_wait(sm_done(g), s.smd_cnt & 1u)) continue;
+            if (s.pass == 0) {
+              // the group has taken the block's row maxima: next block (or start pass B)
+              ++s.smd_cnt;
+              if (++s.j == nb) { s.pass = 1; s.j = 0; }
+              s.st = 0;
+              progress = true;
+              continue;
+            }
+            // ---- O (+)= P_j V_j ----
+            if (!ptx::mbar_test_wait(v_full(stage), kv_par)) continue;
+            if (s.j == 0 && s.o_cnt > 0 && !ptx::mbar_test_wait(o_free(g), (s.o_cnt - 1u) & 1u)) continue;
+            ++s.smd_cnt;
             ptx::tcgen05_fence_after();
-            for (int j = 0; j < n_kstep; ++j) {
-              const uint64_t dp = ptx::make_kmajor_sw128_desc(p_s + g * kPBytes + (j >> 2) * kPBlockBytes) + uint64_t(2 * (j & 3));
-              // V rows are keys: 16 keys per K-step = 2048 bytes further down the [key][64 dims] tile (MN-major operand)
-              uint64_t dv = uint64_t(((v_s + uint32_t(j) * 2048u) >> 4) & 0x3FFFu);
-              dv |= uint64_t(v_lbo_enc) << 16;
-              dv |= uint64_t(v_sbo_enc) << 32;
+            const int n_kstep = Nj >> 4;
+            for (int k = 0; k < n_kstep; ++k) {
+              // V rows are keys: 16 keys per K-step = 2048 bytes further down the [key][64 dims] tile (MN-major operand,
+              // 128B swizzle: 8-key groups 1024 bytes apart (SBO), one 64-wide atom along N (LBO unused))
+              uint64_t dv = uint64_t(((vs + uint32_t(s.j * Nb) * 128u + uint32_t(k) * 2048u) >> 4) & 0x3FFFu);
+              dv |= uint64_t(1) << 16;
+              dv |= uint64_t(1024 >> 4) << 32;
               dv |= uint64_t(1) << 46;
               dv |= uint64_t(2) << 61;
-              ptx::umma_f16<1>(tmem_base + g * 256, dp, dv, idesc_o, j != 0 ? 1u : 0u);
+              umma_f16_ts(region + kOCol, region + uint32_t(8 * k), dv, idesc_o, (s.j | k) != 0 ? 1u : 0u);
             }
-            ptx::umma_commit<1>(o_full(g));
-            if ((++pv_issued & 1) == 0) ptx::umma_commit<1>(v_empty);
-            stage[g] = 0;
-            ++it[g];
+            if (s.j == nb - 1) {
+              ptx::umma_commit<1>(o_full(g));
+              ++s.o_cnt;
+              if (++tiles_done[stage] == nq) {   // every product that reads this item's K/V has been issued
+                ptx::umma_commit<1>(kv_empty(stage));
+                tiles_done[stage] = 0;
+              }
+            }
+            s.st = 0;
+            if (++s.j == nb) {
+              s.j = 0;
+              s.pass = first_pass;
+              s.t += 2;
+              if (s.t >= nq) {
+                s.t = g;
+                if (++s.n >= n_items) s.active = false;
+              }
+            }
             progress = true;
           }
         }
-        if (!progress && (clock64() - t0) > 20 * IIC_MBAR_TIMEOUT_CYCLES) {
+        if (progress) {
+          t_last = clock64();
+        } else if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
           printf("iic: attention MMA scheduler stalled (block %d)\n", int(blockIdx.x));
           __trap();
         }
@@ -187,146 +332,156 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int g = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                 // row inside the 128-row query tile
-    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(g * 256);
-    uint8_t* my_p = p_gen + g * kPBytes + r * 128;  // this row inside each 64-key P block
-    const int sw = r & 7;
-    const int bar_id = 1 + g;
-    uint32_t ph = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ph ^= 1u) {
-      const int b = item / H, h = item - b * H;
-      ptx::mbar_wait(s_full(g), ph);
-      ptx::tcgen05_fence_after();
-      // TMEM -> register bandwidth (64 B/clk per SM) is what bounds this kernel, so S is read exactly ONCE: an online
-      // softmax over 32-column chunks whose running maximum is kept as an INTEGER power of two, m = ceil(max * c).  A P
-      // chunk written under an older (smaller) m is later fixed up in shared memory by an exact multiplication with
-      // 2^(m_old - m_final) - rare after the first chunks, and exact in bf16/fp16, so the result does not depend on the
-      // chunking.  The next chunk's tcgen05.ld is always in flight while the current one is processed.
-      const int n_ch = (TP + 31) >> 5;
-      const bool warp_live = g * 128 + quad * 32 < T;   // warps whose 32 query rows are all padding do no math
-      uint32_t va[32], vb[32];
-      float m_run = -126.f, sum = 0.f;                  // exp2(s*c - m) stays a normal fp32 for any m >= -126
-      float m_used[8];
-      auto emit = [&](uint32_t (&v)[32], int c) {
-        float p[32];
-        if (!warp_live) {
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(g * kRegionCols);
+    const float c = prm.scale_log2e;
+    const uint64_t c2 = pack2(c, c);
+    uint32_t s_cnt = 0, o_cnt = 0;
+    if (g < nq) {
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / H, h = item - b * H;
+        for (int t = g; t < nq; t += 2) {
+          const bool warp_live = t * 128 + quad * 32 < T;   // warps whose 32 query rows are all padding do no math
+          float m = -INFINITY;
+          uint32_t va[32], vb[32];
+          // ---------------- pass A: row maximum over all key blocks ----------------
+          if (nb > 1) {
+            for (int j = 0; j < nb; ++j) {
+              ptx::mbar_wait(s_full(g), s_cnt & 1u);
+              ++s_cnt;
+              ptx::tcgen05_fence_after();
+              if (warp_live) {
+                const int Nj = min(Nb, TP - j * Nb), valid = min(Nj, T - j * Nb);
+                const int n_ch = (Nj + 31) >> 5;
+                ptx::tmem_ld_32x32b_x32(taddr, va);
+                ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) p[i] = 0.f;
-        } else {
-          const bool full = (c + 1) * 32 <= T;
-          float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            c0 = fmaxf(c0, (full || c * 32 + i < T) ? __uint_as_float(v[i]) : -INFINITY);
-            c1 = fmaxf(c1, (full || c * 32 + i + 1 < T) ? __uint_as_float(v[i + 1]) : -INFINITY);
-            c2 = fmaxf(c2, (full || c * 32 + i + 2 < T) ? __uint_as_float(v[i + 2]) : -INFINITY);
-            c3 = fmaxf(c3, (full || c * 32 + i + 3 < T) ? __uint_as_float(v[i + 3]) : -INFINITY);
-          }
-          const float mi = ceilf(fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * scale_log2e);
-          if (mi > m_run) {
-            sum *= exp2f(m_run - mi);   // exact power of two
-            m_run = mi;
-          }
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float e0, e1, e2, e3;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[i]), scale_log2e, -m_run)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -m_run)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(__uint_as_float(v[i + 2]), scale_log2e, -m_run)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(__uint_as_float(v[i + 3]), scale_log2e, -m_run)));
-            if (!full) {
-              e0 = c * 32 + i < T ? e0 : 0.f;     e1 = c * 32 + i + 1 < T ? e1 : 0.f;
-              e2 = c * 32 + i + 2 < T ? e2 : 0.f; e3 = c * 32 + i + 3 < T ? e3 : 0.f;
+                for (int ch = 0; ch < 6; ch += 2) {
+                  if (ch < n_ch) {
+                    if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
+                    m = chunk_max(va, valid - ch * 32, m);
+                    ptx::tmem_ld_wait();
+                  }
+                  if (ch + 1 < n_ch) {
+                    if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
+                    m = chunk_max(vb, valid - (ch + 1) * 32, m);
+                    ptx::tmem_ld_wait();
+                  }
+                }
+              }
+              ptx::tcgen05_fence_before();
+              ptx::mbar_arrive(sm_done(g));
             }
-            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-            p[i] = e0; p[i + 1] = e1; p[i + 2] = e2; p[i + 3] = e3;
           }
-          sum += (s0 + s1) + (s2 + s3);
-        }
-        m_used[c] = m_run;
-        uint8_t* blk = my_p + (c >> 1) * kPBlockBytes;
-        const int j0 = (c & 1) * 4;   // first 16-byte chunk of this 32-key run inside the 64-key block
+          // ---------------- pass B: P = exp2(S*c - m*c) in place, row sum ----------------
+          uint64_t acc0 = 0ull, acc1 = 0ull;   // packed partial row sums (0.0f bit patterns)
+          float mc = m * c;
+          for (int j = 0; j < nb; ++j) {
+            ptx::mbar_wait(s_full(g), s_cnt & 1u);
+            ++s_cnt;
+            ptx::tcgen05_fence_after();
+            if (warp_live) {
+              const int Nj = min(Nb, TP - j * Nb), valid = min(Nj, T - j * Nb);
+              const int n_ch = (Nj + 31) >> 5;
+              if (nb == 1) {
+                ptx::tmem_ld_32x32b_x32(taddr, va);
+                ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 q;
-          q.x = Act<kF16>::pack(p[8 * j], p[8 * j + 1]);
-          q.y = Act<kF16>::pack(p[8 * j + 2], p[8 * j + 3]);
-          q.z = Act<kF16>::pack(p[8 * j + 4], p[8 * j + 5]);
-          q.w = Act<kF16>::pack(p[8 * j + 6], p[8 * j + 7]);
-          *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = q;
-        }
-      };
-      ptx::tmem_ld_32x32b_x32(taddr, va);
-      ptx::tmem_ld_wait();
+                for (int ch = 0; ch < 8; ch += 2) {
+                  if (ch < n_ch) {
+                    if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
+                    m = chunk_max(va, valid - ch * 32, m);
+                    ptx::tmem_ld_wait();
+                  }
+                  if (ch + 1 < n_ch) {
+                    if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
+                    m = chunk_max(vb, valid - (ch + 1) * 32, m);
+                    ptx::tmem_ld_wait();
+                  }
+                }
+                mc = m * c;
+              }
+              const uint64_t nmc2 = pack2(-mc, -mc);
+              auto emit = [&](const uint32_t (&v)[32], int ch) {
+                uint32_t pk[16];
+                const int vl = valid - ch * 32;
+                if (vl >= 32) {
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        if (c < n_ch) {
-          if (c + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((c + 1) * 32), vb);
-          emit(va, c);
-          ptx::tmem_ld_wait();
-          if (c + 1 < n_ch) {
-            if (c + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((c + 2) * 32), va);
-            emit(vb, c + 1);
+                  for (int i = 0; i < 16; ++i) {
+                    float x0, x1;
+                    unpack2(fma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, nmc2), x0, x1);
+                    const float e0 = ex2(x0), e1 = ex2(x1);
+                    if (i & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
+                    pk[i] = Act<kF16>::pack(e0, e1);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    float e0 = ex2(fmaf(__uint_as_float(v[2 * i]), c, -mc)), e1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+                    e0 = 2 * i < vl ? e0 : 0.f;
+                    e1 = 2 * i + 1 < vl ? e1 : 0.f;
+                    acc0 = add2(acc0, pack2(e0, e1));
+                    pk[i] = Act<kF16>::pack(e0, e1);
+                  }
+                }
+                tmem_st16(taddr + uint32_t(ch * 16), pk);   // always behind the S columns still to be read
+              };
+              ptx::tmem_ld_32x32b_x32(taddr, va);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int ch = 0; ch < 8; ch += 2) {
+                if (ch < n_ch) {
+                  if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
+                  emit(va, ch);
+                  ptx::tmem_ld_wait();
+                }
+                if (ch + 1 < n_ch) {
+                  if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
+                  emit(vb, ch + 1);
+                  ptx::tmem_ld_wait();
+                }
+              }
+              tmem_st_wait();
+            }
+            ptx::tcgen05_fence_before();
+            ptx::mbar_arrive(sm_done(g));
+          }
+          // ---------------- O row ----------------
+          ptx::mbar_wait(o_full(g), o_cnt & 1u);
+          ++o_cnt;
+          ptx::tcgen05_fence_after();
+          const int q = t * 128 + r;
+          if (warp_live) {
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(kOCol), va);
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(kOCol + 32), vb);
             ptx::tmem_ld_wait();
           }
-        }
-      }
-      // fix-up of the chunks written before the row maximum settled (this thread's own row only)
-      if (warp_live) {
+          ptx::tcgen05_fence_before();
+          ptx::mbar_arrive(o_free(g));
+          if (q < T) {
+            float s0, s1, s2, s3;
+            unpack2(acc0, s0, s1);
+            unpack2(acc1, s2, s3);
+            const float sum = (s0 + s1) + (s2 + s3);
+            const float inv = 1.0f / sum;
+            const uint64_t inv2 = pack2(inv, inv);
+            uint16_t* orow = prm.out + (size_t(b) * T + q) * d + h * kHd;
+            auto store32 = [&](const uint32_t (&v)[32], int off) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c < n_ch && m_used[c] != m_run) {
-            const float f = exp2f(fmaxf(m_used[c] - m_run, -24.f));   // power of two, representable in bf16 and fp16
-            const uint32_t f2 = Act<kF16>::pack(f, f);
-            uint8_t* blk = my_p + (c >> 1) * kPBlockBytes;
-            const int j0 = (c & 1) * 4;
+              for (int jj = 0; jj < 4; ++jj) {
+                uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4* ptr = reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4));
-              uint4 q = *ptr;
-              q.x = Act<kF16>::mul2(q.x, f2); q.y = Act<kF16>::mul2(q.y, f2);
-              q.z = Act<kF16>::mul2(q.z, f2); q.w = Act<kF16>::mul2(q.w, f2);
-              *ptr = q;
-            }
+                for (int e = 0; e < 4; ++e) {
+                  float x0, x1;
+                  unpack2(mul2f(pack2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1])), inv2), x0, x1);
+                  w[e] = Act<kF16>::pack(x0, x1);
+                }
+                *reinterpret_cast<uint4*>(orow + off + 8 * jj) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            };
+            store32(va, 0);
+            store32(vb, 32);
+            if (prm.lse != nullptr) prm.lse[(size_t(b) * H + h) * T + q] = mc + log2f(sum);
           }
-        }
-      }
-      // P_g complete (and S_g fully read): make it visible to the tensor core, then hand over
-      ptx::tcgen05_fence_before();
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if ((threadIdx.x & 127) == 0) ptx::mbar_arrive(p_full(g));
-      // ---- O row ----
-      ptx::mbar_wait(o_full(g), ph);
-      ptx::tcgen05_fence_after();
-      uint32_t o0[32], o1[32];
-      ptx::tmem_ld_32x32b_x32(taddr, o0);
-      ptx::tmem_ld_32x32b_x32(taddr + 32u, o1);
-      ptx::tmem_ld_wait();
-      ptx::tcgen05_fence_before();
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if ((threadIdx.x & 127) == 0) ptx::mbar_arrive(s_free(g));   // TMEM region g may be overwritten by the next S_g
-      const int q = g * 128 + r;
-      if (q < T) {
-        const float inv = 1.0f / sum;
-        uint16_t* orow = out + (size_t(b) * T + q) * d + h * kHd;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 w;
-          w.x = Act<kF16>::pack(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
-          w.y = Act<kF16>::pack(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
-          w.z = Act<kF16>::pack(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
-          w.w = Act<kF16>::pack(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 8 * j) = w;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 w;
-          w.x = Act<kF16>::pack(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
-          w.y = Act<kF16>::pack(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
-          w.z = Act<kF16>::pack(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
-          w.w = Act<kF16>::pack(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + 8 * j) = w;
         }
       }
     }
@@ -363,35 +518,49 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 }  // namespace
 
 // returns -3 when the shape is outside this kernel's envelope (caller falls back to the mma.sync kernel)
-int launch_attention_sm100(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16, int num_sms,
+int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, int num_sms,
                            cudaStream_t stream) {
   if (B <= 0) return 0;
-  if (head_dim != kHd || T > 256 || T < 16) return -3;
-  const int TP = (T + 15) / 16 * 16;
+  if (head_dim != kHd || T < 1) return -3;
+  AttnParams p;
+  p.TP = (T + 15) / 16 * 16;
+  if (p.TP <= 256) {
+    p.nb = 1;
+    p.Nb = p.TP;
+  } else {
+    p.nb = (p.TP + kOCol - 1) / kOCol;
+    p.Nb = ((p.TP + p.nb - 1) / p.nb + 15) / 16 * 16;
+    p.nb = (p.TP + p.Nb - 1) / p.Nb;
+  }
+  p.kv_bytes = p.nb * p.Nb * 128;
+  const int fixed = 2 * kQTileBytes + kBarBytes + 1024 /*alignment slack*/;
+  if (fixed + 2 * p.kv_bytes > kMaxSmem) return -3;
+  p.kv_stages = fixed + 4 * p.kv_bytes <= kMaxSmem ? 2 : 1;
+  const int smem = fixed + p.kv_stages * 2 * p.kv_bytes;
+  p.nq = (T + 127) / 128;
+  p.items = B * H;
+  p.T = T;
+  p.H = H;
+  p.out = static_cast<uint16_t*>(out);
+  p.lse = lse;
+  p.scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
   const int d = H * kHd;
   CUtensorMap tq, tkv;
   const uint64_t rows = uint64_t(B) * T;
-  if (!make_map(&tq, qkv, rows, uint64_t(3 * d), 256, f16 != 0) || !make_map(&tkv, qkv, rows, uint64_t(3 * d), uint32_t(TP), f16 != 0))
+  if (!make_map(&tq, qkv, rows, uint64_t(3 * d), 128, f16 != 0) || !make_map(&tkv, qkv, rows, uint64_t(3 * d), uint32_t(p.Nb), f16 != 0))
     return -1;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(attention_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
       return -2;
     attr_done = true;
   }
-  // MN-major SW128 operand descriptor for V [key][64 dims]: 8-key groups are 1024 bytes apart (SBO); one 64-wide atom in N (LBO unused)
-  uint32_t lbo = 1, sbo = 1024 >> 4;
-  if (const char* e = getenv("IIC_ATTN_VLBO")) lbo = uint32_t(atoi(e));
-  if (const char* e = getenv("IIC_ATTN_VSBO")) sbo = uint32_t(atoi(e));
-  const int items = B * H;
-  const int grid = items < num_sms ? items : num_sms;
-  const float scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
-  uint16_t* o = static_cast<uint16_t*>(out);
+  const int grid = p.items < num_sms ? p.items : num_sms;
   if (f16)
-    attention_sm100_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(tq, tkv, o, items, T, TP, H, scale_log2e, lbo, sbo);
+    attention_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
   else
-    attention_sm100_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(tq, tkv, o, items, T, TP, H, scale_log2e, lbo, sbo);
+    attention_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

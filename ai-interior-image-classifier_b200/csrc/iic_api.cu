@@ -94,7 +94,7 @@ struct iic_handle {
   std::string err;
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
-  int attn_impl = 0;  // 0 auto (tcgen05 kernel when T <= 256), 1 mma.sync kernel, 2 tcgen05 kernel
+  int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
@@ -151,14 +151,15 @@ bool check_ready(iic_handle* h) {
   return true;
 }
 
-// inference attention: tcgen05/TMEM kernel for short sequences, mma.sync kernel otherwise (and for training, which needs the LSE)
-int run_attention(iic_handle* h, const void* qkv, void* out, int B, int T, int H, int hd, int impl, cudaStream_t s) {
+// attention forward: tcgen05/TMEM kernel whenever the shape is inside its envelope, mma.sync kernel otherwise.
+// lse (nullable): log2-domain log-sum-exp per (image, head, query), kept by the training forward for the backward pass.
+int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, int T, int H, int hd, int impl, cudaStream_t s) {
   if (impl == 0) impl = h->attn_impl;
   if (impl != 1) {
-    int rc = launch_attention_sm100(qkv, out, B, T, H, hd, h->f16, h->num_sms, s);
+    int rc = launch_attention_sm100(qkv, out, lse, B, T, H, hd, h->f16, h->num_sms, s);
     if (rc != -3 || impl == 2) return rc == -3 ? -1 : rc;
   }
-  return launch_attention(qkv, out, nullptr, B, T, H, hd, h->f16, s);
+  return launch_attention(qkv, out, lse, B, T, H, hd, h->f16, s);
 }
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
@@ -227,7 +228,7 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
                               l_in.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
-    IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, w.qkv, w.attn, B, T, H, d / H, 0, s); }));
+    IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, w.qkv, w.attn, nullptr, B, T, H, d / H, 0, s); }));
     if (l_out.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s);
@@ -889,7 +890,7 @@ int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const f
 
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int impl, void* stream) {
   if (!h || !qkv_bf16 || !out_bf16) return fail(h, IIC_ERR_ARG, "iic_op_attention: null argument");
-  int rc = run_attention(h, qkv_bf16, out_bf16, B, T, heads, 64, impl, static_cast<cudaStream_t>(stream));
+  int rc = run_attention(h, qkv_bf16, out_bf16, nullptr, B, T, heads, 64, impl, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention launch failed");
   return IIC_OK;
 }

@@ -25,8 +25,9 @@ int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int 
 // lse (nullable): f32 [B*H, T] log2-domain log-sum-exp of the scaled scores, saved for the backward pass
 int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16,
                      cudaStream_t stream);
-// tcgen05 / TMEM variant for T <= 256 (attention_sm100.cu); returns -3 if the shape is outside its envelope
-int launch_attention_sm100(const void* qkv, void* out, int B, int T, int H, int head_dim, int f16, int num_sms,
+// tcgen05 / TMEM kernel (attention_sm100.cu): head_dim 64, K/V of one head resident in smem (T <= ~760);
+// returns -3 if the shape is outside its envelope
+int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, int num_sms,
                            cudaStream_t stream);
 // dqkv[M, 3d] (16-bit) from d_out[M, d], the saved qkv / out / lse.  T <= 432 (everything of one head lives in smem).
 int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int T,

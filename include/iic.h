@@ -192,7 +192,8 @@ int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const fl
                      void* stream);
 int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const float* lora_a_scaled, int r4, void* p_out,
                      int p_ld, void* stream);
-/* impl: 0 = what the encoder uses (tcgen05/TMEM kernel when T <= 256, else mma.sync), 1 = mma.sync kernel, 2 = tcgen05 kernel */
+/* impl: 0 = what the encoder uses (tcgen05/TMEM kernel while K/V of one head fit in smem, T <= ~760; else mma.sync),
+ * 1 = mma.sync kernel, 2 = tcgen05 kernel */
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int impl, void* stream);
 /* backward operators (same kernels iic_train_backward runs).  iic_op_attention_bwd recomputes the forward into `out`
  * (to obtain the log-sum-exp, lse_scratch f32 [B*heads*T]) and then writes dqkv [M, 3*d]. */

@@ -1,3 +1,4 @@
+"""Attention kernels alone: mma.sync vs tcgen05, ViT-B/16@224 (T=197) and ViT-L/14@336 (T=577) shapes."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import iic_b200
@@ -10,11 +11,13 @@ def timeit(fn, warmup=3, iters=10):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
 eng = iic_b200.Engine(iic_b200.VIT_B_16, "cuda:0")
-B, T, H = 1024, 197, 12
-qkv = torch.randn(B * T, 3 * H * 64, device="cuda").bfloat16()
-for impl, name in ((1, "mma.sync"), (2, "tcgen05")):
-    try:
-        t = timeit(lambda: eng.op_attention(qkv, B, T, H, impl=impl))
-        print(f"{name:10s} {t:.3f} ms   {4.0 * T * T * 64 * B * H / t / 1e9:.0f} TFLOP/s (unpadded)")
-    except Exception as ex:
-        print(name, "FAILED", str(ex)[:200])
+impls = [(1, "mma.sync"), (2, "tcgen05")]
+if len(sys.argv) > 1: impls = [i for i in impls if str(i[0]) in sys.argv[1:]]
+for B, T, H in ((1024, 197, 12), (256, 577, 16)):
+    qkv = torch.randn(B * T, 3 * H * 64, device="cuda").bfloat16()
+    for impl, name in impls:
+        try:
+            t = timeit(lambda: eng.op_attention(qkv, B, T, H, impl=impl))
+            print(f"B={B} T={T} H={H} {name:10s} {t:.3f} ms   {4.0 * T * T * 64 * B * H / t / 1e9:.0f} TFLOP/s (unpadded)", flush=True)
+        except Exception as ex:
+            print(name, "FAILED", str(ex)[:200])
