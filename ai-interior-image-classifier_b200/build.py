@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
         if not force and _newer(obj, [src] + headers + [os.path.abspath(__file__)]):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("IIC_EXTRA_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

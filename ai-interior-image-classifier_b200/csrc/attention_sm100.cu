@@ -1,31 +1,30 @@
-// tcgen05 attention, head_dim 64, any ViT sequence length that fits one SM's shared memory (T <= ~760):
+// tcgen05 attention, head_dim 64, any ViT sequence length whose K/V of one head fit one SM's shared memory (T <= ~640):
 //
 //   softmax(Q K^T / sqrt(64)) V   per (image, head)        [reference: nn.MultiheadAttention inside CLIP's
 //   ResidualAttentionBlock, reached through model.encode_image at /root/reference/main.py:204, 444, 503]
 //
 // One persistent CTA per SM walks (image, head) items; K and V of the item are resident in 128B-swizzled smem (two items
-// in flight when they fit).  The queries form 128-row tiles; two softmax groups (4 warps each) take alternate tiles, so
-// one group's tensor-core round trip hides under the other group's exponentials.  Per tile, with the keys cut into
-// nb blocks of Nb <= 192 (a single block of <= 256 when the whole row fits: ViT-B/16 @ 224, T = 197):
+// in flight when they fit).  The queries form 128-row tiles; two softmax groups (4 warps each) take alternate tiles.
+// The keys are cut into nb blocks of <= 96 (a multiple of 16 each), and per (tile, block) "op":
 //
-//   pass A (nb > 1 only)   S_j = Q K_j^T -> TMEM, row maximum only.  The scores are simply computed twice (the tensor
-//                          pipe is idle most of the time) so that pass B needs no running maximum and no rescaling
-//                          of O: the numerics are those of a plain two-pass softmax for every T.
-//   pass B                 S_j = Q K_j^T -> TMEM (fp32, columns [0, Nj) of the group's 256-column region);
-//                          ONE THREAD PER QUERY ROW: tcgen05.ld 32x32b hands a thread its own row, so max and sum are
-//                          thread-local (no shuffles); p = exp2(s*c - m*c) with packed FFMA2/FADD2, converted to 16 bit
-//                          and written back IN PLACE over S (tcgen05.st, columns [0, Nj/2)): P never touches smem;
-//                          O += P_j V_j with A = P from TMEM, B = V in its natural [key][dim] layout (MN-major operand),
-//                          accumulator in columns [192, 256) of the region.
+//   S = Q K_j^T            tcgen05.mma, fp32 accumulator in one of the group's TWO 96-column S buffers in TMEM, so the
+//                          tensor core always runs one or two ops AHEAD of the softmax (also across tiles and items).
+//   softmax                ONE THREAD PER QUERY ROW: tcgen05.ld 32x32b hands a thread its own row of the block (<= 96
+//                          registers), so max and sum are thread-local: no shuffles, S is read from TMEM exactly once.
+//                          Online softmax with a LAZY running maximum: m only moves when a block exceeds it by more than
+//                          2^8 (then O and the row sum are rescaled, a rare path taken warp-uniformly); otherwise
+//                          p = exp2(s*c - m) may reach 2^8, which is harmless in fp32 / bf16 / fp16.  Packed FFMA2 /
+//                          FADD2, FMNMX3; P -> 16 bit -> written back IN PLACE over S (tcgen05.st): P never touches smem.
+//   O (+)= P_j V_j         tcgen05.mma with A = P from TMEM, B = V in its natural [key][dim] layout (MN-major operand),
+//                          accumulator in columns [192, 256) of the group's region.
 //   epilogue               O row * 1/sum -> 16 bit -> global; optional log2-domain LSE for the backward pass.
 //
-//   warp 0  TMA producer K/V      warp 1  MMA issuer (one thread, event loop over both groups)
-//   warp 2  TMEM allocator        warp 3  TMA producer Q tiles      warps 4-7 / 8-11  softmax groups 0 / 1
+//   warp 0  TMA producer K/V      warp 1 / 2  MMA issuers of group 0 / 1 (warp 2 also owns the TMEM allocation)
+//   warp 3  TMA producer Q tiles (2-deep ring per group)           warps 4-7 / 8-11  softmax groups 0 / 1
 //
 // The softmax is bound by the MUFU pipe (16 ex2/clk/SM, tools/ubench_sm100.cu); everything else in the inner loop is
-// ~2 issue slots per element.  TMEM reads are not a limit (>= 700 B/clk/SM measured), which is why S is read twice
-// rather than kept in registers.  tcgen05.mma instructions of one CTA execute in issue order, which is what orders
-// "PV_j reads P_j" before "S_{j+1} overwrites it".  All waits are bounded (trap, never hang).
+// ~2 issue slots per element.  tcgen05.mma instructions of one CTA execute in issue order, which is what orders
+// "PV_k reads P_k" before "S_{k+2} overwrites it".  All waits are bounded (trap, never hang).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -45,20 +44,25 @@ namespace {
 constexpr int kHd = 64;
 constexpr int kThreads = 384;
 constexpr int kQTileBytes = 128 * 128;   // 128 query rows x 64 dims x 2 B
-constexpr int kRegionCols = 256;         // TMEM columns per softmax group
-constexpr int kOCol = 192;               // O accumulator: columns [192, 256) of the region
+constexpr int kRegionCols = 256;         // TMEM columns per softmax group: S buffers [0,96) [96,192), O [192,256)
+constexpr int kSBufCols = 96;
+constexpr int kMaxUnits = kSBufCols / 16;
+constexpr int kOCol = 192;
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kBarBytes = 256;
+constexpr int kBarBytes = 512;
+constexpr float kLazyLog2 = 8.0f;        // the running maximum is left alone until a block exceeds it by 2^8
 
 struct AttnParams {
   uint16_t* out;
   float* lse;
   int items, T, H;
-  int nq;         // 128-row query tiles per item
-  int nb, Nb;     // key blocks per item, rows per block (multiple of 16)
-  int TP;         // keys rounded up to 16
-  int kv_stages;  // items whose K/V are resident at once (1 or 2)
-  int kv_bytes;   // bytes of one K (or V) buffer = nb * Nb * 128
+  int nq;            // 128-row query tiles per item
+  int nb;            // key blocks per item
+  int bq, brem;      // block j holds bq + (j < brem) units of 16 keys
+  int TP;            // keys rounded up to 16
+  int kv_stages;     // items whose K/V are resident at once (1 or 2)
+  int kv_bytes;      // bytes of one K (or V) buffer (TMA boxes may overshoot TP rows)
+  int kv_box, kv_loads;
   float scale_log2e;
 };
 
@@ -80,13 +84,31 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+// 16 consecutive fp32 columns of this thread's TMEM lane <-> v[o .. o+16) (o is a constant after unrolling)
+__device__ __forceinline__ void tmem_ld16_at(uint32_t taddr, uint32_t* v, int o) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]),
+        "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]),
+        "=r"(v[o + 14]), "=r"(v[o + 15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16_at(uint32_t taddr, const uint32_t* v, int o) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       :
-      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]),
+        "r"(v[o + 7]), "r"(v[o + 8]), "r"(v[o + 9]), "r"(v[o + 10]), "r"(v[o + 11]), "r"(v[o + 12]), "r"(v[o + 13]),
+        "r"(v[o + 14]), "r"(v[o + 15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8_at(uint32_t taddr, const uint32_t* v, int o) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]),
+                 "r"(v[o + 6]), "r"(v[o + 7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -124,20 +146,103 @@ __device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
   return r;
 }
 
-// running maximum over the first `valid` of the 32 columns in v (valid >= 32: no masking)
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int valid, float m) {
-  if (valid >= 32) {
-    float a = m, b = -INFINITY;
+struct SoftmaxRow {
+  float m;               // running maximum, already scaled: max(s) * c (lazy: only moves in steps of > 2^8)
+  uint64_t acc0, acc1;   // packed partial row sums
+};
+
+// One key block (U units of 16 keys) of one query row: S (fp32, TMEM columns [sb, sb + 16U)) -> P (16 bit, in place,
+// columns [sb, sb + 8U)), online softmax state in st.  Straight-line code for the compile-time U; only the block's last
+// unit can hold padding keys (tail < 16 real keys).  All 32 lanes of the warp call this together.
+template <bool kF16, int U>
+__device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float c, bool first, int tail,
+                                              uint32_t pv_bar, uint32_t pv_par) {
+  uint32_t v[16 * U];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      a = max3(a, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-      b = max3(b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-    }
-    return fmaxf(a, b);
+  for (int i = 0; i < U; ++i) tmem_ld16_at(sb + uint32_t(16 * i), v, 16 * i);
+  ptx::tmem_ld_wait();
+  // ---- block maximum (4 independent chains) ----
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < U - 1; ++i) {
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) mx[(e >> 1) & 3] = max3(mx[(e >> 1) & 3], __uint_as_float(v[16 * i + e]), __uint_as_float(v[16 * i + e + 1]));
   }
+  if (tail >= 16) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) m = fmaxf(m, i < valid ? __uint_as_float(v[i]) : -INFINITY);
-  return m;
+    for (int e = 0; e < 16; e += 2)
+      mx[(e >> 1) & 3] = max3(mx[(e >> 1) & 3], __uint_as_float(v[16 * (U - 1) + e]), __uint_as_float(v[16 * (U - 1) + e + 1]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mx[e & 3] = fmaxf(mx[e & 3], e < tail ? __uint_as_float(v[16 * (U - 1) + e]) : -INFINITY);
+  }
+  const float mblk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
+  if (first) {
+    st.m = mblk;
+  } else if (__any_sync(0xffffffffu, mblk > st.m + kLazyLog2)) {
+    // ---- rare: this block raises some row's maximum by more than 2^8: rescale O and the row sum ----
+    const bool mine = mblk > st.m + kLazyLog2;
+    const float f = mine ? exp2f(st.m - mblk) : 1.0f;
+    if (mine) st.m = mblk;
+    const uint64_t f2 = pack2(f, f);
+    st.acc0 = mul2f(st.acc0, f2);
+    st.acc1 = mul2f(st.acc1, f2);
+    ptx::mbar_wait(pv_bar, pv_par);   // P.V of the previous op must have landed in O before O is touched
+    ptx::tcgen05_fence_after();
+    uint32_t o[16];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      tmem_ld16_at(o_addr + uint32_t(16 * cc), o, 0);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+      tmem_st16_at(o_addr + uint32_t(16 * cc), o, 0);
+    }
+  }
+  // ---- p = exp2(s*c - m), row sum, 16-bit P in place ----
+  const float m = st.m;
+  const uint64_t c2 = pack2(c, c), nm2 = pack2(-m, -m);
+  uint64_t acc0 = st.acc0, acc1 = st.acc1;
+  uint32_t pk[8 * U];
+#pragma unroll
+  for (int i = 0; i < U - 1; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float x0, x1;
+      unpack2(fma2(pack2(__uint_as_float(v[16 * i + 2 * e]), __uint_as_float(v[16 * i + 2 * e + 1])), c2, nm2), x0, x1);
+      const float e0 = ex2(x0), e1 = ex2(x1);
+      if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
+      pk[8 * i + e] = Act<kF16>::pack(e0, e1);
+    }
+    tmem_st8_at(sb + uint32_t(8 * i), pk, 8 * i);
+  }
+  {
+    constexpr int i = U - 1;
+    if (tail >= 16) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float x0, x1;
+        unpack2(fma2(pack2(__uint_as_float(v[16 * i + 2 * e]), __uint_as_float(v[16 * i + 2 * e + 1])), c2, nm2), x0, x1);
+        const float e0 = ex2(x0), e1 = ex2(x1);
+        if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
+        pk[8 * i + e] = Act<kF16>::pack(e0, e1);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float e0 = ex2(fmaf(__uint_as_float(v[16 * i + 2 * e]), c, -m));
+        float e1 = ex2(fmaf(__uint_as_float(v[16 * i + 2 * e + 1]), c, -m));
+        e0 = 2 * e < tail ? e0 : 0.f;
+        e1 = 2 * e + 1 < tail ? e1 : 0.f;
+        acc0 = add2(acc0, pack2(e0, e1));
+        pk[8 * i + e] = Act<kF16>::pack(e0, e1);
+      }
+    }
+    tmem_st8_at(sb + uint32_t(8 * i), pk, 8 * i);
+  }
+  st.acc0 = acc0;
+  st.acc1 = acc1;
+  tmem_st_wait();
 }
 
 }  // namespace
@@ -149,36 +254,41 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const uint32_t q_s = base;                                    // two Q tiles (one per group)
-  const uint32_t kv_s = base + 2 * kQTileBytes;                 // stage s: K at kv_s + s*2*kv_bytes, V right behind
+  const uint32_t q_s = base;                                    // Q ring: group g, slot s at (2g + s) * 16 KB
+  const uint32_t kv_s = base + 4 * kQTileBytes;                 // stage s: K at kv_s + s*2*kv_bytes, V right behind
   const uint32_t bar = kv_s + uint32_t(prm.kv_stages) * 2u * uint32_t(prm.kv_bytes);
   const uint32_t bar_off = bar - base;
   auto k_full = [&](int s) { return bar + 8u * s; };
   auto v_full = [&](int s) { return bar + 16 + 8u * s; };
   auto kv_empty = [&](int s) { return bar + 32 + 8u * s; };
-  auto q_full = [&](int g) { return bar + 48 + 8u * g; };
-  auto q_empty = [&](int g) { return bar + 64 + 8u * g; };
-  auto s_full = [&](int g) { return bar + 80 + 8u * g; };
-  auto sm_done = [&](int g) { return bar + 96 + 8u * g; };
-  auto o_full = [&](int g) { return bar + 112 + 8u * g; };
-  auto o_free = [&](int g) { return bar + 128 + 8u * g; };
-  const uint32_t tmem_slot = bar + 144;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + bar_off + 144);
+  auto o_full = [&](int g) { return bar + 48 + 8u * g; };
+  auto o_free = [&](int g) { return bar + 64 + 8u * g; };
+  auto q_full = [&](int g, int s) { return bar + 80 + 8u * (2 * g + s); };
+  auto q_empty = [&](int g, int s) { return bar + 112 + 8u * (2 * g + s); };
+  auto s_full = [&](int g, int s) { return bar + 144 + 8u * (2 * g + s); };
+  auto sm_done = [&](int g, int s) { return bar + 176 + 8u * (2 * g + s); };
+  auto pv_done = [&](int g, int s) { return bar + 208 + 8u * (2 * g + s); };
+  const uint32_t tmem_slot = bar + 240;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + bar_off + 240);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = prm.T, H = prm.H, nq = prm.nq, nb = prm.nb, Nb = prm.Nb, TP = prm.TP, items = prm.items;
+  const int T = prm.T, H = prm.H, nq = prm.nq, nb = prm.nb, items = prm.items;
   const int d = H * kHd;
 
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tm_kv);
   if (warp == 3 && lane == 0) ptx::prefetch_tensormap(&tm_q);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(k_full(s), 1); ptx::mbar_init(v_full(s), 1); ptx::mbar_init(kv_empty(s), 1);
-      ptx::mbar_init(q_full(s), 1); ptx::mbar_init(q_empty(s), 1);
-      ptx::mbar_init(s_full(s), 1);      // tcgen05.commit
-      ptx::mbar_init(sm_done(s), 128);   // every thread of the group
+      ptx::mbar_init(k_full(s), 1); ptx::mbar_init(v_full(s), 1);
+      ptx::mbar_init(kv_empty(s), nq > 1 ? 2 : 1);   // one tcgen05.commit per MMA issuer that reads the stage
       ptx::mbar_init(o_full(s), 1);      // tcgen05.commit
       ptx::mbar_init(o_free(s), 128);    // every thread of the group
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(q_full(s, b), 1); ptx::mbar_init(q_empty(s, b), 1);
+        ptx::mbar_init(s_full(s, b), 1);      // tcgen05.commit
+        ptx::mbar_init(sm_done(s, b), 128);   // every thread of the group
+        ptx::mbar_init(pv_done(s, b), 1);     // tcgen05.commit
+      }
     }
     ptx::fence_mbar_init();
   }
@@ -189,12 +299,17 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_items = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  const int first_pass = nb > 1 ? 0 : 1;
+  auto blk_units = [&](int j) { return prm.bq + (j < prm.brem ? 1 : 0); };
+  auto blk_start = [&](int j) { return j * prm.bq + min(j, prm.brem); };   // in units of 16 keys
 
+  // register budget: the producer / issuer warp group gives registers to the two softmax warp groups
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ======================= K/V producer =======================
     if (ptx::elect_one()) {
       int n = 0;
+      const uint32_t bytes = uint32_t(prm.kv_loads * prm.kv_box) * 128u;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
         const int b = item / H, h = item - b * H;
         const int row0 = b * T;
@@ -202,118 +317,122 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const uint32_t par = uint32_t(n / prm.kv_stages) & 1u;
         const uint32_t ks = kv_s + uint32_t(s) * 2u * uint32_t(prm.kv_bytes), vs = ks + uint32_t(prm.kv_bytes);
         ptx::mbar_wait(kv_empty(s), par ^ 1u);
-        ptx::mbar_arrive_expect_tx(k_full(s), uint32_t(prm.kv_bytes));
-        for (int j = 0; j < nb; ++j)
-          ptx::tma_load_2d(&tm_kv, k_full(s), ks + uint32_t(j * Nb) * 128u, d + h * kHd, row0 + j * Nb, ptx::kEvictFirst);
-        ptx::mbar_arrive_expect_tx(v_full(s), uint32_t(prm.kv_bytes));
-        for (int j = 0; j < nb; ++j)
-          ptx::tma_load_2d(&tm_kv, v_full(s), vs + uint32_t(j * Nb) * 128u, 2 * d + h * kHd, row0 + j * Nb, ptx::kEvictFirst);
+        ptx::mbar_arrive_expect_tx(k_full(s), bytes);
+        for (int l = 0; l < prm.kv_loads; ++l)
+          ptx::tma_load_2d(&tm_kv, k_full(s), ks + uint32_t(l * prm.kv_box) * 128u, d + h * kHd, row0 + l * prm.kv_box,
+                           ptx::kEvictFirst);
+        ptx::mbar_arrive_expect_tx(v_full(s), bytes);
+        for (int l = 0; l < prm.kv_loads; ++l)
+          ptx::tma_load_2d(&tm_kv, v_full(s), vs + uint32_t(l * prm.kv_box) * 128u, 2 * d + h * kHd, row0 + l * prm.kv_box,
+                           ptx::kEvictFirst);
       }
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ======================= Q producer: tile t of every item goes to group t & 1 =======================
+    // ======================= Q producer: tile t of every item goes to group t & 1 (2-deep ring per group) ===========
     if (ptx::elect_one()) {
       uint32_t cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / H, h = item - b * H;
         for (int t = 0; t < nq; ++t) {
-          const int g = t & 1;
-          ptx::mbar_wait(q_empty(g), (cnt[g] & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(q_full(g), kQTileBytes);
-          ptx::tma_load_2d(&tm_q, q_full(g), q_s + g * kQTileBytes, h * kHd, b * T + t * 128, ptx::kEvictFirst);
+          const int g = t & 1, slot = int(cnt[g] & 1u);
+          ptx::mbar_wait(q_empty(g, slot), ((cnt[g] >> 1) & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(q_full(g, slot), kQTileBytes);
+          ptx::tma_load_2d(&tm_q, q_full(g, slot), q_s + uint32_t(2 * g + slot) * kQTileBytes, h * kHd, b * T + t * 128,
+                           ptx::kEvictFirst);
           ++cnt[g];
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ======================= MMA issuer: one thread, a small event loop over both groups =======================
-    if (ptx::elect_one()) {
+  } else if (warp == 1 || warp == 2) {
+    // ======================= MMA issuers: warp 1 serves softmax group 0, warp 2 group 1 =======================
+    // The whole warp runs the loop (so that every operand stays in uniform registers); one elected lane issues.
+    // Two cursors walk the group's (item, tile, block) sequence: s_* = next S to issue, p_* = next P.V to issue.
+    // S op k goes to S buffer k & 1 and may be issued once P.V of op k-2 has been issued (in-order tensor pipe), so
+    // the tensor core runs up to two ops ahead of the softmax, across tiles and items.
+    const int g = warp - 1;
+    if (g < nq && n_items > 0) {
+      const uint32_t region = tmem_base + uint32_t(g * kRegionCols);
       const uint32_t idesc_o = idesc(128, kHd, kF16, true);
-      struct GState {
-        int n, t, pass, j, st;
-        uint32_t q_cnt, smd_cnt, o_cnt;
-        bool active;
-      } gs[2];
-      for (int g = 0; g < 2; ++g) gs[g] = {0, g, first_pass, 0, 0, 0u, 0u, 0u, g < nq && n_items > 0};
-      int tiles_done[2] = {0, 0};
+      const uint32_t total_ops = uint32_t(n_items) * uint32_t((nq - g + 1) / 2) * uint32_t(nb);
+      int s_n = 0, s_t = g, s_j = 0, p_n = 0, p_t = g, p_j = 0;
+      uint32_t s_k = 0, p_k = 0, s_tiles = 0, p_tiles = 0;
       long long t_last = clock64();
-      while (gs[0].active || gs[1].active) {
+      while (p_k < total_ops) {
         bool progress = false;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          GState& s = gs[g];
-          if (!s.active) continue;
-          const int stage = s.n % prm.kv_stages;
-          const uint32_t kv_par = uint32_t(s.n / prm.kv_stages) & 1u;
-          const uint32_t ks = kv_s + uint32_t(stage) * 2u * uint32_t(prm.kv_bytes), vs = ks + uint32_t(prm.kv_bytes);
-          const uint32_t region = tmem_base + uint32_t(g * kRegionCols);
-          const int Nj = min(Nb, TP - s.j * Nb);
-          if (s.st == 0) {
-            // ---- S_j = Q K_j^T ----
-            if (s.j == 0 && s.pass == first_pass) {
-              if (!ptx::mbar_test_wait(q_full(g), s.q_cnt & 1u)) continue;
-              if (!ptx::mbar_test_wait(k_full(stage), kv_par)) continue;
-              // a single-block S wider than 192 columns overlaps the O accumulator of the previous tile
-              if (nb == 1 && TP > kOCol && s.o_cnt > 0 && !ptx::mbar_test_wait(o_free(g), (s.o_cnt - 1u) & 1u)) continue;
-            }
+        // ---- O (+)= P V of the oldest pending op ----
+        if (p_k < s_k) {
+          const int buf = int(p_k & 1u), stage = p_n % prm.kv_stages;
+          bool ready = ptx::mbar_test_wait(sm_done(g, buf), (p_k >> 1) & 1u) &&
+                       ptx::mbar_test_wait(v_full(stage), uint32_t(p_n / prm.kv_stages) & 1u);
+          if (p_j == 0 && p_tiles > 0) ready = ready && ptx::mbar_test_wait(o_free(g), (p_tiles - 1u) & 1u);
+          if (__all_sync(0xffffffffu, ready)) {
             ptx::tcgen05_fence_after();
-            const uint64_t dq = ptx::make_kmajor_sw128_desc(q_s + g * kQTileBytes);
-            const uint64_t dk = ptx::make_kmajor_sw128_desc(ks + uint32_t(s.j * Nb) * 128u);
-            const uint32_t id = idesc(128, uint32_t(Nj), kF16, false);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(region, dq + uint64_t(2 * k), dk + uint64_t(2 * k), id, k != 0 ? 1u : 0u);
-            ptx::umma_commit<1>(s_full(g));
-            if (s.pass == 1 && s.j == nb - 1) {   // last product that reads this Q tile
-              ptx::umma_commit<1>(q_empty(g));
-              ++s.q_cnt;
+            const uint32_t vs = kv_s + uint32_t(stage) * 2u * uint32_t(prm.kv_bytes) + uint32_t(prm.kv_bytes);
+            const int u = blk_units(p_j), u0 = blk_start(p_j);
+            // V rows are keys: 16 keys per K-step = 2048 bytes further down the [key][64 dims] tile (MN-major operand,
+            // 128B swizzle: 8-key groups 1024 bytes apart (SBO), one 64-wide atom along N (LBO unused))
+            uint64_t dv = uint64_t(((vs + uint32_t(u0) * 2048u) >> 4) & 0x3FFFu);
+            dv |= uint64_t(1) << 16;
+            dv |= uint64_t(1024 >> 4) << 32;
+            dv |= uint64_t(1) << 46;
+            dv |= uint64_t(2) << 61;
+            const uint32_t pa = region + uint32_t(buf * kSBufCols);
+            const bool last_blk = p_j == nb - 1, last_tile = p_t + 2 >= nq;
+            if (ptx::elect_one()) {
+              for (int i = 0; i < u; ++i)
+                umma_f16_ts(region + kOCol, pa + uint32_t(8 * i), dv + uint64_t(i * 128), idesc_o, (p_j | i) != 0 ? 1u : 0u);
+              ptx::umma_commit<1>(pv_done(g, buf));
+              if (last_blk) {
+                ptx::umma_commit<1>(o_full(g));
+                if (last_tile) ptx::umma_commit<1>(kv_empty(stage));   // this group's share of the item's K/V reads
+              }
             }
-            s.st = 1;
+            __syncwarp();
+            ++p_k;
+            if (last_blk) {
+              ++p_tiles;
+              p_j = 0;
+              p_t += 2;
+              if (p_t >= nq) { p_t = g; ++p_n; }
+            } else {
+              ++p_j;
+            }
             progress = true;
-          } else {
-            if (!ptx::mbar_test_wait(sm_done(g), s.smd_cnt & 1u)) continue;
-            if (s.pass == 0) {
-              // the group has taken the block's row maxima: next block (or start pass B)
-              ++s.smd_cnt;
-              if (++s.j == nb) { s.pass = 1; s.j = 0; }
-              s.st = 0;
-              progress = true;
-              continue;
-            }
-            // ---- O (+)= P_j V_j ----
-            if (!ptx::mbar_test_wait(v_full(stage), kv_par)) continue;
-            if (s.j == 0 && s.o_cnt > 0 && !ptx::mbar_test_wait(o_free(g), (s.o_cnt - 1u) & 1u)) continue;
-            ++s.smd_cnt;
+          }
+        }
+        // ---- S = Q K_j^T of the next op ----
+        if (s_k < total_ops && s_k < p_k + 2u) {
+          const int buf = int(s_k & 1u), stage = s_n % prm.kv_stages, slot = int(s_tiles & 1u);
+          bool ready = true;
+          if (s_j == 0)
+            ready = ptx::mbar_test_wait(q_full(g, slot), (s_tiles >> 1) & 1u) &&
+                    ptx::mbar_test_wait(k_full(stage), uint32_t(s_n / prm.kv_stages) & 1u);
+          if (__all_sync(0xffffffffu, ready)) {
             ptx::tcgen05_fence_after();
-            const int n_kstep = Nj >> 4;
-            for (int k = 0; k < n_kstep; ++k) {
-              // V rows are keys: 16 keys per K-step = 2048 bytes further down the [key][64 dims] tile (MN-major operand,
-              // 128B swizzle: 8-key groups 1024 bytes apart (SBO), one 64-wide atom along N (LBO unused))
-              uint64_t dv = uint64_t(((vs + uint32_t(s.j * Nb) * 128u + uint32_t(k) * 2048u) >> 4) & 0x3FFFu);
-              dv |= uint64_t(1) << 16;
-              dv |= uint64_t(1024 >> 4) << 32;
-              dv |= uint64_t(1) << 46;
-              dv |= uint64_t(2) << 61;
-              umma_f16_ts(region + kOCol, region + uint32_t(8 * k), dv, idesc_o, (s.j | k) != 0 ? 1u : 0u);
+            const uint32_t ks = kv_s + uint32_t(stage) * 2u * uint32_t(prm.kv_bytes);
+            const int u = blk_units(s_j), u0 = blk_start(s_j);
+            const uint64_t dq = ptx::make_kmajor_sw128_desc(q_s + uint32_t(2 * g + slot) * kQTileBytes);
+            const uint64_t dk = ptx::make_kmajor_sw128_desc(ks + uint32_t(u0) * 2048u);
+            const uint32_t id = idesc(128, uint32_t(16 * u), kF16, false);
+            const bool last_blk = s_j == nb - 1;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16<1>(region + uint32_t(buf * kSBufCols), dq + uint64_t(2 * kk), dk + uint64_t(2 * kk), id, kk != 0 ? 1u : 0u);
+              ptx::umma_commit<1>(s_full(g, buf));
+              if (last_blk) ptx::umma_commit<1>(q_empty(g, slot));   // last product that reads this Q tile
             }
-            if (s.j == nb - 1) {
-              ptx::umma_commit<1>(o_full(g));
-              ++s.o_cnt;
-              if (++tiles_done[stage] == nq) {   // every product that reads this item's K/V has been issued
-                ptx::umma_commit<1>(kv_empty(stage));
-                tiles_done[stage] = 0;
-              }
-            }
-            s.st = 0;
-            if (++s.j == nb) {
-              s.j = 0;
-              s.pass = first_pass;
-              s.t += 2;
-              if (s.t >= nq) {
-                s.t = g;
-                if (++s.n >= n_items) s.active = false;
-              }
+            __syncwarp();
+            ++s_k;
+            if (last_blk) {
+              ++s_tiles;
+              s_j = 0;
+              s_t += 2;
+              if (s_t >= nq) { s_t = g; ++s_n; }
+            } else {
+              ++s_j;
             }
             progress = true;
           }
@@ -321,138 +440,87 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (progress) {
           t_last = clock64();
         } else if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
-          printf("iic: attention MMA scheduler stalled (block %d)\n", int(blockIdx.x));
+          if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
           __trap();
         }
       }
     }
-    __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
     // ======================= softmax / output: one thread per query row =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int g = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                 // row inside the 128-row query tile
     const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(g * kRegionCols);
     const float c = prm.scale_log2e;
-    const uint64_t c2 = pack2(c, c);
-    uint32_t s_cnt = 0, o_cnt = 0;
+    uint32_t k = 0, o_cnt = 0;   // ops / tiles processed by this group so far
+#ifdef IIC_ATTN_PROF
+    long long pf_ws = 0, pf_wo = 0, pf_cmp = 0, pf_epi = 0;
+    const long long pf_t0 = clock64();
+#endif
     if (g < nq) {
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / H, h = item - b * H;
         for (int t = g; t < nq; t += 2) {
           const bool warp_live = t * 128 + quad * 32 < T;   // warps whose 32 query rows are all padding do no math
-          float m = -INFINITY;
-          uint32_t va[32], vb[32];
-          // ---------------- pass A: row maximum over all key blocks ----------------
-          if (nb > 1) {
-            for (int j = 0; j < nb; ++j) {
-              ptx::mbar_wait(s_full(g), s_cnt & 1u);
-              ++s_cnt;
-              ptx::tcgen05_fence_after();
-              if (warp_live) {
-                const int Nj = min(Nb, TP - j * Nb), valid = min(Nj, T - j * Nb);
-                const int n_ch = (Nj + 31) >> 5;
-                ptx::tmem_ld_32x32b_x32(taddr, va);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int ch = 0; ch < 6; ch += 2) {
-                  if (ch < n_ch) {
-                    if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
-                    m = chunk_max(va, valid - ch * 32, m);
-                    ptx::tmem_ld_wait();
-                  }
-                  if (ch + 1 < n_ch) {
-                    if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
-                    m = chunk_max(vb, valid - (ch + 1) * 32, m);
-                    ptx::tmem_ld_wait();
-                  }
-                }
-              }
-              ptx::tcgen05_fence_before();
-              ptx::mbar_arrive(sm_done(g));
-            }
-          }
-          // ---------------- pass B: P = exp2(S*c - m*c) in place, row sum ----------------
-          uint64_t acc0 = 0ull, acc1 = 0ull;   // packed partial row sums (0.0f bit patterns)
-          float mc = m * c;
-          for (int j = 0; j < nb; ++j) {
-            ptx::mbar_wait(s_full(g), s_cnt & 1u);
-            ++s_cnt;
+          SoftmaxRow st;
+          st.m = 0.f;
+          st.acc0 = 0ull;
+          st.acc1 = 0ull;
+          for (int j = 0; j < nb; ++j, ++k) {
+            const int buf = int(k & 1u);
+            const uint32_t sb = taddr + uint32_t(buf * kSBufCols);
+#ifdef IIC_ATTN_PROF
+            const long long pf_a = clock64();
+#endif
+            ptx::mbar_wait(s_full(g, buf), (k >> 1) & 1u);
+#ifdef IIC_ATTN_PROF
+            const long long pf_b = clock64();
+            pf_ws += pf_b - pf_a;
+#endif
             ptx::tcgen05_fence_after();
             if (warp_live) {
-              const int Nj = min(Nb, TP - j * Nb), valid = min(Nj, T - j * Nb);
-              const int n_ch = (Nj + 31) >> 5;
-              if (nb == 1) {
-                ptx::tmem_ld_32x32b_x32(taddr, va);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int ch = 0; ch < 8; ch += 2) {
-                  if (ch < n_ch) {
-                    if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
-                    m = chunk_max(va, valid - ch * 32, m);
-                    ptx::tmem_ld_wait();
-                  }
-                  if (ch + 1 < n_ch) {
-                    if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
-                    m = chunk_max(vb, valid - (ch + 1) * 32, m);
-                    ptx::tmem_ld_wait();
-                  }
-                }
-                mc = m * c;
+              const int u = blk_units(j);
+              // real keys in the block's last unit (16: no masking)
+              const int tail = min(16, T - 16 * (blk_start(j) + u - 1));
+              const uint32_t pv_bar = pv_done(g, buf ^ 1), pv_par = ((k - 1u) >> 1) & 1u;
+              const uint32_t o_addr = taddr + uint32_t(kOCol);
+              switch (u) {
+                case 1: softmax_block<kF16, 1>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                case 2: softmax_block<kF16, 2>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                case 3: softmax_block<kF16, 3>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                case 4: softmax_block<kF16, 4>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                case 5: softmax_block<kF16, 5>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                default: softmax_block<kF16, 6>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
               }
-              const uint64_t nmc2 = pack2(-mc, -mc);
-              auto emit = [&](const uint32_t (&v)[32], int ch) {
-                uint32_t pk[16];
-                const int vl = valid - ch * 32;
-                if (vl >= 32) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    float x0, x1;
-                    unpack2(fma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, nmc2), x0, x1);
-                    const float e0 = ex2(x0), e1 = ex2(x1);
-                    if (i & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
-                    pk[i] = Act<kF16>::pack(e0, e1);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    float e0 = ex2(fmaf(__uint_as_float(v[2 * i]), c, -mc)), e1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-                    e0 = 2 * i < vl ? e0 : 0.f;
-                    e1 = 2 * i + 1 < vl ? e1 : 0.f;
-                    acc0 = add2(acc0, pack2(e0, e1));
-                    pk[i] = Act<kF16>::pack(e0, e1);
-                  }
-                }
-                tmem_st16(taddr + uint32_t(ch * 16), pk);   // always behind the S columns still to be read
-              };
-              ptx::tmem_ld_32x32b_x32(taddr, va);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int ch = 0; ch < 8; ch += 2) {
-                if (ch < n_ch) {
-                  if (ch + 1 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 1) * 32), vb);
-                  emit(va, ch);
-                  ptx::tmem_ld_wait();
-                }
-                if (ch + 1 < n_ch) {
-                  if (ch + 2 < n_ch) ptx::tmem_ld_32x32b_x32(taddr + uint32_t((ch + 2) * 32), va);
-                  emit(vb, ch + 1);
-                  ptx::tmem_ld_wait();
-                }
-              }
-              tmem_st_wait();
             }
             ptx::tcgen05_fence_before();
-            ptx::mbar_arrive(sm_done(g));
+            ptx::mbar_arrive(sm_done(g, buf));
+#ifdef IIC_ATTN_PROF
+            pf_cmp += clock64() - pf_b;
+#endif
           }
+          const float m = st.m;
+          const uint64_t acc0 = st.acc0, acc1 = st.acc1;
+          uint32_t v[64];
           // ---------------- O row ----------------
+#ifdef IIC_ATTN_PROF
+          const long long pf_c = clock64();
+#endif
           ptx::mbar_wait(o_full(g), o_cnt & 1u);
+#ifdef IIC_ATTN_PROF
+          const long long pf_d = clock64();
+          pf_wo += pf_d - pf_c;
+#endif
           ++o_cnt;
           ptx::tcgen05_fence_after();
           const int q = t * 128 + r;
           if (warp_live) {
-            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(kOCol), va);
-            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(kOCol + 32), vb);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              tmem_ld16_at(taddr + uint32_t(kOCol + 16 * cc), v, 16 * cc);
+            }
             ptx::tmem_ld_wait();
           }
           ptx::tcgen05_fence_before();
@@ -465,26 +533,30 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             const float inv = 1.0f / sum;
             const uint64_t inv2 = pack2(inv, inv);
             uint16_t* orow = prm.out + (size_t(b) * T + q) * d + h * kHd;
-            auto store32 = [&](const uint32_t (&v)[32], int off) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                uint32_t w[4];
+            for (int jj = 0; jj < 8; ++jj) {
+              uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float x0, x1;
-                  unpack2(mul2f(pack2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1])), inv2), x0, x1);
-                  w[e] = Act<kF16>::pack(x0, x1);
-                }
-                *reinterpret_cast<uint4*>(orow + off + 8 * jj) = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int e = 0; e < 4; ++e) {
+                float x0, x1;
+                unpack2(mul2f(pack2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1])), inv2), x0, x1);
+                w[e] = Act<kF16>::pack(x0, x1);
               }
-            };
-            store32(va, 0);
-            store32(vb, 32);
-            if (prm.lse != nullptr) prm.lse[(size_t(b) * H + h) * T + q] = mc + log2f(sum);
+              *reinterpret_cast<uint4*>(orow + 8 * jj) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (prm.lse != nullptr) prm.lse[(size_t(b) * H + h) * T + q] = m + log2f(sum);
           }
+#ifdef IIC_ATTN_PROF
+          pf_epi += clock64() - pf_d;
+#endif
         }
       }
     }
+#ifdef IIC_ATTN_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("attn prof softmax warp %d: total %lld | wait S %lld | block math %lld | wait O %lld | epilogue %lld\n", warp,
+             clock64() - pf_t0, pf_ws, pf_cmp, pf_wo, pf_epi);
+#endif
   }
 
   ptx::tcgen05_fence_before();
@@ -524,16 +596,21 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   if (head_dim != kHd || T < 1) return -3;
   AttnParams p;
   p.TP = (T + 15) / 16 * 16;
-  if (p.TP <= 256) {
-    p.nb = 1;
-    p.Nb = p.TP;
-  } else {
-    p.nb = (p.TP + kOCol - 1) / kOCol;
-    p.Nb = ((p.TP + p.nb - 1) / p.nb + 15) / 16 * 16;
-    p.nb = (p.TP + p.Nb - 1) / p.Nb;
+  const int units = p.TP / 16;
+  p.nb = (units + kMaxUnits - 1) / kMaxUnits;
+  p.bq = units / p.nb;
+  p.brem = units % p.nb;
+  // K/V arrive in TMA boxes of 16*dd rows; pick the box (<= 256 rows) that overshoots TP the least
+  int best_d = 1, best_rows = 1 << 30;
+  for (int dd = 16; dd >= 4; --dd) {
+    const int rows = (units + dd - 1) / dd * dd;
+    if (rows < best_rows) { best_rows = rows; best_d = dd; }
   }
-  p.kv_bytes = p.nb * p.Nb * 128;
-  const int fixed = 2 * kQTileBytes + kBarBytes + 1024 /*alignment slack*/;
+  if (units <= 16) { best_d = units; best_rows = units; }
+  p.kv_box = 16 * best_d;
+  p.kv_loads = best_rows / best_d;
+  p.kv_bytes = best_rows * 16 * 128;
+  const int fixed = 4 * kQTileBytes + kBarBytes + 1024 /*alignment slack*/;
   if (fixed + 2 * p.kv_bytes > kMaxSmem) return -3;
   p.kv_stages = fixed + 4 * p.kv_bytes <= kMaxSmem ? 2 : 1;
   const int smem = fixed + p.kv_stages * 2 * p.kv_bytes;
@@ -547,7 +624,7 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   const int d = H * kHd;
   CUtensorMap tq, tkv;
   const uint64_t rows = uint64_t(B) * T;
-  if (!make_map(&tq, qkv, rows, uint64_t(3 * d), 128, f16 != 0) || !make_map(&tkv, qkv, rows, uint64_t(3 * d), uint32_t(p.Nb), f16 != 0))
+  if (!make_map(&tq, qkv, rows, uint64_t(3 * d), 128, f16 != 0) || !make_map(&tkv, qkv, rows, uint64_t(3 * d), uint32_t(p.kv_box), f16 != 0))
     return -1;
   static bool attr_done = false;
   if (!attr_done) {

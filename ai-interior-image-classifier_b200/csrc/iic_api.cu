@@ -369,7 +369,7 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
       return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
     }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, nullptr, nullptr, kEpiBiasBf16, b.b_qkv, nullptr, t.qkv, 3 * d, 1, s));
-    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention(t.qkv, t.attn, t.lse, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, t.qkv, t.attn, t.lse, B, T, H, d / H, 0, s); }));
     IIC_TRY(run_gemm(h, t.attn, d, b.w_out, M, d, d, nullptr, nullptr, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     if (cudaMemcpyAsync(t.x_mid, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
@@ -814,7 +814,7 @@ int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* 
   if (!h || !qkv || !out || !d_out || !dqkv || !lse_scratch) return fail(h, IIC_ERR_ARG, "iic_op_attention_bwd: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // recompute the forward into `out`'s twin to obtain the log-sum-exp (op-level test helper)
-  int rc = launch_attention(qkv, out, lse_scratch, B, T, heads, 64, h->f16, s);
+  int rc = run_attention(h, qkv, out, lse_scratch, B, T, heads, 64, 0, s);
   if (rc == 0) rc = launch_attention_bwd(qkv, out, d_out, lse_scratch, dqkv, B, T, heads, 64, h->f16, s);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention backward: unsupported shape (T <= 432) or launch failure");
   return IIC_OK;

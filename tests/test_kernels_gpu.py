@@ -157,7 +157,7 @@ def test_layernorm(engine, D):
 
 
 @pytest.mark.parametrize("impl", [1, 2], ids=["mma_sync", "tcgen05"])
-@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12), (197, 40, 12), (256, 2, 12), (129, 1, 12), (257, 3, 12), (577, 20, 16), (730, 1, 4), (1, 2, 12)])
+@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (577, 2, 16), (50, 2, 12), (16, 1, 12), (197, 40, 12), (256, 2, 12), (129, 1, 12), (257, 3, 12), (577, 20, 16), (640, 1, 4), (1, 2, 12)])
 def test_attention(engine, T, B, H, impl):
     d = H * 64
     g = torch.Generator(device="cuda").manual_seed(6)
@@ -167,6 +167,25 @@ def test_attention(engine, T, B, H, impl):
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v)  # fp32 math
     ref = ref.permute(0, 2, 1, 3).reshape(B * T, d)
     # P is rounded to bf16 before the PV product and the output is bf16: 2^-8 relative on values O(1)
+    assert torch.allclose(out.float(), ref, rtol=2 ** -6, atol=2e-2), (out.float() - ref).abs().max()
+    assert _rel(out.float(), ref) < 8e-3
+
+
+@pytest.mark.parametrize("T,B,H", [(197, 2, 12), (577, 1, 16)])
+def test_attention_rising_scores(engine, T, B, H):
+    """Scores that grow along the key axis force the tcgen05 kernel's running maximum to move in every key block
+    (the O / row-sum rescale path); a flat tail checks that the lazy maximum (left alone below 2^8) stays exact."""
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(16)
+    qkv = torch.randn(B, T, 3, H, 64, device="cuda", generator=g)
+    ramp = torch.arange(T, device="cuda", dtype=torch.float32)
+    qkv[:, :, 0, :, 0] = 4.0                                     # q[..., 0]
+    qkv[:, :, 1, 0::2, 0] = (0.2 * ramp)[None, :, None]          # even heads: steadily rising scores
+    qkv[:, :, 1, 1::2, 0] = (0.05 * ramp.clamp(max=T // 2))[None, :, None]   # odd heads: slow rise, then flat
+    qkv = _bf16(qkv.reshape(B * T, 3 * d))
+    out = engine.op_attention(qkv, B, T, H, impl=2)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, d)
     assert torch.allclose(out.float(), ref, rtol=2 ** -6, atol=2e-2), (out.float() - ref).abs().max()
     assert _rel(out.float(), ref) < 8e-3
 
