@@ -100,11 +100,11 @@ size_t gemm_smem_bytes(int ctas) {
 }
 
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err) {
-  static const char* e_shape = "gemm: unsupported shape (need M,N,K > 0, N % 32 == 0, pitches % 8 == 0)";
+  static const char* e_shape = "gemm: unsupported shape (need M,N,K > 0, N % 32 == 0 (N % 8 without bias), pitches % 8 == 0)";
   static const char* e_map = "gemm: cuTensorMapEncodeTiled failed (driver entry point missing or bad pointer/pitch)";
   static const char* e_launch = "gemm: kernel launch failed";
   static const char* e_lora = "gemm: LoRA rank pad must be a multiple of 16 and <= 64";
-  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.N % 32 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldc % 8 != 0 ||
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.N % (p.bias != nullptr ? 32 : 8) != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0 || p.ldc % 8 != 0 ||
       (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) {
     if (err) *err = e_shape;
     return -1;

@@ -33,6 +33,9 @@ struct LoraSlot {
   float scaling = 1.f;
   float* grad_a = nullptr;           // f32 [in, rank]   d(loss)/d(lora_A)
   float* grad_b = nullptr;           // f32 [rank, out]  d(loss)/d(lora_B)
+  // rank > 4: the down-projections run on the tcgen05 GEMM (N = lora_pad) with 16-bit operands (iic_set_lora_operands16)
+  const void* at16 = nullptr;        // 16-bit [lora_pad, in]  = (scaling * lora_A)^T, zero-padded rows
+  const void* b16 = nullptr;         // 16-bit [lora_pad, out] = lora_B, zero-padded rows (training: dP = dY . B^T)
 };
 
 struct Block {
@@ -164,7 +167,8 @@ int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, 
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
              const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
-             int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr) {
+             int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr,
+             int prof_class = kGemm) {
   GemmProblem g;
   g.down_a = down_a;
   g.down_part = down_part;
@@ -181,9 +185,16 @@ int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N,
   const int d_ = h->cfg.width, mlp_ = h->cfg.mlp_dim;
   const int sub = (epi == kEpiPosF32) ? kGemmOther : (N == 3 * d_ && K == d_) ? kGemmQkv : (N == d_ && K == d_) ? kGemmOut
                   : (N == mlp_ && K == d_) ? kGemmFc : (N == d_ && K == mlp_) ? kGemmProj : kGemmOther;
-  Scope sc(h->prof, kGemm, s);
-  Scope sc2(h->prof, sub, s);
-  int rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
+  // the skinny LoRA down-projection GEMMs are booked under their own class, not under the encoder GEMMs
+  int rc;
+  if (prof_class == kGemm) {
+    Scope sc(h->prof, kGemm, s);
+    Scope sc2(h->prof, sub, s);
+    rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
+  } else {
+    Scope sc(h->prof, prof_class, s);
+    rc = launch_gemm(g, h->ctas, h->num_sms, s, &e);
+  }
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
   return 0;
 }
@@ -192,6 +203,16 @@ template <class F>
 int timed(iic_handle* h, int cls, cudaStream_t s, F&& f) {
   Scope sc(h->prof, cls, s);
   return f();
+}
+
+// P[M, lora_pad] (16-bit) = x[M, K] . A  for one LoRA slot: rank <= 4 -> the fp32-A row kernel; larger ranks -> the tcgen05
+// GEMM with N = lora_pad and the 16-bit transposed operand w16 [lora_pad, K] (memory-bound on reading x either way).
+int run_lora_down(iic_handle* h, const void* x, int K, int M, const float* a32, const void* w16, int r4, void* p_out,
+                  cudaStream_t s) {
+  if (r4 > 4 && w16 != nullptr)
+    return run_gemm(h, x, K, w16, M, h->lora_pad, K, nullptr, nullptr, kEpiBiasBf16, nullptr, nullptr, p_out, h->lora_pad, 1, s,
+                    nullptr, nullptr, kLoraDown);
+  return timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(x, K, M, a32, r4, p_out, h->lora_pad, h->f16, s); });
 }
 
 #define IIC_TRY(expr)                                                  \
@@ -223,22 +244,24 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
     const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     // x = x + attn(ln_1(x))
+    // LoRA down-projections of rank <= 4 ride inside the LayerNorm kernel; larger ranks go through the GEMM (run_lora_down)
+    const bool in_gemm = l_in.rank > 0 && l_in.r4 > 4 && l_in.at16 != nullptr;
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, l_in.rank ? l_in.a : nullptr,
+      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, (l_in.rank && !in_gemm) ? l_in.a : nullptr,
                               l_in.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
+    if (in_gemm) IIC_TRY(run_lora_down(h, w.xln, d, M, l_in.a, l_in.at16, l_in.r4, w.p_a, s));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
     IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, w.qkv, w.attn, nullptr, B, T, H, d / H, 0, s); }));
-    if (l_out.rank)
-      IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_down_bf16(w.attn, d, M, l_out.a, l_out.r4, w.p_b, h->lora_pad, h->f16, s);
-      }));
+    if (l_out.rank) IIC_TRY(run_lora_down(h, w.attn, d, M, l_out.a, l_out.at16, l_out.r4, w.p_b, s));
     IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
+    const bool fc_gemm = l_fc.rank > 0 && l_fc.r4 > 4 && l_fc.at16 != nullptr;
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr,
+      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
                               l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
     }));
+    if (fc_gemm) IIC_TRY(run_lora_down(h, w.xln, d, M, l_fc.a, l_fc.at16, l_fc.r4, w.p_a, s));
     // c_proj's LoRA down-projection (h . A2) rides in the c_fc epilogue while h is still in registers (rank <= 4)
     const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
     IIC_TRY(run_gemm(h, w.xln, d, b.w_fc, M, mlp, d, &l_fc, w.p_a, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
@@ -248,9 +271,7 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
         return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, w.p_b, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
-      IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, w.p_b, h->lora_pad, h->f16, s);
-      }));
+      IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, w.p_b, s));
     IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
   }
   return 0;
@@ -372,10 +393,12 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
     IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, t.qkv, t.attn, t.lse, B, T, H, d / H, 0, s); }));
     IIC_TRY(run_gemm(h, t.attn, d, b.w_out, M, d, d, nullptr, nullptr, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     if (cudaMemcpyAsync(t.x_mid, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
+    const bool fc_gemm = l_fc.rank > 0 && l_fc.r4 > 4 && l_fc.at16 != nullptr;
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, t.y2, nullptr, d, M, d, eps, l_fc.rank ? l_fc.a : nullptr, l_fc.r4,
-                              t.p1, h->lora_pad, h->f16, s);
+      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, t.y2, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
+                              l_fc.r4, t.p1, h->lora_pad, h->f16, s);
     }));
+    if (fc_gemm) IIC_TRY(run_lora_down(h, t.y2, d, M, l_fc.a, l_fc.at16, l_fc.r4, t.p1, s));
     const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
     IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
                      fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
@@ -384,9 +407,7 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
         return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, t.p2, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
-      IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_down_bf16(w.hid, mlp, M, l_pr.a, l_pr.r4, t.p2, h->lora_pad, h->f16, s);
-      }));
+      IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, t.p2, s));
     IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, t.p2, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
   }
   // class-token rows of the final residual stream (input of ln_post), [B, d] contiguous
@@ -417,7 +438,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     // ---- c_proj:  x_out = x_mid + h W2^T + b2 + P2 B2   (P2 = s2 h A2) ----
     LoraSlot bw_pr;   // LoRA k-step of the dX GEMM: dh += dP2 . (s2 A2)^T
     if (l_pr.rank) {
-      IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.g16, d, M, l_pr.bt32, l_pr.r4, w.dp2, h->lora_pad, h->f16, s); }));
+      IIC_TRY(run_lora_down(h, w.g16, d, M, l_pr.bt32, l_pr.b16, l_pr.r4, w.dp2, s));   // dP2 = dY . B2^T
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, h->f16, s);
       }));
@@ -434,7 +455,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     // ---- c_fc:  u = y2 W1^T + b1 + P1 B1   (P1 = s1 y2 A1) ----
     LoraSlot bw_fc;
     if (l_fc.rank) {
-      IIC_TRY(timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(w.dh, mlp, M, l_fc.bt32, l_fc.r4, w.dp1, h->lora_pad, h->f16, s); }));
+      IIC_TRY(run_lora_down(h, w.dh, mlp, M, l_fc.bt32, l_fc.b16, l_fc.r4, w.dp1, s));   // dP1 = dU . B1^T
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, h->f16, s);
       }));
@@ -598,6 +619,19 @@ int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, con
   s.rank = rank;
   s.r4 = (rank + 3) / 4 * 4;
   s.r_pad = (rank + 15) / 16 * 16;
+  return IIC_OK;
+}
+
+int iic_set_lora_operands16(iic_handle* h, int layer, int which, const void* a_t16, const void* b16) {
+  if (!h) return IIC_ERR_ARG;
+  if (layer < 0 || layer >= int(h->blocks.size()) || which < 0 || which > 3)
+    return fail(h, IIC_ERR_ARG, "iic_set_lora_operands16: bad layer / projection id");
+  LoraSlot& s = h->blocks[layer].lora[which];
+  if (s.rank <= 0) return fail(h, IIC_ERR_STATE, "iic_set_lora_operands16: call iic_set_lora for this slot first");
+  if ((reinterpret_cast<uintptr_t>(a_t16) & 15) || (reinterpret_cast<uintptr_t>(b16) & 15))
+    return fail(h, IIC_ERR_ARG, "iic_set_lora_operands16: unaligned pointer");
+  s.at16 = a_t16;
+  s.b16 = b16;
   return IIC_OK;
 }
 

@@ -173,6 +173,13 @@ class Engine:
             bt[:, :r] = lora_b.detach().to(self.device, torch.float32).t().to(self.op_dtype)
             L.check(self.h, self.lib.iic_set_lora(self.h, layer, which, a.data_ptr(), bt.data_ptr(), r), "iic_set_lora")
             self._lora[(layer, which)] = (a, bt)
+            if r > 4:
+                # ranks above 4: the down-projection x . A runs on the tcgen05 GEMM and wants (s A)^T in the operand format
+                at16 = torch.zeros(pad, lora_a.shape[0], device=self.device, dtype=self.op_dtype)
+                at16[:r] = a[:, :r].t().to(self.op_dtype)
+                L.check(self.h, self.lib.iic_set_lora_operands16(self.h, layer, which, at16.data_ptr(), None),
+                        "iic_set_lora_operands16")
+                self._lora[(layer, which)] = (a, bt, at16)
 
     def set_labels(self, text_features: torch.Tensor, group_sizes: Sequence[int],
                    group_split: Optional[Sequence[int]] = None, topk: int = 5, logit_scale: float = 100.0) -> None:
@@ -337,6 +344,13 @@ class Engine:
             L.check(self.h, self.lib.iic_set_lora_train(self.h, layer, which, a16.data_ptr(), bt32.data_ptr(), float(scaling),
                                                         grad_a.data_ptr(), grad_b.data_ptr()), "iic_set_lora_train")
             self._lora[(layer, which, "train")] = (a16, bt32, grad_a, grad_b)
+            if r > 4:
+                at16 = self._lora[(layer, which)][2]
+                b16 = torch.zeros(self.dims.lora_pad, lora_b.shape[1], device=self.device, dtype=self.op_dtype)
+                b16[:r] = lora_b.detach().to(self.device, torch.float32).to(self.op_dtype)
+                L.check(self.h, self.lib.iic_set_lora_operands16(self.h, layer, which, at16.data_ptr(), b16.data_ptr()),
+                        "iic_set_lora_operands16")
+                self._lora[(layer, which, "train16")] = (b16,)
 
     def _train_ws(self, B: int) -> torch.Tensor:
         need = int(self.lib.iic_train_workspace_bytes(self.h, B))

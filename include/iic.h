@@ -106,6 +106,13 @@ int iic_load_weight(iic_handle* h, const char* name, const void* dev_ptr, int dt
  * Passing rank == 0 clears the slot.  A cleared slot costs nothing. */
 int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, const void* b_t, int rank);
 
+/* Optional 16-bit operands of one LoRA slot (after iic_set_lora), needed for ranks > 4: the down-projections
+ * P = s (x . A) (forward) and dP = dY . B^T (training backward) then run on the tcgen05 GEMM with N = lora_pad instead of
+ * the fp32-A row kernels.  a_t16: 16-bit [lora_pad, in] = (scaling * lora_A)^T, b16: 16-bit [lora_pad, out] = lora_B
+ * (rows >= rank zero; b16 may be NULL for inference).  Borrowed device pointers.
+ * Replaces: `x @ self.lora_A` of LoRALayer.forward (/root/reference/main.py:31, train_lora.py:28) for rank-16 adapters. */
+int iic_set_lora_operands16(iic_handle* h, int layer, int which, const void* a_t16, const void* b16);
+
 /* Label text embeddings the head scores against (reference: text_features_cache, main.py:296-311 and
  * detector text_features, main.py:179-182): text f32 [L, embed_dim], rows L2-normalised by the caller exactly as
  * the reference does.  group_offsets (host, G+1 ints) partitions the L labels into softmax groups;
