@@ -2,6 +2,7 @@
 Usage: ncu_lines.py rep object.o kernel_substr [topn]"""
 import csv, collections, os, re, subprocess, sys, tempfile
 rep, obj, ksub = sys.argv[1:4]; topn = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+skip = sys.argv[5] if len(sys.argv) > 5 else "0"   # which launch inside the report
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -19,6 +20,11 @@ for l in dis.splitlines():
         line_of.append(cur)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
+# one section per profiled launch: ["Kernel Name", name], header row, instruction rows
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sel = int(skip)
+print("launches in report:", [rows[i][1][:60] for i in starts], "-> using", sel)
+rows = rows[starts[sel]:(starts[sel + 1] if sel + 1 < len(starts) else len(rows))]
 h = rows[1]; iN = h.index("# Samples"); iI = h.index("Instructions Executed"); iS = h.index("Source")
 stall_cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
 ins = [r for r in rows[2:] if len(r) > iI]

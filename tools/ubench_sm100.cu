@@ -79,6 +79,49 @@ __global__ void __launch_bounds__(256, 1) k_mufu(long long* out, float* sink, in
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[warp] = t1 - t0;
 }
 
+template <int OP>
+__global__ void __launch_bounds__(256, 1) k_mufu_op(long long* out, float* sink, int iters, int nwarps) {
+  const int warp = threadIdx.x >> 5;
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = 0.37f + 0.001f * (threadIdx.x + j);
+  long long t0 = clock64();
+  if (warp < nwarps)
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (OP == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(x[j]));
+        if (OP == 1) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[j]));
+      }
+    }
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += x[j];
+  if (s == 1.2345f) sink[0] = s;
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[warp] = t1 - t0;
+}
+
+// accuracy of two QuickGELU formulations against double precision: out[0] = max abs err (ex2+rcp), out[1] = max abs err (tanh),
+// out[2], out[3] = the same relative to max(|h|, 2^-6)
+__global__ void k_gelu_acc(float* out) {
+  const float x = -12.f + 24.f * (blockIdx.x * blockDim.x + threadIdx.x) / float(gridDim.x * blockDim.x);
+  const double ref = double(x) / (1.0 + exp(-1.702 * double(x)));
+  float e, r, t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  const float h0 = x * r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float hx = 0.5f * x;
+  const float h1 = fmaf(hx, t, hx);
+  const float e0 = fabsf(float(double(h0) - ref)), e1 = fabsf(float(double(h1) - ref));
+  const float den = fmaxf(fabsf(float(ref)), 0.015625f);
+  atomicMax(reinterpret_cast<int*>(out + 0), __float_as_int(e0));
+  atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(e1));
+  atomicMax(reinterpret_cast<int*>(out + 2), __float_as_int(e0 / den));
+  atomicMax(reinterpret_cast<int*>(out + 3), __float_as_int(e1 / den));
+}
+
 __global__ void __launch_bounds__(256, 1) k_fma2(long long* out, float* sink, int iters, int nwarps, int packed) {
   const int warp = threadIdx.x >> 5;
   float2 x[16];
@@ -129,6 +172,22 @@ int main() {
     cudaDeviceSynchronize();
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     printf("mufu.ex2 warps %d: %.2f clk per warp-inst, %.1f lanes/clk/SM\n", nw, double(h[0]) / (iters * 16.0), nw * iters * 16.0 * 32 / double(h[0]));
+  }
+  for (int nw : {4, 8}) {
+    k_mufu_op<0><<<148, 256>>>(d, sink, iters, nw);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("mufu.tanh warps %d: %.2f clk per warp-inst\n", nw, double(h[0]) / (iters * 16.0));
+    k_mufu_op<1><<<148, 256>>>(d, sink, iters, nw);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("mufu.rcp  warps %d: %.2f clk per warp-inst\n", nw, double(h[0]) / (iters * 16.0));
+  }
+  {
+    float* acc; cudaMalloc(&acc, 16); cudaMemset(acc, 0, 16);
+    k_gelu_acc<<<4096, 256>>>(acc);
+    float ha[4]; cudaMemcpy(ha, acc, 16, cudaMemcpyDeviceToHost);
+    printf("quickgelu max abs err: ex2+rcp %.3e  tanh %.3e | rel to max(|h|,2^-6): ex2+rcp %.3e  tanh %.3e\n", ha[0], ha[1], ha[2], ha[3]);
   }
   for (int packed = 0; packed < 2; ++packed)
     for (int nw : {4, 8}) {
