@@ -5,11 +5,11 @@
 //
 // One persistent CTA per SM walks (image, head) items; K and V of the item are resident in 128B-swizzled smem (two items
 // in flight when they fit).  The queries form 128-row tiles; two softmax groups (4 warps each) take alternate tiles.
-// The keys are cut into nb blocks of <= 96 (a multiple of 16 each), and per (tile, block) "op":
+// The keys are cut into nb blocks of <= 80 (a multiple of 16 each), and per (tile, block) "op":
 //
-//   S = Q K_j^T            tcgen05.mma, fp32 accumulator in one of the group's TWO 96-column S buffers in TMEM, so the
+//   S = Q K_j^T            tcgen05.mma, fp32 accumulator in one of the group's TWO 80-column S buffers in TMEM, so the
 //                          tensor core always runs one or two ops AHEAD of the softmax (also across tiles and items).
-//   softmax                ONE THREAD PER QUERY ROW: tcgen05.ld 32x32b hands a thread its own row of the block (<= 96
+//   softmax                ONE THREAD PER QUERY ROW: tcgen05.ld 32x32b hands a thread its own row of the block (<= 80
 //                          registers), so max and sum are thread-local: no shuffles, S is read from TMEM exactly once.
 //                          Online softmax with a LAZY running maximum: m only moves when a block exceeds it by more than
 //                          2^8 (then O and the row sum are rescaled, a rare path taken warp-uniformly); otherwise
@@ -44,9 +44,7 @@ namespace {
 constexpr int kHd = 64;
 constexpr int kThreads = 384;
 constexpr int kQTileBytes = 128 * 128;   // 128 query rows x 64 dims x 2 B
-constexpr int kRegionCols = 256;         // TMEM columns per softmax group: S buffers [0,96) [96,192), O [192,256)
-constexpr int kSBufCols = 96;
-constexpr int kMaxUnits = kSBufCols / 16;
+constexpr int kRegionCols = 256;         // TMEM columns per softmax group: S buffers [0,80) [80,160), O [192,256)
 constexpr int kOCol = 192;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBarBytes = 512;
@@ -64,6 +62,7 @@ struct AttnParams {
   int kv_bytes;      // bytes of one K (or V) buffer (TMA boxes may overshoot TP rows)
   int kv_box, kv_loads;
   float scale_log2e;
+  unsigned issuer_sleep_ns;   // back-off of an idle MMA issuer warp between polls
 };
 
 // instruction descriptor: D f32, A/B 16-bit, A K-major (or TMEM), B K-major (b_mn = false) or MN-major (b_mn = true)
@@ -151,9 +150,56 @@ struct SoftmaxRow {
   uint64_t acc0, acc1;   // packed partial row sums
 };
 
+// Rare path of softmax_block: some row's maximum rises by more than 2^8 in this block.  The speculative P of the block
+// (computed with the old maximum) is dropped: the row sum and O are rescaled, S is read again from TMEM (it has not been
+// overwritten yet) and the block is redone with the new maximum.  Out of line: never on the fast path.
+template <bool kF16>
+__device__ __noinline__ void softmax_block_redo(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float mblk, float c, int units,
+                                                int tail, uint32_t pv_bar, uint32_t pv_par) {
+  const bool mine = mblk > st.m + kLazyLog2;
+  const float f = mine ? exp2f(st.m - mblk) : 1.0f;
+  if (mine) st.m = mblk;
+  const uint64_t f2 = pack2(f, f);
+  uint64_t acc0 = mul2f(st.acc0, f2), acc1 = mul2f(st.acc1, f2);
+  ptx::mbar_wait(pv_bar, pv_par);   // P.V of the previous op must have landed in O before O is touched
+  ptx::tcgen05_fence_after();
+  uint32_t o[16];
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    tmem_ld16_at(o_addr + uint32_t(16 * cc), o, 0);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+    tmem_st16_at(o_addr + uint32_t(16 * cc), o, 0);
+  }
+  const float m = st.m;
+#pragma unroll 1
+  for (int i = 0; i < units; ++i) {
+    tmem_ld16_at(sb + uint32_t(16 * i), o, 0);
+    ptx::tmem_ld_wait();
+    const int lim = i == units - 1 ? tail : 16;
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float e0 = ex2(fmaf(__uint_as_float(o[2 * e]), c, -m)), e1 = ex2(fmaf(__uint_as_float(o[2 * e + 1]), c, -m));
+      e0 = 2 * e < lim ? e0 : 0.f;
+      e1 = 2 * e + 1 < lim ? e1 : 0.f;
+      if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
+      pk[e] = Act<kF16>::pack(e0, e1);
+    }
+    tmem_st8_at(sb + uint32_t(8 * i), pk, 0);   // columns [8i, 8i+8) lie behind the S columns still to be read
+  }
+  st.acc0 = acc0;
+  st.acc1 = acc1;
+  tmem_st_wait();
+}
+
 // One key block (U units of 16 keys) of one query row: S (fp32, TMEM columns [sb, sb + 16U)) -> P (16 bit, in place,
-// columns [sb, sb + 8U)), online softmax state in st.  Straight-line code for the compile-time U; only the block's last
-// unit can hold padding keys (tail < 16 real keys).  All 32 lanes of the warp call this together.
+// columns [sb, sb + 8U)), online softmax state in st.  Straight-line code for the compile-time U.  Only the block's last
+// unit can hold padding keys (tail < 16 real keys): they are set to -inf once, right after the load.
+// First block of a tile: maximum, then exponentials.  Later blocks: the exponentials are computed SPECULATIVELY with the
+// running maximum while the block maximum is reduced alongside (independent instruction streams, no max -> exp
+// serialisation); only if some row needs a new maximum (rare) the block is redone.  All 32 lanes call this together.
 template <bool kF16, int U>
 __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float c, bool first, int tail,
                                               uint32_t pv_bar, uint32_t pv_par) {
@@ -161,51 +207,29 @@ __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, Soft
 #pragma unroll
   for (int i = 0; i < U; ++i) tmem_ld16_at(sb + uint32_t(16 * i), v, 16 * i);
   ptx::tmem_ld_wait();
-  // ---- block maximum (4 independent chains) ----
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (tail < 16) {
 #pragma unroll
-  for (int i = 0; i < U - 1; ++i) {
-#pragma unroll
-    for (int e = 0; e < 16; e += 2) mx[(e >> 1) & 3] = max3(mx[(e >> 1) & 3], __uint_as_float(v[16 * i + e]), __uint_as_float(v[16 * i + e + 1]));
+    for (int e = 0; e < 16; ++e)
+      if (e >= tail) v[16 * (U - 1) + e] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
   }
-  if (tail >= 16) {
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  auto unit_max = [&](int i) {
 #pragma unroll
     for (int e = 0; e < 16; e += 2)
-      mx[(e >> 1) & 3] = max3(mx[(e >> 1) & 3], __uint_as_float(v[16 * (U - 1) + e]), __uint_as_float(v[16 * (U - 1) + e + 1]));
-  } else {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) mx[e & 3] = fmaxf(mx[e & 3], e < tail ? __uint_as_float(v[16 * (U - 1) + e]) : -INFINITY);
-  }
-  const float mblk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
+      mx[(e >> 1) & 3] = max3(mx[(e >> 1) & 3], __uint_as_float(v[16 * i + e]), __uint_as_float(v[16 * i + e + 1]));
+  };
   if (first) {
-    st.m = mblk;
-  } else if (__any_sync(0xffffffffu, mblk > st.m + kLazyLog2)) {
-    // ---- rare: this block raises some row's maximum by more than 2^8: rescale O and the row sum ----
-    const bool mine = mblk > st.m + kLazyLog2;
-    const float f = mine ? exp2f(st.m - mblk) : 1.0f;
-    if (mine) st.m = mblk;
-    const uint64_t f2 = pack2(f, f);
-    st.acc0 = mul2f(st.acc0, f2);
-    st.acc1 = mul2f(st.acc1, f2);
-    ptx::mbar_wait(pv_bar, pv_par);   // P.V of the previous op must have landed in O before O is touched
-    ptx::tcgen05_fence_after();
-    uint32_t o[16];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      tmem_ld16_at(o_addr + uint32_t(16 * cc), o, 0);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
-      tmem_st16_at(o_addr + uint32_t(16 * cc), o, 0);
-    }
+    for (int i = 0; i < U; ++i) unit_max(i);
+    st.m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
   }
-  // ---- p = exp2(s*c - m), row sum, 16-bit P in place ----
   const float m = st.m;
   const uint64_t c2 = pack2(c, c), nm2 = pack2(-m, -m);
   uint64_t acc0 = st.acc0, acc1 = st.acc1;
   uint32_t pk[8 * U];
 #pragma unroll
-  for (int i = 0; i < U - 1; ++i) {
+  for (int i = 0; i < U; ++i) {
+    if (!first) unit_max(i);   // independent of the exponentials: the two instruction streams interleave
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float x0, x1;
@@ -214,32 +238,16 @@ __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, Soft
       if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
       pk[8 * i + e] = Act<kF16>::pack(e0, e1);
     }
-    tmem_st8_at(sb + uint32_t(8 * i), pk, 8 * i);
   }
-  {
-    constexpr int i = U - 1;
-    if (tail >= 16) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float x0, x1;
-        unpack2(fma2(pack2(__uint_as_float(v[16 * i + 2 * e]), __uint_as_float(v[16 * i + 2 * e + 1])), c2, nm2), x0, x1);
-        const float e0 = ex2(x0), e1 = ex2(x1);
-        if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
-        pk[8 * i + e] = Act<kF16>::pack(e0, e1);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float e0 = ex2(fmaf(__uint_as_float(v[16 * i + 2 * e]), c, -m));
-        float e1 = ex2(fmaf(__uint_as_float(v[16 * i + 2 * e + 1]), c, -m));
-        e0 = 2 * e < tail ? e0 : 0.f;
-        e1 = 2 * e + 1 < tail ? e1 : 0.f;
-        acc0 = add2(acc0, pack2(e0, e1));
-        pk[8 * i + e] = Act<kF16>::pack(e0, e1);
-      }
+  if (!first) {
+    const float mblk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
+    if (__any_sync(0xffffffffu, mblk > m + kLazyLog2)) {
+      softmax_block_redo<kF16>(sb, o_addr, st, mblk, c, U, tail, pv_bar, pv_par);
+      return;
     }
-    tmem_st8_at(sb + uint32_t(8 * i), pk, 8 * i);
   }
+#pragma unroll
+  for (int i = 0; i < U; ++i) tmem_st8_at(sb + uint32_t(8 * i), pk, 8 * i);
   st.acc0 = acc0;
   st.acc1 = acc1;
   tmem_st_wait();
@@ -247,10 +255,12 @@ __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, Soft
 
 }  // namespace
 
-template <bool kF16>
+// kMaxUnits: key-block size limit in units of 16 keys (5 -> 80-column S buffers, 6 -> 96)
+template <bool kF16, int kMaxUnits>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                        const __grid_constant__ AttnParams prm) {
+  constexpr int kSBufCols = 16 * kMaxUnits;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -439,9 +449,13 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         if (progress) {
           t_last = clock64();
-        } else if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
-          if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
-          __trap();
+        } else {
+          // nothing to issue: leave the issue slots (and the power budget) of this scheduler to the softmax warps for a moment
+          if (prm.issuer_sleep_ns > 0) __nanosleep(prm.issuer_sleep_ns);
+          if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
+            if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
+            __trap();
+          }
         }
       }
     }
@@ -455,10 +469,50 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(g * kRegionCols);
     const float c = prm.scale_log2e;
     uint32_t k = 0, o_cnt = 0;   // ops / tiles processed by this group so far
-#ifdef IIC_ATTN_PROF
-    long long pf_ws = 0, pf_wo = 0, pf_cmp = 0, pf_epi = 0;
-    const long long pf_t0 = clock64();
-#endif
+    // The epilogue of a tile (wait for its last P.V, read O, normalise, store) is deferred until the FIRST block of the
+    // group's next tile has been processed: the tensor-core round trip of the last P.V hides under those exponentials.
+    struct Pending {
+      bool valid, live;
+      int b, h, t;
+      float m;
+      uint64_t acc0, acc1;
+    } pend;
+    pend.valid = false;
+    auto epilogue = [&](const Pending& pd) {
+      ptx::mbar_wait(o_full(g), o_cnt & 1u);
+      ++o_cnt;
+      ptx::tcgen05_fence_after();
+      uint32_t v[64];
+      if (pd.live) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld16_at(taddr + uint32_t(kOCol + 16 * cc), v, 16 * cc);
+        ptx::tmem_ld_wait();
+      }
+      ptx::tcgen05_fence_before();
+      ptx::mbar_arrive(o_free(g));
+      const int q = pd.t * 128 + r;
+      if (q < T) {
+        float s0, s1, s2, s3;
+        unpack2(pd.acc0, s0, s1);
+        unpack2(pd.acc1, s2, s3);
+        const float sum = (s0 + s1) + (s2 + s3);
+        const float inv = 1.0f / sum;
+        const uint64_t inv2 = pack2(inv, inv);
+        uint16_t* orow = prm.out + (size_t(pd.b) * T + q) * d + pd.h * kHd;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0, x1;
+            unpack2(mul2f(pack2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1])), inv2), x0, x1);
+            w[e] = Act<kF16>::pack(x0, x1);
+          }
+          *reinterpret_cast<uint4*>(orow + 8 * jj) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (prm.lse != nullptr) prm.lse[(size_t(pd.b) * H + pd.h) * T + q] = pd.m + log2f(sum);
+      }
+    };
     if (g < nq) {
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / H, h = item - b * H;
@@ -471,14 +525,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           for (int j = 0; j < nb; ++j, ++k) {
             const int buf = int(k & 1u);
             const uint32_t sb = taddr + uint32_t(buf * kSBufCols);
-#ifdef IIC_ATTN_PROF
-            const long long pf_a = clock64();
-#endif
             ptx::mbar_wait(s_full(g, buf), (k >> 1) & 1u);
-#ifdef IIC_ATTN_PROF
-            const long long pf_b = clock64();
-            pf_ws += pf_b - pf_a;
-#endif
             ptx::tcgen05_fence_after();
             if (warp_live) {
               const int u = blk_units(j);
@@ -492,71 +539,24 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 case 3: softmax_block<kF16, 3>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
                 case 4: softmax_block<kF16, 4>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
                 case 5: softmax_block<kF16, 5>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
-                default: softmax_block<kF16, 6>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                default:
+                  if constexpr (kMaxUnits >= 6) softmax_block<kF16, 6>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par);
+                  break;
               }
             }
             ptx::tcgen05_fence_before();
             ptx::mbar_arrive(sm_done(g, buf));
-#ifdef IIC_ATTN_PROF
-            pf_cmp += clock64() - pf_b;
-#endif
-          }
-          const float m = st.m;
-          const uint64_t acc0 = st.acc0, acc1 = st.acc1;
-          uint32_t v[64];
-          // ---------------- O row ----------------
-#ifdef IIC_ATTN_PROF
-          const long long pf_c = clock64();
-#endif
-          ptx::mbar_wait(o_full(g), o_cnt & 1u);
-#ifdef IIC_ATTN_PROF
-          const long long pf_d = clock64();
-          pf_wo += pf_d - pf_c;
-#endif
-          ++o_cnt;
-          ptx::tcgen05_fence_after();
-          const int q = t * 128 + r;
-          if (warp_live) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              tmem_ld16_at(taddr + uint32_t(kOCol + 16 * cc), v, 16 * cc);
+            if (j == 0 && pend.valid) {
+              epilogue(pend);
+              pend.valid = false;
             }
-            ptx::tmem_ld_wait();
           }
-          ptx::tcgen05_fence_before();
-          ptx::mbar_arrive(o_free(g));
-          if (q < T) {
-            float s0, s1, s2, s3;
-            unpack2(acc0, s0, s1);
-            unpack2(acc1, s2, s3);
-            const float sum = (s0 + s1) + (s2 + s3);
-            const float inv = 1.0f / sum;
-            const uint64_t inv2 = pack2(inv, inv);
-            uint16_t* orow = prm.out + (size_t(b) * T + q) * d + h * kHd;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0, x1;
-                unpack2(mul2f(pack2(__uint_as_float(v[8 * jj + 2 * e]), __uint_as_float(v[8 * jj + 2 * e + 1])), inv2), x0, x1);
-                w[e] = Act<kF16>::pack(x0, x1);
-              }
-              *reinterpret_cast<uint4*>(orow + 8 * jj) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            if (prm.lse != nullptr) prm.lse[(size_t(b) * H + h) * T + q] = m + log2f(sum);
-          }
-#ifdef IIC_ATTN_PROF
-          pf_epi += clock64() - pf_d;
-#endif
+          pend.valid = true; pend.live = warp_live; pend.b = b; pend.h = h; pend.t = t;
+          pend.m = st.m; pend.acc0 = st.acc0; pend.acc1 = st.acc1;
         }
       }
+      if (pend.valid) epilogue(pend);
     }
-#ifdef IIC_ATTN_PROF
-    if (blockIdx.x == 0 && lane == 0)
-      printf("attn prof softmax warp %d: total %lld | wait S %lld | block math %lld | wait O %lld | epilogue %lld\n", warp,
-             clock64() - pf_t0, pf_ws, pf_cmp, pf_wo, pf_epi);
-#endif
   }
 
   ptx::tcgen05_fence_before();
@@ -597,7 +597,9 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   AttnParams p;
   p.TP = (T + 15) / 16 * 16;
   const int units = p.TP / 16;
-  p.nb = (units + kMaxUnits - 1) / kMaxUnits;
+  int max_units = 5;   // 80-key blocks: S row + packed P stay in registers without spills (96 spills in the hot loop)
+  if (const char* e = getenv("IIC_ATTN_MAXU")) max_units = atoi(e) == 6 ? 6 : 5;
+  p.nb = (units + max_units - 1) / max_units;
   p.bq = units / p.nb;
   p.brem = units % p.nb;
   // K/V arrive in TMA boxes of 16*dd rows; pick the box (<= 256 rows) that overshoots TP the least
@@ -621,6 +623,8 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   p.out = static_cast<uint16_t*>(out);
   p.lse = lse;
   p.scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
+  p.issuer_sleep_ns = 0;
+  if (const char* e = getenv("IIC_ATTN_SLEEP")) p.issuer_sleep_ns = unsigned(atoi(e));
   const int d = H * kHd;
   CUtensorMap tq, tkv;
   const uint64_t rows = uint64_t(B) * T;
@@ -628,16 +632,21 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
     return -1;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(attention_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_sm100_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_sm100_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_sm100_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_sm100_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
       return -2;
     attr_done = true;
   }
   const int grid = p.items < num_sms ? p.items : num_sms;
-  if (f16)
-    attention_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
-  else
-    attention_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
+  if (max_units == 6) {
+    if (f16) attention_sm100_kernel<true, 6><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
+    else attention_sm100_kernel<false, 6><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
+  } else {
+    if (f16) attention_sm100_kernel<true, 5><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
+    else attention_sm100_kernel<false, 5><<<grid, kThreads, smem, stream>>>(tq, tkv, p);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

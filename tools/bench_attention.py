@@ -2,7 +2,9 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import iic_b200
-def timeit(fn, warmup=3, iters=10):
+def timeit(fn, warmup=5, iters=30, reps=3):
+    return min(_timeit(fn, warmup, iters) for _ in range(reps))
+def _timeit(fn, warmup, iters):
     for _ in range(warmup): fn()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
