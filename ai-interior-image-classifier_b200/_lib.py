@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libiic_b200.so")
+# IIC_LIB: developer override used by tools/ to A/B two builds of the same library inside one GPU call
+LIB_PATH = os.environ.get("IIC_LIB") or os.path.join(_HERE, "_lib", "libiic_b200.so")
 
 IIC_OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2

@@ -43,6 +43,8 @@ enum GemmEpilogue : int {
   kEpiBiasResF32 = 2,    // out f32  = acc + bias + residual (in place ok) (attn.out_proj, mlp.c_proj)
   kEpiPosF32 = 3,        // out f32[row + row/G + 1] = acc + pos[row%G + 1] (visual.conv1 patch embedding)
   kEpiGeluExactBf16 = 4, // out 16-bit = gelu_erf(acc + bias)              (non-OpenAI checkpoints)
+  kEpiBiasResF32DeepK = 5,  // kEpiBiasResF32 with a deeper operand ring and a shorter residual ring: chosen by the
+                            // launcher for long reductions (K >= 2048: mlp.c_proj), where TMA look-ahead matters more
 };
 
 struct GemmArgs {
@@ -67,7 +69,7 @@ constexpr int kSlabBytes = kBlockM * 128;  // epilogue staging slab: 128 rows x 
 
 template <int kCtas, int kBlockN, int kEpi>
 struct GemmSmem {
-  static constexpr bool kResidual = kEpi == kEpiBiasResF32;
+  static constexpr bool kResidual = kEpi == kEpiBiasResF32 || kEpi == kEpiBiasResF32DeepK;
   static constexpr bool kDirect = kEpi == kEpiPosF32;  // old direct-store epilogue, no staging ring
   static constexpr int kLoadN = kBlockN / kCtas;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -77,9 +79,9 @@ struct GemmSmem {
   // MUFU / TMEM latency hides under the other's ALU work), 1 otherwise (measured: a second group only adds contention
   // for the bias-only and the residual epilogues)
   static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect) ? 2 : 1;
-  static constexpr int kSlabs = kDirect ? 0 : (kResidual ? 4 : 2);  // staging ring depth (all groups together)
+  static constexpr int kSlabs = kDirect ? 0 : (kResidual ? (kEpi == kEpiBiasResF32DeepK ? 3 : 4) : 2);  // staging ring depth
   static constexpr int kBufPerGroup = kDirect ? 1 : kSlabs / kGroups;
-  static constexpr int kRingBudget = 192 * 1024 - kSlabs * kSlabBytes;
+  static constexpr int kRingBudget = (kEpi == kEpiBiasResF32DeepK ? 208 : 192) * 1024 - kSlabs * kSlabBytes;
   static constexpr int kStages = kRingBudget / kStageBytes;  // 2 CTA: 6 / 5 / 4;  1 CTA: 4 / 3 / 2 ... see static_assert
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * kBlockN;  // 512 when kBlockN = 256
