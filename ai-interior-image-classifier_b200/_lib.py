@@ -26,7 +26,7 @@ EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RES_F32, EPI_POS_F32, EPI_GELU_ERF_B
 class IicConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "image_size", "patch_size", "width", "layers", "heads", "mlp_dim", "embed_dim", "activation", "device",
-        "gemm_ctas", "operand_dtype")]
+        "gemm_ctas", "operand_dtype", "seq_tokens", "causal")]
 
 
 class IicDims(C.Structure):
@@ -55,6 +55,8 @@ PROTOTYPES = {
     "iic_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "iic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "iic_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "iic_encode_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_void_p]),
     "iic_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(IicHeadOut), C.c_void_p]),
     "iic_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
                                C.POINTER(IicHeadOut), C.c_void_p]),

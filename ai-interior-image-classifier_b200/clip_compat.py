@@ -2,7 +2,9 @@
 
     model, preprocess = load("ViT-B/16", device="cuda")        # /root/reference/main.py:152, 241; train_lora.py:174
     model.encode_image(batch)   -> CUDA engine (csrc/, through the C ABI)      main.py:204, 444, 503
-    model.encode_text(tokens)   -> PyTorch (label embeddings are an INPUT of the hot path)
+    model.encode_text(tokens)   -> PyTorch by default (label embeddings are an INPUT of the hot path, SURVEY.md row X1);
+                                   with `model.text_on_engine = True` the same CUDA engine runs the text tower
+                                   (causal attention, live text LoRA: SURVEY.md 8(f) row N3)
     preprocess(PIL.Image)       -> CUDA preprocess kernel, returns Tensor[3,R,R] like clip._transform
 
 The module tree and parameter names are OpenAI CLIP's (`visual.transformer.resblocks.{i}.mlp.c_fc.weight`, ...), so
@@ -194,6 +196,15 @@ class CLIP(nn.Module):
         self.ln_final = _Fp32LayerNorm(transformer_width)
         self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        # run encode_text on the CUDA engine too (same GEMM / LayerNorm / attention kernels, causal mask,
+        # T = 77, LoRA pairs hanging off the text MLPs fused exactly like the vision ones).  Off by default: the label
+        # matrix is an input of the image hot path and the reference computes it in fp32.
+        self.text_on_engine = os.environ.get("IIC_TEXT_ON_ENGINE", "0") == "1"
+        self._text_engine: Optional[Engine] = None
+        self._text_sig = None
+        self._text_arch = VisionArch(image_size=224, patch_size=16, width=transformer_width, layers=transformer_layers,
+                                     heads=transformer_heads, embed_dim=embed_dim, activation=L.ACT_QUICK_GELU,
+                                     seq_tokens=context_length, causal=True)
         self._init()
 
     def _init(self):
@@ -216,7 +227,54 @@ class CLIP(nn.Module):
     def encode_image(self, image: torch.Tensor) -> torch.Tensor:
         return self.visual(image)
 
+    # -- text tower on the engine ---------------------------------------------------------------------------------
+    def sync_text_engine(self, force: bool = False) -> Engine:
+        dev = self.token_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("text_on_engine needs the model on a CUDA device (B200); there is no CPU fallback for the engine")
+        v = self.visual
+        want = torch.float16 if str(v.operand_dtype).lower() in ("f16", "fp16", "float16", "torch.float16") else torch.bfloat16
+        if self._text_engine is None or self._text_engine.device != dev or self._text_engine.op_dtype != want:
+            self._text_engine = Engine(self._text_arch, dev, operand_dtype=want)
+            self._text_sig = None
+        eng = self._text_engine
+        sd: Dict[str, torch.Tensor] = {"ln_final.weight": self.ln_final.weight, "ln_final.bias": self.ln_final.bias,
+                                       "text_projection": self.text_projection}
+        lora: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, float]] = {}
+        for i, blk in enumerate(self.transformer.resblocks):
+            p = f"transformer.resblocks.{i}."
+            sd[p + "ln_1.weight"], sd[p + "ln_1.bias"] = blk.ln_1.weight, blk.ln_1.bias
+            sd[p + "ln_2.weight"], sd[p + "ln_2.bias"] = blk.ln_2.weight, blk.ln_2.bias
+            sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"] = blk.attn.in_proj_weight, blk.attn.in_proj_bias
+            for which, name, mod in ((L.LORA_OUT_PROJ, "attn.out_proj", blk.attn.out_proj),
+                                     (L.LORA_C_FC, "mlp.c_fc", blk.mlp.c_fc), (L.LORA_C_PROJ, "mlp.c_proj", blk.mlp.c_proj)):
+                sd[p + name + ".weight"], sd[p + name + ".bias"] = mod.weight, mod.bias  # proxies on a LoRALinear
+                # an attn.out_proj LoRA is dead in the reference's forward (F4): never applied
+                if _is_lora_wrapped(mod) and which != L.LORA_OUT_PROJ and bool((mod.lora.lora_B != 0).any()):
+                    lora[(i, which)] = (mod.lora.lora_A, mod.lora.lora_B, float(getattr(mod.lora, "scaling", 1.0)))
+        sig_w = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
+        sig_l = tuple((k, a.data_ptr(), a._version, b.data_ptr(), b._version, s) for k, (a, b, s) in sorted(lora.items()))
+        old_w, old_l = self._text_sig if self._text_sig is not None else (None, None)
+        with torch.no_grad():
+            if force or sig_w != old_w:
+                eng.load_text_state_dict(sd)
+            if force or sig_l != old_l:
+                for i in range(self._text_arch.layers):
+                    for which in (L.LORA_IN_PROJ, L.LORA_OUT_PROJ, L.LORA_C_FC, L.LORA_C_PROJ):
+                        if (i, which) in lora:
+                            a, b, s = lora[(i, which)]
+                            eng.set_lora(i, which, a, b, s)
+                        else:
+                            eng.set_lora(i, which, None, None)
+        self._text_sig = (sig_w, sig_l)
+        return eng
+
     def encode_text(self, text: torch.Tensor) -> torch.Tensor:
+        if self.text_on_engine:
+            eng = self.sync_text_engine()
+            with torch.no_grad():
+                x = self.token_embedding(text).float() + self.positional_embedding.float()   # the caller's gather + add
+                return eng.encode_sequence(x, text.argmax(dim=-1)).to(self.dtype)
         x = self.token_embedding(text).to(self.dtype) + self.positional_embedding.to(self.dtype)
         x = self.transformer(x.permute(1, 0, 2)).permute(1, 0, 2)
         x = self.ln_final(x)

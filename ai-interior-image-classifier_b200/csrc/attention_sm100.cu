@@ -63,6 +63,7 @@ struct AttnParams {
   int kv_box, kv_loads;
   float scale_log2e;
   unsigned issuer_sleep_ns;   // back-off of an idle MMA issuer warp between polls
+  int causal;                 // 1: key j is visible to query i only if j <= i (CLIP text tower)
 };
 
 // instruction descriptor: D f32, A/B 16-bit, A K-major (or TMEM), B K-major (b_mn = false) or MN-major (b_mn = true)
@@ -155,7 +156,7 @@ struct SoftmaxRow {
 // overwritten yet) and the block is redone with the new maximum.  Out of line: never on the fast path.
 template <bool kF16>
 __device__ __noinline__ void softmax_block_redo(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float mblk, float c, int units,
-                                                int tail, uint32_t pv_bar, uint32_t pv_par) {
+                                                int nvalid, uint32_t pv_bar, uint32_t pv_par) {
   const bool mine = mblk > st.m + kLazyLog2;
   const float f = mine ? exp2f(st.m - mblk) : 1.0f;
   if (mine) st.m = mblk;
@@ -177,7 +178,7 @@ __device__ __noinline__ void softmax_block_redo(uint32_t sb, uint32_t o_addr, So
   for (int i = 0; i < units; ++i) {
     tmem_ld16_at(sb + uint32_t(16 * i), o, 0);
     ptx::tmem_ld_wait();
-    const int lim = i == units - 1 ? tail : 16;
+    const int lim = nvalid - 16 * i;   // visible keys of this unit (>= 16: all)
     uint32_t pk[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -201,16 +202,24 @@ __device__ __noinline__ void softmax_block_redo(uint32_t sb, uint32_t o_addr, So
 // running maximum while the block maximum is reduced alongside (independent instruction streams, no max -> exp
 // serialisation); only if some row needs a new maximum (rare) the block is redone.  All 32 lanes call this together.
 template <bool kF16, int U>
-__device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float c, bool first, int tail,
-                                              uint32_t pv_bar, uint32_t pv_par) {
+__device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, SoftmaxRow& st, float c, bool first, int nvalid,
+                                              bool causal, uint32_t pv_bar, uint32_t pv_par) {
+  // nvalid: leading columns of the block this row may see (padding keys beyond T; with a causal mask also keys after the
+  // query).  Without a causal mask it is warp-uniform and only ever cuts into the last unit.
   uint32_t v[16 * U];
 #pragma unroll
   for (int i = 0; i < U; ++i) tmem_ld16_at(sb + uint32_t(16 * i), v, 16 * i);
   ptx::tmem_ld_wait();
-  if (tail < 16) {
+  if (!causal) {
+    if (nvalid < 16 * U) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (e >= tail) v[16 * (U - 1) + e] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
+      for (int e = 0; e < 16; ++e)
+        if (16 * (U - 1) + e >= nvalid) v[16 * (U - 1) + e] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
+    }
+  } else if (__any_sync(0xffffffffu, nvalid < 16 * U)) {
+#pragma unroll
+    for (int e = 0; e < 16 * U; ++e)
+      if (e >= nvalid) v[e] = 0xff800000u;
   }
   float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   auto unit_max = [&](int i) {
@@ -242,7 +251,7 @@ __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, Soft
   if (!first) {
     const float mblk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * c;
     if (__any_sync(0xffffffffu, mblk > m + kLazyLog2)) {
-      softmax_block_redo<kF16>(sb, o_addr, st, mblk, c, U, tail, pv_bar, pv_par);
+      softmax_block_redo<kF16>(sb, o_addr, st, mblk, c, U, nvalid, pv_bar, pv_par);
       return;
     }
   }
@@ -529,18 +538,20 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             ptx::tcgen05_fence_after();
             if (warp_live) {
               const int u = blk_units(j);
-              // real keys in the block's last unit (16: no masking)
-              const int tail = min(16, T - 16 * (blk_start(j) + u - 1));
+              // columns of the block this row may see: real keys (< T) and, under a causal mask, keys up to the query itself
+              const int k0 = 16 * blk_start(j);
+              const int nvalid = (prm.causal ? min(T, t * 128 + r + 1) : T) - k0;
+              const bool causal = prm.causal != 0;
               const uint32_t pv_bar = pv_done(g, buf ^ 1), pv_par = ((k - 1u) >> 1) & 1u;
               const uint32_t o_addr = taddr + uint32_t(kOCol);
               switch (u) {
-                case 1: softmax_block<kF16, 1>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
-                case 2: softmax_block<kF16, 2>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
-                case 3: softmax_block<kF16, 3>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
-                case 4: softmax_block<kF16, 4>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
-                case 5: softmax_block<kF16, 5>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par); break;
+                case 1: softmax_block<kF16, 1>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par); break;
+                case 2: softmax_block<kF16, 2>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par); break;
+                case 3: softmax_block<kF16, 3>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par); break;
+                case 4: softmax_block<kF16, 4>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par); break;
+                case 5: softmax_block<kF16, 5>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par); break;
                 default:
-                  if constexpr (kMaxUnits >= 6) softmax_block<kF16, 6>(sb, o_addr, st, c, j == 0, tail, pv_bar, pv_par);
+                  if constexpr (kMaxUnits >= 6) softmax_block<kF16, 6>(sb, o_addr, st, c, j == 0, nvalid, causal, pv_bar, pv_par);
                   break;
               }
             }
@@ -590,8 +601,8 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 }  // namespace
 
 // returns -3 when the shape is outside this kernel's envelope (caller falls back to the mma.sync kernel)
-int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, int num_sms,
-                           cudaStream_t stream) {
+int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, bool causal,
+                           int num_sms, cudaStream_t stream) {
   if (B <= 0) return 0;
   if (head_dim != kHd || T < 1) return -3;
   AttnParams p;
@@ -624,6 +635,7 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   p.lse = lse;
   p.scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
   p.issuer_sleep_ns = 0;
+  p.causal = causal ? 1 : 0;
   if (const char* e = getenv("IIC_ATTN_SLEEP")) p.issuer_sleep_ns = unsigned(atoi(e));
   const int d = H * kHd;
   CUtensorMap tq, tkv;

@@ -145,8 +145,9 @@ Workspace carve(const iic_handle* h, int B, void* base) {
 }
 
 bool check_ready(iic_handle* h) {
-  if (!h->conv_w || !h->cls || !h->pos || !h->lnpre_g || !h->lnpre_b || !h->lnpost_g || !h->lnpost_b || !h->proj)
-    return false;
+  if (!h->lnpost_g || !h->lnpost_b || !h->proj) return false;
+  // sequence (text-tower) handles have no patch embedding / class token / ln_pre: the caller supplies the embedded tokens
+  if (h->cfg.seq_tokens <= 0 && (!h->conv_w || !h->cls || !h->pos || !h->lnpre_g || !h->lnpre_b)) return false;
   for (const Block& b : h->blocks)
     if (!b.ln1_g || !b.ln1_b || !b.ln2_g || !b.ln2_b || !b.w_qkv || !b.w_out || !b.w_fc || !b.w_proj || !b.b_qkv ||
         !b.b_out || !b.b_fc || !b.b_proj)
@@ -159,9 +160,10 @@ bool check_ready(iic_handle* h) {
 int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, int T, int H, int hd, int impl, cudaStream_t s) {
   if (impl == 0) impl = h->attn_impl;
   if (impl != 1) {
-    int rc = launch_attention_sm100(qkv, out, lse, B, T, H, hd, h->f16, h->num_sms, s);
+    int rc = launch_attention_sm100(qkv, out, lse, B, T, H, hd, h->f16, h->cfg.causal != 0, h->num_sms, s);
     if (rc != -3 || impl == 2) return rc == -3 ? -1 : rc;
   }
+  if (h->cfg.causal) return -1;   // the mma.sync kernel has no causal mask (text sequences always fit the tcgen05 kernel)
   return launch_attention(qkv, out, lse, B, T, H, hd, h->f16, s);
 }
 
@@ -224,9 +226,11 @@ int run_lora_down(iic_handle* h, const void* x, int K, int M, const float* a32, 
     }                                                                  \
   } while (0)
 
+int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s);
+
 // patches -> residual stream after the last block (x f32 [M, d] in the workspace)
 int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, cudaStream_t s) {
-  const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  const int d = h->cfg.width, T = h->T, M = B * T;
   const int gg = h->g * h->g;
   const float eps = 1e-5f;
   h->err.clear();
@@ -237,6 +241,14 @@ int run_encoder(iic_handle* h, const void* patches, int B, const Workspace& w, c
   IIC_TRY(timed(h, kLayerNorm, s, [&] {
     return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
   }));
+  return run_blocks(h, B, w, s);
+}
+
+// the residual blocks on the stream x f32 [M, d] of the workspace (vision tower after ln_pre; text tower after the
+// token + positional embedding, with the causal mask of iic_config.causal)
+int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
+  const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
+  const float eps = 1e-5f;
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
   for (Block& b : h->blocks) {
     const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
@@ -510,7 +522,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   iic_handle* h = new iic_handle();
   h->cfg = *cfg;
   h->g = cfg->image_size / cfg->patch_size;
-  h->T = h->g * h->g + 1;
+  h->T = cfg->seq_tokens > 0 ? cfg->seq_tokens : h->g * h->g + 1;
   h->patch_k = 3 * cfg->patch_size * cfg->patch_size;
   h->patch_kpad = (h->patch_k + 7) / 8 * 8;
   h->lora_pad = 16;
@@ -723,6 +735,29 @@ int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_
   rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
   return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, nullptr, s);
+}
+
+int iic_encode_sequence(iic_handle* h, const float* x_in, const int32_t* row_index, int B, void* workspace,
+                        size_t workspace_bytes, float* emb_out, void* stream) {
+  if (!h || !x_in || !row_index || !emb_out) return fail(h, IIC_ERR_ARG, "iic_encode_sequence: null argument");
+  if (h->cfg.seq_tokens <= 0) return fail(h, IIC_ERR_STATE, "iic_encode_sequence: handle was not created with iic_config.seq_tokens");
+  Workspace w;
+  int rc = check_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int d = h->cfg.width, T = h->T;
+  h->err.clear();
+  if (cudaMemcpyAsync(w.x, x_in, size_t(B) * T * d * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return fail(h, IIC_ERR_CUDA, "iic_encode_sequence: copy failed");
+  rc = run_blocks(h, B, w, s);
+  if (rc) return rc;
+  // row row_index[b] of every sequence (the EOT token) -> ln_final -> @ text_projection
+  float* rows = reinterpret_cast<float*>(w.xln);   // [B, d] f32 scratch (xln is free after the last block)
+  {
+    Scope sc(h->prof, kMisc, s);
+    if (launch_gather_rows(w.x, row_index, T, d, B, rows, s) != 0) return fail(h, IIC_ERR_CUDA, "row gather launch failed");
+  }
+  return run_head(h, rows, (long long)d, nullptr, B, emb_out, nullptr, s);
 }
 
 int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, void* stream) {

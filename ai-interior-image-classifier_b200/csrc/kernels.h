@@ -16,6 +16,8 @@ int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, i
                           int p_ld, int f16, cudaStream_t stream);
 // sums the per-column-tile partials written by the c_fc GEMM epilogue (GemmProblem::down_*) into the 16-bit P matrix
 int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, int p_ld, int f16, cudaStream_t stream);
+// out[b, :] = x[b * T + row_index[b], :]   (f32, D % 4 == 0)
+int launch_gather_rows(const float* x, const int32_t* row_index, int T, int D, int B, float* out, cudaStream_t stream);
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 // dtype: 0 = f32, 1 = bf16, 2 = f16
 int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int f16,
@@ -27,8 +29,8 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H
                      cudaStream_t stream);
 // tcgen05 / TMEM kernel (attention_sm100.cu): head_dim 64, K/V of one head resident in smem (T <= ~760);
 // returns -3 if the shape is outside its envelope
-int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, int num_sms,
-                           cudaStream_t stream);
+int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, bool causal,
+                           int num_sms, cudaStream_t stream);
 // dqkv[M, 3d] (16-bit) from d_out[M, d], the saved qkv / out / lse.  T <= 432 (everything of one head lives in smem).
 int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int T,
                          int H, int head_dim, int f16, cudaStream_t stream);

@@ -326,6 +326,25 @@ int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, in
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// text tower: the EOT row of every sequence, out[b, :] = x[b * T + row_index[b], :]
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_index, int T, int D4, int B,
+                                   float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D4) return;
+  const int b = i / D4, c = i - b * D4;
+  int r = row_index[b];
+  r = r < 0 ? 0 : (r >= T ? T - 1 : r);
+  out[i] = reinterpret_cast<const float4*>(x)[(size_t(b) * T + r) * D4 + c];
+}
+
+int launch_gather_rows(const float* x, const int32_t* row_index, int T, int D, int B, float* out, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if (D % 4 != 0) return -1;
+  const int n = B * (D / 4);
+  gather_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, row_index, T, D / 4, B, reinterpret_cast<float4*>(out));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream) {
   const int n = B * D;
   if (n <= 0) return 0;

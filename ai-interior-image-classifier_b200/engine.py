@@ -28,6 +28,9 @@ class VisionArch:
     heads: int = 12
     embed_dim: int = 512
     activation: int = L.ACT_QUICK_GELU
+    # sequence (text-tower) engines: seq_tokens = context length (77), causal attention; no patch embedding / ln_pre
+    seq_tokens: int = 0
+    causal: bool = False
 
     @property
     def mlp_dim(self) -> int:
@@ -39,7 +42,7 @@ class VisionArch:
 
     @property
     def tokens(self) -> int:
-        return self.grid * self.grid + 1
+        return self.seq_tokens if self.seq_tokens > 0 else self.grid * self.grid + 1
 
 
 VIT_B_16 = VisionArch()
@@ -90,7 +93,8 @@ class Engine:
         self.op_dtype = operand_dtype
         cfg = L.IicConfig(arch.image_size, arch.patch_size, arch.width, arch.layers, arch.heads, arch.mlp_dim,
                           arch.embed_dim, arch.activation, self.device.index, gemm_ctas,
-                          L.DTYPE_F16 if operand_dtype == torch.float16 else L.DTYPE_BF16)
+                          L.DTYPE_F16 if operand_dtype == torch.float16 else L.DTYPE_BF16, int(arch.seq_tokens),
+                          1 if arch.causal else 0)
         h = C.c_void_p()
         rc = self.lib.iic_create(C.byref(h), C.byref(cfg))
         if rc != L.IIC_OK:
@@ -146,6 +150,23 @@ class Engine:
                 self.load_weight(p + n, f32(sd[p + n]))
             for n in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
                 self.load_weight(p + n, bf16(sd[p + n]))
+
+    def load_text_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Text tower on a sequence engine (arch.seq_tokens > 0).  `sd`: `transformer.resblocks.*`, `ln_final.*` and
+        `text_projection` of OpenAI CLIP (fp32, any device); ln_final / text_projection occupy the engine's ln_post / proj slots."""
+        a = self.arch
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        w16 = lambda t: t.detach().to(self.device, torch.float32).to(self.op_dtype).contiguous()
+        self.load_weight("ln_post.weight", f32(sd["ln_final.weight"]))
+        self.load_weight("ln_post.bias", f32(sd["ln_final.bias"]))
+        self.load_weight("proj", f32(sd["text_projection"]))
+        for i in range(a.layers):
+            p = f"transformer.resblocks.{i}."
+            for n in ("ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_bias", "attn.out_proj.bias",
+                      "mlp.c_fc.bias", "mlp.c_proj.bias"):
+                self.load_weight(p + n, f32(sd[p + n]))
+            for n in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
+                self.load_weight(p + n, w16(sd[p + n]))
 
     def set_lora(self, layer: int, which: int, lora_a: Optional[torch.Tensor], lora_b: Optional[torch.Tensor],
                  scaling: float = 1.0) -> None:
@@ -270,6 +291,23 @@ class Engine:
             ws = self._ws(B)
             L.check(self.h, self.lib.iic_encode(self.h, patches.data_ptr(), B, ws.data_ptr(), ws.numel(),
                                                 emb.data_ptr(), _stream_ptr(self.device)), "iic_encode")
+        return emb
+
+    def encode_sequence(self, x: torch.Tensor, row_index: torch.Tensor) -> torch.Tensor:
+        """x f32 [B, T, width] (token + positional embedding), row_index [B] (EOT position) -> [B, E] fp32, un-normalised:
+        the engine behind model.encode_text (residual blocks with the causal mask, ln_final of the EOT row, text_projection)."""
+        if self.arch.seq_tokens <= 0:
+            raise RuntimeError("encode_sequence needs an engine built with VisionArch(seq_tokens=...)")
+        B, T, d = x.shape
+        if T != self.arch.seq_tokens or d != self.arch.width:
+            raise ValueError(f"expected [B, {self.arch.seq_tokens}, {self.arch.width}], got {tuple(x.shape)}")
+        x = x.detach().to(self.device, torch.float32).contiguous()
+        idx = row_index.detach().to(self.device, torch.int32).contiguous()
+        emb = torch.empty(B, self.arch.embed_dim, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._ws(B)
+            L.check(self.h, self.lib.iic_encode_sequence(self.h, x.data_ptr(), idx.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                                                         emb.data_ptr(), _stream_ptr(self.device)), "iic_encode_sequence")
         return emb
 
     def encode_image(self, chw: torch.Tensor) -> torch.Tensor:

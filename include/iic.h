@@ -69,6 +69,10 @@ typedef struct iic_config {
   int operand_dtype; /* 16-bit format of activations and matmul weights: IIC_DTYPE_BF16 (default, also for 0) or
                         IIC_DTYPE_F16 (OpenAI CLIP's own GPU dtype; same tensor-core rate, 3 more mantissa bits).
                         Accumulation, LayerNorm, softmax, the residual stream and the head are fp32 in both. */
+  int seq_tokens; /* 0: vision tower (T = (R/P)^2 + 1).  > 0: a SEQUENCE handle for CLIP's text tower - T = seq_tokens (77),
+                     no patch embedding / class token / ln_pre; see iic_encode_sequence.  image_size / patch_size are
+                     then only validated, not used. */
+  int causal;     /* 1: causal attention mask (CLIP text tower), 0: full attention */
 } iic_config;
 
 typedef struct iic_dims {
@@ -136,6 +140,14 @@ size_t iic_workspace_bytes(const iic_handle* h, int B);
 /* patches bf16 [B*g*g, patch_kpad] -> emb f32 [B, embed_dim] (un-normalised, == model.encode_image output) */
 int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
                void* stream);
+
+/* Text tower (reference: model.encode_text, /root/reference/main.py:181, 308; train_lora.py:237; main_API.py:161) on
+ * a handle created with seq_tokens > 0.  x_in f32 [B*T, width] = token_embedding[tokens] + positional_embedding (the
+ * caller's gather + add), row_index int32 [B] (device) = tokens.argmax(-1), the EOT position.  Runs the residual blocks
+ * (LoRA slots as for the vision tower, causal mask per iic_config.causal), then ln_final (loaded as `ln_post.*`) of row
+ * row_index[b] of every sequence, then @ text_projection (loaded as `proj`): emb f32 [B, embed_dim], un-normalised. */
+int iic_encode_sequence(iic_handle* h, const float* x_in, const int32_t* row_index, int B, void* workspace,
+                        size_t workspace_bytes, float* emb_out, void* stream);
 
 typedef struct iic_head_out {
   float* logits;    /* [B, L]      logit_scale * cos            (nullable) */
