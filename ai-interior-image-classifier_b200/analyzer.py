@@ -68,6 +68,61 @@ def load_image(path_or_url: str, timeout: int = 30):
         return None
 
 
+class DeviceImage:
+    """An image that was decoded ON the GPU (nvJPEG): uint8 HWC tensor, ready for the preprocess kernel - no PIL object,
+    no host copy of the pixels.  Quacks enough like a PIL image for the code that only forwards it (`.size`, `.convert`)."""
+
+    def __init__(self, hwc_u8: torch.Tensor):
+        self.tensor = hwc_u8
+        self.size = (int(hwc_u8.shape[1]), int(hwc_u8.shape[0]))   # (W, H) like PIL
+
+    def convert(self, mode: str):
+        if mode != "RGB":
+            raise ValueError("DeviceImage is always RGB")
+        return self
+
+
+def load_images(paths: Sequence[str], device=None, gpu_decode: bool = False, timeout: int = 30):
+    """Batch version of `load_image` (image ingest, main.py:322-346, 404-417).  With gpu_decode, local
+    JPEG files are read as bytes and decoded in ONE batched nvJPEG call on `device` (torchvision.io.decode_jpeg), so
+    the pixels never exist on the host and the preprocess kernel reads them where they were decoded; everything else (URLs,
+    PNG, CMYK JPEGs, a decode error) goes through `load_image` on a small thread pool, exactly like the reference."""
+    out: List[object] = [None] * len(paths)
+    rest = list(range(len(paths)))
+    if gpu_decode and device is not None and torch.device(device).type == "cuda":
+        try:
+            from torchvision.io import ImageReadMode, decode_jpeg
+            idx, blobs = [], []
+            for i, p in enumerate(paths):
+                if isinstance(p, str) and not p.startswith("http") and p.lower().endswith((".jpg", ".jpeg")) and os.path.isfile(p):
+                    with open(p, "rb") as f:
+                        b = f.read()
+                    if b[:2] == b"\xff\xd8":
+                        idx.append(i)
+                        blobs.append(torch.frombuffer(bytearray(b), dtype=torch.uint8))
+            if blobs:
+                try:
+                    dec = decode_jpeg(blobs, device=device, mode=ImageReadMode.RGB)
+                except Exception:  # noqa: BLE001 - one bad file must not take the batch down: decode one by one
+                    dec = []
+                    for b in blobs:
+                        try:
+                            dec.append(decode_jpeg(b, device=device, mode=ImageReadMode.RGB))
+                        except Exception:  # noqa: BLE001
+                            dec.append(None)
+                for i, t in zip(idx, dec):
+                    if t is not None and t.dim() == 3 and t.shape[0] == 3:
+                        out[i] = DeviceImage(t.permute(1, 2, 0).contiguous())
+                rest = [i for i in rest if out[i] is None]
+        except ImportError:
+            pass
+    if rest:
+        with ThreadPoolExecutor(max_workers=4) as ex:   # host-side fetch/decode, as the reference does (main.py:345-346)
+            for i, im in zip(rest, ex.map(lambda q: load_image(q, timeout), [paths[i] for i in rest])):
+                out[i] = im
+    return out
+
+
 def _encode_labels(model, texts: Sequence[str], device) -> torch.Tensor:
     with torch.no_grad():
         tok = clip.tokenize(list(texts)).to(device)
@@ -153,6 +208,8 @@ class CachedInteriorAnalyzer:
             print("Nie używam LoRA - model bez modyfikacji")
         # One encode can serve both heads only while the LoRA'd vision tower equals the base tower (always true for
         # the shipped checkpoints: they hold text-tower tensors only and lora_B initialises to zero - SURVEY F7).
+        # decode local JPEGs on the GPU (nvJPEG) instead of PIL on the host; opt-in, see load_images()
+        self.gpu_decode = os.environ.get("IIC_GPU_DECODE", "0") == "1"
         self._vision_lora_is_zero = self._check_vision_lora_zero()
         self.share_detector_encoder = (self._vision_lora_is_zero if share_detector_encoder is None
                                        else share_detector_encoder)
@@ -245,8 +302,7 @@ class CachedInteriorAnalyzer:
     # -- public API (reference signatures) -------------------------------------------------------------------
     def filter_interior_images(self, image_paths, confidence_threshold: float = 0.3):
         print(f" Filtrowanie {len(image_paths)} obrazów - wykrywanie wnętrz...")
-        with ThreadPoolExecutor(max_workers=4) as ex:  # host-side fetch/decode only; GPU work is batched below
-            imgs = list(ex.map(load_image, image_paths))
+        imgs = load_images(image_paths, self.device, self.gpu_decode)   # fetch/decode only; GPU work is batched below
         ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
         interior_images, non_interior_info = [], []
         for p, im in zip(image_paths, imgs):
@@ -266,8 +322,7 @@ class CachedInteriorAnalyzer:
 
     def _analyze_shared(self, image_paths, batch_size: int, confidence_threshold: float):
         """filter + analyse in ONE encode per image (valid while the vision LoRA delta is zero)."""
-        with ThreadPoolExecutor(max_workers=4) as ex:
-            imgs = list(ex.map(load_image, image_paths))
+        imgs = load_images(image_paths, self.device, self.gpu_decode)
         results = {}
         ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
         for p, im in zip(image_paths, imgs):
@@ -304,8 +359,7 @@ class CachedInteriorAnalyzer:
                 image_metadata.append({"path": path, "interior_confidence": confidence, "is_interior": True})
         else:
             print("  Pomijam filtrowanie wnętrz - przetwarzam wszystkie obrazy")
-            for path in image_paths:
-                img = load_image(path)
+            for path, img in zip(image_paths, load_images(image_paths, self.device, self.gpu_decode)):
                 if img is not None:
                     valid_images.append(img)
                     image_metadata.append({"path": path, "interior_confidence": 1.0, "is_interior": True})

@@ -301,6 +301,11 @@ class Preprocess:
     @staticmethod
     def _to_u8(img, device) -> torch.Tensor:
         import numpy as np
+        if hasattr(img, "tensor") and isinstance(img.tensor, torch.Tensor):   # analyzer.DeviceImage: decoded on the GPU already
+            t = img.tensor
+            if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+                raise ValueError(f"expected a uint8 HWC RGB tensor, got {t.dtype} {tuple(t.shape)}")
+            return t.to(device).contiguous()
         if hasattr(img, "convert"):
             img = img.convert("RGB")
         arr = np.array(img, dtype=np.uint8, order="C")  # owning, writable copy of the decoded pixels
