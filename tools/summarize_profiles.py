@@ -65,9 +65,19 @@ def read_rep(path):
 
 
 gem = read_rep(os.path.join(G, f"{tag}_gemm_full.ncu-rep"))
-for d, shape in zip(gem, ["qkv (N=2304,K=768, bias)", "out_proj (N=768,K=768, +residual f32)", "c_fc (N=3072,K=768, QuickGELU + LoRA + fused down-proj)",
-                          "c_proj (N=768,K=3072, +residual f32 + LoRA)"]):
-    d["shape"] = shape
+def gemm_shape(d):
+    # identify the launch by its epilogue template argument and its DRAM read volume (c_proj reads the [M, 4d] operand)
+    m = re.search(r"gemm_bf16_tn_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)", d["kernel"])
+    epi = int(m.group(3)) if m else -1
+    if epi == 0: return "qkv (N=2304,K=768, bias)"
+    if epi == 1: return "c_fc (N=3072,K=768, QuickGELU + LoRA + fused down-proj)"
+    if epi == 5: return "c_proj (N=768,K=3072, +residual f32 + LoRA)"
+    if epi == 2: return "c_proj (N=768,K=3072, +residual f32 + LoRA)" if d.get("dram__bytes_read.sum", 0) > 1.5e9 else "out_proj (N=768,K=768, +residual f32)"
+    return "patch embedding" if epi == 3 else "?"
+
+
+for d in gem:
+    d["shape"] = gemm_shape(d)
     d["dram_bytes"] = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
 json.dump(gem, open(os.path.join(P, f"{name}_gemm_ncu.json"), "w"), indent=1)
 att = read_rep(os.path.join(G, f"{tag}_attn_full.ncu-rep"))
