@@ -84,6 +84,8 @@ PROTOTYPES = {
     "iic_op_lora_down": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p]),
     "iic_set_lora_operands16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "iic_set_lora_source": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float]),
+    "iic_refresh_lora": (C.c_int, [C.c_void_p, C.c_void_p]),
     "iic_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -36,6 +36,9 @@ struct LoraSlot {
   // rank > 4: the down-projections run on the tcgen05 GEMM (N = lora_pad) with 16-bit operands (iic_set_lora_operands16)
   const void* at16 = nullptr;        // 16-bit [lora_pad, in]  = (scaling * lora_A)^T, zero-padded rows
   const void* b16 = nullptr;         // 16-bit [lora_pad, out] = lora_B, zero-padded rows (training: dP = dY . B^T)
+  // iic_set_lora_source: the fp32 parameters themselves, so that iic_refresh_lora can rebuild every operand above in place
+  const float* src_a = nullptr;      // f32 [in, rank]
+  const float* src_b = nullptr;      // f32 [rank, out]
 };
 
 struct Block {
@@ -644,6 +647,37 @@ int iic_set_lora_operands16(iic_handle* h, int layer, int which, const void* a_t
     return fail(h, IIC_ERR_ARG, "iic_set_lora_operands16: unaligned pointer");
   s.at16 = a_t16;
   s.b16 = b16;
+  return IIC_OK;
+}
+
+int iic_set_lora_source(iic_handle* h, int layer, int which, const float* lora_a, const float* lora_b, float scaling) {
+  if (!h) return IIC_ERR_ARG;
+  if (layer < 0 || layer >= int(h->blocks.size()) || which < 0 || which > 3)
+    return fail(h, IIC_ERR_ARG, "iic_set_lora_source: bad layer / projection id");
+  LoraSlot& s = h->blocks[layer].lora[which];
+  if (s.rank <= 0) return fail(h, IIC_ERR_STATE, "iic_set_lora_source: call iic_set_lora for this slot first");
+  s.src_a = lora_a;
+  s.src_b = lora_b;
+  s.scaling = scaling;
+  return IIC_OK;
+}
+
+int iic_refresh_lora(iic_handle* h, void* stream) {
+  if (!h) return IIC_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = h->cfg.width, mlp = h->cfg.mlp_dim;
+  const int dims[4][2] = {{d, 3 * d}, {d, d}, {d, mlp}, {mlp, d}};   // (in, out) of in_proj, out_proj, c_fc, c_proj
+  for (Block& b : h->blocks)
+    for (int which = 0; which < 4; ++which) {
+      LoraSlot& s = b.lora[which];
+      if (s.rank <= 0 || s.src_a == nullptr || s.src_b == nullptr) continue;
+      Scope sc(h->prof, kMisc, st);
+      // the operand buffers are caller-owned device memory registered through iic_set_lora / _train / _operands16
+      int rc = launch_lora_refresh(s.src_a, s.src_b, dims[which][0], dims[which][1], s.rank, s.r4, h->lora_pad, s.scaling,
+                                   const_cast<float*>(s.a), const_cast<void*>(s.bt), const_cast<void*>(s.a16),
+                                   const_cast<float*>(s.bt32), const_cast<void*>(s.at16), const_cast<void*>(s.b16), h->f16, st);
+      if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "iic_refresh_lora: launch failed");
+    }
   return IIC_OK;
 }
 

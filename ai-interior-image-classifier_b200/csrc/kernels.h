@@ -46,6 +46,10 @@ size_t lora_outer_scratch_bytes(int N, int M);
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
                       float* out, float* scratch, int f16, cudaStream_t stream);
 
+// derived operands of one LoRA slot from its fp32 parameters A [in, rank], B [rank, out] (see train_ops.cu); null outputs skipped
+int launch_lora_refresh(const float* A, const float* B, int in, int out, int rank, int r4, int pad, float scaling, float* a,
+                        void* bt, void* a16, float* bt32, void* at16, void* b16, int f16, cudaStream_t stream);
+
 // ---- head.cu ----
 int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,
                 const float* proj, int W, int E, const float* text, int L, const int* group_off,

@@ -251,4 +251,51 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+
+// ---- per-step refresh of the derived LoRA operands of one slot from the fp32 parameters (after the optimizer step) -------
+// A f32 [in, rank], B f32 [rank, out]  ->  a f32 [in, r4] = s*A;  bt 16-bit [out, pad] = B^T;  a16 16-bit [in, pad] = s*A;
+// bt32 f32 [out, r4] = B^T;  at16 16-bit [pad, in] = (s*A)^T;  b16 16-bit [pad, out] = B.   Null destinations are skipped;
+// padding columns / rows are written as zeros.  Same roundings as the host-side preparation (round to nearest).
+template <bool kF16>
+__global__ void lora_refresh_kernel(const float* __restrict__ A, const float* __restrict__ B, int in, int out, int rank, int r4,
+                                    int pad, float s, float* __restrict__ a, typename Act<kF16>::T* __restrict__ bt,
+                                    typename Act<kF16>::T* __restrict__ a16, float* __restrict__ bt32,
+                                    typename Act<kF16>::T* __restrict__ at16, typename Act<kF16>::T* __restrict__ b16) {
+  using T = typename Act<kF16>::T;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < in) {
+    for (int c = 0; c < pad; ++c) {
+      const float v = c < rank ? A[size_t(i) * rank + c] * s : 0.f;
+      if (c < r4 && a != nullptr) a[size_t(i) * r4 + c] = v;
+      if (a16 != nullptr) a16[size_t(i) * pad + c] = Act<kF16>::from_float(v);
+      if (at16 != nullptr) at16[size_t(c) * in + i] = Act<kF16>::from_float(v);
+    }
+  }
+  if (i < out) {
+    for (int c = 0; c < pad; ++c) {
+      const float v = c < rank ? B[size_t(c) * out + i] : 0.f;
+      if (bt != nullptr) bt[size_t(i) * pad + c] = Act<kF16>::from_float(v);
+      if (c < r4 && bt32 != nullptr) bt32[size_t(i) * r4 + c] = v;
+      if (b16 != nullptr) b16[size_t(c) * out + i] = Act<kF16>::from_float(v);
+    }
+  }
+  (void)sizeof(T);
+}
+
+int launch_lora_refresh(const float* A, const float* B, int in, int out, int rank, int r4, int pad, float scaling, float* a,
+                        void* bt, void* a16, float* bt32, void* at16, void* b16, int f16, cudaStream_t stream) {
+  if (A == nullptr || B == nullptr || rank <= 0 || rank > pad || in <= 0 || out <= 0) return -1;
+  const int n = in > out ? in : out;
+  if (f16)
+    lora_refresh_kernel<true><<<(n + 127) / 128, 128, 0, stream>>>(A, B, in, out, rank, r4, pad, scaling, a, static_cast<__half*>(bt),
+                                                                 static_cast<__half*>(a16), bt32, static_cast<__half*>(at16),
+                                                                 static_cast<__half*>(b16));
+  else
+    lora_refresh_kernel<false><<<(n + 127) / 128, 128, 0, stream>>>(A, B, in, out, rank, r4, pad, scaling, a,
+                                                                  static_cast<__nv_bfloat16*>(bt), static_cast<__nv_bfloat16*>(a16),
+                                                                  bt32, static_cast<__nv_bfloat16*>(at16),
+                                                                  static_cast<__nv_bfloat16*>(b16));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 }  // namespace iic

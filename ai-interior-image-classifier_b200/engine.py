@@ -390,6 +390,21 @@ class Engine:
                         "iic_set_lora_operands16")
                 self._lora[(layer, which, "train16")] = (b16,)
 
+    def set_lora_source(self, layer: int, which: int, lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float) -> None:
+        """Register the fp32 parameters of a slot (after set_lora [+ set_lora_train]) for `refresh_lora`."""
+        for t in (lora_a, lora_b):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("set_lora_source needs contiguous fp32 CUDA parameters")
+        with self._lock:
+            L.check(self.h, self.lib.iic_set_lora_source(self.h, layer, which, lora_a.data_ptr(), lora_b.data_ptr(), float(scaling)),
+                    "iic_set_lora_source")
+            self._lora[(layer, which, "src")] = (lora_a, lora_b)
+
+    def refresh_lora(self) -> None:
+        """Rebuild every derived LoRA operand from the registered parameters (one small kernel per slot, no host sync)."""
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_refresh_lora(self.h, _stream_ptr(self.device)), "iic_refresh_lora")
+
     def _train_ws(self, B: int) -> torch.Tensor:
         need = int(self.lib.iic_train_workspace_bytes(self.h, B))
         ws = getattr(self, "_train_workspace", None)

@@ -76,9 +76,20 @@ class VisionLoRATrainer:
 
     # ------------------------------------------------------------------------------------------------------------
     def _sync(self) -> None:
+        """Bring the engine up to date with the parameters.  First call (or after anything but the LoRA VALUES changed):
+        full upload.  Every later step: the frozen tensors and all pointers are unchanged, only lora_A / lora_B moved under
+        the optimizer, so one `iic_refresh_lora` call rebuilds the derived operands on the device - no host round trip."""
         v = self.visual
-        eng = v.sync_engine(keep_zero_lora=True)
-        sd, _ = v._tensors()
+        sd, _ = v._tensors(keep_zero_lora=True)
+        sig_w = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
+        sig_p = tuple((i, which, mod.lora.lora_A.data_ptr(), mod.lora.lora_B.data_ptr(), float(mod.lora.scaling),
+                       mod.lora.lora_A.grad.data_ptr(), mod.lora.lora_B.grad.data_ptr()) for i, which, mod in self.slots)
+        fast = (sig_w, sig_p, id(v._engine), None if v._engine is None else v._engine.op_dtype)
+        if v._engine is not None and fast == getattr(self, "_fast_sig", None) and v._sig is not None and v._sig[1] is None:
+            self.eng.refresh_lora()
+            return
+        eng = v.sync_engine(force=getattr(self, "_fast_sig", None) is not None, keep_zero_lora=True)
+        self.eng = eng
         sig = tuple((k, t.data_ptr(), t._version) for k, t in sd.items() if k.endswith(".weight") and "ln_" not in k)
         if sig != self._training_weights_sig:
             eng.enable_training(sd)
@@ -86,6 +97,11 @@ class VisionLoRATrainer:
         for i, which, mod in self.slots:
             lo = mod.lora
             eng.set_lora_train(i, which, lo.lora_A, lo.lora_B, float(lo.scaling), lo.lora_A.grad, lo.lora_B.grad)
+            eng.set_lora_source(i, which, lo.lora_A, lo.lora_B, float(lo.scaling))
+        self._fast_sig = (sig_w, sig_p, id(eng), eng.op_dtype)
+        # the engine's LoRA operands are from now on refreshed behind sync_engine's back: forget its LoRA signature so that
+        # an inference call on the same model re-uploads them
+        v._sig = (v._sig[0], None)
 
     def head_and_loss(self, x_cls: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
         """ln_post -> proj -> L2 -> symmetric InfoNCE (train_lora.py:241-246), fp32."""
@@ -100,8 +116,8 @@ class VisionLoRATrainer:
     def forward_backward(self, images: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
         """One forward + backward; LoRA gradients land in the parameters' .grad (averaged over ranks when distributed)."""
         import torch.distributed as dist
-        eng = self.eng
         self._sync()
+        eng = self.eng
         if images.dtype == torch.uint8:
             patches, B = eng.preprocess_same_size(images.to(eng.device)), images.shape[0]
         else:

@@ -117,6 +117,14 @@ int iic_set_lora(iic_handle* h, int layer, int which, const float* a_scaled, con
  * Replaces: `x @ self.lora_A` of LoRALayer.forward (/root/reference/main.py:31, train_lora.py:28) for rank-16 adapters. */
 int iic_set_lora_operands16(iic_handle* h, int layer, int which, const void* a_t16, const void* b16);
 
+/* Training loops change lora_A / lora_B every step.  iic_set_lora_source registers the fp32 parameters of a slot
+ * (lora_a f32 [in, rank], lora_b f32 [rank, out] as the reference stores them, main.py:26-27; scaling = alpha / rank);
+ * iic_refresh_lora then rebuilds, with one small kernel per registered slot on `stream`, every derived operand buffer that
+ * was handed to iic_set_lora / iic_set_lora_train / iic_set_lora_operands16 (those buffers must be writable).  Replaces the
+ * implicit "parameters are read at every forward" of LoRALayer.forward (main.py:30-31) after optimizer.step() (train_lora.py:252). */
+int iic_set_lora_source(iic_handle* h, int layer, int which, const float* lora_a, const float* lora_b, float scaling);
+int iic_refresh_lora(iic_handle* h, void* stream);
+
 /* Label text embeddings the head scores against (reference: text_features_cache, main.py:296-311 and
  * detector text_features, main.py:179-182): text f32 [L, embed_dim], rows L2-normalised by the caller exactly as
  * the reference does.  group_offsets (host, G+1 ints) partitions the L labels into softmax groups;
