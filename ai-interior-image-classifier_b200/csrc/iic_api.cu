@@ -101,6 +101,7 @@ struct iic_handle {
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
   int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
+  int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 256), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
@@ -168,6 +169,16 @@ int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, 
   }
   if (h->cfg.causal) return -1;   // the mma.sync kernel has no causal mask (text sequences always fit the tcgen05 kernel)
   return launch_attention(qkv, out, lse, B, T, H, hd, h->f16, s);
+}
+
+// attention backward: tcgen05 kernel for T <= 256 (needs a [B*H*T] f32 scratch for D), mma.sync kernel otherwise
+int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum,
+                      void* dqkv, int B, int T, int H, int hd, cudaStream_t s) {
+  if (h->attn_bwd_impl != 1 && dsum != nullptr) {
+    int rc = launch_attention_bwd_sm100(qkv, out, d_out, lse, dsum, dqkv, B, T, H, hd, h->f16, h->num_sms, s);
+    if (rc != -3) return rc;
+  }
+  return launch_attention_bwd(qkv, out, d_out, lse, dqkv, B, T, H, hd, h->f16, s);
 }
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
@@ -320,7 +331,7 @@ struct TrainLayer {
 };
 struct TrainWorkspace {
   std::vector<TrainLayer> layers;
-  float *x, *xpre, *dx, *down_part, *outer_scratch;
+  float *x, *xpre, *dx, *down_part, *outer_scratch, *attn_d;
   uint16_t *xln, *hid, *u, *dh, *g16, *dy, *dqkv, *da, *dp1, *dp2;
   size_t total;
 };
@@ -350,6 +361,7 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
   w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), int(M))));
+  w.attn_d = static_cast<float*>(take(size_t(B) * H * h->T * 4));   // D = rowsum(dO o O) of the attention backward
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.layers.resize(h->blocks.size());
   for (TrainLayer& l : w.layers) {
@@ -484,7 +496,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     if (li == 0) return 0;   // nothing below the first block's MLP carries a LoRA parameter
     // ---- attention block:  x_mid = x_in + attn(ln_1(x_in)) W_o^T + b_o ----
     IIC_TRY(run_gemm(h, w.g16, d, b.w_out_t, M, d, d, &none, nullptr, kEpiBiasBf16, nullptr, nullptr, w.da, d, 1, s));
-    IIC_TRY(timed(h, kAttention, s, [&] { return launch_attention_bwd(t.qkv, t.attn, w.da, t.lse, w.dqkv, B, T, H, d / H, h->f16, s); }));
+    IIC_TRY(timed(h, kAttention, s, [&] { return run_attention_bwd(h, t.qkv, t.attn, w.da, t.lse, w.attn_d, w.dqkv, B, T, H, d / H, s); }));
     IIC_TRY(run_gemm(h, w.dqkv, 3 * d, b.w_qkv_t, M, d, 3 * d, &none, nullptr, kEpiBiasBf16, nullptr, nullptr, w.dy, d, 1, s));
     IIC_TRY(timed(h, kLayerNorm, s, [&] { return launch_layernorm_bwd(w.dy, t.x_in, b.ln1_g, w.dx, w.g16, M, d, eps, h->f16, s); }));
   }
@@ -533,6 +545,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->ctas = cfg->gemm_ctas == 1 ? 1 : 2;
   h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
   if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
+  if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -918,7 +931,7 @@ int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // recompute the forward into `out`'s twin to obtain the log-sum-exp (op-level test helper)
   int rc = run_attention(h, qkv, out, lse_scratch, B, T, heads, 64, 0, s);
-  if (rc == 0) rc = launch_attention_bwd(qkv, out, d_out, lse_scratch, dqkv, B, T, heads, 64, h->f16, s);
+  if (rc == 0) rc = run_attention_bwd(h, qkv, out, d_out, lse_scratch, lse_scratch + size_t(B) * heads * T, dqkv, B, T, heads, 64, s);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "attention backward: unsupported shape (T <= 432) or launch failure");
   return IIC_OK;
 }

@@ -457,11 +457,11 @@ class Engine:
     def op_attention_bwd(self, qkv: torch.Tensor, d_out: torch.Tensor, B: int, T: int, heads: int):
         out = torch.empty(B * T, heads * 64, dtype=self.op_dtype, device=self.device)
         dqkv = torch.empty_like(qkv)
-        lse = torch.empty(B * heads * T, dtype=torch.float32, device=self.device)
+        lse = torch.empty(2 * B * heads * T, dtype=torch.float32, device=self.device)   # lse + the backward's D scratch
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_attention_bwd(self.h, qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(),
                                                           lse.data_ptr(), B, T, heads, _stream_ptr(self.device)), "iic_op_attention_bwd")
-        return out, dqkv, lse
+        return out, dqkv, lse[:B * heads * T]
 
     def op_layernorm_bwd(self, dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: torch.Tensor):
         rows, D = x.shape

@@ -223,7 +223,8 @@ int iic_op_lora_down(iic_handle* h, const void* x_bf16, int K, int rows, const f
  * 1 = mma.sync kernel, 2 = tcgen05 kernel */
 int iic_op_attention(iic_handle* h, const void* qkv_bf16, void* out_bf16, int B, int T, int heads, int impl, void* stream);
 /* backward operators (same kernels iic_train_backward runs).  iic_op_attention_bwd recomputes the forward into `out`
- * (to obtain the log-sum-exp, lse_scratch f32 [B*heads*T]) and then writes dqkv [M, 3*d]. */
+ * (to obtain the log-sum-exp) and then writes dqkv [M, 3*d].  lse_scratch f32 [2*B*heads*T]: the log-sum-exp followed by
+ * the backward's D = rowsum(dO o O) scratch. */
 int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* d_out, void* dqkv, float* lse_scratch,
                          int B, int T, int heads, void* stream);
 int iic_op_layernorm_bwd(iic_handle* h, const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows,
