@@ -224,8 +224,10 @@ int timed(iic_handle* h, int cls, cudaStream_t s, F&& f) {
 // P[M, lora_pad] (16-bit) = x[M, K] . A  for one LoRA slot: rank <= 4 -> the fp32-A row kernel; larger ranks -> the tcgen05
 // GEMM with N = lora_pad and the 16-bit transposed operand w16 [lora_pad, K] (memory-bound on reading x either way).
 int run_lora_down(iic_handle* h, const void* x, int K, int M, const float* a32, const void* w16, int r4, void* p_out,
-                  cudaStream_t s) {
-  if (r4 > 4 && w16 != nullptr)
+                  cudaStream_t s, bool prefer_gemm = false) {
+  // prefer_gemm: the backward's dP = dY . B^T has no producer kernel to ride in, and the GEMM (one 256-wide tile column, the
+  // rest of the weight tile zero-filled by TMA) reads dY at several TB/s where the row kernel manages a fraction of that
+  if ((r4 > 4 || prefer_gemm) && w16 != nullptr)
     return run_gemm(h, x, K, w16, M, h->lora_pad, K, nullptr, nullptr, kEpiBiasBf16, nullptr, nullptr, p_out, h->lora_pad, 1, s,
                     nullptr, nullptr, kLoraDown);
   return timed(h, kLoraDown, s, [&] { return launch_lora_down_bf16(x, K, M, a32, r4, p_out, h->lora_pad, h->f16, s); });
@@ -465,7 +467,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     // ---- c_proj:  x_out = x_mid + h W2^T + b2 + P2 B2   (P2 = s2 h A2) ----
     LoraSlot bw_pr;   // LoRA k-step of the dX GEMM: dh += dP2 . (s2 A2)^T
     if (l_pr.rank) {
-      IIC_TRY(run_lora_down(h, w.g16, d, M, l_pr.bt32, l_pr.b16, l_pr.r4, w.dp2, s));   // dP2 = dY . B2^T
+      IIC_TRY(run_lora_down(h, w.g16, d, M, l_pr.bt32, l_pr.b16, l_pr.r4, w.dp2, s, true));   // dP2 = dY . B2^T
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, h->f16, s);
       }));
@@ -482,7 +484,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     // ---- c_fc:  u = y2 W1^T + b1 + P1 B1   (P1 = s1 y2 A1) ----
     LoraSlot bw_fc;
     if (l_fc.rank) {
-      IIC_TRY(run_lora_down(h, w.dh, mlp, M, l_fc.bt32, l_fc.b16, l_fc.r4, w.dp1, s));   // dP1 = dU . B1^T
+      IIC_TRY(run_lora_down(h, w.dh, mlp, M, l_fc.bt32, l_fc.b16, l_fc.r4, w.dp1, s, true));   // dP1 = dU . B1^T
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, h->f16, s);
       }));

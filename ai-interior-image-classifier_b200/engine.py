@@ -382,13 +382,13 @@ class Engine:
             L.check(self.h, self.lib.iic_set_lora_train(self.h, layer, which, a16.data_ptr(), bt32.data_ptr(), float(scaling),
                                                         grad_a.data_ptr(), grad_b.data_ptr()), "iic_set_lora_train")
             self._lora[(layer, which, "train")] = (a16, bt32, grad_a, grad_b)
-            if r > 4:
-                at16 = self._lora[(layer, which)][2]
-                b16 = torch.zeros(self.dims.lora_pad, lora_b.shape[1], device=self.device, dtype=self.op_dtype)
-                b16[:r] = lora_b.detach().to(self.device, torch.float32).to(self.op_dtype)
-                L.check(self.h, self.lib.iic_set_lora_operands16(self.h, layer, which, at16.data_ptr(), b16.data_ptr()),
-                        "iic_set_lora_operands16")
-                self._lora[(layer, which, "train16")] = (b16,)
+            # 16-bit lora_B [lora_pad, out] for the backward's dP = dY . B^T on the tcgen05 GEMM (all ranks); (s A)^T exists for r > 4
+            at16 = self._lora[(layer, which)][2] if r > 4 else None
+            b16 = torch.zeros(self.dims.lora_pad, lora_b.shape[1], device=self.device, dtype=self.op_dtype)
+            b16[:r] = lora_b.detach().to(self.device, torch.float32).to(self.op_dtype)
+            L.check(self.h, self.lib.iic_set_lora_operands16(self.h, layer, which, _ptr(at16), b16.data_ptr()),
+                    "iic_set_lora_operands16")
+            self._lora[(layer, which, "train16")] = (b16,)
 
     def set_lora_source(self, layer: int, which: int, lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float) -> None:
         """Register the fp32 parameters of a slot (after set_lora [+ set_lora_train]) for `refresh_lora`."""
