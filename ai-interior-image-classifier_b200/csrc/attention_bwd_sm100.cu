@@ -1,29 +1,29 @@
-// tcgen05 attention backward for sequences that fit one TMEM tile pair (T <= 256: ViT-B/16 @ 224, T = 197):
+// tcgen05 attention backward, head_dim 64, T <= 592 (ViT-B/16 @ 224: T = 197; ViT-L/14 @ 336: T = 577):
 //   (dO, saved Q/K/V, O, log-sum-exp) -> dQ, dK, dV, packed like qkv.
 //
 // Reference semantics: torch.autograd through nn.MultiheadAttention's softmax(Q K^T / sqrt(64)) V inside CLIP's
 // ResidualAttentionBlock; needed only to carry dX through the frozen attention blocks down to the LoRA-adapted MLPs
 // (/root/reference/train_lora.py:249 `loss.backward()` restricted to parameters named '*lora*').
 //
-// One persistent CTA per SM walks (image, head) items; Q, K, V, dO of the item are TMA-loaded into 128B-swizzled smem (two
-// items in flight when they fit) and serve both as K-major operands (S = Q K^T ...) and as MN-major operands
-// (dQ = dS K ...) - same bytes, different descriptors.  Per item, four 128-row tiles, all products on tcgen05:
+// One persistent CTA per SM walks (image, head) items; every item is two passes, all products on tcgen05:
 //
 //   pass Q, query tile t:  S = Q_t K^T, dP = dO_t V^T  (fp32, TMEM)  ->  dS = P o (dP - D) / 8  ->  dQ_t = dS K
 //   pass K, key tile u:    S^T = K_u Q^T, dP^T = V_u dO^T            ->  P^T, dS^T              ->  dV_u = P^T dO, dK_u = dS^T Q
 //
 // with P = exp2(S c - lse) recomputed from the saved log-sum-exp and D[q] = sum_d dO[q,d] O[q,d] from a small pre-kernel.
-// The backward softmax is purely elementwise (no row reductions), so the 8 compute warps split the COLUMNS of a tile:
+// Shared memory per pass: the two operands that span the whole sequence (X, Y = K, V in pass Q; Q, dO in pass K; TMA,
+// 128B swizzle; the next pass is prefetched when two stages fit) and a 2-deep ring of 128-row tiles (Q_t, dO_t / K_u, V_u).
+// X and Y serve both as K-major operands (S = Q_t K^T ...) and as MN-major operands (dQ = dS K ...): same bytes, different
+// descriptors.  Sequences longer than 256 are cut into column blocks of <= 192 whose second products accumulate in TMEM.
+// The backward softmax is purely elementwise (no row reductions), so the 8 compute warps split the COLUMNS of a block:
 // warps 4-7 take the first half, warps 8-11 the second half of every row (a thread still owns one TMEM lane = one row).
 // P / dS go back to TMEM as 16-bit A operands IN PLACE, each group packing into the start of ITS OWN fp32 columns (a K-step of
 // the second product takes its A operand from any column, so the two halves need not be contiguous): a group only ever
 // overwrites columns it has already read, and the groups never wait for each other.  The 64-column accumulators of the second
-// products sit in the dead top columns [192, 256) of the two regions, so the whole pipeline needs 2 x 256 = 512 TMEM columns.
-// The two halves of S / dP are separate products with their own barriers: the first group starts while the tensor core still
-// works on the second half.
+// products sit in the top columns [192, 256) of the two 256-column regions.
 //
-//   warp 0  TMA producer      warp 1  MMA issuer (whole warp, uniform operands, one elected lane issues)
-//   warp 2  TMEM allocator    warps 4-11  compute
+//   warp 0  TMA producer X/Y    warp 3  TMA producer tiles    warp 1  MMA issuer (whole warp, one elected lane issues)
+//   warp 2  TMEM allocator      warps 4-11  compute
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -43,13 +43,18 @@ constexpr int kHd = 64;
 constexpr int kThreads = 384;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBarBytes = 256;
+constexpr int kTileBytes = 128 * 128;   // one 128-row tile
+constexpr int kVecFloats = 640;         // lse / D of one item (T <= 592 rounded up)
 
 struct BwdParams {
   const float* lse;   // [B*H, T] log2-domain log-sum-exp of the scaled scores
   const float* dsum;  // [B*H, T] D = rowsum(dO o O)
   uint16_t* dqkv;     // [B*T, 3d]
   int items, T, H, TP;
-  int stages;         // items resident at once (1 or 2)
+  int nblk, bq, brem;   // column blocks: block j holds bq + (j < brem) units of 16 columns
+  int stages;           // (item, pass) units whose X / Y are resident at once (1 or 2)
+  int xy_bytes;         // bytes of one X (or Y) buffer (TMA boxes may overshoot TP rows)
+  int xy_box, xy_loads;
   float scale, scale_log2e;
 };
 
@@ -100,44 +105,51 @@ __device__ __forceinline__ float ex2(float x) {
 
 }  // namespace
 
-// kHU: compile-time bound on the 16-column units one warp group handles (7: TP <= 224, i.e. ViT-B/16; 8: TP <= 256)
-template <bool kF16, int kHU>
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1)
-attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_tile,
+                           const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_do_tile,
                            const __grid_constant__ BwdParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const int T = prm.T, H = prm.H, TP = prm.TP, items = prm.items;
+  const int T = prm.T, H = prm.H, items = prm.items;
   const int d = H * kHd;
-  const uint32_t tile_bytes = uint32_t(TP) * 128u;                      // one of Q, K, V, dO
-  const uint32_t stage_bytes = 4u * tile_bytes;
-  auto q_s = [&](int s) { return base + uint32_t(s) * stage_bytes; };
-  auto k_s = [&](int s) { return q_s(s) + tile_bytes; };
-  auto v_s = [&](int s) { return q_s(s) + 2u * tile_bytes; };
-  auto do_s = [&](int s) { return q_s(s) + 3u * tile_bytes; };
-  const uint32_t vec_off = uint32_t(prm.stages) * stage_bytes;          // lse / D of the current item: 2 x 256 floats
+  // smem: tile ring (2 slots x (A0, A1)), X / Y stages, per-item vectors, barriers
+  auto ta_s = [&](int slot, int which) { return base + uint32_t(2 * slot + which) * kTileBytes; };
+  const uint32_t xy_base = base + 4u * kTileBytes;
+  auto x_s = [&](int s) { return xy_base + uint32_t(2 * s) * uint32_t(prm.xy_bytes); };
+  auto y_s = [&](int s) { return xy_base + uint32_t(2 * s + 1) * uint32_t(prm.xy_bytes); };
+  const uint32_t vec_off = 4u * kTileBytes + uint32_t(prm.stages) * 2u * uint32_t(prm.xy_bytes);
   float* s_lse = reinterpret_cast<float*>(gen + vec_off);
-  float* s_d = s_lse + 256;
-  const uint32_t bar = base + vec_off + 2048u;
-  auto op_full = [&](int s) { return bar + 8u * s; };
-  auto op_empty = [&](int s) { return bar + 16 + 8u * s; };
-  auto sd_full = [&](int g) { return bar + 32 + 8u * g; };
-  auto ds_ready = [&](int g) { return bar + 48 + 8u * g; };
-  const uint32_t acc_full = bar + 64, acc_free = bar + 72;
-  const uint32_t tmem_slot = bar + 80;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + vec_off + 2048u + 80u);
+  float* s_d = s_lse + kVecFloats;
+  const uint32_t bar_off = vec_off + 2u * kVecFloats * 4u;
+  const uint32_t bar = base + bar_off;
+  auto xy_full = [&](int s) { return bar + 8u * s; };
+  auto xy_empty = [&](int s) { return bar + 16 + 8u * s; };
+  auto tile_full = [&](int s) { return bar + 32 + 8u * s; };
+  auto tile_empty = [&](int s) { return bar + 48 + 8u * s; };
+  auto sd_full = [&](int g) { return bar + 64 + 8u * g; };
+  auto ds_ready = [&](int g) { return bar + 80 + 8u * g; };
+  const uint32_t acc_full = bar + 96, acc_free = bar + 104;
+  const uint32_t tmem_slot = bar + 112;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + bar_off + 112u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_qkv);
-    ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_qkv_full);
+    ptx::prefetch_tensormap(&tm_do_full);
+  }
+  if (warp == 3 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_qkv_tile);
+    ptx::prefetch_tensormap(&tm_do_tile);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(op_full(s), 1); ptx::mbar_init(op_empty(s), 1); }
-    for (int g = 0; g < 2; ++g) {
-      ptx::mbar_init(sd_full(g), 1);      // tcgen05.commit
-      ptx::mbar_init(ds_ready(g), 128);   // every thread of the group
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(xy_full(s), 1); ptx::mbar_init(xy_empty(s), 1);
+      ptx::mbar_init(tile_full(s), 1); ptx::mbar_init(tile_empty(s), 1);
+      ptx::mbar_init(sd_full(s), 1);       // tcgen05.commit
+      ptx::mbar_init(ds_ready(s), 128);    // every thread of the column group
     }
     ptx::mbar_init(acc_full, 1);     // tcgen05.commit
     ptx::mbar_init(acc_free, 256);   // every compute thread
@@ -150,97 +162,137 @@ attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_items = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  const int n_tiles = (T + 127) / 128;          // 128-row tiles per pass (1 or 2)
-  // TMEM columns: S / S^T at [0, TP), dP / dP^T at [256, 256 + TP).  Column group 0 owns units [0, ua) of 16 columns,
-  // group 1 units [ua, units); the packed 16-bit unit u of a group sits at the group's first column + 8 * (u - first unit).
+  const int n_tiles = (T + 127) / 128;          // 128-row tiles per pass
+  const int nblk = prm.nblk;
+  auto blk_units = [&](int j) { return prm.bq + (j < prm.brem ? 1 : 0); };
+  auto blk_start = [&](int j) { return j * prm.bq + min(j, prm.brem); };   // in units of 16 columns
+  // TMEM columns: S / S^T block at [0, 16 u), dP / dP^T block at [256, 256 + 16 u).  Column group 0 owns the block's units
+  // [0, ua), group 1 units [ua, u); the packed 16-bit unit v of a group sits at the group's first column + 8 * (v - first).
   // 64-column accumulators in the top columns of the regions: [192, 256) and [448, 512).
   constexpr uint32_t kColS = 0, kColDp = 256, kAcc0 = 192, kAcc1 = 448;
-  const int units = TP / 16;
-  const int ua = (units + 1) / 2;
-  auto packed_col = [&](int u) { return uint32_t(u < ua ? 8 * u : 16 * ua + 8 * (u - ua)); };
+  auto packed_col = [&](int v, int ua) { return uint32_t(v < ua ? 8 * v : 16 * ua + 8 * (v - ua)); };
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
-    // ======================= TMA producer =======================
+    // ======================= TMA producer: X / Y of every (item, pass) =======================
     if (ptx::elect_one()) {
-      int n = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+      const uint32_t bytes = uint32_t(prm.xy_loads * prm.xy_box) * 128u;
+      int m = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / H, h = item - b * H;
-        const int s = n % prm.stages;
-        const uint32_t par = uint32_t(n / prm.stages) & 1u;
-        ptx::mbar_wait(op_empty(s), par ^ 1u);
-        ptx::mbar_arrive_expect_tx(op_full(s), stage_bytes);
-        ptx::tma_load_2d(&tm_qkv, op_full(s), q_s(s), h * kHd, b * T, ptx::kEvictFirst);
-        ptx::tma_load_2d(&tm_qkv, op_full(s), k_s(s), d + h * kHd, b * T, ptx::kEvictFirst);
-        ptx::tma_load_2d(&tm_qkv, op_full(s), v_s(s), 2 * d + h * kHd, b * T, ptx::kEvictFirst);
-        ptx::tma_load_2d(&tm_do, op_full(s), do_s(s), h * kHd, b * T, ptx::kEvictFirst);
+        for (int pass = 0; pass < 2; ++pass, ++m) {
+          const int s = m % prm.stages;
+          ptx::mbar_wait(xy_empty(s), (uint32_t(m / prm.stages) & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(xy_full(s), 2u * bytes);
+          for (int l = 0; l < prm.xy_loads; ++l) {
+            const uint32_t off = uint32_t(l * prm.xy_box) * 128u;
+            const int row = b * T + l * prm.xy_box;
+            if (pass == 0) {   // X = K, Y = V
+              ptx::tma_load_2d(&tm_qkv_full, xy_full(s), x_s(s) + off, d + h * kHd, row, ptx::kEvictFirst);
+              ptx::tma_load_2d(&tm_qkv_full, xy_full(s), y_s(s) + off, 2 * d + h * kHd, row, ptx::kEvictFirst);
+            } else {           // X = Q, Y = dO
+              ptx::tma_load_2d(&tm_qkv_full, xy_full(s), x_s(s) + off, h * kHd, row, ptx::kEvictFirst);
+              ptx::tma_load_2d(&tm_do_full, xy_full(s), y_s(s) + off, h * kHd, row, ptx::kEvictFirst);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ======================= TMA producer: 128-row tiles (A operands of the first products) =======================
+    if (ptx::elect_one()) {
+      uint32_t tc = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / H, h = item - b * H;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int t = 0; t < n_tiles; ++t, ++tc) {
+            const int slot = int(tc & 1u);
+            ptx::mbar_wait(tile_empty(slot), ((tc >> 1) & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx(tile_full(slot), 2u * kTileBytes);
+            const int row = b * T + t * 128;
+            if (pass == 0) {   // Q_t, dO_t
+              ptx::tma_load_2d(&tm_qkv_tile, tile_full(slot), ta_s(slot, 0), h * kHd, row, ptx::kEvictFirst);
+              ptx::tma_load_2d(&tm_do_tile, tile_full(slot), ta_s(slot, 1), h * kHd, row, ptx::kEvictFirst);
+            } else {           // K_u, V_u
+              ptx::tma_load_2d(&tm_qkv_tile, tile_full(slot), ta_s(slot, 0), d + h * kHd, row, ptx::kEvictFirst);
+              ptx::tma_load_2d(&tm_qkv_tile, tile_full(slot), ta_s(slot, 1), 2 * d + h * kHd, row, ptx::kEvictFirst);
+            }
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     const uint32_t id_acc = idesc(128, kHd, kF16, true);
-    uint32_t tile_cnt = 0;   // tiles issued so far: phase of sd_full / ds_ready / acc_full / acc_free
+    uint32_t tile_cnt = 0, blk_cnt = 0;   // phases of acc_full / acc_free / tile ring, and of sd_full / ds_ready
+    int m = 0;
     for (int n = 0; n < n_items; ++n) {
-      const int s = n % prm.stages;
-      ptx::mbar_wait(op_full(s), uint32_t(n / prm.stages) & 1u);
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < 2; ++pass, ++m) {
+        const int s = m % prm.stages;
+        ptx::mbar_wait(xy_full(s), uint32_t(m / prm.stages) & 1u);
         for (int t = 0; t < n_tiles; ++t, ++tile_cnt) {
-          // the accumulators of the previous tile live inside the S / dP regions: they must have been read out
-          if (tile_cnt > 0) ptx::mbar_wait(acc_free, (tile_cnt - 1u) & 1u);
-          ptx::tcgen05_fence_after();
-          // pass Q: A = Q_t / dO_t, B = K / V.   pass K: A = K_u / V_u, B = Q / dO.   (all K-major)
-          const uint32_t a0 = (pass == 0 ? q_s(s) : k_s(s)) + uint32_t(t) * 128u * 128u;
-          const uint32_t a1 = (pass == 0 ? do_s(s) : v_s(s)) + uint32_t(t) * 128u * 128u;
-          const uint64_t da0 = ptx::make_kmajor_sw128_desc(a0), da1 = ptx::make_kmajor_sw128_desc(a1);
-          const uint64_t db0 = ptx::make_kmajor_sw128_desc(pass == 0 ? k_s(s) : q_s(s));
-          const uint64_t db1 = ptx::make_kmajor_sw128_desc(pass == 0 ? v_s(s) : do_s(s));
-          // the two column halves are separate products with their own barriers (N = 16 * ua and 16 * (units - ua))
-          const uint32_t id_h0 = idesc(128, uint32_t(16 * ua), kF16, false), id_h1 = idesc(128, uint32_t(16 * (units - ua)), kF16, false);
-          const uint64_t boff = uint64_t((uint32_t(ua) * 16u * 128u) >> 4);   // B rows [16 ua, TP): descriptor address offset
-          if (ptx::elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16<1>(tmem_base + kColS, da0 + uint64_t(2 * kk), db0 + uint64_t(2 * kk), id_h0, kk != 0 ? 1u : 0u);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16<1>(tmem_base + kColDp, da1 + uint64_t(2 * kk), db1 + uint64_t(2 * kk), id_h0, kk != 0 ? 1u : 0u);
-            ptx::umma_commit<1>(sd_full(0));
-            if (units > ua) {
+          const int slot = int(tile_cnt & 1u);
+          ptx::mbar_wait(tile_full(slot), (tile_cnt >> 1) & 1u);
+          // a single block wider than 192 columns overlaps the accumulators of the previous tile: they must have been read
+          // out before S / dP are written; with several blocks (<= 192 columns) only the first accumulating product must wait
+          bool acc_waited = tile_cnt == 0;
+          if (!acc_waited && nblk == 1) { ptx::mbar_wait(acc_free, (tile_cnt - 1u) & 1u); acc_waited = true; }
+          const uint64_t da0 = ptx::make_kmajor_sw128_desc(ta_s(slot, 0)), da1 = ptx::make_kmajor_sw128_desc(ta_s(slot, 1));
+          for (int j = 0; j < nblk; ++j, ++blk_cnt) {
+            const int u = blk_units(j), u0 = blk_start(j), ua = (u + 1) / 2;
+            ptx::tcgen05_fence_after();
+            // first products over the block's columns = rows [16 u0, 16 (u0 + u)) of X / Y, as two halves with their own barriers
+            const uint64_t db0 = ptx::make_kmajor_sw128_desc(x_s(s) + uint32_t(u0) * 2048u);
+            const uint64_t db1 = ptx::make_kmajor_sw128_desc(y_s(s) + uint32_t(u0) * 2048u);
+            const uint32_t id_h0 = idesc(128, uint32_t(16 * ua), kF16, false), id_h1 = idesc(128, uint32_t(16 * (u - ua)), kF16, false);
+            const uint64_t boff = uint64_t((uint32_t(ua) * 2048u) >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16<1>(tmem_base + kColS + uint32_t(16 * ua), da0 + uint64_t(2 * kk), db0 + boff + uint64_t(2 * kk), id_h1, kk != 0 ? 1u : 0u);
+                ptx::umma_f16<1>(tmem_base + kColS, da0 + uint64_t(2 * kk), db0 + uint64_t(2 * kk), id_h0, kk != 0 ? 1u : 0u);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16<1>(tmem_base + kColDp + uint32_t(16 * ua), da1 + uint64_t(2 * kk), db1 + boff + uint64_t(2 * kk), id_h1, kk != 0 ? 1u : 0u);
+                ptx::umma_f16<1>(tmem_base + kColDp, da1 + uint64_t(2 * kk), db1 + uint64_t(2 * kk), id_h0, kk != 0 ? 1u : 0u);
+              ptx::umma_commit<1>(sd_full(0));
+              if (u > ua) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::umma_f16<1>(tmem_base + kColS + uint32_t(16 * ua), da0 + uint64_t(2 * kk), db0 + boff + uint64_t(2 * kk), id_h1, kk != 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::umma_f16<1>(tmem_base + kColDp + uint32_t(16 * ua), da1 + uint64_t(2 * kk), db1 + boff + uint64_t(2 * kk), id_h1, kk != 0 ? 1u : 0u);
+              }
+              ptx::umma_commit<1>(sd_full(1));
+              if (j == nblk - 1) ptx::umma_commit<1>(tile_empty(slot));   // last product that reads this tile pair
             }
-            ptx::umma_commit<1>(sd_full(1));
-          }
-          __syncwarp();
-          const uint64_t dmn0 = mn_desc(pass == 0 ? k_s(s) : do_s(s));   // dQ = dS K   |  dV = P^T dO
-          const uint64_t dmn1 = mn_desc(q_s(s));                          //             |  dK = dS^T Q
-          // both halves must be done before the accumulators (which overlap the top fp32 columns of the second half) are written
-          ptx::mbar_wait(ds_ready(0), tile_cnt & 1u);
-          ptx::mbar_wait(ds_ready(1), tile_cnt & 1u);
-          ptx::tcgen05_fence_after();
-          if (ptx::elect_one()) {
-            if (pass == 0) {
-              for (int ks = 0; ks < units; ++ks)
-                umma_ts(tmem_base + kAcc0, tmem_base + kColDp + packed_col(ks), dmn0 + uint64_t(ks * 128), id_acc, ks != 0 ? 1u : 0u);
-            } else {
-              for (int ks = 0; ks < units; ++ks)
-                umma_ts(tmem_base + kAcc0, tmem_base + kColS + packed_col(ks), dmn0 + uint64_t(ks * 128), id_acc, ks != 0 ? 1u : 0u);
-              for (int ks = 0; ks < units; ++ks)
-                umma_ts(tmem_base + kAcc1, tmem_base + kColDp + packed_col(ks), dmn1 + uint64_t(ks * 128), id_acc, ks != 0 ? 1u : 0u);
+            __syncwarp();
+            // both halves must be done before the second products: they read the packed operands of both
+            ptx::mbar_wait(ds_ready(0), blk_cnt & 1u);
+            ptx::mbar_wait(ds_ready(1), blk_cnt & 1u);
+            if (!acc_waited) { ptx::mbar_wait(acc_free, (tile_cnt - 1u) & 1u); acc_waited = true; }
+            ptx::tcgen05_fence_after();
+            // second products: reduction over the block's columns = rows [16 u0, ...) of X / Y as MN-major operands
+            const uint64_t dx = mn_desc(x_s(s) + uint32_t(u0) * 2048u), dy = mn_desc(y_s(s) + uint32_t(u0) * 2048u);
+            if (ptx::elect_one()) {
+              if (pass == 0) {       // dQ_t += dS K
+                for (int ks = 0; ks < u; ++ks)
+                  umma_ts(tmem_base + kAcc0, tmem_base + kColDp + packed_col(ks, ua), dx + uint64_t(ks * 128), id_acc, (j | ks) != 0 ? 1u : 0u);
+              } else {               // dV_u += P^T dO,  dK_u += dS^T Q
+                for (int ks = 0; ks < u; ++ks)
+                  umma_ts(tmem_base + kAcc0, tmem_base + kColS + packed_col(ks, ua), dy + uint64_t(ks * 128), id_acc, (j | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < u; ++ks)
+                  umma_ts(tmem_base + kAcc1, tmem_base + kColDp + packed_col(ks, ua), dx + uint64_t(ks * 128), id_acc, (j | ks) != 0 ? 1u : 0u);
+              }
+              if (j == nblk - 1) {
+                ptx::umma_commit<1>(acc_full);
+                if (t == n_tiles - 1) ptx::umma_commit<1>(xy_empty(s));   // last product that reads this pass's X / Y
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
-          if (ptx::elect_one()) {
-            ptx::umma_commit<1>(acc_full);
-            if (pass == 1 && t == n_tiles - 1) ptx::umma_commit<1>(op_empty(s));   // last product that reads the item's operands
-          }
-          __syncwarp();
         }
       }
     }
@@ -252,18 +304,17 @@ attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
-    const int u_lo = grp == 0 ? 0 : ua, u_hi = grp == 0 ? ua : units;
     const float c = prm.scale_log2e, scale = prm.scale;
     const int ctid = threadIdx.x - 128;                    // 0..255
-    uint32_t tile_cnt = 0;
+    uint32_t tile_cnt = 0, blk_cnt = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int b = item / H, h = item - b * H;
       // ---- per-item vectors: lse (log2 domain) and D of every query; padded queries get lse = +inf (P = 0), D = 0 ----
       asm volatile("bar.sync 1, 256;" ::: "memory");       // previous item's readers are done with the vectors
-      if (ctid < 256) {
-        const bool ok = ctid < T;
-        s_lse[ctid] = ok ? prm.lse[(size_t(b) * H + h) * T + ctid] : INFINITY;
-        s_d[ctid] = ok ? prm.dsum[(size_t(b) * H + h) * T + ctid] : 0.f;
+      for (int i = ctid; i < kVecFloats; i += 256) {
+        const bool ok = i < T;
+        s_lse[i] = ok ? prm.lse[(size_t(b) * H + h) * T + i] : INFINITY;
+        s_d[i] = ok ? prm.dsum[(size_t(b) * H + h) * T + i] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int pass = 0; pass < 2; ++pass) {
@@ -271,49 +322,53 @@ attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
           const int row = t * 128 + r;                     // query (pass Q) or key (pass K) this thread owns
           const bool row_ok = row < T;
           const bool warp_live = t * 128 + quad * 32 < T;  // warps whose 32 rows are all padding skip the math (rows are independent)
-          const float lse_r = (pass == 0 && row < 256) ? s_lse[row] : 0.f;
-          const float d_r = (pass == 0 && row < 256) ? s_d[row] : 0.f;
-          ptx::mbar_wait(sd_full(grp), tile_cnt & 1u);
-          ptx::tcgen05_fence_after();
+          const float lse_r = (pass == 0 && row < kVecFloats) ? s_lse[row] : 0.f;
+          const float d_r = (pass == 0 && row < kVecFloats) ? s_d[row] : 0.f;
+          for (int j = 0; j < nblk; ++j, ++blk_cnt) {
+            const int u = blk_units(j), u0 = blk_start(j), ua = (u + 1) / 2;
+            const int v_lo = grp == 0 ? 0 : ua, v_hi = grp == 0 ? ua : u;
+            ptx::mbar_wait(sd_full(grp), blk_cnt & 1u);
+            ptx::tcgen05_fence_after();
 #pragma unroll
-          for (int uu = 0; uu < kHU; ++uu) {
-            const int u = u_lo + uu;
-            if (u < u_hi && warp_live) {
-              uint32_t sv[16], dv[16];
-              ld16(lane_addr + kColS + uint32_t(16 * u), sv);
-              ld16(lane_addr + kColDp + uint32_t(16 * u), dv);
-              ptx::tmem_ld_wait();
-              uint32_t pp[8], pds[8];
+            for (int vv = 0; vv < 8; ++vv) {
+              const int v = v_lo + vv;                     // unit inside the block
+              if (v < v_hi && warp_live) {
+                uint32_t sv[16], dv[16];
+                ld16(lane_addr + kColS + uint32_t(16 * v), sv);
+                ld16(lane_addr + kColDp + uint32_t(16 * v), dv);
+                ptx::tmem_ld_wait();
+                uint32_t pp[8], pds[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int c0 = 16 * u + 2 * e;
-                float l0, l1, dd0, dd1;
-                if (pass == 0) {
-                  l0 = l1 = lse_r; dd0 = dd1 = d_r;
-                } else {
-                  const float2 lv = *reinterpret_cast<const float2*>(&s_lse[c0]);   // warp-uniform address: broadcast
-                  const float2 dvv = *reinterpret_cast<const float2*>(&s_d[c0]);
-                  l0 = lv.x; l1 = lv.y; dd0 = dvv.x; dd1 = dvv.y;
+                for (int e = 0; e < 8; ++e) {
+                  const int c0 = 16 * (u0 + v) + 2 * e;    // column inside the whole sequence
+                  float l0, l1, dd0, dd1;
+                  if (pass == 0) {
+                    l0 = l1 = lse_r; dd0 = dd1 = d_r;
+                  } else {
+                    const float2 lv = *reinterpret_cast<const float2*>(&s_lse[c0]);   // warp-uniform address: broadcast
+                    const float2 dvv = *reinterpret_cast<const float2*>(&s_d[c0]);
+                    l0 = lv.x; l1 = lv.y; dd0 = dvv.x; dd1 = dvv.y;
+                  }
+                  float p0 = ex2(fmaf(__uint_as_float(sv[2 * e]), c, -l0));
+                  float p1 = ex2(fmaf(__uint_as_float(sv[2 * e + 1]), c, -l1));
+                  if (pass == 0) {                         // key columns beyond T hold another image's keys
+                    p0 = c0 < T ? p0 : 0.f;
+                    p1 = c0 + 1 < T ? p1 : 0.f;
+                  }
+                  const float ds0 = p0 * (__uint_as_float(dv[2 * e]) - dd0) * scale;
+                  const float ds1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dd1) * scale;
+                  pp[e] = Act<kF16>::pack(p0, p1);
+                  pds[e] = Act<kF16>::pack(ds0, ds1);
                 }
-                float p0 = ex2(fmaf(__uint_as_float(sv[2 * e]), c, -l0));
-                float p1 = ex2(fmaf(__uint_as_float(sv[2 * e + 1]), c, -l1));
-                if (pass == 0) {                           // key columns beyond T hold another image's keys
-                  p0 = c0 < T ? p0 : 0.f;
-                  p1 = c0 + 1 < T ? p1 : 0.f;
-                }
-                const float ds0 = p0 * (__uint_as_float(dv[2 * e]) - dd0) * scale;
-                const float ds1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dd1) * scale;
-                pp[e] = Act<kF16>::pack(p0, p1);
-                pds[e] = Act<kF16>::pack(ds0, ds1);
+                // in place: the packed unit lands in fp32 columns this group has already read (see packed_col)
+                if (pass == 1) st8(lane_addr + kColS + packed_col(v, ua), pp);
+                st8(lane_addr + kColDp + packed_col(v, ua), pds);
               }
-              // in place: the packed unit lands in fp32 columns this group has already read (see packed_col)
-              if (pass == 1) st8(lane_addr + kColS + packed_col(u), pp);
-              st8(lane_addr + kColDp + packed_col(u), pds);
             }
+            st_wait();
+            ptx::tcgen05_fence_before();
+            ptx::mbar_arrive(ds_ready(grp));
           }
-          st_wait();
-          ptx::tcgen05_fence_before();
-          ptx::mbar_arrive(ds_ready(grp));
           // ---- accumulators -> global ----
           ptx::mbar_wait(acc_full, tile_cnt & 1u);
           ptx::tcgen05_fence_after();
@@ -337,14 +392,14 @@ attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             const int col0 = pass == 0 ? h * kHd + 32 * grp : (grp == 0 ? 2 * d : d) + h * kHd;
             uint16_t* dst = prm.dqkv + (size_t(b) * T + row) * (3 * d) + col0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (8 * j < ncol) {
+            for (int jj = 0; jj < 8; ++jj) {
+              if (8 * jj < ncol) {
                 uint4 w;
-                w.x = Act<kF16>::pack(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1]));
-                w.y = Act<kF16>::pack(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3]));
-                w.z = Act<kF16>::pack(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5]));
-                w.w = Act<kF16>::pack(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7]));
-                *reinterpret_cast<uint4*>(dst + 8 * j) = w;
+                w.x = Act<kF16>::pack(__uint_as_float(a[8 * jj]), __uint_as_float(a[8 * jj + 1]));
+                w.y = Act<kF16>::pack(__uint_as_float(a[8 * jj + 2]), __uint_as_float(a[8 * jj + 3]));
+                w.z = Act<kF16>::pack(__uint_as_float(a[8 * jj + 4]), __uint_as_float(a[8 * jj + 5]));
+                w.w = Act<kF16>::pack(__uint_as_float(a[8 * jj + 6]), __uint_as_float(a[8 * jj + 7]));
+                *reinterpret_cast<uint4*>(dst + 8 * jj) = w;
               }
             }
           }
@@ -419,18 +474,28 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum_scratch,
                                void* dqkv, int B, int T, int H, int head_dim, int f16, int num_sms, cudaStream_t stream) {
   if (B <= 0) return 0;
-  if (head_dim != kHd || T < 1 || T > 256 || dsum_scratch == nullptr) return -3;
+  if (head_dim != kHd || T < 1 || T > kVecFloats - 48 || dsum_scratch == nullptr) return -3;
   BwdParams p;
   p.TP = (T + 15) / 16 * 16;
-  const int tile_bytes = p.TP * 128;
-  const int fixed = 2048 + kBarBytes + 1024 /*alignment slack*/;
-  // an A operand always covers 128 rows: the last tile of a TP-row buffer is read up to row n_tiles * 128 - 1, past the buffer
-  // (those rows only produce output rows that are never stored); keep the over-read inside the allocation
-  const int n_tiles = (T + 127) / 128;
-  const int over = n_tiles * 128 * 128 - tile_bytes;
-  if (fixed + 4 * tile_bytes + over > kMaxSmem) return -3;
-  p.stages = fixed + 8 * tile_bytes + over <= kMaxSmem ? 2 : 1;
-  const int smem = fixed + p.stages * 4 * tile_bytes + over;
+  const int units = p.TP / 16;
+  // one column block while the sequence fits a 256-column TMEM region, else blocks of <= 192 columns (12 units)
+  p.nblk = units <= 16 ? 1 : (units + 11) / 12;
+  p.bq = units / p.nblk;
+  p.brem = units % p.nblk;
+  // X / Y arrive in TMA boxes of 16*dd rows; pick the box (<= 256 rows) that overshoots TP the least
+  int best_d = 1, best_rows = 1 << 30;
+  for (int dd = 16; dd >= 4; --dd) {
+    const int rows = (units + dd - 1) / dd * dd;
+    if (rows < best_rows) { best_rows = rows; best_d = dd; }
+  }
+  if (units <= 16) { best_d = units; best_rows = units; }
+  p.xy_box = 16 * best_d;
+  p.xy_loads = best_rows / best_d;
+  p.xy_bytes = best_rows * 16 * 128;
+  const int fixed = 4 * kTileBytes + 2 * kVecFloats * 4 + kBarBytes + 1024 /*alignment slack*/;
+  if (fixed + 2 * p.xy_bytes > kMaxSmem) return -3;
+  p.stages = fixed + 4 * p.xy_bytes <= kMaxSmem ? 2 : 1;
+  const int smem = fixed + p.stages * 2 * p.xy_bytes;
   p.items = B * H;
   p.T = T;
   p.H = H;
@@ -449,27 +514,24 @@ int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_o
       attention_bwd_dsum_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(d_out), static_cast<const uint16_t*>(out), dsum_scratch, B, T, H);
     if (cudaGetLastError() != cudaSuccess) return -2;
   }
-  CUtensorMap tq, tdo;
+  CUtensorMap tqf, tqt, tdf, tdt;
   const uint64_t rows = uint64_t(B) * T;
-  if (!make_map(&tq, qkv, rows, uint64_t(3 * d), uint32_t(p.TP), f16 != 0) || !make_map(&tdo, d_out, rows, uint64_t(d), uint32_t(p.TP), f16 != 0))
+  const bool h16 = f16 != 0;
+  if (!make_map(&tqf, qkv, rows, uint64_t(3 * d), uint32_t(p.xy_box), h16) || !make_map(&tqt, qkv, rows, uint64_t(3 * d), 128, h16) ||
+      !make_map(&tdf, d_out, rows, uint64_t(d), uint32_t(p.xy_box), h16) || !make_map(&tdt, d_out, rows, uint64_t(d), 128, h16))
     return -1;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(attention_bwd_sm100_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_bwd_sm100_kernel<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_bwd_sm100_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_bwd_sm100_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_bwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_bwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
       return -2;
     attr_done = true;
   }
   const int grid = p.items < num_sms ? p.items : num_sms;
-  if (p.TP <= 224) {
-    if (f16) attention_bwd_sm100_kernel<true, 7><<<grid, kThreads, smem, stream>>>(tq, tdo, p);
-    else attention_bwd_sm100_kernel<false, 7><<<grid, kThreads, smem, stream>>>(tq, tdo, p);
-  } else {
-    if (f16) attention_bwd_sm100_kernel<true, 8><<<grid, kThreads, smem, stream>>>(tq, tdo, p);
-    else attention_bwd_sm100_kernel<false, 8><<<grid, kThreads, smem, stream>>>(tq, tdo, p);
-  }
+  if (f16)
+    attention_bwd_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(tqf, tqt, tdf, tdt, p);
+  else
+    attention_bwd_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(tqf, tqt, tdf, tdt, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -101,7 +101,7 @@ struct iic_handle {
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
   int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
-  int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 256), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
+  int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
@@ -171,7 +171,7 @@ int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, 
   return launch_attention(qkv, out, lse, B, T, H, hd, h->f16, s);
 }
 
-// attention backward: tcgen05 kernel for T <= 256 (needs a [B*H*T] f32 scratch for D), mma.sync kernel otherwise
+// attention backward: tcgen05 kernel for T <= 592 (needs a [B*H*T] f32 scratch for D), mma.sync kernel otherwise
 int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum,
                       void* dqkv, int B, int T, int H, int hd, cudaStream_t s) {
   if (h->attn_bwd_impl != 1 && dsum != nullptr) {

@@ -35,7 +35,7 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
 int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int T,
                          int H, int head_dim, int f16, cudaStream_t stream);
 
-// tcgen05 / TMEM variant for T <= 256 (attention_bwd_sm100.cu); dsum_scratch f32 [B*H*T]; returns -3 outside its envelope
+// tcgen05 / TMEM variant for T <= 592 (attention_bwd_sm100.cu); dsum_scratch f32 [B*H*T]; returns -3 outside its envelope
 int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum_scratch,
                                void* dqkv, int B, int T, int H, int head_dim, int f16, int num_sms, cudaStream_t stream);
 

@@ -24,11 +24,11 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("B,T,H", [(3, 197, 12), (40, 197, 12), (2, 256, 12), (5, 50, 8), (2, 129, 12), (1, 16, 12), (2, 300, 4)])
+@pytest.mark.parametrize("B,T,H", [(3, 197, 12), (40, 197, 12), (2, 256, 12), (5, 50, 8), (2, 129, 12), (1, 16, 12), (2, 300, 4), (2, 577, 16), (12, 577, 16)])
 @pytest.mark.parametrize("mode", ["bf16", "f16"])
 def test_attention_backward(engine, engine_f16, mode, B, T, H):
-    """T <= 256 runs the tcgen05 backward (attention_bwd_sm100.cu), longer sequences the mma.sync one; B = 40 makes every
-    SM walk several (image, head) items (operand ring, barrier phases)"""
+    """tcgen05 backward (attention_bwd_sm100.cu): one column block for T <= 256, blocks of <= 192 accumulating in TMEM for the
+    longer sequences (ViT-L/14 @ 336: T = 577); the larger batches make every SM walk several (image, head) items"""
     eng = engine if mode == "bf16" else engine_f16
     dt = eng.op_dtype
     d = H * 64
