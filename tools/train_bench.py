@@ -19,11 +19,13 @@ def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     B = int(os.environ.get("TRAIN_B", "128")); steps = int(os.environ.get("STEPS", "10")); r = int(os.environ.get("RANK_LORA", "4"))
     mode = os.environ.get("IIC_OPERAND_DTYPE", "bf16")
+    name = os.environ.get("MODEL", "ViT-B/16")              # or "ViT-L/14@336px" (BASELINE configs[4])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    vis = clipc.build_visual("ViT-B/16", seed=0).to(dev)
+    vis = clipc.build_visual(name, seed=0).to(dev)
+    R, E = vis.input_resolution, vis.output_dim
     vis.operand_dtype = mode
     for blk in vis.transformer.resblocks:
         blk.mlp.c_fc = lora.LoRALinear(blk.mlp.c_fc, rank=r, alpha=2 * r)
@@ -33,8 +35,8 @@ def main():
         if n.endswith("lora_A"): p.data = (torch.randn(p.shape) * 0.02).to(dev)
         if n.endswith("lora_B"): p.data = (torch.randn(p.shape) * 0.004).to(dev)
     g = torch.Generator(device=dev).manual_seed(100 + rank)   # different data per rank
-    images = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
-    text = torch.nn.functional.normalize(torch.randn(B, 512, device=dev, generator=g), dim=-1)
+    images = torch.randint(0, 256, (B, R, R, 3), dtype=torch.uint8, device=dev, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(B, E, device=dev, generator=g), dim=-1)
     out = {}
     for overlap in (True, False):
         tr = iic_b200.VisionLoRATrainer(vis, logit_scale=100.0, overlap=overlap)
@@ -64,9 +66,9 @@ def main():
     if rank == 0:
         ms = out["ms_per_step_overlap"]
         print(json.dumps({"metric": "LoRA fine-tune step images/s (fwd+bwd, LoRA-only grads, AdamW, NCCL all-reduce)", "value": world * B / (ms * 1e-3),
-                          "unit": "images/s", "n_gpus": world, "batch_per_gpu": B, "lora_rank": r, "operand_dtype": mode, **out,
+                          "unit": "images/s", "model": name, "n_gpus": world, "batch_per_gpu": B, "lora_rank": r, "operand_dtype": mode, **out,
                           "grad_bytes_allreduced_per_step": int(flat.numel() * 4), "ranks_hold_identical_grads": same,
-                          "train_gflop_per_image": 72.1}), flush=True)
+                          "train_gflop_per_image": 72.1 if name == "ViT-B/16" else 810.2}), flush=True)
     if world > 1: dist.destroy_process_group()
 
 main()
