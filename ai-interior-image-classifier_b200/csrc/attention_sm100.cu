@@ -62,7 +62,6 @@ struct AttnParams {
   int kv_bytes;      // bytes of one K (or V) buffer (TMA boxes may overshoot TP rows)
   int kv_box, kv_loads;
   float scale_log2e;
-  unsigned issuer_sleep_ns;   // back-off of an idle MMA issuer warp between polls
   int causal;                 // 1: key j is visible to query i only if j <= i (CLIP text tower)
 };
 
@@ -458,13 +457,10 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         if (progress) {
           t_last = clock64();
-        } else {
-          // nothing to issue: leave the issue slots (and the power budget) of this scheduler to the softmax warps for a moment
-          if (prm.issuer_sleep_ns > 0) __nanosleep(prm.issuer_sleep_ns);
-          if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
-            if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
-            __trap();
-          }
+        } else if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
+          // (a __nanosleep back-off of the idle issuer was measured: no effect on the kernel or on the step)
+          if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
+          __trap();
         }
       }
     }
@@ -634,9 +630,7 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   p.out = static_cast<uint16_t*>(out);
   p.lse = lse;
   p.scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
-  p.issuer_sleep_ns = 0;
   p.causal = causal ? 1 : 0;
-  if (const char* e = getenv("IIC_ATTN_SLEEP")) p.issuer_sleep_ns = unsigned(atoi(e));
   const int d = H * kHd;
   CUtensorMap tq, tkv;
   const uint64_t rows = uint64_t(B) * T;
