@@ -176,6 +176,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: anything libraries write to fd 1 meanwhile (NCCL prints its version banner
+    # there) is sent to stderr, and fd 1 is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
@@ -296,6 +301,8 @@ def main():
                 line["cpu_baseline"], _ = cpu_reference(args, batch=16, budget_s=15.0)
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": str(ex)[:200]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
