@@ -507,6 +507,48 @@ class Engine:
             out = (r.topk_val.cpu(), r.topk_idx.cpu(), r.split_sum.cpu())
         return out
 
+    def classify_host_stream(self, batches):
+        """Streaming form of `classify_host_u8` for many batches: `batches` yields pinned uint8 [B,R,R,3] host tensors, the
+        generator yields (topk_val, topk_idx, split_sum) host tensors in the same order.  Every batch still pays its own H2D
+        copy and D2H read, but the copy of batch i+1 runs on a side stream while batch i is being encoded, and the host only
+        waits for batch i-1 while batch i is in flight (two staging buffers, two pinned result sets)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            copy = torch.cuda.Stream(device=dev)
+            staging = [None, None]
+            outs = [None, None]
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            pending = None   # slot whose results have been enqueued but not yet handed out
+            for i, host in enumerate(batches):
+                k = i & 1
+                if staging[k] is None or staging[k].shape != host.shape:
+                    staging[k] = torch.empty(host.shape, dtype=torch.uint8, device=dev)
+                with torch.cuda.stream(copy):
+                    if i >= 2:
+                        copy.wait_event(done[k])          # the encode that read this staging buffer two batches ago
+                    staging[k].copy_(host, non_blocking=True)
+                    copied[k].record(copy)
+                main.wait_event(copied[k])
+                with self._lock:
+                    r = self.classify_same_size(staging[k], want_embedding=False)
+                    if outs[k] is None or outs[k][0].shape != r.topk_val.shape:
+                        outs[k] = (torch.empty(r.topk_val.shape, dtype=r.topk_val.dtype, pin_memory=True),
+                                   torch.empty(r.topk_idx.shape, dtype=r.topk_idx.dtype, pin_memory=True),
+                                   torch.empty(r.split_sum.shape, dtype=r.split_sum.dtype, pin_memory=True))
+                    outs[k][0].copy_(r.topk_val, non_blocking=True)
+                    outs[k][1].copy_(r.topk_idx, non_blocking=True)
+                    outs[k][2].copy_(r.split_sum, non_blocking=True)
+                    done[k].record(main)
+                if pending is not None:
+                    done[pending].synchronize()
+                    yield tuple(t.clone() for t in outs[pending])
+                pending = k
+            if pending is not None:
+                done[pending].synchronize()
+                yield tuple(t.clone() for t in outs[pending])
+
     # ------------------------------------------------------------------ single operators (tests / profiling)
     def op_gemm(self, a: torch.Tensor, w: torch.Tensor, epilogue: int, bias: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,

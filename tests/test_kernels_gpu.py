@@ -256,3 +256,20 @@ def test_f16_layernorm_attention(engine_f16):
     q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     r = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
     assert torch.allclose(o.float(), r, rtol=2 ** -8, atol=3e-3), (o.float() - r).abs().max()
+
+
+def test_classify_host_stream_matches_blocking_call(engine):
+    """the pipelined host-buffer API returns, batch by batch and in order, what the blocking call returns"""
+    from importlib import import_module
+    clipc = import_module("ai-interior-image-classifier_b200.clip_compat")
+    vis = clipc.build_visual("ViT-B/16", seed=0).cuda()
+    eng = vis.sync_engine()
+    g = torch.Generator().manual_seed(31)
+    text = torch.nn.functional.normalize(torch.randn(60, 512, generator=g), dim=-1).cuda()
+    eng.set_labels(text, [40, 20], [11, 0], topk=5, logit_scale=100.0)
+    batches = [torch.randint(0, 256, (6, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(5)]
+    want = [eng.classify_host_u8(b) for b in batches]
+    got = list(eng.classify_host_stream(iter(batches)))
+    assert len(got) == len(want)
+    for (tv, ti, ss), (wv, wi, ws) in zip(got, want):
+        assert torch.equal(ti, wi) and torch.equal(tv, wv) and torch.equal(ss, ws)
