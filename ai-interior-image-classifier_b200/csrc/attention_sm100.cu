@@ -459,7 +459,8 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           t_last = clock64();
         } else if ((clock64() - t_last) > IIC_MBAR_TIMEOUT_CYCLES) {
           // (a __nanosleep back-off of the idle issuer was measured: no effect on the kernel or on the step)
-          if (lane == 0) printf("iic: attention MMA issuer stalled (block %d group %d)\n", int(blockIdx.x), g);
+          if (lane == 0)
+            printf("iic: attention MMA issuer stalled (block %d group %d: S ops %u, P.V ops %u of %u)\n", int(blockIdx.x), g, s_k, p_k, total_ops);
           __trap();
         }
       }
