@@ -189,3 +189,34 @@ def test_encode_image_entry_point(product, iic):
     assert cos.min().item() >= COS_BAR, cos.min()
     assert emb.dtype == torch.float32 and emb.shape == (16, 512)
     model.visual.apply_out_proj_lora = saved
+
+
+def test_batch_invariance_and_determinism(product, iic):
+    """Size-independent properties of the path: an image's result does not depend on the batch it travels in (rows never mix:
+    bit-exact for any batch split), a second run gives the same bits, and at the BASELINE batch size (1024 / GPU) a
+    permutation of the inputs permutes the outputs."""
+    model, _ = product
+    lab, sizes, split = label_layout()
+    text = torch.from_numpy(golden_npz("text_features.npz")["text"]).cuda()
+    crops = torch.from_numpy(golden_npz("crops_u8.npz")["crops"]).cuda()
+    eng = model.visual.sync_engine(use_lora=False)
+    eng.set_labels(text, sizes, split, topk=5, logit_scale=100.0)
+    eng._labels_owner = None
+    full = eng.classify_same_size(crops)
+    logits, emb, ti = full.logits.clone(), full.embedding.clone(), full.topk_idx.clone()
+    again = eng.classify_same_size(crops)
+    assert torch.equal(again.logits, logits) and torch.equal(again.embedding, emb)
+    for chunk in (1, 7, 64):
+        parts = [eng.classify_same_size(crops[i:i + chunk]) for i in range(0, min(crops.shape[0], 3 * chunk), chunk)]
+        got = torch.cat([p.logits for p in parts], 0)
+        assert torch.equal(got, logits[:got.shape[0]]), chunk
+    # full size: 1024 images (the 151 crops tiled), a random permutation
+    g = torch.Generator(device="cuda").manual_seed(3)
+    idx = torch.randint(0, crops.shape[0], (1024,), device="cuda", generator=g)
+    big = crops[idx]
+    r1 = eng.classify_same_size(big)
+    l1 = r1.logits.clone()
+    assert torch.equal(l1, logits[idx])
+    perm = torch.randperm(1024, device="cuda", generator=g)
+    r2 = eng.classify_same_size(big[perm])
+    assert torch.equal(r2.logits, l1[perm]) and torch.equal(r2.topk_idx, ti[idx][perm])
