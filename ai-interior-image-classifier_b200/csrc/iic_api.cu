@@ -398,33 +398,33 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const int gg = h->g * h->g;
   const float eps = 1e-5f;
-  const size_t xbytes = size_t(M) * d * 4;
   h->err.clear();
   IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
                    nullptr, h->pos, w.xpre, d, gg, s));
   IIC_TRY(timed(h, kMisc, s, [&] { return launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s); }));
+  // The residual stream is never copied: every residual epilogue writes straight into the buffer the backward pass will read
+  // (block l: x_in(l) -> out_proj -> x_mid(l) -> c_proj -> x_in(l+1); the last block writes the workspace stream w.x).
   IIC_TRY(timed(h, kLayerNorm, s, [&] {
-    return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.x, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+    return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.layers[0].x_in, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
   }));
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
   for (size_t li = 0; li < h->blocks.size(); ++li) {
     Block& b = h->blocks[li];
     TrainLayer& t = w.layers[li];
+    float* x_next = li + 1 < h->blocks.size() ? w.layers[li + 1].x_in : w.x;
     const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     if (b.lora[IIC_LORA_IN_PROJ].rank || b.lora[IIC_LORA_OUT_PROJ].rank)
       return fail(h, IIC_ERR_ARG, "training supports LoRA on mlp.c_fc / mlp.c_proj (what the reference's wrap makes effective)");
-    if (cudaMemcpyAsync(t.x_in, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+      return launch_layernorm(t.x_in, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
     }));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, nullptr, nullptr, kEpiBiasBf16, b.b_qkv, nullptr, t.qkv, 3 * d, 1, s));
     IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, t.qkv, t.attn, t.lse, B, T, H, d / H, 0, s); }));
-    IIC_TRY(run_gemm(h, t.attn, d, b.w_out, M, d, d, nullptr, nullptr, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
-    if (cudaMemcpyAsync(t.x_mid, w.x, xbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "copy failed");
+    IIC_TRY(run_gemm(h, t.attn, d, b.w_out, M, d, d, nullptr, nullptr, kEpiBiasResF32, b.b_out, t.x_in, t.x_mid, d, 1, s));
     const bool fc_gemm = l_fc.rank > 0 && l_fc.r4 > 4 && l_fc.at16 != nullptr;
     IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, t.y2, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
+      return launch_layernorm(t.x_mid, d, b.ln2_g, b.ln2_b, t.y2, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
                               l_fc.r4, t.p1, h->lora_pad, h->f16, s);
     }));
     if (fc_gemm) IIC_TRY(run_lora_down(h, t.y2, d, M, l_fc.a, l_fc.at16, l_fc.r4, t.p1, s));
@@ -437,7 +437,7 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
       }));
     else if (l_pr.rank)
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, t.p2, s));
-    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, t.p2, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
+    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, t.p2, kEpiBiasResF32, b.b_proj, t.x_mid, x_next, d, 1, s));
   }
   // class-token rows of the final residual stream (input of ln_post), [B, d] contiguous
   return copy_rows_async(x_cls_out, size_t(d) * 4, w.x, size_t(T) * d * 4, size_t(d) * 4, size_t(B), s) ? fail(h, IIC_ERR_CUDA, "copy failed") : 0;
