@@ -121,6 +121,12 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// pairs of a 16-column unit whose exponentials run on the FMA pipe (polynomial) instead of the MUFU pipe: bit e of the mask
+#ifndef IIC_ATTN_POLY_MASK
+#define IIC_ATTN_POLY_MASK 0x24   // pairs 2 and 5 of 8: a quarter of the exponentials (measured best: 0.47 -> 0.42 ms at T = 197;
+                                  // 1/8 and 3/8 are both slower than 2/8 - the MUFU pipe is not the only limiter)
+#endif
+
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -143,6 +149,25 @@ __device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
   uint64_t r;
   asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
+}
+// exp2 of two values on the FMA pipe (the MUFU pipe, 16 ex2/clk/SM, is what bounds the softmax): x = n + f with n = rint(x)
+// from the magic-number add, 2^f by a degree-3 polynomial on [-0.5, 0.5] (max relative error 7.5e-5 = 2^-13.7, below the
+// 16-bit rounding of P), 2^n by adding n to the exponent field.  Valid for x in [-125, 100].
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const uint64_t xc = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const uint64_t t2 = add2(xc, pack2(12582912.f, 12582912.f));             // 1.5 * 2^23: the integer part lands in the low bits
+  const uint64_t n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), xc);
+  uint64_t p2 = fma2(pack2(0.0551716685f, 0.0551716685f), f2, pack2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f2, pack2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f2, pack2(0.9999280572f, 0.9999280572f));
+  float t0, t1, p0, p1;
+  unpack2(t2, t0, t1);
+  unpack2(p2, p0, p1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 struct SoftmaxRow {
@@ -240,9 +265,16 @@ __device__ __forceinline__ void softmax_block(uint32_t sb, uint32_t o_addr, Soft
     if (!first) unit_max(i);   // independent of the exponentials: the two instruction streams interleave
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float x0, x1;
-      unpack2(fma2(pack2(__uint_as_float(v[16 * i + 2 * e]), __uint_as_float(v[16 * i + 2 * e + 1])), c2, nm2), x0, x1);
-      const float e0 = ex2(x0), e1 = ex2(x1);
+      const uint64_t xx = fma2(pack2(__uint_as_float(v[16 * i + 2 * e]), __uint_as_float(v[16 * i + 2 * e + 1])), c2, nm2);
+      float e0, e1;
+      if ((IIC_ATTN_POLY_MASK >> e) & 1) {
+        ex2_poly2(xx, e0, e1);
+      } else {
+        float x0, x1;
+        unpack2(xx, x0, x1);
+        e0 = ex2(x0);
+        e1 = ex2(x1);
+      }
       if (e & 1) acc1 = add2(acc1, pack2(e0, e1)); else acc0 = add2(acc0, pack2(e0, e1));
       pk[8 * i + e] = Act<kF16>::pack(e0, e1);
     }
