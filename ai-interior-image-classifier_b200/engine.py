@@ -110,6 +110,11 @@ class Engine:
         self._labels: Optional[Tuple[torch.Tensor, List[int], int]] = None
         self._workspace: Optional[torch.Tensor] = None
         self._patches: Optional[torch.Tensor] = None
+        # CUDA graphs of the whole path for small batches (latency path): keyed by batch size, dropped whenever a pointer the
+        # captured kernels read could have changed (weights, LoRA operands, labels)
+        self._graphs: Dict[int, tuple] = {}
+        self._profiling = False
+        self.graph_max_batch = int(os.environ.get("IIC_GRAPH_MAX_BATCH", "16"))
 
     def __del__(self):
         try:
@@ -129,6 +134,7 @@ class Engine:
             L.check(self.h, self.lib.iic_load_weight(self.h, name.encode(), t.data_ptr(), dt, t.dim(), shape),
                     f"iic_load_weight({name})")
             self._weights[name] = t
+            self._graphs.clear()
 
     def load_visual_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """`sd`: OpenAI-CLIP `visual.*` tensors keyed WITHOUT the `visual.` prefix (fp32, any device).
@@ -173,6 +179,7 @@ class Engine:
         """lora_a [in, r], lora_b [r, out] exactly as the reference stores them (main.py:26-27); `scaling` is
         alpha / rank (main.py:28).  None clears the slot."""
         with self._lock:
+            self._graphs.clear()
             if lora_a is None or lora_b is None:
                 L.check(self.h, self.lib.iic_set_lora(self.h, layer, which, None, None, 0), "iic_set_lora")
                 self._lora.pop((layer, which), None)
@@ -218,6 +225,7 @@ class Engine:
             L.check(self.h, self.lib.iic_set_labels(self.h, t.data_ptr(), t.shape[0], c_off, c_split, G, int(topk),
                                                     float(logit_scale)), "iic_set_labels")
             self._labels = (t, offs, int(topk))
+            self._graphs.clear()
 
     # ------------------------------------------------------------------ buffers
     def _ws(self, B: int) -> torch.Tensor:
@@ -347,10 +355,57 @@ class Engine:
                                                   C.byref(out), _stream_ptr(self.device)), "iic_classify")
         return HeadResult(emb, logits, probs, tv, ti, ss)
 
-    def classify_same_size(self, images_u8: torch.Tensor, want_embedding: bool = True) -> HeadResult:
-        """uint8 [B,R,R,3] device tensor -> preprocess + encoder + head."""
+    def classify_same_size(self, images_u8: torch.Tensor, want_embedding: bool = True, use_graph: Optional[bool] = None) -> HeadResult:
+        """uint8 [B,R,R,3] device tensor -> preprocess + encoder + head.  Small batches (<= graph_max_batch) replay a CUDA
+        graph of the ~100 launches of the path (the single-image case of main.py is launch-bound otherwise)."""
+        B = images_u8.shape[0]
+        if use_graph is None:
+            use_graph = 0 < B <= self.graph_max_batch and not self._profiling and not torch.cuda.is_current_stream_capturing()
         with self._lock:
-            return self.classify_patches(self.preprocess_same_size(images_u8), images_u8.shape[0], want_embedding)
+            if use_graph:
+                return self._classify_graphed(images_u8, want_embedding)
+            return self.classify_patches(self.preprocess_same_size(images_u8), B, want_embedding)
+
+    def _classify_graphed(self, images_u8: torch.Tensor, want_embedding: bool) -> HeadResult:
+        B = images_u8.shape[0]
+        assert images_u8.dtype == torch.uint8 and images_u8.is_cuda and images_u8.is_contiguous()
+        assert tuple(images_u8.shape[1:]) == (self.arch.image_size, self.arch.image_size, 3), images_u8.shape
+        entry = self._graphs.get(B)
+        if entry is None:
+            dev = self.device
+            with torch.cuda.device(dev):
+                # private, static buffers: nothing the captured kernels touch may move or be reused while the graph lives
+                static_in = torch.empty_like(images_u8)
+                patches = torch.zeros(B * self.arch.grid * self.arch.grid, self.dims.patch_kpad, dtype=self.op_dtype, device=dev)
+                ws = torch.empty(int(self.lib.iic_workspace_bytes(self.h, B)), dtype=torch.uint8, device=dev)
+                out, logits, probs, tv, ti, ss = self._head_out(B)
+                emb = torch.empty(B, self.arch.embed_dim, dtype=torch.float32, device=dev)
+
+                def run():
+                    s = _stream_ptr(dev)
+                    L.check(self.h, self.lib.iic_preprocess_same_size(self.h, static_in.data_ptr(), B, patches.data_ptr(),
+                                                                      L.OUT_PATCHES_BF16, s), "iic_preprocess_same_size")
+                    L.check(self.h, self.lib.iic_classify(self.h, patches.data_ptr(), B, ws.data_ptr(), ws.numel(), emb.data_ptr(),
+                                                          C.byref(out), s), "iic_classify")
+
+                static_in.copy_(images_u8)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    run()                      # warm-up outside capture: one-off attribute / descriptor setup
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    run()
+            entry = (graph, static_in, (emb, logits, probs, tv, ti, ss), (patches, ws, out))
+            self._graphs[B] = entry
+        graph, static_in, (emb, logits, probs, tv, ti, ss), _keep = entry
+        with torch.cuda.device(self.device):
+            static_in.copy_(images_u8, non_blocking=True)
+            graph.replay()
+            # hand out copies: the static outputs are overwritten by the next replay
+            return HeadResult(emb.clone() if want_embedding else None, logits.clone(), probs.clone(), tv.clone(), ti.clone(), ss.clone())
 
     def classify(self, images_u8: Sequence[torch.Tensor], want_embedding: bool = True) -> HeadResult:
         """list of uint8 [H,W,3] device tensors (any size) -> preprocess + encoder + head."""
@@ -488,6 +543,7 @@ class Engine:
 
     # ------------------------------------------------------------------ measurement
     def profile(self, enable: bool = True) -> None:
+        self._profiling = bool(enable)
         L.check(self.h, self.lib.iic_profile(self.h, 1 if enable else 0), "iic_profile")
 
     def profile_read(self) -> Dict[str, Dict[str, float]]:

@@ -273,3 +273,38 @@ def test_classify_host_stream_matches_blocking_call(engine):
     assert len(got) == len(want)
     for (tv, ti, ss), (wv, wi, ws) in zip(got, want):
         assert torch.equal(ti, wi) and torch.equal(tv, wv) and torch.equal(ss, ws)
+
+
+def test_small_batch_cuda_graph_matches_direct_launches(engine):
+    """batches <= Engine.graph_max_batch replay a CUDA graph of the whole path: same bits as the direct launches, also after the
+    labels or a LoRA pair changed (the graphs are dropped then) and when the input buffer moves"""
+    from importlib import import_module
+    clipc = import_module("ai-interior-image-classifier_b200.clip_compat")
+    lora = import_module("ai-interior-image-classifier_b200.lora")
+    vis = clipc.build_visual("ViT-B/16", seed=0).cuda()
+    eng = vis.sync_engine()
+    g = torch.Generator().manual_seed(41)
+    text = torch.nn.functional.normalize(torch.randn(60, 512, generator=g), dim=-1).cuda()
+    eng.set_labels(text, [40, 20], [11, 0], topk=5, logit_scale=100.0)
+    for B in (1, 5, 16):
+        imgs = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=g).cuda()
+        want = eng.classify_same_size(imgs, use_graph=False)
+        for _ in range(2):                                   # capture, then replay
+            got = eng.classify_same_size(imgs.clone())       # default: graph for B <= 16
+            assert torch.equal(got.logits, want.logits) and torch.equal(got.topk_idx, want.topk_idx)
+            assert torch.equal(got.embedding, want.embedding) and torch.equal(got.split_sum, want.split_sum)
+    assert set(eng._graphs) == {1, 5, 16}
+    imgs = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g).cuda()
+    # new labels -> graphs dropped, results follow
+    text2 = torch.nn.functional.normalize(torch.randn(60, 512, generator=g), dim=-1).cuda()
+    eng.set_labels(text2, [40, 20], [11, 0], topk=5, logit_scale=100.0)
+    assert not eng._graphs
+    assert torch.equal(eng.classify_same_size(imgs).logits, eng.classify_same_size(imgs, use_graph=False).logits)
+    # a LoRA pair appears -> graphs dropped, results follow
+    blk = vis.transformer.resblocks[3]
+    blk.mlp.c_fc = lora.LoRALinear(blk.mlp.c_fc, rank=4, alpha=8)
+    blk.mlp.c_fc.lora.lora_B.data.normal_(0, 0.02)
+    eng = vis.sync_engine()
+    a = eng.classify_same_size(imgs)
+    b = eng.classify_same_size(imgs, use_graph=False)
+    assert torch.equal(a.logits, b.logits) and not torch.equal(a.logits, eng.classify_same_size(imgs, use_graph=False).logits * 0)
