@@ -330,7 +330,8 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(k_full(s), 1); ptx::mbar_init(v_full(s), 1);
-      ptx::mbar_init(kv_empty(s), nq > 1 ? 2 : 1);   // one tcgen05.commit per MMA issuer that reads the stage
+      ptx::mbar_init(kv_empty(s), nq > 1 ? 2 : 1);   // one tcgen05.commit per MMA issuer that reads the stage (single-tile
+                                                      // sequences: the item belongs to one group)
       ptx::mbar_init(o_full(s), 1);      // tcgen05.commit
       ptx::mbar_init(o_free(s), 128);    // every thread of the group
       for (int b = 0; b < 2; ++b) {
@@ -349,6 +350,9 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_items = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  // Tile t of the CTA's n-th item belongs to softmax group (t & 1) ^ (n & nq & 1): with an odd tile count the group that gets
+  // the extra tile alternates from item to item (ViT-L/14: 5 tiles; text tower: 1 tile, so both groups work at all).
+  auto first_tile = [&](int g, int n) { return g ^ (n & nq & 1); };
   auto blk_units = [&](int j) { return prm.bq + (j < prm.brem ? 1 : 0); };
   auto blk_start = [&](int j) { return j * prm.bq + min(j, prm.brem); };   // in units of 16 keys
 
@@ -382,10 +386,11 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     // ======================= Q producer: tile t of every item goes to group t & 1 (2-deep ring per group) ===========
     if (ptx::elect_one()) {
       uint32_t cnt[2] = {0, 0};
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int n = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
         const int b = item / H, h = item - b * H;
         for (int t = 0; t < nq; ++t) {
-          const int g = t & 1, slot = int(cnt[g] & 1u);
+          const int g = (t & 1) ^ (n & nq & 1), slot = int(cnt[g] & 1u);
           ptx::mbar_wait(q_empty(g, slot), ((cnt[g] >> 1) & 1u) ^ 1u);
           ptx::mbar_arrive_expect_tx(q_full(g, slot), kQTileBytes);
           ptx::tma_load_2d(&tm_q, q_full(g, slot), q_s + uint32_t(2 * g + slot) * kQTileBytes, h * kHd, b * T + t * 128,
@@ -402,11 +407,21 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     // S op k goes to S buffer k & 1 and may be issued once P.V of op k-2 has been issued (in-order tensor pipe), so
     // the tensor core runs up to two ops ahead of the softmax, across tiles and items.
     const int g = warp - 1;
-    if (g < nq && n_items > 0) {
+    uint32_t total_ops = 0;
+    for (int n = 0; n < n_items; ++n) {
+      const int t0 = first_tile(g, n);
+      if (t0 < nq) total_ops += uint32_t((nq - t0 + 1) / 2) * uint32_t(nb);
+    }
+    if (total_ops > 0) {
       const uint32_t region = tmem_base + uint32_t(g * kRegionCols);
       const uint32_t idesc_o = idesc(128, kHd, kF16, true);
-      const uint32_t total_ops = uint32_t(n_items) * uint32_t((nq - g + 1) / 2) * uint32_t(nb);
-      int s_n = 0, s_t = g, s_j = 0, p_n = 0, p_t = g, p_j = 0;
+      // cursor = (item, tile, block); items in which this group has no tile (single-tile sequences) are skipped
+      auto next_item = [&](int& n, int& t) {
+        do { ++n; t = first_tile(g, n); } while (n < n_items && t >= nq);
+      };
+      int s_n = -1, s_t = 0, s_j = 0, p_n = -1, p_t = 0, p_j = 0;
+      next_item(s_n, s_t);
+      next_item(p_n, p_t);
       uint32_t s_k = 0, p_k = 0, s_tiles = 0, p_tiles = 0;
       long long t_last = clock64();
       while (p_k < total_ops) {
@@ -445,7 +460,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
               ++p_tiles;
               p_j = 0;
               p_t += 2;
-              if (p_t >= nq) { p_t = g; ++p_n; }
+              if (p_t >= nq) next_item(p_n, p_t);
             } else {
               ++p_j;
             }
@@ -480,7 +495,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
               ++s_tiles;
               s_j = 0;
               s_t += 2;
-              if (s_t >= nq) { s_t = g; ++s_n; }
+              if (s_t >= nq) next_item(s_n, s_t);
             } else {
               ++s_j;
             }
@@ -551,10 +566,11 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (prm.lse != nullptr) prm.lse[(size_t(pd.b) * H + pd.h) * T + q] = pd.m + log2f(sum);
       }
     };
-    if (g < nq) {
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    {
+      int n_loc = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++n_loc) {
         const int b = item / H, h = item - b * H;
-        for (int t = g; t < nq; t += 2) {
+        for (int t = first_tile(g, n_loc); t < nq; t += 2) {
           const bool warp_live = t * 128 + quad * 32 < T;   // warps whose 32 query rows are all padding do no math
           SoftmaxRow st;
           st.m = 0.f;
