@@ -172,16 +172,51 @@ lora_outer_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __re
   }
 }
 
-// out = scale * sum_split part[split][c][n]   written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r))
+// Ranks 5..16 in ONE pass over Y (the 4-column kernel above would stream Y once per 4 ranks): thread = 2 adjacent columns of Y
+// and all 16 columns of P (zero padded beyond the rank), 32 accumulators; CTA = 128 threads = 256 columns x one split.
+// part[split][c][n], c < 16.
+template <bool kF16>
+__global__ void __launch_bounds__(128)
+lora_outer16_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int rows_per_split,
+                    int act, float* __restrict__ part) {
+  const int n = blockIdx.x * 256 + threadIdx.x * 2;
+  const int split = blockIdx.y;
+  const int m0 = split * rows_per_split;
+  const int m1 = min(M, m0 + rows_per_split);
+  if (n >= N) return;
+  float a0[16], a1[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a0[c] = a1[c] = 0.f;
+#pragma unroll 4
+  for (int m = m0; m < m1; ++m) {
+    const uint4 pa = *reinterpret_cast<const uint4*>(P + size_t(m) * p_ld);        // warp-uniform: broadcast
+    const uint4 pb = *reinterpret_cast<const uint4*>(P + size_t(m) * p_ld + 8);
+    float2 y = Act<kF16>::unpack(*reinterpret_cast<const uint32_t*>(Y + size_t(m) * N + n));
+    if (act != 0) { y.x = act_fwd(y.x, act); y.y = act_fwd(y.y, act); }
+    const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 pv = Act<kF16>::unpack(pw[e]);
+      a0[2 * e] = fmaf(pv.x, y.x, a0[2 * e]);         a1[2 * e] = fmaf(pv.x, y.y, a1[2 * e]);
+      a0[2 * e + 1] = fmaf(pv.y, y.x, a0[2 * e + 1]); a1[2 * e + 1] = fmaf(pv.y, y.y, a1[2 * e + 1]);
+    }
+  }
+  float* o = part + (size_t(split) * 16) * N + n;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) *reinterpret_cast<float2*>(o + size_t(c) * N) = make_float2(a0[c], a1[c]);
+}
+
+// out = scale * sum_split part[split][c][n], c < rc (4 or 16 columns per pass)
+// written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r))
 __global__ void __launch_bounds__(256)
-lora_outer_reduce_kernel(const float* __restrict__ part, int splits, int N, int rank, int c0, float scale, int transpose,
+lora_outer_reduce_kernel(const float* __restrict__ part, int splits, int N, int rank, int c0, int rc, float scale, int transpose,
                          float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 4 * N) return;
+  if (i >= rc * N) return;
   const int c = i / N, n = i - c * N;
   if (c0 + c >= rank) return;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += part[(size_t(sp) * 4 + c) * N + n];
+  for (int sp = 0; sp < splits; ++sp) s += part[(size_t(sp) * rc + c) * N + n];
   s *= scale;
   if (transpose) out[size_t(n) * rank + c0 + c] = s;
   else out[size_t(c0 + c) * N + n] = s;
@@ -238,15 +273,24 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
                       float* out, float* scratch, int f16, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   if (rank < 1 || (rank + 3) / 4 * 4 > p_ld || N % 8 != 0) return -1;
+  const uint16_t* p = static_cast<const uint16_t*>(P);
+  const uint16_t* y = static_cast<const uint16_t*>(Y);
+  if (rank > 4 && rank <= 16 && p_ld >= 16) {
+    // one pass over Y for all ranks: 256-row splits keep the partial buffer at M/16 * N floats (same as the rank-4 path)
+    const int rps = 256, splits = (M + rps - 1) / rps;
+    dim3 grid(unsigned((N + 255) / 256), unsigned(splits));
+    if (f16) lora_outer16_kernel<true><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, rps, act, scratch);
+    else lora_outer16_kernel<false><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, rps, act, scratch);
+    lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, 0, 16, scale, transpose, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   const int splits = lora_outer_splits(M);
   const int rps = 64;
   dim3 grid(unsigned((N + 1023) / 1024), unsigned(splits));
-  const uint16_t* p = static_cast<const uint16_t*>(P);
-  const uint16_t* y = static_cast<const uint16_t*>(Y);
   for (int c0 = 0; c0 < rank; c0 += 4) {   // 4 LoRA columns per pass over Y (rank 4: one pass)
     if (f16) lora_outer_kernel<true><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
     else lora_outer_kernel<false><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
-    lora_outer_reduce_kernel<<<(4 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, c0, scale, transpose, out);
+    lora_outer_reduce_kernel<<<(4 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, c0, 4, scale, transpose, out);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
