@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "act_types.cuh"
 #include "kernels.h"
 
@@ -206,6 +208,127 @@ lora_outer16_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __
   for (int c = 0; c < 16; ++c) *reinterpret_cast<float2*>(o + size_t(c) * N) = make_float2(a0[c], a1[c]);
 }
 
+// ---- LoRA gradient reductions on the (legacy) tensor cores -----------------------------------------------------------------
+// part[split][c][n] = sum over the split's rows m of P[m, c] * f(Y[m, n]),  c < 16 (P zero padded beyond the rank).
+// A standalone kernel, so warp-level mma.sync does not fight a tcgen05 mainloop for the tensor pipe: the reduction is a
+// [16 x rows] . [rows x 64] product per warp - 2 FLOP per byte of Y per rank - which the CUDA-core kernels above could not
+// keep HBM-bound beyond rank 4.  CTA = 4 warps x 128 rows of one 64-column tile; per 16-row step a warp cp.asyncs its
+// [16 x 64] slice of Y (XOR-swizzled 128-byte rows) and [16 x 16] slice of P into a private 2-stage buffer, loads
+// A = P^T and B = Y with ldmatrix.trans and issues 8 m16n8k16 MMAs; the four warps' accumulators are added through smem.
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+template <bool kF16>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (kF16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+constexpr int kOuterRowsPerCta = 512;   // 4 warps x 128 rows
+
+template <bool kF16>
+__global__ void __launch_bounds__(128)
+lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int act,
+                      float* __restrict__ part) {
+  // per warp: 2 stages x (Y slice 16 x 128 B = 2 KB, P slice 16 x 32 B = 512 B); then the CTA-wide reduction buffer
+  __shared__ __align__(128) uint8_t sbuf[4][2][2560];
+  __shared__ float red[4][16][64 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 64;
+  const int m_begin = blockIdx.y * kOuterRowsPerCta + warp * 128;
+  const int m_end = min(M, m_begin + 128);
+  const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(&sbuf[warp][0][0]));
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+  auto issue = [&](int step, int stage) {
+    const int m0 = m_begin + step * 16;
+    const uint32_t ys = sb + uint32_t(stage) * 2560u, ps = ys + 2048u;
+    // Y slice: 16 rows x 8 chunks of 16 B; lane -> (row = lane / 2 (+8 on the second round), 4 chunks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * 32 + lane;            // 0..127
+      const int row = idx >> 3, ch = idx & 7;
+      const int m = m0 + row;
+      const bool ok = m < m_end && n0 + ch * 8 < N;
+      cp16(ys + uint32_t(row * 128 + ((ch ^ (row & 7)) << 4)), Y + size_t(ok ? m : 0) * N + n0 + ch * 8, ok);
+    }
+    {   // P slice: 16 rows x 2 chunks
+      const int row = lane >> 1, ch = lane & 1;
+      const int m = m0 + row;
+      const bool ok = m < m_end;
+      cp16(ps + uint32_t(row * 32 + ch * 16), P + size_t(ok ? m : 0) * p_ld + ch * 8, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int steps = m_begin < m_end ? (m_end - m_begin + 15) / 16 : 0;
+  if (steps > 0) issue(0, 0);
+  for (int st = 0; st < steps; ++st) {
+    const int stage = st & 1;
+    if (st + 1 < steps) {
+      issue(st + 1, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t ys = sb + uint32_t(stage) * 2560u, ps = ys + 2048u;
+    // A = P^T (16 ranks x 16 rows): four transposed 8x8 blocks of the [row][rank] slice
+    uint32_t a[4];
+    {
+      const int mat = lane >> 3, r8 = lane & 7;
+      const int row = (mat >> 1) * 8 + r8;        // matrices 0,1: rows 0-7; 2,3: rows 8-15
+      const int chunk = mat & 1;                  // matrices 0,2: ranks 0-7; 1,3: ranks 8-15
+      ldsm4t(ps + uint32_t(row * 32 + chunk * 16), a);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {              // pairs of 8-column tiles
+      uint32_t b[4];
+      const int mat = lane >> 3, r8 = lane & 7;
+      const int row = (mat & 1) * 8 + r8;         // matrices 0,2: rows 0-7; 1,3: rows 8-15
+      const int ch = jp * 2 + (mat >> 1);         // matrices 0,1: tile 2 jp; 2,3: tile 2 jp + 1
+      ldsm4t(ys + uint32_t(row * 128 + ((ch ^ (row & 7)) << 4)), b);
+      if (act != 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 y = Act<kF16>::unpack(b[e]);
+          b[e] = Act<kF16>::pack(act_fwd(y.x, act), act_fwd(y.y, act));
+        }
+      }
+      mma16816<kF16>(acc[2 * jp], a, b[0], b[1]);
+      mma16816<kF16>(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+    __syncwarp();   // every lane is done with this stage before it is refilled two steps later
+  }
+  // accumulator layout of m16n8: lane (g, t) holds ranks g, g + 8 and columns 2t, 2t + 1 of tile j
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[warp][g][8 * j + 2 * t] = acc[j][0];
+    red[warp][g][8 * j + 2 * t + 1] = acc[j][1];
+    red[warp][g + 8][8 * j + 2 * t] = acc[j][2];
+    red[warp][g + 8][8 * j + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 64; i += 128) {
+    const int c = i >> 6, n = i & 63;
+    if (n0 + n < N)
+      part[(size_t(blockIdx.y) * 16 + c) * N + n0 + n] = (red[0][c][n] + red[1][c][n]) + (red[2][c][n] + red[3][c][n]);
+  }
+}
+
 // out = scale * sum_split part[split][c][n], c < rc (4 or 16 columns per pass)
 // written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r))
 __global__ void __launch_bounds__(256)
@@ -267,7 +390,10 @@ int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaS
 }
 
 int lora_outer_splits(int M) { return (M + 63) / 64; }   // 64 rows per split
-size_t lora_outer_scratch_bytes(int N, int M) { return size_t(lora_outer_splits(M)) * 4 * N * sizeof(float); }
+size_t lora_outer_scratch_bytes(int N, int M) {   // the largest partial buffer of the three reduction kernels
+  const size_t rows = size_t(lora_outer_splits(M)) * 4, rows_mma = size_t((M + 511) / 512) * 16, rows16 = size_t((M + 255) / 256) * 16;
+  return (rows > rows_mma ? (rows > rows16 ? rows : rows16) : (rows_mma > rows16 ? rows_mma : rows16)) * N * sizeof(float);
+}
 
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
                       float* out, float* scratch, int f16, cudaStream_t stream) {
@@ -275,6 +401,16 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
   if (rank < 1 || (rank + 3) / 4 * 4 > p_ld || N % 8 != 0) return -1;
   const uint16_t* p = static_cast<const uint16_t*>(P);
   const uint16_t* y = static_cast<const uint16_t*>(Y);
+  static const int impl = [] { const char* e = getenv("IIC_LORA_OUTER_IMPL"); return e ? atoi(e) : 0; }();   // 1: CUDA-core kernels
+  if (impl == 0 && rank <= 16 && p_ld >= 16 && (reinterpret_cast<uintptr_t>(P) & 15) == 0 && (p_ld % 8) == 0) {
+    // tensor-core reduction: one pass over Y for every rank; one partial per 512-row CTA
+    const int splits = (M + kOuterRowsPerCta - 1) / kOuterRowsPerCta;
+    dim3 grid(unsigned((N + 63) / 64), unsigned(splits));
+    if (f16) lora_outer_mma_kernel<true><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, scratch);
+    else lora_outer_mma_kernel<false><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, scratch);
+    lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, 0, 16, scale, transpose, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   if (rank > 4 && rank <= 16 && p_ld >= 16) {
     // one pass over Y for all ranks: 256-row splits keep the partial buffer at M/16 * N floats (same as the rank-4 path)
     const int rps = 256, splits = (M + rps - 1) / rps;

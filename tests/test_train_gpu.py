@@ -87,8 +87,12 @@ def test_lora_gradient_reductions(engine, rank):
     assert torch.allclose(dB, ref, rtol=1e-3, atol=2e-2), (dB - ref).abs().max()
     dA = engine.op_lora_outer(P, Y, rank, act=1, scale=2.0, transpose=True)     # [N, r] = 2 * gelu(Y)^T P
     yf = Y.float()
-    ref = 2.0 * (yf * torch.sigmoid(1.702 * yf)).t() @ P[:, :rank].float()
-    assert torch.allclose(dA, ref, rtol=1e-3, atol=2e-2), (dA - ref).abs().max()
+    # the tensor-core reduction feeds gelu(Y) rounded to the operand type - the same value the forward's c_proj GEMM consumed
+    h = (yf * torch.sigmoid(1.702 * yf)).to(torch.bfloat16).float()
+    ref = 2.0 * h.t() @ P[:, :rank].float()
+    assert torch.allclose(dA, ref, rtol=1e-3, atol=3e-2), (dA - ref).abs().max()
+    ref32 = 2.0 * (yf * torch.sigmoid(1.702 * yf)).t() @ P[:, :rank].float()
+    assert (dA - ref32).abs().max() < 1e-2 * ref32.abs().max()      # vs un-rounded gelu: the operand rounding, 2^-9 relative per term
 
 
 @pytest.mark.parametrize("rank", [4, 16])
