@@ -2,6 +2,7 @@
 #include "gemm_sm100.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.h"
@@ -49,7 +50,8 @@ bool make_tile_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 
 template <int kCtas, int kBlockN, int kEpi, bool kF16>
 int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
-               const CUtensorMap& tout, const CUtensorMap& tres, const GemmArgs& args, int num_sms, cudaStream_t stream) {
+               const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
+               cudaStream_t stream) {
   using S = GemmSmem<kCtas, kBlockN, kEpi>;
   auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi, kF16>;
   static bool attr_done = false;
@@ -60,7 +62,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   const int tile_m = kBlockM * kCtas;
   const int m_tiles = (args.M + tile_m - 1) / tile_m;
   const int n_tiles = (args.N + kBlockN - 1) / kBlockN;
-  const int total = m_tiles * n_tiles;
+  const int total = S::kLn ? m_tiles : m_tiles * n_tiles;   // fused LayerNorm: clusters own whole row blocks
   int clusters = num_sms / kCtas;
   if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
@@ -75,21 +77,23 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, tbl, tout, tres, args);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, tbl, tout, tres, tln, args);
   return e == cudaSuccess ? 0 : -2;
 }
 
 template <int kCtas, bool kF16>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
-                 const CUtensorMap& tout, const CUtensorMap& tres, const GemmArgs& args, int num_sms,
+                 const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
                  cudaStream_t stream) {
   switch (epi) {
-    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
-    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
-    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
-    case kEpiBiasResF32DeepK: return launch_one<kCtas, 256, kEpiBiasResF32DeepK, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
-    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
-    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    case kEpiBiasResF32Ln: return launch_one<kCtas, 256, kEpiBiasResF32Ln, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasResF32LnDeepK: return launch_one<kCtas, 256, kEpiBiasResF32LnDeepK, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasResF32DeepK: return launch_one<kCtas, 256, kEpiBiasResF32DeepK, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiPosF32: return launch_one<kCtas, 256, kEpiPosF32, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiGeluExactBf16: return launch_one<kCtas, 256, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     default: return -1;
   }
 }
@@ -140,6 +144,17 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
       else ok = make_tile_map_kind(&tres, p.residual, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, 2);
     }
   }
+  const bool ln = p.ln_out != nullptr;
+  CUtensorMap tln = ta;
+  if (ln) {
+    static const char* e_ln = "gemm: fused LayerNorm needs the fp32 residual epilogue, N % 256 == 0, gamma/beta, and (with ln_lora_a) ln_p_out with ln_p_ld % 4 == 0";
+    if (p.epilogue != kEpiBiasResF32 || p.N % 256 != 0 || p.ln_gamma == nullptr || p.ln_beta == nullptr ||
+        (p.ln_lora_a != nullptr && (p.ln_p_out == nullptr || p.ln_p_ld < 4 || p.ln_p_ld % 4 != 0))) {
+      if (err) *err = e_ln;
+      return -1;
+    }
+    ok = ok && make_tile_map_kind(&tln, p.ln_out, uint64_t(p.M), uint64_t(p.N), uint64_t(p.N), kBlockM, f16 ? 1 : 0);
+  }
   if (!ok) {
     if (err) *err = e_map;
     return -1;
@@ -156,16 +171,23 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   args.group = p.group > 0 ? p.group : 1;
   args.down_a = p.down_a;
   args.down_part = p.down_part;
+  args.ln_gamma = p.ln_gamma;
+  args.ln_beta = p.ln_beta;
+  args.ln_eps = p.ln_eps;
+  args.ln_lora_a = p.ln_lora_a;
+  args.ln_p_out = p.ln_p_out;
+  args.ln_p_ld = p.ln_p_ld;
   // long reductions get the deep-ring variant of the residual epilogue (measured: c_proj 1268 -> 1322 TFLOP/s; the short-K
   // out_proj is bound by its fp32 residual traffic and prefers the 4-slab residual ring)
-  const int epi = (p.epilogue == kEpiBiasResF32 && p.K >= 2048) ? int(kEpiBiasResF32DeepK) : p.epilogue;
+  const bool deep = p.epilogue == kEpiBiasResF32 && p.K >= 2048;
+  const int epi = ln ? int(deep ? kEpiBiasResF32LnDeepK : kEpiBiasResF32Ln) : (deep ? int(kEpiBiasResF32DeepK) : p.epilogue);
   int rc;
   if (f16)
-    rc = ctas == 2 ? dispatch_epi<2, true>(epi, ta, tb, tal, tbl, tout, tres, args, num_sms, stream)
-                   : dispatch_epi<1, true>(epi, ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, true>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
+                   : dispatch_epi<1, true>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
   else
-    rc = ctas == 2 ? dispatch_epi<2, false>(epi, ta, tb, tal, tbl, tout, tres, args, num_sms, stream)
-                   : dispatch_epi<1, false>(epi, ta, tb, tal, tbl, tout, tres, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, false>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
+                   : dispatch_epi<1, false>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
   if (rc != 0 && err) *err = rc == -1 ? e_shape : e_launch;
   return rc;
 }

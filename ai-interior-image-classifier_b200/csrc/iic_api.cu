@@ -101,6 +101,7 @@ struct iic_handle {
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
   int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
+  int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): LayerNorms ride in the residual GEMM that produces their input - measured slower, see gemm_sm100.cuh
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
@@ -181,11 +182,24 @@ int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const voi
   return launch_attention_bwd(qkv, out, d_out, lse, dqkv, B, T, H, hd, h->f16, s);
 }
 
+// LayerNorm fused behind a residual GEMM: y = LN(out rows) -> 16-bit `out` [M, N], optional rank-4 down-projection into p_out
+struct LnFuse {
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  void* out = nullptr;
+  const float* lora_a = nullptr;
+  void* p_out = nullptr;
+};
+
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
              const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
              int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr,
-             int prof_class = kGemm) {
+             int prof_class = kGemm, const LnFuse* ln = nullptr) {
   GemmProblem g;
+  if (ln != nullptr && ln->out != nullptr) {
+    g.ln_gamma = ln->gamma; g.ln_beta = ln->beta; g.ln_out = ln->out;
+    g.ln_lora_a = ln->lora_a; g.ln_p_out = ln->p_out; g.ln_p_ld = h->lora_pad;
+  }
   g.down_a = down_a;
   g.down_part = down_part;
   g.a = a; g.lda = lda; g.w = w; g.ldw = K; g.M = M; g.N = N; g.K = K;
@@ -266,29 +280,45 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const float eps = 1e-5f;
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
-  for (Block& b : h->blocks) {
+  // A LayerNorm whose input is produced by a residual GEMM (ln_2 after attn.out_proj, the next block's ln_1 after mlp.c_proj)
+  // rides in that GEMM (kEpiBiasResF32Ln): possible when the width is a multiple of the 256-column tile and the LayerNorm's
+  // own LoRA down-projection is absent, of rank <= 4 (fused too) or large enough to run as a GEMM on the LayerNorm output.
+  auto ln_fusable = [&](const LoraSlot& l, bool via_gemm) {
+    return h->fuse_ln != 0 && d % 256 == 0 && (l.rank == 0 || via_gemm || l.r4 == 4);
+  };
+  bool ln1_done = false;   // this block's ln_1 was already produced by the previous block's c_proj
+  for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
+    Block& b = h->blocks[bi];
     const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
     const LoraSlot& l_out = b.lora[IIC_LORA_OUT_PROJ];
     const LoraSlot& l_fc = b.lora[IIC_LORA_C_FC];
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     // x = x + attn(ln_1(x))
-    // LoRA down-projections of rank <= 4 ride inside the LayerNorm kernel; larger ranks go through the GEMM (run_lora_down)
+    // LoRA down-projections of rank <= 4 ride inside the LayerNorm; larger ranks go through the GEMM (run_lora_down)
     const bool in_gemm = l_in.rank > 0 && l_in.r4 > 4 && l_in.at16 != nullptr;
-    IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, (l_in.rank && !in_gemm) ? l_in.a : nullptr,
-                              l_in.r4, w.p_a, h->lora_pad, h->f16, s);
-    }));
+    if (!ln1_done)
+      IIC_TRY(timed(h, kLayerNorm, s, [&] {
+        return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, (l_in.rank && !in_gemm) ? l_in.a : nullptr,
+                                l_in.r4, w.p_a, h->lora_pad, h->f16, s);
+      }));
     if (in_gemm) IIC_TRY(run_lora_down(h, w.xln, d, M, l_in.a, l_in.at16, l_in.r4, w.p_a, s));
     IIC_TRY(run_gemm(h, w.xln, d, b.w_qkv, M, 3 * d, d, &l_in, w.p_a, kEpiBiasBf16, b.b_qkv, nullptr, w.qkv, 3 * d, 1, s));
     IIC_TRY(timed(h, kAttention, s, [&] { return run_attention(h, w.qkv, w.attn, nullptr, B, T, H, d / H, 0, s); }));
     if (l_out.rank) IIC_TRY(run_lora_down(h, w.attn, d, M, l_out.a, l_out.at16, l_out.r4, w.p_b, s));
-    IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
     // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
     const bool fc_gemm = l_fc.rank > 0 && l_fc.r4 > 4 && l_fc.at16 != nullptr;
-    IIC_TRY(timed(h, kLayerNorm, s, [&] {
-      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
-                              l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
-    }));
+    LnFuse ln2;
+    if (ln_fusable(l_fc, fc_gemm)) {
+      ln2.gamma = b.ln2_g; ln2.beta = b.ln2_b; ln2.out = w.xln;
+      if (l_fc.rank && !fc_gemm) { ln2.lora_a = l_fc.a; ln2.p_out = w.p_a; }
+    }
+    IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s, nullptr, nullptr,
+                     kGemm, &ln2));
+    if (ln2.out == nullptr)
+      IIC_TRY(timed(h, kLayerNorm, s, [&] {
+        return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
+                                l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
+      }));
     if (fc_gemm) IIC_TRY(run_lora_down(h, w.xln, d, M, l_fc.a, l_fc.at16, l_fc.r4, w.p_a, s));
     // c_proj's LoRA down-projection (h . A2) rides in the c_fc epilogue while h is still in registers (rank <= 4)
     const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
@@ -300,7 +330,21 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
       }));
     else if (l_pr.rank)
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, w.p_b, s));
-    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
+    // the next block's ln_1 (its input is this GEMM's output); xln and p_a are free again: c_fc has consumed them
+    LnFuse ln1n;
+    ln1_done = false;
+    if (bi + 1 < h->blocks.size()) {
+      Block& nb = h->blocks[bi + 1];
+      const LoraSlot& n_in = nb.lora[IIC_LORA_IN_PROJ];
+      const bool n_in_gemm = n_in.rank > 0 && n_in.r4 > 4 && n_in.at16 != nullptr;
+      if (ln_fusable(n_in, n_in_gemm)) {
+        ln1n.gamma = nb.ln1_g; ln1n.beta = nb.ln1_b; ln1n.out = w.xln;
+        if (n_in.rank && !n_in_gemm) { ln1n.lora_a = n_in.a; ln1n.p_out = w.p_a; }
+        ln1_done = true;
+      }
+    }
+    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s, nullptr, nullptr,
+                     kGemm, &ln1n));
   }
   return 0;
 }
@@ -548,6 +592,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
   if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
   if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
+  if (const char* e = getenv("IIC_FUSE_LN")) h->fuse_ln = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -981,6 +1026,28 @@ int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, i
   g.f16 = h->f16;
   g.r_pad = r_pad; g.lora_ld = lora_ld;
   g.epilogue = epilogue; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
+  const char* e = nullptr;
+  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
+  return IIC_OK;
+}
+
+int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
+                       const void* lora_bt, int r_pad, int lora_ld, const float* bias, const float* residual, float* out,
+                       const float* gamma, const float* beta, void* ln_out, const float* ln_lora_a_scaled, void* ln_p_out,
+                       int ln_p_ld, int ctas, void* stream) {
+  if (!h || !a || !w || !out || !residual || !gamma || !beta || !ln_out) return fail(h, IIC_ERR_ARG, "iic_op_gemm_res_ln: null argument");
+  GemmProblem g;
+  g.a = a; g.lda = lda;
+  g.w = w; g.ldw = ldw;
+  g.M = M; g.N = N; g.K = K;
+  g.lora_p = lora_p;
+  g.lora_bt = lora_bt;
+  g.f16 = h->f16;
+  g.r_pad = r_pad; g.lora_ld = lora_ld;
+  g.epilogue = kEpiBiasResF32; g.bias = bias; g.residual = residual; g.out = out; g.ldc = N; g.group = 1;
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_out = ln_out;
+  g.ln_lora_a = ln_lora_a_scaled; g.ln_p_out = ln_p_out; g.ln_p_ld = ln_p_ld;
   const char* e = nullptr;
   int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");

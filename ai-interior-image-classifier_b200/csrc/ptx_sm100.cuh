@@ -174,6 +174,7 @@ __device__ __forceinline__ void tma_store_wait() {
 }
 // make generic-proxy smem writes visible to the async proxy (before a TMA store reads them)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, ld

@@ -88,6 +88,43 @@ def test_gemm_residual_f32_inplace(engine, ctas):
 
 
 @pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+@pytest.mark.parametrize("shape", [(197 * 8 + 3, 768, 3072), (197 * 40 + 5, 768, 768), (577 * 3, 1024, 1024), (77 * 9, 512, 2048),
+                                   (100, 256, 64)])
+@pytest.mark.parametrize("with_lora", [False, True], ids=["plain", "lora4"])
+def test_gemm_residual_layernorm_fused(engine, ctas, shape, with_lora):
+    """x = x + a.W^T + bias (in place) and LayerNorm(x) -> bf16 (+ the LayerNorm consumer's rank-4 LoRA down-projection)
+    from one launch: the residual output must equal the unfused epilogue's bit for bit, the LayerNorm output a separately
+    computed fp32 LayerNorm of it to 16-bit rounding (the row statistics are gathered in one shifted pass)."""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(12)
+    a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    x = torch.randn(M, N, device="cuda", generator=g)
+    x[:, 5] += 40.0      # CLIP-like outlier channels: large mean offsets must not hurt the one-pass variance
+    x[:, N - 3] -= 25.0
+    x[7] += 3.0
+    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    la = (torch.randn(N, 4, device="cuda", generator=g) * 0.05) if with_lora else None
+    unfused = engine.op_gemm(a, w, L.EPI_BIAS_RES_F32, bias=bias, residual=x, ctas=ctas)
+    res = engine.op_gemm_res_ln(a, w, bias, x.clone(), gamma, beta, ln_lora_a_scaled=la, ctas=ctas)
+    assert torch.equal(res[0], unfused)
+    ref = torch.nn.functional.layer_norm(unfused, (N,), gamma, beta, 1e-5)
+    # bf16 rounding of the output (2^-9 relative) + statistics differences (~1e-6)
+    assert torch.allclose(res[1].float(), ref, rtol=4e-3, atol=2e-3), (res[1].float() - ref).abs().max()
+    assert _rel(res[1].float(), ref) < 2.5e-3
+    if with_lora:
+        p = res[2].float()
+        assert torch.allclose(p[:, :4], ref @ la, rtol=1e-2, atol=1e-2), (p[:, :4] - ref @ la).abs().max()
+        assert p[:, 4:].abs().max() == 0
+    # in place on the residual stream, as the encoder runs it
+    x2 = x.clone()
+    res2 = engine.op_gemm_res_ln(a, w, bias, x2, gamma, beta, ln_lora_a_scaled=la, ctas=ctas, out=x2)
+    assert torch.equal(x2, unfused) and torch.equal(res2[1], res[1])
+
+
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
 def test_gemm_patch_embed_scatter(engine, ctas):
     B, G, N, K = 5, 196, 768, 768
     g = torch.Generator(device="cuda").manual_seed(3)
