@@ -21,6 +21,7 @@ OUT_PATCHES_BF16, OUT_CHW_F32, OUT_CHW_BF16 = 0, 1, 2
 KERNEL_CLASSES = ("gemm", "layernorm", "attention", "lora_down", "head", "preprocess", "misc",
                   "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_other")
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RES_F32, EPI_POS_F32, EPI_GELU_ERF_BF16 = 0, 1, 2, 3, 4
+EPI_ACT_GRAD_BF16 = 8   # training: acc * act'(u), u passed as `residual` (16-bit), group = 1 QuickGELU / 2 erf GELU
 
 
 class IicConfig(C.Structure):
@@ -79,6 +80,9 @@ PROTOTYPES = {
     "iic_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "iic_op_gemm_act_dual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_void_p]),
     "iic_op_gemm_res_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -86,6 +86,8 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
                  const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
                  cudaStream_t stream) {
   switch (epi) {
+    case kEpiActGradBf16: return launch_one<kCtas, 256, kEpiActGradBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasActDualBf16: return launch_one<kCtas, 256, kEpiBiasActDualBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasResF32Ln: return launch_one<kCtas, 256, kEpiBiasResF32Ln, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasResF32LnDeepK: return launch_one<kCtas, 256, kEpiBiasResF32LnDeepK, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
@@ -144,8 +146,16 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
       else ok = make_tile_map_kind(&tres, p.residual, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, 2);
     }
   }
+  if (ok && p.epilogue == kEpiActGradBf16) {   // 16-bit pre-activation tile, same geometry as the output
+    if (p.residual == nullptr) ok = false;
+    else ok = make_tile_map_kind(&tres, p.residual, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f16 ? 1 : 0);
+  }
   const bool ln = p.ln_out != nullptr;
   CUtensorMap tln = ta;
+  if (ok && p.epilogue == kEpiBiasActDualBf16) {
+    if (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 15) != 0) ok = false;
+    else ok = make_tile_map_kind(&tln, p.out2, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f16 ? 1 : 0);
+  }
   if (ln) {
     static const char* e_ln = "gemm: fused LayerNorm needs the fp32 residual epilogue, N % 256 == 0, gamma/beta, and (with ln_lora_a) ln_p_out with ln_p_ld % 4 == 0";
     if (p.epilogue != kEpiBiasResF32 || p.N % 256 != 0 || p.ln_gamma == nullptr || p.ln_beta == nullptr ||

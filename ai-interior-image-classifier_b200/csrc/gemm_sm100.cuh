@@ -57,6 +57,13 @@ enum GemmEpilogue : int {
   // ~9 us per row block, and one 16 KB slab in flight per SM cannot cover the ~2.5 us re-read latency.
   kEpiBiasResF32Ln = 6,
   kEpiBiasResF32LnDeepK = 7,
+  // training: out 16-bit = acc * act'(u), u = the forward's pre-activation tile, TMA-loaded (16-bit, through tm_res) into the
+  // staging slab ahead of the epilogue: dU = (dY . W2 + dP2 . A2^T) o act'(U) without a round trip of dH through HBM.
+  // GemmArgs.group = activation (1 QuickGELU, 2 erf GELU).
+  kEpiActGradBf16 = 8,
+  // training forward of mlp.c_fc: out 16-bit = act(acc + bias) AND out2 16-bit = acc + bias (the pre-activation the
+  // backward needs) from one pass over the accumulator.  GemmArgs.group = activation (1 QuickGELU, 2 erf GELU).
+  kEpiBiasActDualBf16 = 9,
 };
 
 struct GemmArgs {
@@ -91,6 +98,9 @@ struct GemmSmem {
   static constexpr bool kLn = kEpi == kEpiBiasResF32Ln || kEpi == kEpiBiasResF32LnDeepK;
   static constexpr bool kDeepK = kEpi == kEpiBiasResF32DeepK || kEpi == kEpiBiasResF32LnDeepK;
   static constexpr bool kResidual = kEpi == kEpiBiasResF32 || kEpi == kEpiBiasResF32DeepK || kLn;
+  static constexpr bool kActGrad = kEpi == kEpiActGradBf16;
+  static constexpr bool kDual = kEpi == kEpiBiasActDualBf16;
+  static constexpr bool kSlabLoad = kResidual || kActGrad;   // warp 3 TMA-loads a tile of a second input into the staging slabs
   static constexpr bool kDirect = kEpi == kEpiPosF32;  // old direct-store epilogue, no staging ring
   static constexpr int kLoadN = kBlockN / kCtas;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -99,9 +109,9 @@ struct GemmSmem {
   // epilogue warp groups working on alternate slabs of a tile: 2 for the MUFU-heavy activation epilogues (one group's
   // MUFU / TMEM latency hides under the other's ALU work), 1 otherwise (measured: a second group only adds contention
   // for the bias-only and the residual epilogues)
-  static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect) ? 2 : 1;
+  static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect || kActGrad || kDual) ? 2 : 1;
   static constexpr int kSlabs =   // staging ring depth
-      kDirect ? 0 : (kResidual ? (kLn ? (kDeepK ? 2 : 3) : (kDeepK ? 3 : 4)) : 2);
+      kDirect ? 0 : (kResidual ? (kLn ? (kDeepK ? 2 : 3) : (kDeepK ? 3 : 4)) : ((kActGrad || kDual) ? 4 : 2));
   // fused LayerNorm tail: fp32 input slabs (re-read of the stored rows) and one 16-bit output slab
   static constexpr int kLnIn = kLn ? (kDeepK ? 1 : 2) : 0;
   static constexpr int kLnSlabs = kLn ? kLnIn + 1 : 0;
@@ -152,7 +162,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   constexpr bool kDirect = S::kDirect;
   constexpr bool kLn = S::kLn;
   constexpr int kLnIn = S::kLnIn;
-  constexpr bool kAct = kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16;
+  constexpr bool kActGrad = S::kActGrad;
+  constexpr bool kDual = S::kDual;
+  constexpr bool kAct = kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDual;
   constexpr int kSlabCols = kResidual ? 32 : 64;           // columns per staging slab
   constexpr int kSlabsPerTile = kBlockN / kSlabCols;       // 8 (fp32) or 4 (16-bit)
 
@@ -196,8 +208,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       ptx::prefetch_tensormap(&tm_bl);
     }
     if constexpr (!kDirect) ptx::prefetch_tensormap(&tm_out);
-    if constexpr (kResidual) ptx::prefetch_tensormap(&tm_res);
-    if constexpr (kLn) ptx::prefetch_tensormap(&tm_ln);
+    if constexpr (S::kSlabLoad) ptx::prefetch_tensormap(&tm_res);
+    if constexpr (kLn || kDual) ptx::prefetch_tensormap(&tm_ln);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -313,8 +325,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ======================= residual producer (fp32-residual epilogue) =======================
-    if constexpr (kResidual) {
+    // ======================= residual producer (fp32-residual / activation-gradient epilogues) =======================
+    if constexpr (S::kSlabLoad) {
       if (ptx::elect_one()) {
         int slab = 0;  // running slab counter of this CTA
         int m_blk, n_blk;
@@ -584,9 +596,59 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 ptx::mbar_arrive(rempty_bar((my_slab - kGroups) % kSlabs));
               }
             }
+          } else if constexpr (kActGrad) {
+            // ---- out = acc * act'(u): the slab already holds the 64 pre-activations of this row (TMA-loaded by warp 3) ----
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64), v0);
+            ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64 + 32), v1);
+            ptx::mbar_wait(rfull_bar(b), uint32_t(my_slab / kSlabs) & 1u);
+            ptx::tmem_ld_wait();
+            if (s + kGroups >= kSlabsPerTile) release_tmem();
+            const bool erf_act = args.group == 2;
+            auto grad = [&](float u) {
+              if (erf_act) {
+                const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+                return cdf + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+              }
+              // QuickGELU: s = sigmoid(1.702 u) = 0.5 + 0.5 tanh(0.851 u);  d/du = s + 1.702 u s (1 - s)
+              float t;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * u));
+              const float sg = fmaf(0.5f, t, 0.5f);
+              return fmaf(1.702f * u * sg, 1.0f - sg, sg);
+            };
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4* p = reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4));
+              uint4 uu = *p;
+              uint32_t* pu = reinterpret_cast<uint32_t*>(&uu);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 u2 = Act<kF16>::unpack(pu[e]);
+                const int c = j * 8 + 2 * e;
+                const float a0 = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
+                const float a1 = __uint_as_float(c < 32 ? v0[(c + 1) & 31] : v1[(c + 1) & 31]);
+                pu[e] = Act<kF16>::pack(a0 * grad(u2.x), a1 * grad(u2.y));
+              }
+              *p = uu;
+            }
+            ptx::fence_proxy_async_smem();
+            epi_bar_sync(grp);
+            if (storer) {
+              ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
+              ptx::tma_store_commit();
+              if (my_slab >= kGroups) {
+                ptx::tma_store_wait_read<1>();
+                ptx::mbar_arrive(rempty_bar((my_slab - kGroups) % kSlabs));
+              }
+            }
           } else {
             // ---- 16-bit outputs: 64 columns per slab ----
             uint32_t v0[32], v1[32];
+            if constexpr (kDual) {
+              // both staging slabs of the group (pre-activation: grp, activation: grp + 2) are reused by every slab
+              if (storer) ptx::tma_store_wait_read<0>();
+              epi_bar_sync(grp);
+            }
             ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64), v0);
             ptx::tmem_ld_32x32b_x32(taddr + uint32_t(s * 64 + 32), v1);
             // bias of the first 32 columns rides under the TMEM load latency (the wait below is a compiler barrier)
@@ -623,7 +685,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 f[i + 2] = __uint_as_float(half == 0 ? v0[i + 2] : v1[i + 2]) + b4.z;
                 f[i + 3] = __uint_as_float(half == 0 ? v0[i + 3] : v1[i + 3]) + b4.w;
               }
-              if constexpr (kEpi == kEpiBiasGeluBf16) {
+              if constexpr (kDual) {
+                uint8_t* u_row = slab_gen + grp * kSlabBytes + r_in_tile * 128;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 q;
+                  q.x = Act<kF16>::pack(f[i], f[i + 1]);
+                  q.y = Act<kF16>::pack(f[i + 2], f[i + 3]);
+                  q.z = Act<kF16>::pack(f[i + 4], f[i + 5]);
+                  q.w = Act<kF16>::pack(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(u_row + (((half * 4 + i / 8) ^ sw) << 4)) = q;
+                }
+                if (args.group == 2) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+                }
+              } else if constexpr (kEpi == kEpiBiasGeluBf16) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
               } else if constexpr (kEpi == kEpiGeluExactBf16) {
@@ -653,16 +733,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 pk[half * 4 + i / 8] = q;
               }
             }
-            // the slab this group wrote kBufPG steps ago used the same buffer: its TMA store must have read it by now
-            if (storer) ptx::tma_store_wait_read<kBufPG - 1>();
-            epi_bar_sync(grp);
+            if constexpr (kDual) {
+              uint8_t* h_row = slab_gen + (grp + 2) * kSlabBytes + r_in_tile * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = pk[j];
-            ptx::fence_proxy_async_smem();
-            epi_bar_sync(grp);
-            if (storer) {
-              ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
-              ptx::tma_store_commit();
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(h_row + ((j ^ sw) << 4)) = pk[j];
+              ptx::fence_proxy_async_smem();
+              epi_bar_sync(grp);
+              if (storer) {
+                ptx::tma_store_2d(&tm_ln, slab_base + grp * kSlabBytes, col, row0);          // pre-activation
+                ptx::tma_store_2d(&tm_out, slab_base + (grp + 2) * kSlabBytes, col, row0);   // activation
+                ptx::tma_store_commit();
+              }
+            } else {
+              // the slab this group wrote kBufPG steps ago used the same buffer: its TMA store must have read it by now
+              if (storer) ptx::tma_store_wait_read<kBufPG - 1>();
+              epi_bar_sync(grp);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = pk[j];
+              ptx::fence_proxy_async_smem();
+              epi_bar_sync(grp);
+              if (storer) {
+                ptx::tma_store_2d(&tm_out, slab_base + b * kSlabBytes, col, row0);
+                ptx::tma_store_commit();
+              }
             }
           }
         }

@@ -101,6 +101,8 @@ struct iic_handle {
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
   int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
+  int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
+                          // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): LayerNorms ride in the residual GEMM that produces their input - measured slower, see gemm_sm100.cuh
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
@@ -194,8 +196,9 @@ struct LnFuse {
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
              const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
              int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr,
-             int prof_class = kGemm, const LnFuse* ln = nullptr) {
+             int prof_class = kGemm, const LnFuse* ln = nullptr, void* out2 = nullptr) {
   GemmProblem g;
+  g.out2 = out2;
   if (ln != nullptr && ln->out != nullptr) {
     g.ln_gamma = ln->gamma; g.ln_beta = ln->beta; g.ln_out = ln->out;
     g.ln_lora_a = ln->lora_a; g.ln_p_out = ln->p_out; g.ln_p_ld = h->lora_pad;
@@ -373,6 +376,7 @@ struct TrainLayer {
   float *x_in, *x_mid;            // f32 [M, d]: inputs of ln_1 / ln_2
   uint16_t *qkv, *attn, *y2;      // 16-bit [M, 3d], [M, d], [M, d] (ln_2 output = c_fc operand)
   uint16_t *p1, *p2;              // 16-bit [M, lora_pad]: s1*(y2.A1), s2*(h.A2)
+  uint16_t* u;                    // 16-bit [M, mlp]: c_fc pre-activation (train_fused; else recomputed into the shared buffer)
   float* lse;                     // f32 [B*H, T]
 };
 struct TrainWorkspace {
@@ -419,6 +423,7 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
     l.p1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
     l.p2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
     l.lse = static_cast<float*>(take(size_t(B) * H * h->T * 4));
+    l.u = h->train_fused ? static_cast<uint16_t*>(take(M * mlp * 2)) : w.u;
   }
   w.total = off;
   return w;
@@ -473,8 +478,13 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
     }));
     if (fc_gemm) IIC_TRY(run_lora_down(h, t.y2, d, M, l_fc.a, l_fc.at16, l_fc.r4, t.p1, s));
     const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
-    IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
-                     fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
+    if (h->train_fused)   // h -> hid (c_proj operand), u -> kept for the backward
+      IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasActDualBf16, b.b_fc, nullptr, w.hid, mlp,
+                       act_epi == kEpiGeluExactBf16 ? 2 : 1, s, fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr,
+                       kGemm, nullptr, t.u));
+    else
+      IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
+                       fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
     if (fuse_down)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, t.p2, h->lora_pad, h->f16, s);
@@ -517,14 +527,21 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
       }));
       bw_pr.rank = l_pr.rank; bw_pr.r4 = l_pr.r4; bw_pr.r_pad = l_pr.r_pad; bw_pr.bt = l_pr.a16;
     }
-    // recompute the pre-activation u = y2 W1^T + b1 + P1 B1 (cheaper than keeping [M, 4d] per layer)
-    IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasBf16, b.b_fc, nullptr, w.u, mlp, 1, s));
+    // the pre-activation u = y2 W1^T + b1 + P1 B1: kept by the forward (train_fused; 2 bytes x M x 4d per layer is small
+    // change on a 180 GB part) or recomputed here
+    if (!h->train_fused)
+      IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasBf16, b.b_fc, nullptr, t.u, mlp, 1, s));
     if (l_pr.rank)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(w.dp2, h->lora_pad, w.u, mlp, M, act, l_pr.rank, l_pr.scaling * h->grad_unscale, 1, l_pr.grad_a, w.outer_scratch, h->f16, s);
+        return launch_lora_outer(w.dp2, h->lora_pad, t.u, mlp, M, act, l_pr.rank, l_pr.scaling * h->grad_unscale, 1, l_pr.grad_a, w.outer_scratch, h->f16, s);
       }));
-    IIC_TRY(run_gemm(h, w.g16, d, b.w_proj_t, M, mlp, d, &bw_pr, w.dp2, kEpiBiasBf16, nullptr, nullptr, w.dh, mlp, 1, s));
-    IIC_TRY(timed(h, kMisc, s, [&] { return launch_act_bwd(w.dh, w.u, (long long)M * mlp, act, h->f16, s); }));   // dh := du
+    if (h->train_fused) {   // dh := du = (dY . W2 + dP2 . (s2 A2)^T) o act'(u) in the GEMM epilogue
+      IIC_TRY(run_gemm(h, w.g16, d, b.w_proj_t, M, mlp, d, &bw_pr, w.dp2, kEpiActGradBf16, nullptr, reinterpret_cast<const float*>(t.u),
+                       w.dh, mlp, act, s));
+    } else {
+      IIC_TRY(run_gemm(h, w.g16, d, b.w_proj_t, M, mlp, d, &bw_pr, w.dp2, kEpiBiasBf16, nullptr, nullptr, w.dh, mlp, 1, s));
+      IIC_TRY(timed(h, kMisc, s, [&] { return launch_act_bwd(w.dh, t.u, (long long)M * mlp, act, h->f16, s); }));   // dh := du
+    }
     // ---- c_fc:  u = y2 W1^T + b1 + P1 B1   (P1 = s1 y2 A1) ----
     LoraSlot bw_fc;
     if (l_fc.rank) {
@@ -593,6 +610,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
   if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
   if (const char* e = getenv("IIC_FUSE_LN")) h->fuse_ln = atoi(e);
+  if (const char* e = getenv("IIC_TRAIN_FUSED")) h->train_fused = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -1026,6 +1044,26 @@ int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, i
   g.f16 = h->f16;
   g.r_pad = r_pad; g.lora_ld = lora_ld;
   g.epilogue = epilogue; g.bias = bias; g.residual = residual; g.out = out; g.ldc = ldc; g.group = group;
+  const char* e = nullptr;
+  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
+  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
+  return IIC_OK;
+}
+
+int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
+                         const void* lora_bt, int r_pad, int lora_ld, const float* bias, void* out_act, void* out_pre, int act,
+                         int ctas, void* stream) {
+  if (!h || !a || !w || !out_act || !out_pre) return fail(h, IIC_ERR_ARG, "iic_op_gemm_act_dual: null argument");
+  GemmProblem g;
+  g.a = a; g.lda = lda;
+  g.w = w; g.ldw = ldw;
+  g.M = M; g.N = N; g.K = K;
+  g.lora_p = lora_p;
+  g.lora_bt = lora_bt;
+  g.f16 = h->f16;
+  g.r_pad = r_pad; g.lora_ld = lora_ld;
+  g.epilogue = kEpiBiasActDualBf16; g.bias = bias; g.residual = nullptr; g.out = out_act; g.out2 = out_pre; g.ldc = N;
+  g.group = act == IIC_ACT_GELU_ERF ? 2 : 1;
   const char* e = nullptr;
   int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");

@@ -98,6 +98,7 @@ struct GemmProblem {
   // (two per column tile: one from each epilogue warp group).
   const float* down_a = nullptr;
   float* down_part = nullptr;
+  void* out2 = nullptr;  // kEpiBiasActDualBf16: 16-bit [M, ldc] pre-activation output (out receives the activation)
   // optional, kEpiBiasResF32 only: also emit the LayerNorm of the output rows (the LayerNorm that consumes the new residual
   // stream) as 16-bit ln_out [M, N] (pitch N), with its rank-4 LoRA down-projection ln_p_out [M, ln_p_ld] = y . ln_lora_a
   // when ln_lora_a (f32 [N, 4]) is given.  Needs N % 256 == 0.

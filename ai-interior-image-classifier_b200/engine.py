@@ -624,6 +624,21 @@ class Engine:
                                                  _ptr(down_part), _stream_ptr(self.device)), "iic_op_gemm")
         return out
 
+    def op_gemm_act_dual(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,
+                         lora_p: Optional[torch.Tensor] = None, lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0,
+                         ctas: int = 0):
+        """(act(a . w^T + bias), a . w^T + bias), both in the operand dtype, from one launch (training forward of c_fc)."""
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty(M, N, dtype=self.op_dtype, device=self.device)
+        pre = torch.empty(M, N, dtype=self.op_dtype, device=self.device)
+        lora_ld = lora_p.stride(0) if lora_p is not None else 0
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_gemm_act_dual(
+                self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(lora_p), _ptr(lora_bt), r_pad,
+                lora_ld, _ptr(bias), out.data_ptr(), pre.data_ptr(), act, ctas, _stream_ptr(self.device)), "iic_op_gemm_act_dual")
+        return out, pre
+
     def op_gemm_res_ln(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
                        gamma: torch.Tensor, beta: torch.Tensor, lora_p: Optional[torch.Tensor] = None,
                        lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0, ln_lora_a_scaled: Optional[torch.Tensor] = None,

@@ -208,12 +208,20 @@ int iic_profile_read(iic_handle* h, double* ms_by_class, long long* launches_by_
 
 /* ---- single operators (exported for parity tests and profiling; same kernels the encoder runs) -------------- */
 /* D = epilogue(A[M,K] . W[N,K]^T (+ P[M,r] . Bt[N,r]^T));  epilogue: 0 bias->bf16, 1 bias+QuickGELU->bf16,
- * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16.  lora_p/lora_bt nullable.
+ * 2 bias+residual->f32, 3 pos-emb scatter->f32, 4 bias+GELU(erf)->bf16, 8 (training backward of mlp.c_proj + activation)
+ * acc * act'(u) -> 16-bit with u = `residual` reinterpreted as the 16-bit pre-activation [M, ldc] and group = 1 QuickGELU /
+ * 2 erf GELU.  lora_p/lora_bt nullable.
  * down_a f32 [N,4] / down_part f32 [2*ceil(N/256)][M][4] (nullable, activation epilogues): the consumer's LoRA
  * down-projection fused into this epilogue as per-column-tile partials. */
 int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                 const void* lora_bt, int r_pad, int lora_ld, int epilogue, const float* bias, const float* residual,
                 void* out, int ldc, int group, int ctas, const float* down_a, float* down_part, void* stream);
+/* Training forward of mlp.c_fc (train_lora.py:233 through LoRALinear.forward, train_lora.py:43-44): out_act 16-bit [M,N] =
+ * act(A . W^T (+ LoRA) + bias) and out_pre 16-bit [M,N] = the pre-activation the backward needs, from one pass.
+ * act: IIC_ACT_QUICK_GELU / IIC_ACT_GELU_ERF. */
+int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
+                         const void* lora_bt, int r_pad, int lora_ld, const float* bias, void* out_act, void* out_pre, int act,
+                         int ctas, void* stream);
 /* out f32 [M,N] = A . W^T (+ LoRA) + bias + residual  AND  ln_out 16-bit [M,N] = LayerNorm(out rows; gamma, beta, eps 1e-5)
  * from the same launch (the LayerNorm group of the kernel re-reads the stored rows from L2): x = x + attn.out_proj(..);
  * ln_2(x), and x = x + mlp.c_proj(..); next block's ln_1(x) of clip/model.py ResidualAttentionBlock.forward (called through

@@ -95,6 +95,41 @@ def test_lora_gradient_reductions(engine, rank):
     assert (dA - ref32).abs().max() < 1e-2 * ref32.abs().max()      # vs un-rounded gelu: the operand rounding, 2^-9 relative per term
 
 
+@pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
+@pytest.mark.parametrize("act", [0, 1], ids=["quickgelu", "erf"])
+def test_gemm_training_epilogues(iic, engine, ctas, act):
+    """c_fc forward with two outputs (activation + kept pre-activation) and the c_proj dX GEMM with act'(u) applied in the
+    epilogue, against fp32 references from the same bf16 operands."""
+    L = iic._lib
+    M, d, mlp = 197 * 5 + 7, 768, 3072
+    g = torch.Generator(device="cuda").manual_seed(31)
+    y2 = torch.randn(M, d, device="cuda", generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(mlp, d, device="cuda", generator=g) * d ** -0.5).to(torch.bfloat16)
+    b1 = torch.randn(mlp, device="cuda", generator=g) * 0.2
+    p = torch.zeros(M, 16, device="cuda", dtype=torch.bfloat16)
+    p[:, :4] = (torch.randn(M, 4, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    bt = torch.zeros(mlp, 16, device="cuda", dtype=torch.bfloat16)
+    bt[:, :4] = (torch.randn(mlp, 4, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    h, u = engine.op_gemm_act_dual(y2, w1, b1, act=act, lora_p=p, lora_bt=bt, r_pad=16, ctas=ctas)
+    u_ref = y2.float() @ w1.float().t() + b1 + p.float() @ bt.float().t()
+    fwd = (lambda v: v * torch.sigmoid(1.702 * v)) if act == 0 else (lambda v: torch.nn.functional.gelu(v))
+    # bf16 rounding of the outputs: 2^-9 relative
+    assert torch.allclose(u.float(), u_ref, rtol=4e-3, atol=4e-3), (u.float() - u_ref).abs().max()
+    assert torch.allclose(h.float(), fwd(u_ref), rtol=4e-3, atol=4e-3), (h.float() - fwd(u_ref)).abs().max()
+    # same pre-activation as the single-output epilogue produces
+    assert torch.equal(u, engine.op_gemm(y2, w1, L.EPI_BIAS_BF16, bias=b1, lora_p=p, lora_bt=bt, r_pad=16, ctas=ctas))
+    assert torch.equal(h, engine.op_gemm(y2, w1, L.EPI_GELU_ERF_BF16 if act else L.EPI_BIAS_GELU_BF16, bias=b1, lora_p=p, lora_bt=bt,
+                                         r_pad=16, ctas=ctas))
+    # backward: du = (dy . W2) o act'(u), with W2^T stored [mlp, d] as the engine keeps it
+    dy = torch.randn(M, d, device="cuda", generator=g).to(torch.bfloat16)
+    w2t = (torch.randn(mlp, d, device="cuda", generator=g) * mlp ** -0.5).to(torch.bfloat16)
+    du = engine.op_gemm(dy, w2t, L.EPI_ACT_GRAD_BF16, residual=u, group=2 if act else 1, ctas=ctas,
+                        out=torch.empty(M, mlp, device="cuda", dtype=torch.bfloat16))
+    uf = u.float().requires_grad_(True)
+    fwd(uf).backward(dy.float() @ w2t.float().t())
+    assert torch.allclose(du.float(), uf.grad, rtol=6e-3, atol=2e-3), (du.float() - uf.grad).abs().max()
+
+
 @pytest.mark.parametrize("rank", [4, 16])
 @pytest.mark.parametrize("mode", ["f16", "bf16"])
 def test_lora_gradients_match_oracle_autograd(iic, mode, rank):
