@@ -73,6 +73,8 @@ PROTOTYPES = {
     "iic_op_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_void_p]),
     "iic_op_act_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "iic_op_lora_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "iic_op_lora_outer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_int, C.c_void_p, C.c_void_p]),
     "iic_profile": (C.c_int, [C.c_void_p, C.c_int]),

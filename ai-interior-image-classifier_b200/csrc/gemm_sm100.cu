@@ -85,6 +85,10 @@ template <int kCtas, bool kF16>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
                  const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
                  cudaStream_t stream) {
+  // skinny outputs (the LoRA down-projection GEMMs, N = 16): a 64-column tile - the 256-wide MMAs on a zero-filled weight tile
+  // were what bounded them (K = 3072: 13 us of tensor time per 256-row tile for 16 useful columns)
+  if (epi == kEpiBiasBf16 && args.N <= 64)
+    return launch_one<kCtas, 64, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
   switch (epi) {
     case kEpiActGradBf16: return launch_one<kCtas, 256, kEpiActGradBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasActDualBf16: return launch_one<kCtas, 256, kEpiBiasActDualBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
@@ -121,7 +125,7 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     if (err) *err = e_lora;
     return -1;
   }
-  const uint32_t box_b = uint32_t(256 / ctas);
+  const uint32_t box_b = uint32_t(((p.epilogue == kEpiBiasBf16 && p.N <= 64) ? 64 : 256) / ctas);
   CUtensorMap ta, tb, tal, tbl;
   const bool f16 = p.f16 != 0;
   bool ok = make_tile_map(&ta, p.a, uint64_t(p.M), uint64_t(p.K), uint64_t(p.lda), kBlockM, f16) &&

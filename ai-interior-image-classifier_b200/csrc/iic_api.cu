@@ -103,6 +103,7 @@ struct iic_handle {
   int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
   int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
+  int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
   int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): LayerNorms ride in the residual GEMM that produces their input - measured slower, see gemm_sm100.cuh
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
@@ -520,11 +521,22 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     const LoraSlot& l_pr = b.lora[IIC_LORA_C_PROJ];
     // ---- c_proj:  x_out = x_mid + h W2^T + b2 + P2 B2   (P2 = s2 h A2) ----
     LoraSlot bw_pr;   // LoRA k-step of the dX GEMM: dh += dP2 . (s2 A2)^T
+    // dP = dOut . B^T and dB = P^T . dOut of one LoRA pair: one pass over dOut (lora_bwd_kernel), else skinny GEMM + reduction
+    auto lora_dp_db = [&](const LoraSlot& l, const void* p_fwd, const void* dout, int n_out, void* dp_out) -> int {
+      int rc = -3;
+      if (h->lora_bwd_fused && l.b16 != nullptr)
+        rc = timed(h, kLoraDown, s, [&] {
+          return launch_lora_bwd(p_fwd, h->lora_pad, dout, n_out, M, l.b16, l.rank, h->grad_unscale, l.grad_b, dp_out, w.outer_scratch,
+                                 h->f16, s);
+        });
+      if (rc != -3) return rc;
+      IIC_TRY(run_lora_down(h, dout, n_out, M, l.bt32, l.b16, l.r4, dp_out, s, true));
+      return timed(h, kLoraDown, s, [&] {
+        return launch_lora_outer(p_fwd, h->lora_pad, dout, n_out, M, 0, l.rank, h->grad_unscale, 0, l.grad_b, w.outer_scratch, h->f16, s);
+      });
+    };
     if (l_pr.rank) {
-      IIC_TRY(run_lora_down(h, w.g16, d, M, l_pr.bt32, l_pr.b16, l_pr.r4, w.dp2, s, true));   // dP2 = dY . B2^T
-      IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(t.p2, h->lora_pad, w.g16, d, M, 0, l_pr.rank, h->grad_unscale, 0, l_pr.grad_b, w.outer_scratch, h->f16, s);
-      }));
+      IIC_TRY(lora_dp_db(l_pr, t.p2, w.g16, d, w.dp2));   // dP2 = dY . B2^T, dB2 = P2^T . dY
       bw_pr.rank = l_pr.rank; bw_pr.r4 = l_pr.r4; bw_pr.r_pad = l_pr.r_pad; bw_pr.bt = l_pr.a16;
     }
     // the pre-activation u = y2 W1^T + b1 + P1 B1: kept by the forward (train_fused; 2 bytes x M x 4d per layer is small
@@ -545,10 +557,7 @@ int run_train_backward_layer(iic_handle* h, int B, TrainWorkspace& w, int li, cu
     // ---- c_fc:  u = y2 W1^T + b1 + P1 B1   (P1 = s1 y2 A1) ----
     LoraSlot bw_fc;
     if (l_fc.rank) {
-      IIC_TRY(run_lora_down(h, w.dh, mlp, M, l_fc.bt32, l_fc.b16, l_fc.r4, w.dp1, s, true));   // dP1 = dU . B1^T
-      IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_outer(t.p1, h->lora_pad, w.dh, mlp, M, 0, l_fc.rank, h->grad_unscale, 0, l_fc.grad_b, w.outer_scratch, h->f16, s);
-      }));
+      IIC_TRY(lora_dp_db(l_fc, t.p1, w.dh, mlp, w.dp1));   // dP1 = dU . B1^T, dB1 = P1^T . dU
       IIC_TRY(timed(h, kLoraDown, s, [&] {
         return launch_lora_outer(w.dp1, h->lora_pad, t.y2, d, M, 0, l_fc.rank, l_fc.scaling * h->grad_unscale, 1, l_fc.grad_a, w.outer_scratch, h->f16, s);
       }));
@@ -611,6 +620,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
   if (const char* e = getenv("IIC_FUSE_LN")) h->fuse_ln = atoi(e);
   if (const char* e = getenv("IIC_TRAIN_FUSED")) h->train_fused = atoi(e);
+  if (const char* e = getenv("IIC_LORA_BWD_FUSED")) h->lora_bwd_fused = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
   h->blocks.resize(cfg->layers);
   h->pre = preprocess_plan_create();
@@ -1013,6 +1023,18 @@ int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act,
   if (!h || !dh || !u) return fail(h, IIC_ERR_ARG, "iic_op_act_bwd: null argument");
   int rc = launch_act_bwd(dh, u, n, act, h->f16, static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "activation backward failed");
+  return IIC_OK;
+}
+
+int iic_op_lora_bwd(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale,
+                    float* out_db, void* out_dp16, void* stream) {
+  if (!h || !P || !Y || !Bm || !out_db || !out_dp16) return fail(h, IIC_ERR_ARG, "iic_op_lora_bwd: null argument");
+  float* scratch = nullptr;
+  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, M)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
+  int rc = launch_lora_bwd(P, p_ld, Y, N, M, Bm, rank, scale, out_db, out_dp16, scratch, h->f16, static_cast<cudaStream_t>(stream));
+  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(scratch);
+  if (rc != 0) return fail(h, rc == -2 ? IIC_ERR_CUDA : IIC_ERR_ARG, rc == -3 ? "lora_bwd: needs N % 256 == 0 and p_ld == 16" : "lora_bwd failed");
   return IIC_OK;
 }
 

@@ -46,6 +46,11 @@ int launch_cast16(const float* in, void* out, long long n, int f16, cudaStream_t
 // act: 0 identity, 1 QuickGELU, 2 GELU(erf)
 int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaStream_t stream);
 size_t lora_outer_scratch_bytes(int N, int M);
+// One pass over Y [M, N] (16-bit) for the two LoRA gradients that read it: out_db f32 [rank, N] = scale * P^T . Y (P 16-bit
+// [M, 16]) and out_dp16 16-bit [M, 16] = Y . Bm^T (Bm 16-bit [16, N], rows >= rank zero).  Returns -3 outside its envelope
+// (N % 256, p_ld == 16); scratch as lora_outer_scratch_bytes(N, M).
+int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale, float* out_db,
+                    void* out_dp16, float* scratch, int f16, cudaStream_t stream);
 // out = scale * P[:, :rank]^T . act(Y)  ->  [rank, N] (transpose = 0: dB) or [N, rank] (transpose = 1: dA); deterministic
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,
                       float* out, float* scratch, int f16, cudaStream_t stream);

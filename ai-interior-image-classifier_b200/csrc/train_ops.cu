@@ -56,13 +56,19 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ 
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += n_warps) {
     const float4* xr = reinterpret_cast<const float4*>(x + size_t(row) * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + size_t(row) * D);
-    float4 xv[kVec], gv[kVec];
+    float4 xv[kVec], gv[kVec], acc[kVec];
+    uint2 draw[kVec];
+    float4* o = reinterpret_cast<float4*>(dx + size_t(row) * D);
+    // all three input streams of the row are requested before the first reduction: one round of memory latency per row
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) xv[j] = xr[lane + 32 * j];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) draw[j] = dr[lane + 32 * j];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) acc[j] = o[lane + 32 * j];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < kVec; ++j) {
-      xv[j] = xr[lane + 32 * j];
-      s += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
-    }
+    for (int j = 0; j < kVec; ++j) s += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
     const float mean = warp_sum(s) * (1.0f / D);
     float q = 0.f;
 #pragma unroll
@@ -74,7 +80,7 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ 
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-      const uint2 raw = dr[lane + 32 * j];
+      const uint2 raw = draw[j];
       const float2 d01 = Act<kF16>::unpack(raw.x), d23 = Act<kF16>::unpack(raw.y);
       const float4 g = __ldg(g4 + lane + 32 * j);
       xv[j].x *= rstd; xv[j].y *= rstd; xv[j].z *= rstd; xv[j].w *= rstd;   // xhat
@@ -84,11 +90,10 @@ layernorm_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ 
     }
     c1 = warp_sum(c1) * (1.0f / D);
     c2 = warp_sum(c2) * (1.0f / D);
-    float4* o = reinterpret_cast<float4*>(dx + size_t(row) * D);
     uint2* o16 = dx16 ? reinterpret_cast<uint2*>(dx16 + size_t(row) * D) : nullptr;
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
-      float4 r = o[lane + 32 * j];
+      float4 r = acc[j];
       r.x += rstd * (gv[j].x - c1 - xv[j].x * c2);
       r.y += rstd * (gv[j].y - c1 - xv[j].y * c2);
       r.z += rstd * (gv[j].z - c1 - xv[j].z * c2);
@@ -235,14 +240,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 constexpr int kOuterRowsPerCta = 512;   // 4 warps x 128 rows
+constexpr int kOuterStages = 4;
 
 template <bool kF16>
 __global__ void __launch_bounds__(128)
 lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int act,
                       float* __restrict__ part) {
-  // per warp: 2 stages x (Y slice 16 x 128 B = 2 KB, P slice 16 x 32 B = 512 B); then the CTA-wide reduction buffer
-  __shared__ __align__(128) uint8_t sbuf[4][2][2560];
-  __shared__ float red[4][16][64 + 1];
+  // per warp: kOuterStages x (Y slice 16 x 128 B = 2 KB, P slice 16 x 32 B = 512 B) - three slices in flight per warp keep
+  // the kernel on the HBM roofline; the CTA-wide reduction buffer red[4][16][65] aliases the stage buffers after the loop
+  __shared__ __align__(128) uint8_t sbuf[4][kOuterStages][2560];
+  static_assert(sizeof(float) * 4 * 16 * 65 <= 4 * kOuterStages * 2560, "reduction buffer must fit in the stage buffers");
+  float (*red)[16][65] = reinterpret_cast<float (*)[16][65]>(&sbuf[0][0][0]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 64;
   const int m_begin = blockIdx.y * kOuterRowsPerCta + warp * 128;
@@ -274,15 +282,18 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
   };
 
   const int steps = m_begin < m_end ? (m_end - m_begin + 15) / 16 : 0;
-  if (steps > 0) issue(0, 0);
+  // one commit group per step slot (empty beyond the last step), so "all but the newest kOuterStages - 1 groups" is always
+  // the right wait
+#pragma unroll
+  for (int st = 0; st < kOuterStages - 1; ++st) {
+    if (st < steps) issue(st, st);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int st = 0; st < steps; ++st) {
-    const int stage = st & 1;
-    if (st + 1 < steps) {
-      issue(st + 1, stage ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int stage = st % kOuterStages;
+    if (st + kOuterStages - 1 < steps) issue(st + kOuterStages - 1, (st + kOuterStages - 1) % kOuterStages);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kOuterStages - 1) : "memory");
     __syncwarp();
     const uint32_t ys = sb + uint32_t(stage) * 2560u, ps = ys + 2048u;
     // A = P^T (16 ranks x 16 rows): four transposed 8x8 blocks of the [row][rank] slice
@@ -314,6 +325,7 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
   }
   // accumulator layout of m16n8: lane (g, t) holds ranks g, g + 8 and columns 2t, 2t + 1 of tile j
   const int g = lane >> 2, t = lane & 3;
+  __syncthreads();   // every warp is done with its stage buffers before they become the reduction buffer
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     red[warp][g][8 * j + 2 * t] = acc[j][0];
@@ -327,6 +339,149 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
     if (n0 + n < N)
       part[(size_t(blockIdx.y) * 16 + c) * N + n0 + n] = (red[0][c][n] + red[1][c][n]) + (red[2][c][n] + red[3][c][n]);
   }
+}
+
+// ---- both LoRA gradients that read the same activation gradient, in one pass ---------------------------------------------
+// For Y = dOut [M, N] of a LoRALinear (main.py:42-43):  dB = P^T . Y  (P = s x A, [M, 16])  and  dP = Y . B^T  (B [16, N]).
+// CTA = R rows x C columns, 4 warps; warp w owns C/4 columns (kTW 64-column tiles) for all R rows: its dB accumulators
+// [16 x C/4] live in registers for the whole CTA, the [16 rows x 16] dP block of every 16-row step is added to a CTA-wide
+// fp32 buffer in shared memory (4-way contention at most).  Partials: part_db[row block][16][N], part_dp[column group][M][16].
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+constexpr int kBwdStages = 3;
+
+template <bool kF16, int kTW>
+__global__ void __launch_bounds__(128)
+lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M,
+                const uint16_t* __restrict__ Bm, int rows_per_cta, float* __restrict__ part_db, float* __restrict__ part_dp) {
+  constexpr int kWarpCols = kTW * 64, kCtaCols = 4 * kWarpCols;
+  constexpr int kYBytes = 16 * kTW * 128, kStageBytes = kYBytes + 512;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* bm_gen = dsm + 4 * kBwdStages * kStageBytes;              // [16 ranks][kCtaCols] 16-bit, 16-byte chunks XOR-swizzled
+  float* dp_s = reinterpret_cast<float*>(bm_gen + 16 * kCtaCols * 2);   // [rows_per_cta][16]
+  const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(dsm)) + uint32_t(warp * kBwdStages * kStageBytes);
+  const uint32_t bm_s = static_cast<uint32_t>(__cvta_generic_to_shared(bm_gen));
+  const int c_cta = blockIdx.x * kCtaCols, c_warp = c_cta + warp * kWarpCols;
+  const int m_begin = blockIdx.y * rows_per_cta;
+  const int m_end = min(M, m_begin + rows_per_cta);
+  const int steps = (m_end - m_begin + 15) / 16;
+
+  auto issue = [&](int step, int stage) {
+    const int m0 = m_begin + step * 16;
+    const uint32_t ys = sb + uint32_t(stage * kStageBytes), ps = ys + kYBytes;
+#pragma unroll
+    for (int q = 0; q < kTW * 4; ++q) {
+      const int idx = q * 32 + lane;                    // 16 rows x (kTW * 8) chunks
+      const int row = idx / (kTW * 8), chf = idx % (kTW * 8);
+      const int t = chf >> 3, ch = chf & 7;
+      const int m = m0 + row;
+      const bool ok = m < m_end;
+      cp16(ys + uint32_t(t * 2048 + row * 128 + ((ch ^ (row & 7)) << 4)), Y + size_t(ok ? m : 0) * N + c_warp + chf * 8, ok);
+    }
+    {
+      const int row = lane >> 1, ch = lane & 1;
+      const int m = m0 + row;
+      const bool ok = m < m_end;
+      cp16(ps + uint32_t(row * 32 + ch * 16), P + size_t(ok ? m : 0) * p_ld + ch * 8, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int st = 0; st < kBwdStages - 1; ++st) {
+    if (st < steps) issue(st, st);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // B slice of the CTA's columns and the zeroed dP buffer (plain stores; visible after the barrier below)
+  for (int i = threadIdx.x; i < 16 * (kCtaCols / 8); i += 128) {
+    const int r = i / (kCtaCols / 8), ch = i % (kCtaCols / 8);
+    const uint4 v = *reinterpret_cast<const uint4*>(Bm + size_t(r) * N + c_cta + ch * 8);
+    *reinterpret_cast<uint4*>(bm_gen + r * (kCtaCols * 2) + ((ch ^ (r & 7)) << 4)) = v;
+  }
+  for (int i = threadIdx.x; i < rows_per_cta * 4; i += 128) reinterpret_cast<float4*>(dp_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  float acc[kTW * 8][4];
+#pragma unroll
+  for (int j = 0; j < kTW * 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const int mat = lane >> 3, r8 = lane & 7;
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int st = 0; st < steps; ++st) {
+    const int stage = st % kBwdStages;
+    if (st + kBwdStages - 1 < steps) issue(st + kBwdStages - 1, (st + kBwdStages - 1) % kBwdStages);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(kBwdStages - 1) : "memory");
+    __syncwarp();
+    const uint32_t ys = sb + uint32_t(stage * kStageBytes), ps = ys + kYBytes;
+    uint32_t a[4];   // P^T: 16 ranks x 16 rows
+    ldsm4t(ps + uint32_t(((mat >> 1) * 8 + r8) * 32 + (mat & 1) * 16), a);
+    float dp[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+#pragma unroll
+    for (int t = 0; t < kTW; ++t) {
+      const uint32_t yt = ys + uint32_t(t * 2048);
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {   // dB: B operand = Y (k = rows), pairs of 8-column tiles
+        uint32_t b[4];
+        const int row = (mat & 1) * 8 + r8, ch = jp * 2 + (mat >> 1);
+        ldsm4t(yt + uint32_t(row * 128 + ((ch ^ (row & 7)) << 4)), b);
+        mma16816<kF16>(acc[t * 8 + 2 * jp], a, b[0], b[1]);
+        mma16816<kF16>(acc[t * 8 + 2 * jp + 1], a, b[2], b[3]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {   // dP: A operand = Y (k = 16 columns per step), B operand = the B slice
+        uint32_t ya[4], bb[4];
+        {
+          const int row = (mat & 1) * 8 + r8, ch = ks * 2 + (mat >> 1);
+          ldsm4(yt + uint32_t(row * 128 + ((ch ^ (row & 7)) << 4)), ya);
+        }
+        {
+          const int rk = (mat >> 1) * 8 + r8, ch = (warp * kWarpCols + t * 64 + ks * 16) / 8 + (mat & 1);
+          ldsm4(bm_s + uint32_t(rk * (kCtaCols * 2) + ((ch ^ (rk & 7)) << 4)), bb);
+        }
+        mma16816<kF16>(dp[0], ya, bb[0], bb[1]);
+        mma16816<kF16>(dp[1], ya, bb[2], bb[3]);
+      }
+    }
+    {
+      float* d0 = dp_s + (st * 16 + g) * 16 + 2 * t4;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        atomicAdd(d0 + n * 8, dp[n][0]);
+        atomicAdd(d0 + n * 8 + 1, dp[n][1]);
+        atomicAdd(d0 + 128 + n * 8, dp[n][2]);
+        atomicAdd(d0 + 128 + n * 8 + 1, dp[n][3]);
+      }
+    }
+    __syncwarp();
+  }
+  // dB partial of this row block: rank g / g + 8, columns 2 t4, 2 t4 + 1 of each 8-column tile
+#pragma unroll
+  for (int j = 0; j < kTW * 8; ++j) {
+    const int col = c_warp + j * 8 + 2 * t4;
+    *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g) * N + col) = make_float2(acc[j][0], acc[j][1]);
+    *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g + 8) * N + col) = make_float2(acc[j][2], acc[j][3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (m_end - m_begin) * 4; i += 128)
+    reinterpret_cast<float4*>(part_dp + (size_t(blockIdx.x) * M + m_begin) * 16)[i] = reinterpret_cast<const float4*>(dp_s)[i];
+}
+
+// dP 16-bit [M, 16] = sum over column groups of part_dp[group][M][16]
+template <bool kF16>
+__global__ void __launch_bounds__(256)
+lora_dp_reduce_kernel(const float* __restrict__ part, int groups, int M, uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (row, 4-rank group)
+  if (i >= M * 4) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int gq = 0; gq < groups; ++gq) {
+    const float4 v = reinterpret_cast<const float4*>(part)[size_t(gq) * M * 4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(Act<kF16>::pack(s.x, s.y), Act<kF16>::pack(s.z, s.w));
 }
 
 // out = scale * sum_split part[split][c][n], c < rc (4 or 16 columns per pass)
@@ -389,10 +544,60 @@ int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaS
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// fused dB + dP pass (lora_bwd_kernel): 512 x 512 CTAs when N % 512 == 0 and there are enough of them, else 256 x 256
+static void lora_bwd_geometry(int N, int M, int* tw, int* rows, int* cta_cols) {
+  const bool big = N % 512 == 0 && (long long)(N / 512) * ((M + 511) / 512) >= 2 * 148;
+  *tw = big ? 2 : 1;
+  *rows = big ? 512 : 256;
+  *cta_cols = big ? 512 : 256;
+}
+
+int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale, float* out_db,
+                    void* out_dp16, float* scratch, int f16, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (rank < 1 || rank > 16 || p_ld != 16 || N % 256 != 0 || (reinterpret_cast<uintptr_t>(P) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(Bm) & 15) != 0)
+    return -3;   // not this kernel's envelope: the caller runs the separate dP GEMM + dB reduction
+  int tw, rows, cta_cols;
+  lora_bwd_geometry(N, M, &tw, &rows, &cta_cols);
+  const int row_blocks = (M + rows - 1) / rows, col_groups = N / cta_cols;
+  float* part_db = scratch;
+  float* part_dp = scratch + size_t(row_blocks) * 16 * N;
+  const size_t smem = size_t(4 * kBwdStages * (16 * tw * 128 + 512)) + size_t(16) * cta_cols * 2 + size_t(rows) * 64;
+  const uint16_t* p = static_cast<const uint16_t*>(P);
+  const uint16_t* y = static_cast<const uint16_t*>(Y);
+  const uint16_t* bm = static_cast<const uint16_t*>(Bm);
+  const dim3 grid = dim3(static_cast<unsigned>(col_groups), static_cast<unsigned>(row_blocks), 1u);
+#define IIC_LB(F16, TW)                                                                                                   \
+  {                                                                                                                       \
+    auto kern = lora_bwd_kernel<F16, TW>;                                                                                 \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) return -2;  \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    kern<<<grid, 128, smem, stream>>>(p, p_ld, y, N, M, bm, rows, part_db, part_dp);                                      \
+  }
+  if (f16) { if (tw == 2) IIC_LB(true, 2) else IIC_LB(true, 1) }
+  else { if (tw == 2) IIC_LB(false, 2) else IIC_LB(false, 1) }
+#undef IIC_LB
+  lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(part_db, row_blocks, N, rank, 0, 16, scale, 0, out_db);
+  if (f16) lora_dp_reduce_kernel<true><<<(M * 4 + 255) / 256, 256, 0, stream>>>(part_dp, col_groups, M, static_cast<uint16_t*>(out_dp16));
+  else lora_dp_reduce_kernel<false><<<(M * 4 + 255) / 256, 256, 0, stream>>>(part_dp, col_groups, M, static_cast<uint16_t*>(out_dp16));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int lora_outer_splits(int M) { return (M + 63) / 64; }   // 64 rows per split
 size_t lora_outer_scratch_bytes(int N, int M) {   // the largest partial buffer of the three reduction kernels
   const size_t rows = size_t(lora_outer_splits(M)) * 4, rows_mma = size_t((M + 511) / 512) * 16, rows16 = size_t((M + 255) / 256) * 16;
-  return (rows > rows_mma ? (rows > rows16 ? rows : rows16) : (rows_mma > rows16 ? rows_mma : rows16)) * N * sizeof(float);
+  size_t bytes = (rows > rows_mma ? (rows > rows16 ? rows : rows16) : (rows_mma > rows16 ? rows_mma : rows16)) * N * sizeof(float);
+  if (N % 256 == 0) {   // lora_bwd_kernel: dB partials per row block + dP partials per column group
+    int tw, r, c;
+    lora_bwd_geometry(N, M, &tw, &r, &c);
+    const size_t fused = (size_t((M + r - 1) / r) * 16 * N + size_t(N / c) * M * 16) * sizeof(float);
+    if (fused > bytes) bytes = fused;
+  }
+  return bytes;
 }
 
 int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale, int transpose,

@@ -531,6 +531,17 @@ class Engine:
             L.check(self.h, self.lib.iic_op_act_bwd(self.h, dh.data_ptr(), u.data_ptr(), dh.numel(), act,
                                                     _stream_ptr(self.device)), "iic_op_act_bwd")
 
+    def op_lora_bwd(self, P: torch.Tensor, Y: torch.Tensor, Bm: torch.Tensor, rank: int, scale: float = 1.0):
+        """(dB f32 [rank, N] = scale * P^T . Y,  dP 16-bit [M, 16] = Y . Bm^T) from one pass over Y."""
+        M, N = Y.shape
+        db = torch.zeros(rank, N, dtype=torch.float32, device=self.device)
+        dp = torch.zeros(M, 16, dtype=self.op_dtype, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_op_lora_bwd(self.h, P.data_ptr(), P.stride(0), Y.data_ptr(), N, M, Bm.data_ptr(), rank,
+                                                     float(scale), db.data_ptr(), dp.data_ptr(), _stream_ptr(self.device)),
+                    "iic_op_lora_bwd")
+        return db, dp
+
     def op_lora_outer(self, P: torch.Tensor, Y: torch.Tensor, rank: int, act: int = 0, scale: float = 1.0,
                       transpose: bool = False) -> torch.Tensor:
         M, N = Y.shape

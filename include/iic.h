@@ -247,6 +247,11 @@ int iic_op_attention_bwd(iic_handle* h, const void* qkv, void* out, const void* 
 int iic_op_layernorm_bwd(iic_handle* h, const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows,
                          int D, void* stream);
 int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act, void* stream);
+/* Both gradients of a LoRA pair (main.py:30-31, 42-43) that read the output gradient Y 16-bit [M, N], in one pass:
+ * out_db f32 [rank, N] = scale * P^T . Y with P 16-bit [M, p_ld = 16] the forward's s * x . A, and out_dp16 16-bit [M, 16] =
+ * Y . Bm^T with Bm 16-bit [16, N] = lora_B (rows >= rank zero).  N % 256 == 0. */
+int iic_op_lora_bwd(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale,
+                    float* out_db, void* out_dp16, void* stream);
 int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale,
                       int transpose, float* out, void* stream);
 

@@ -95,6 +95,26 @@ def test_lora_gradient_reductions(engine, rank):
     assert (dA - ref32).abs().max() < 1e-2 * ref32.abs().max()      # vs un-rounded gelu: the operand rounding, 2^-9 relative per term
 
 
+@pytest.mark.parametrize("rank", [4, 16])
+@pytest.mark.parametrize("shape", [(197 * 9 + 3, 3072), (197 * 9 + 3, 768), (197 * 128, 3072), (577 * 2, 1024), (40, 256)])
+def test_lora_bwd_fused(engine, rank, shape):
+    """dB = P^T . Y and dP = Y . B^T from one pass over Y, against fp32 products of the same bf16 operands"""
+    M, N = shape
+    g = torch.Generator(device="cuda").manual_seed(29)
+    P = torch.zeros(M, 16, device="cuda", dtype=torch.bfloat16)
+    P[:, :rank] = torch.randn(M, rank, device="cuda", generator=g).to(torch.bfloat16)
+    Bm = torch.zeros(16, N, device="cuda", dtype=torch.bfloat16)
+    Bm[:rank] = (torch.randn(rank, N, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    Y = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    db, dp = engine.op_lora_bwd(P, Y, Bm, rank, scale=0.5)
+    ref_db = 0.5 * P[:, :rank].float().t() @ Y.float()
+    ref_dp = Y.float() @ Bm.float().t()
+    assert torch.allclose(db, ref_db, rtol=1e-3, atol=2e-2 * max(1.0, (M / 1776) ** 0.5)), (db - ref_db).abs().max()
+    # 16-bit output: 2^-9 relative
+    assert torch.allclose(dp.float(), ref_dp, rtol=4e-3, atol=4e-3), (dp.float() - ref_dp).abs().max()
+    assert rank == 16 or dp[:, rank:].abs().max() == 0
+
+
 @pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
 @pytest.mark.parametrize("act", [0, 1], ids=["quickgelu", "erf"])
 def test_gemm_training_epilogues(iic, engine, ctas, act):
