@@ -355,7 +355,8 @@ constexpr int kBwdStages = 3;
 template <bool kF16, int kTW>
 __global__ void __launch_bounds__(128)
 lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M,
-                const uint16_t* __restrict__ Bm, int rows_per_cta, float* __restrict__ part_db, float* __restrict__ part_dp) {
+                const uint16_t* __restrict__ Bm, int rows_per_cta, int rank, float* __restrict__ part_db,
+                float* __restrict__ part_dp) {
   constexpr int kWarpCols = kTW * 64, kCtaCols = 4 * kWarpCols;
   constexpr int kYBytes = 16 * kTW * 128, kStageBytes = kYBytes + 512;
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -443,7 +444,7 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
           ldsm4(bm_s + uint32_t(rk * (kCtaCols * 2) + ((ch ^ (rk & 7)) << 4)), bb);
         }
         mma16816<kF16>(dp[0], ya, bb[0], bb[1]);
-        mma16816<kF16>(dp[1], ya, bb[2], bb[3]);
+        if (rank > 8) mma16816<kF16>(dp[1], ya, bb[2], bb[3]);   // ranks 8..15 are zero rows of B otherwise
       }
     }
     {
@@ -576,7 +577,7 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) return -2;  \
       attr = true;                                                                                                        \
     }                                                                                                                     \
-    kern<<<grid, 128, smem, stream>>>(p, p_ld, y, N, M, bm, rows, part_db, part_dp);                                      \
+    kern<<<grid, 128, smem, stream>>>(p, p_ld, y, N, M, bm, rows, rank, part_db, part_dp);                                    \
   }
   if (f16) { if (tw == 2) IIC_LB(true, 2) else IIC_LB(true, 1) }
   else { if (tw == 2) IIC_LB(false, 2) else IIC_LB(false, 1) }
