@@ -418,9 +418,12 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
     const uint32_t ys = sb + uint32_t(stage * kStageBytes), ps = ys + kYBytes;
     uint32_t a[4];   // P^T: 16 ranks x 16 rows
     ldsm4t(ps + uint32_t(((mat >> 1) * 8 + r8) * 32 + (mat & 1) * 16), a);
-    float dp[2][4];
+    float dp[2][4], dq[2][4];   // two accumulation chains (even / odd k-steps): half the dependent-MMA latency per step
 #pragma unroll
-    for (int n = 0; n < 2; ++n) dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    for (int n = 0; n < 2; ++n) {
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+    }
 #pragma unroll
     for (int t = 0; t < kTW; ++t) {
       const uint32_t yt = ys + uint32_t(t * 2048);
@@ -443,18 +446,23 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
           const int rk = (mat >> 1) * 8 + r8, ch = (warp * kWarpCols + t * 64 + ks * 16) / 8 + (mat & 1);
           ldsm4(bm_s + uint32_t(rk * (kCtaCols * 2) + ((ch ^ (rk & 7)) << 4)), bb);
         }
-        mma16816<kF16>(dp[0], ya, bb[0], bb[1]);
-        if (rank > 8) mma16816<kF16>(dp[1], ya, bb[2], bb[3]);   // ranks 8..15 are zero rows of B otherwise
+        if (ks & 1) {
+          mma16816<kF16>(dq[0], ya, bb[0], bb[1]);
+          if (rank > 8) mma16816<kF16>(dq[1], ya, bb[2], bb[3]);
+        } else {
+          mma16816<kF16>(dp[0], ya, bb[0], bb[1]);
+          if (rank > 8) mma16816<kF16>(dp[1], ya, bb[2], bb[3]);   // ranks 8..15 are zero rows of B otherwise
+        }
       }
     }
     {
       float* d0 = dp_s + (st * 16 + g) * 16 + 2 * t4;
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        atomicAdd(d0 + n * 8, dp[n][0]);
-        atomicAdd(d0 + n * 8 + 1, dp[n][1]);
-        atomicAdd(d0 + 128 + n * 8, dp[n][2]);
-        atomicAdd(d0 + 128 + n * 8 + 1, dp[n][3]);
+        atomicAdd(d0 + n * 8, dp[n][0] + dq[n][0]);
+        atomicAdd(d0 + n * 8 + 1, dp[n][1] + dq[n][1]);
+        atomicAdd(d0 + 128 + n * 8, dp[n][2] + dq[n][2]);
+        atomicAdd(d0 + 128 + n * 8 + 1, dp[n][3] + dq[n][3]);
       }
     }
     __syncwarp();
