@@ -62,7 +62,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   const int tile_m = kBlockM * kCtas;
   const int m_tiles = (args.M + tile_m - 1) / tile_m;
   const int n_tiles = (args.N + kBlockN - 1) / kBlockN;
-  const int total = S::kLn ? m_tiles : m_tiles * n_tiles;   // fused LayerNorm: clusters own whole row blocks
+  const int total = m_tiles * n_tiles;
   int clusters = num_sms / kCtas;
   if (clusters > total) clusters = total;
   cudaLaunchConfig_t cfg = {};
@@ -105,6 +105,11 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 }  // namespace
+
+size_t gemm_ln_scratch_bytes(int M, int N) {
+  const size_t m_pad = (size_t(M) + 255) / 256 * 256;   // covers 128- and 256-row tiles
+  return ((m_pad / 128) * sizeof(int) + 1023) / 1024 * 1024 + size_t((N + 255) / 256) * m_pad * sizeof(float2);
+}
 
 size_t gemm_smem_bytes(int ctas) {
   return ctas == 2 ? GemmSmem<2, 256, kEpiBiasBf16>::kTotal : GemmSmem<1, 256, kEpiBiasBf16>::kTotal;
@@ -161,9 +166,8 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     else ok = make_tile_map_kind(&tln, p.out2, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f16 ? 1 : 0);
   }
   if (ln) {
-    static const char* e_ln = "gemm: fused LayerNorm needs the fp32 residual epilogue, N % 256 == 0, gamma/beta, and (with ln_lora_a) ln_p_out with ln_p_ld % 4 == 0";
-    if (p.epilogue != kEpiBiasResF32 || p.N % 256 != 0 || p.ln_gamma == nullptr || p.ln_beta == nullptr ||
-        (p.ln_lora_a != nullptr && (p.ln_p_out == nullptr || p.ln_p_ld < 4 || p.ln_p_ld % 4 != 0))) {
+    static const char* e_ln = "gemm: fused LayerNorm needs the fp32 residual epilogue, N % 256 == 0 (<= 2048), gamma/beta and ln_scratch";
+    if (p.epilogue != kEpiBiasResF32 || p.N % 256 != 0 || p.N > 2048 || p.ln_gamma == nullptr || p.ln_beta == nullptr || p.ln_scratch == nullptr) {
       if (err) *err = e_ln;
       return -1;
     }
@@ -188,9 +192,22 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   args.ln_gamma = p.ln_gamma;
   args.ln_beta = p.ln_beta;
   args.ln_eps = p.ln_eps;
-  args.ln_lora_a = p.ln_lora_a;
-  args.ln_p_out = p.ln_p_out;
-  args.ln_p_ld = p.ln_p_ld;
+  args.ln_out = p.ln_out;
+  args.ln_part = nullptr;
+  args.ln_cnt = nullptr;
+  args.ln_mpad = 0;
+  if (ln) {
+    // [counters: one per 128-row block][(mean, M2) partials: N/256 x rows padded to whole 256-row tiles]
+    const int m_tiles = (p.M + kBlockM * ctas - 1) / (kBlockM * ctas);
+    const size_t cnt_bytes = (size_t(m_tiles) * ctas * sizeof(int) + 1023) & ~size_t(1023);
+    args.ln_cnt = static_cast<int*>(p.ln_scratch);
+    args.ln_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(p.ln_scratch) + cnt_bytes);
+    args.ln_mpad = m_tiles * kBlockM * ctas;
+    if (cudaMemsetAsync(args.ln_cnt, 0, cnt_bytes, stream) != cudaSuccess) {
+      if (err) *err = e_launch;
+      return -2;
+    }
+  }
   // long reductions get the deep-ring variant of the residual epilogue (measured: c_proj 1268 -> 1322 TFLOP/s; the short-K
   // out_proj is bound by its fp32 residual traffic and prefers the 4-slab residual ring)
   const bool deep = p.epilogue == kEpiBiasResF32 && p.K >= 2048;

@@ -46,15 +46,13 @@ enum GemmEpilogue : int {
   kEpiBiasResF32DeepK = 5,  // kEpiBiasResF32 with a deeper operand ring and a shorter residual ring: chosen by the
                             // launcher for long reductions (K >= 2048: mlp.c_proj), where TMA look-ahead matters more
   // kEpiBiasResF32 + the LayerNorm that consumes the new residual stream (ln_2 after attn.out_proj, the next block's ln_1
-  // after mlp.c_proj), with that LayerNorm's rank-4 LoRA down-projection.  Each CTA pair owns whole 256-row blocks (all
-  // column tiles of them, in order), the accumulate group gathers per-row statistics while the sums pass through its
-  // registers, and the otherwise idle second epilogue group re-reads the freshly stored rows from L2 (TMA), normalises
-  // and TMA-stores the 16-bit LayerNorm output: the LayerNorm costs no HBM read and no launch.
-  // OPT-IN (IIC_FUSE_LN=1), not the default: measured on the B200 at batch 1024 it is slower than GEMM + LayerNorm kernel
-  // (out_proj 0.57 vs 0.29 + 0.19 ms, c_proj 1.11 vs 0.75 + 0.19 ms).  Row-block ownership re-reads c_proj's A operand
-  // three times from HBM (74 pairs x 1.5 MB of A rows do not stay in L2; the default schedule shares them between the
-  // three pairs working on a row block at the same time), the wait for the stores' completion before the re-read costs
-  // ~9 us per row block, and one 16 KB slab in flight per SM cannot cover the ~2.5 us re-read latency.
+  // after mlp.c_proj) in the same launch.  Tile schedule unchanged.  The
+  // accumulate group gathers per-row (mean, M2) of its 256 columns while acc + bias + residual passes through its registers
+  // and publishes them to global memory (counter per 128-row block, release/acquire); the otherwise idle second epilogue
+  // group waits until all column tiles of its row block have published and its own tile's TMA stores are complete, combines
+  // the partial statistics (Chan), re-reads its tile from L2 by TMA, normalises and writes the 16-bit LayerNorm output: the
+  // LayerNorm costs no HBM read of the residual stream and no launch.  OPT-IN (IIC_FUSE_LN=1): measured on the B200 the fused
+  // c_proj is 0.83 ms against 0.74 + 0.14 ms, but the power-capped step does not get faster; history and numbers in DESIGN.md.
   kEpiBiasResF32Ln = 6,
   kEpiBiasResF32LnDeepK = 7,
   // training: out 16-bit = acc * act'(u), u = the forward's pre-activation tile, TMA-loaded (16-bit, through tm_res) into the
@@ -83,9 +81,10 @@ struct GemmArgs {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
-  const float* ln_lora_a;   // f32 [N, 4] = scaling * lora_A of the LayerNorm's consumer (rank <= 4, zero padded) or nullptr
-  void* ln_p_out;           // 16-bit [M, ln_p_ld]: y . ln_lora_a in columns 0..3, zeros beyond
-  int ln_p_ld;
+  void* ln_out;             // 16-bit [M, N] (pitch N)
+  float2* ln_part;          // [n_tiles][ln_mpad]: (mean, M2) of each row over the tile's columns
+  int* ln_cnt;              // [m_tiles * kCtas], zeroed before the launch: column tiles of the 128-row block published so far
+  int ln_mpad;
 };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
@@ -111,19 +110,18 @@ struct GemmSmem {
   // for the bias-only and the residual epilogues)
   static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect || kActGrad || kDual) ? 2 : 1;
   static constexpr int kSlabs =   // staging ring depth
-      kDirect ? 0 : (kResidual ? (kLn ? (kDeepK ? 2 : 3) : (kDeepK ? 3 : 4)) : ((kActGrad || kDual) ? 4 : 2));
+      kDirect ? 0 : (kResidual ? (kDeepK ? 3 : 4) : ((kActGrad || kDual) ? 4 : 2));
   // fused LayerNorm tail: fp32 input slabs (re-read of the stored rows) and one 16-bit output slab
-  static constexpr int kLnIn = kLn ? (kDeepK ? 1 : 2) : 0;
-  static constexpr int kLnSlabs = kLn ? kLnIn + 1 : 0;
+  static constexpr int kLnSlabs = 0;   // the LayerNorm group re-reads its tile with plain (L2) loads into registers
   static constexpr int kBufPerGroup = kDirect ? 1 : kSlabs / kGroups;
   static constexpr int kRingBudget =
-      kLn ? (kDeepK ? 160 : 128) * 1024 : (kDeepK ? 208 : 192) * 1024 - kSlabs * kSlabBytes;
+      (kDeepK ? 208 : 192) * 1024 - kSlabs * kSlabBytes;
   static constexpr int kStages = kRingBudget / kStageBytes;  // 2 CTA: 6 / 5 / 4;  1 CTA: 4 / 3 / 2 ... see static_assert
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * kBlockN;  // 512 when kBlockN = 256
-  static constexpr int kBarBytes = kLn ? 2048 : 1024;   // LN: barriers + the per-row (mean, rstd) hand-off [128] float2
+  static constexpr int kBarBytes = kLn ? 2048 : 1024;   // LN: + the (scale, shift) of the tile's 128 rows
   // consumer LoRA-A slice of the current tile [kBlockN][4] fp32 + the tile's bias slice [kBlockN] fp32 (activation epilogues)
-  static constexpr int kDownBytes = kLn ? 0 : kBlockN * 20;
+  static constexpr int kDownBytes = kBlockN * 20;
   static constexpr int kTotal = kStages * kStageBytes + (kSlabs + kLnSlabs) * kSlabBytes + kBarBytes + kDownBytes +
                                 1024 /*alignment slack*/;
   static_assert(kStages >= 2, "smem ring too shallow");
@@ -162,7 +160,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   constexpr bool kResidual = S::kResidual;
   constexpr bool kDirect = S::kDirect;
   constexpr bool kLn = S::kLn;
-  constexpr int kLnIn = S::kLnIn;
   constexpr bool kActGrad = S::kActGrad;
   constexpr bool kDual = S::kDual;
   constexpr bool kAct = kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDual;
@@ -174,8 +171,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t slab_base = smem_base + kStages * S::kStageBytes;
-  const uint32_t lnin_base = slab_base + kSlabs * kSlabBytes;          // LN tail: fp32 input slabs, then the output slab
-  const uint32_t lnout_base = lnin_base + kLnIn * kSlabBytes;
   const uint32_t bar_base = slab_base + (kSlabs + S::kLnSlabs) * kSlabBytes;
   auto smem_a = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
@@ -185,13 +180,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + S::kAccStages + a); };
   auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + b); };
   auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 4 + b); };
-  auto lnfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 8 + b); };   // b < 2
-  const uint32_t lnready_bar = bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 10);
-  const uint32_t lnfree_bar = bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 11);
   constexpr int kTmemSlotOff = 8 * (2 * kStages + 2 * S::kAccStages + 12);
   const uint32_t tmem_slot = bar_base + kTmemSlotOff;
   uint8_t* bar_gen = smem_gen + kStages * S::kStageBytes + (kSlabs + S::kLnSlabs) * kSlabBytes;
-  float2* ln_stats = reinterpret_cast<float2*>(bar_gen + 1024);   // kLn only (kBarBytes = 2048)
+  // kLn: number of this CTA's tiles whose TMA stores are complete (accumulate group's storer -> LayerNorm group)
+  volatile int* ln_done = reinterpret_cast<volatile int*>(bar_gen + kTmemSlotOff + 8);
+  float2* ln_ss = reinterpret_cast<float2*>(bar_gen + 1024);   // kLn only (kBarBytes = 2048)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_gen + kTmemSlotOff);
   float4* down_s = reinterpret_cast<float4*>(bar_gen + S::kBarBytes);
   float* bias_s = reinterpret_cast<float*>(bar_gen + S::kBarBytes + kBlockN * 16);
@@ -226,11 +220,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       ptx::mbar_init(rfull_bar(b), 1);   // residual producer's arrive.expect_tx
       ptx::mbar_init(rempty_bar(b), 1);  // the storing epilogue thread, once the TMA store has read the slab
     }
-    if constexpr (kLn) {
-      for (int b = 0; b < 2; ++b) ptx::mbar_init(lnfull_bar(b), 1);
-      ptx::mbar_init(lnready_bar, 128);  // accumulate group: statistics written, rows of the block stored
-      ptx::mbar_init(lnfree_bar, 128);   // LN group: statistics read
-    }
+    if constexpr (kLn) *ln_done = 0;
     ptx::fence_mbar_init();
   }
   if constexpr (kCtas > 1) ptx::cluster_sync();  // peer barriers exist before anybody signals them / allocs TMEM
@@ -246,22 +236,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int cluster_id = blockIdx.x / kCtas;
   const int num_clusters = gridDim.x / kCtas;
   const int k_iters = args.num_k_blocks + (args.lora_ksteps > 0 ? 1 : 0);
-  // static persistent schedule, `it` = this cluster's running tile counter.  Default: tile = cluster + it * clusters with n
-  // fastest.  kLn: a cluster owns whole row blocks (m_blk = cluster + j * clusters) and walks their column tiles in order, so
-  // that every output row is completed - and its LayerNorm statistics known - inside one CTA.
+  // static persistent schedule, `it` = this cluster's running tile counter: tile = cluster + it * clusters with n fastest
   auto tile_at = [&](int it, int& m_blk, int& n_blk) -> bool {
-    if constexpr (kLn) {
-      const int j = it / n_tiles;
-      n_blk = it - j * n_tiles;
-      m_blk = cluster_id + j * num_clusters;
-      return m_blk < m_tiles;
-    } else {
-      const int tile = cluster_id + it * num_clusters;
-      if (tile >= total_tiles) return false;
-      m_blk = tile / n_tiles;
-      n_blk = tile - m_blk * n_tiles;
-      return true;
-    }
+    const int tile = cluster_id + it * num_clusters;
+    if (tile >= total_tiles) return false;
+    m_blk = tile / n_tiles;
+    n_blk = tile - m_blk * n_tiles;
+    return true;
   };
 
   if (warp == 0) {
@@ -357,130 +338,106 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const bool storer = (threadIdx.x & 127) == 0;  // first thread of each group issues that group's TMA stores
     int my_slab = grp;                   // running index (over the whole kernel) of the next slab this group handles
     int m_blk = 0, n_blk = 0;
-    // LayerNorm statistics of this thread's row, gathered over the column tiles of the row block: sums of (x - shift) and
-    // (x - shift)^2 with shift = mean of the row's first 32 columns (one pass without cancellation trouble)
+    // LayerNorm statistics of this thread's row over the tile's 256 columns: sums of (x - shift) and (x - shift)^2 with
+    // shift = mean of the tile's first 32 columns (one pass without cancellation trouble)
     float ln_shift = 0.f, ln_s = 0.f, ln_q = 0.f;
     if constexpr (kLn) {
       if (grp == 1) {
         // ======================= fused LayerNorm tail (second epilogue group) =======================
         // Thread t owns the 16-byte column chunk (t & 7) of eight rows of every 32-column input slab, so gamma / beta / the
-        // LoRA-A rows of its four columns are three loads per slab (with ~all of L1 carved out as shared memory, the
+        // LoRA-A rows of its four columns are a handful of loads per slab (with ~all of L1 carved out as shared memory, a
         // one-thread-per-row layout's 48 L2-latency loads per slab made this group the kernel's bottleneck).
         const int t = threadIdx.x & 127;
         const bool tstorer = t == 0;
         const int chunk = t & 7;
-        // rows i * 16 + rsel: the four rows of a warp have (row & 7) in {0,4,1,5} / {2,6,3,7}, which spreads the 8-byte
-        // stores into the swizzled output slab over both bank halves
-        const int w4 = t >> 5, l4 = (t >> 3) & 3;
-        const int rsel = (w4 >> 1) * 8 + (w4 & 1) * 2 + (l4 >> 1) + (l4 & 1) * 4;
-        const int slabs_per_row = args.N / 32;
+        const int rsel = t >> 3;   // rows i * 16 + rsel
         const float4* g4 = reinterpret_cast<const float4*>(args.ln_gamma);
         const float4* b4 = reinterpret_cast<const float4*>(args.ln_beta);
-        const float4* a4 = reinterpret_cast<const float4*>(args.ln_lora_a);
-        const bool has_a = a4 != nullptr;
-        uint8_t* lnin_gen = slab_gen + kSlabs * kSlabBytes;
-        uint8_t* lnout_gen = lnin_gen + kLnIn * kSlabBytes;
-        uint32_t cnt = 0;   // running input-slab counter (buffer = cnt % kLnIn, phase = (cnt / kLnIn) & 1)
-        for (int j = 0;; ++j) {
-          m_blk = cluster_id + j * num_clusters;
-          if (m_blk >= m_tiles) break;
+        uint16_t* ln_out = static_cast<uint16_t*>(args.ln_out);
+        const float* xnew = static_cast<const float*>(args.out);
+        const float inv_tiles = 1.0f / float(n_tiles), inv_n = 1.0f / float(args.N);
+        for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
           const int row0 = m_blk * kTileM + int(cta_rank) * kBlockM;
-          auto issue_load = [&](int q, uint32_t c) {
-            const uint32_t b = c % kLnIn;
-            ptx::mbar_arrive_expect_tx(lnfull_bar(b), kSlabBytes);
-            ptx::tma_load_2d(&tm_out, lnfull_bar(b), lnin_base + b * kSlabBytes, q * 32, row0, ptx::kEvictNormal);
-          };
-          ptx::mbar_wait(lnready_bar, uint32_t(j) & 1u);   // statistics written and the block's rows stored (complete)
+          const int col0 = n_blk * kBlockN;
           if (tstorer) {
+            // (1) this tile's rows are stored (complete, not merely read); (2) every column tile of the 128-row block has
+            // published its partial statistics.  Both waits are bounded like the mbarrier waits (trap, not hang).
+            uint32_t spins = 0;
+            while (*ln_done <= it) {
+              __nanosleep(64);
+              if (++spins > (1u << 24)) __trap();
+            }
+            const int* flag = args.ln_cnt + (m_blk * kCtas + int(cta_rank));
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+              if (seen < n_tiles) {
+                __nanosleep(128);
+                if (++spins > (1u << 24)) __trap();
+              }
+            } while (seen < n_tiles);
             ptx::fence_proxy_async_global();
-            for (int q = 0; q < kLnIn && q < slabs_per_row; ++q) issue_load(q, cnt + q);
           }
-          float sc[8], sh[8];   // y = (x * sc + sh) * gamma + beta with sc = rstd, sh = -mean * rstd
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 st = ln_stats[i * 16 + rsel];
-            sc[i] = st.y;
-            sh[i] = -st.x * st.y;
-          }
-          ptx::mbar_arrive(lnfree_bar);
-          float acc[8][4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-#pragma unroll 1
-          for (int q = 0; q < slabs_per_row; ++q, ++cnt) {
-            const float4 g = __ldg(g4 + q * 8 + chunk), be = __ldg(b4 + q * 8 + chunk);
-            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;
-            if (has_a) {
-              w0 = __ldg(a4 + q * 32 + chunk * 4);
-              w1 = __ldg(a4 + q * 32 + chunk * 4 + 1);
-              w2 = __ldg(a4 + q * 32 + chunk * 4 + 2);
-              w3 = __ldg(a4 + q * 32 + chunk * 4 + 3);
-            }
-            const uint32_t b = cnt % kLnIn;
-            const int hq = q & 1;
-            ptx::mbar_wait(lnfull_bar(b), (cnt / kLnIn) & 1u);
-            uint2 pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 16 + rsel;
-              float4 x = *reinterpret_cast<const float4*>(lnin_gen + b * kSlabBytes + r * 128 + ((chunk ^ (r & 7)) << 4));
-              x.x = fmaf(fmaf(x.x, sc[i], sh[i]), g.x, be.x);
-              x.y = fmaf(fmaf(x.y, sc[i], sh[i]), g.y, be.y);
-              x.z = fmaf(fmaf(x.z, sc[i], sh[i]), g.z, be.z);
-              x.w = fmaf(fmaf(x.w, sc[i], sh[i]), g.w, be.w);
-              if (has_a) {
-                acc[i][0] += x.x * w0.x + x.y * w1.x + x.z * w2.x + x.w * w3.x;
-                acc[i][1] += x.x * w0.y + x.y * w1.y + x.z * w2.y + x.w * w3.y;
-                acc[i][2] += x.x * w0.z + x.y * w1.z + x.z * w2.z + x.w * w3.z;
-                acc[i][3] += x.x * w0.w + x.y * w1.w + x.z * w2.w + x.w * w3.w;
-              }
-              pk[i] = make_uint2(Act<kF16>::pack(x.x, x.y), Act<kF16>::pack(x.z, x.w));
-            }
-            // even slab: the output slab's previous TMA store must have read it before the writes below
-            if (hq == 0 && tstorer) ptx::tma_store_wait_read<0>();
-            epi_bar_sync(1);   // every thread is done reading input buffer b (and the output slab is free)
-            if (tstorer && q + kLnIn < slabs_per_row) issue_load(q + kLnIn, cnt + kLnIn);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 16 + rsel;
-              const int c16 = hq * 4 + (chunk >> 1);   // 16-byte chunk of the 64-column 16-bit row
-              *reinterpret_cast<uint2*>(lnout_gen + r * 128 + ((c16 ^ (r & 7)) << 4) + (chunk & 1) * 8) = pk[i];
-            }
-            if (hq == 1) {
-              ptx::fence_proxy_async_smem();
-              epi_bar_sync(1);
-              if (tstorer) {
-                ptx::tma_store_2d(&tm_ln, lnout_base, (q - 1) * 32, row0);
-                ptx::tma_store_commit();
-              }
-            }
-          }
-          if (has_a) {
-            // the eight threads sharing a row (consecutive lanes) hold its partial dot products
+          epi_bar_sync(1);   // the statistics and the stored rows are visible to the whole group (acquire above + barrier)
+          // the re-read of the tile: thread = 16-byte chunk `chunk` of rows i * 16 + rsel of each 32-column slab (8 lanes cover
+          // 128 contiguous bytes of a row), one slab ahead in registers.  Plain L2 loads rather than TMA: a TMA load queues
+          // behind the operand ring's requests (measured 5-7 us per slab).
+          const float* xb = xnew + size_t(row0 + rsel) * args.N + col0 + chunk * 4;
+          auto load_slab = [&](int q, float4 (&dst)[8]) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
+              dst[i] = (row0 + i * 16 + rsel < args.M) ? __ldcg(reinterpret_cast<const float4*>(xb + size_t(i) * 16 * args.N + q * 32))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          float4 cur[8], nxt[8];
+          load_slab(0, cur);
+          {
+            // thread t combines the partial statistics of row t (independent loads, one L2 round trip) ...
+            const float2* pp = args.ln_part + (row0 + t);
+            float2 st[8];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                float v = acc[i][c];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                acc[i][c] = v;
+            for (int n = 0; n < 8; ++n)
+              if (n < n_tiles) st[n] = __ldcg(pp + size_t(n) * args.ln_mpad);
+            float msum = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+              if (n < n_tiles) msum += st[n].x;
+            const float mean = msum * inv_tiles;
+            float m2 = 0.f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+              if (n < n_tiles) {
+                const float dm = st[n].x - mean;
+                m2 += st[n].y + float(kBlockN) * dm * dm;
               }
-            // lane `chunk` = i writes row i's values, the other chunk lanes the zero padding of their row i
+            const float rstd = rsqrtf(m2 * inv_n + args.ln_eps);
+            ln_ss[t] = make_float2(rstd, -mean * rstd);
+          }
+          epi_bar_sync(1);
+          // ... y = (x * sc + sh) * gamma + beta with (sc, sh) = (rstd, -mean * rstd) read back per row (registers are short)
+#pragma unroll 1
+          for (int q = 0; q < kBlockN / 32; ++q) {
+            if (q + 1 < kBlockN / 32) load_slab(q + 1, nxt);
+            const int c4 = (col0 >> 2) + q * 8 + chunk;   // float4 index of this thread's four columns
+            const float4 g = __ldg(g4 + c4), be = __ldg(b4 + c4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = row0 + i * 16 + rsel;
-              if (row < args.M) {
-                uint16_t* po = static_cast<uint16_t*>(args.ln_p_out) + size_t(row) * args.ln_p_ld;
-                if (chunk == 0) *reinterpret_cast<uint2*>(po) =
-                    make_uint2(Act<kF16>::pack(acc[i][0], acc[i][1]), Act<kF16>::pack(acc[i][2], acc[i][3]));
-                else if (chunk * 4 < args.ln_p_ld) *reinterpret_cast<uint2*>(po + chunk * 4) = make_uint2(0u, 0u);
-              }
+              const int r = i * 16 + rsel;
+              float4 x = cur[i];
+              const float2 ss = ln_ss[r];
+              x.x = fmaf(fmaf(x.x, ss.x, ss.y), g.x, be.x);
+              x.y = fmaf(fmaf(x.y, ss.x, ss.y), g.y, be.y);
+              x.z = fmaf(fmaf(x.z, ss.x, ss.y), g.z, be.z);
+              x.w = fmaf(fmaf(x.w, ss.x, ss.y), g.w, be.w);
+              // eight chunk lanes write 64 contiguous bytes of the row: full 32-byte sectors
+              if (row0 + r < args.M)
+                *reinterpret_cast<uint2*>(ln_out + size_t(row0 + r) * args.N + c4 * 4) =
+                    make_uint2(Act<kF16>::pack(x.x, x.y), Act<kF16>::pack(x.z, x.w));
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
           }
         }
-        if (tstorer) ptx::tma_store_wait<0>();
       }
     }
     for (int it = 0; grp < kGroups && tile_at(it, m_blk, n_blk); ++it) {
@@ -491,7 +448,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int col0 = n_blk * kBlockN;
       const bool row_ok = row < args.M;
 
-      if constexpr (!kDirect && !kLn) {
+      if constexpr (!kDirect) {
         // stage this tile's bias slice (and, activation epilogues, its slice of the consumer's LoRA-A) while the MMAs of the tile
         // are still running: with ~all of L1 carved out as shared memory a __ldg in the slab loop is an exposed L2 round trip
         // per 32 columns (c_fc in-step 0.93 -> 0.81 ms)
@@ -564,18 +521,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               float4* p = reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4));
               float4 r = *p;
               float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-              if constexpr (kLn) {
-                if (args.bias != nullptr && col + 4 * j < args.N) bb = __ldg(reinterpret_cast<const float4*>(args.bias + col + 4 * j));
-              } else {
-                bb = reinterpret_cast<const float4*>(bias_s + s * 32)[j];
-              }
+              bb = reinterpret_cast<const float4*>(bias_s + s * 32)[j];
               r.x += __uint_as_float(v[4 * j]) + bb.x;
               r.y += __uint_as_float(v[4 * j + 1]) + bb.y;
               r.z += __uint_as_float(v[4 * j + 2]) + bb.z;
               r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
               *p = r;
               if constexpr (kLn) {
-                if (n_blk == 0 && s == 0) {
+                if (s == 0) {
                   v[4 * j] = __float_as_uint(r.x); v[4 * j + 1] = __float_as_uint(r.y);   // keep: the shift comes first
                   v[4 * j + 2] = __float_as_uint(r.z); v[4 * j + 3] = __float_as_uint(r.w);
                 } else {
@@ -586,7 +539,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               }
             }
             if constexpr (kLn) {
-              if (n_blk == 0 && s == 0) {
+              if (s == 0) {
                 float t = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) t += __uint_as_float(v[i]);
@@ -764,15 +717,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
         if constexpr (kLn) {
-          if (n_blk == n_tiles - 1) {
-            const int j = it / n_tiles;
-            const float inv_n = 1.0f / float(args.N);
-            const float ms = ln_s * inv_n;
-            const float var = fmaxf(ln_q * inv_n - ms * ms, 0.f);
-            ptx::mbar_wait(lnfree_bar, (uint32_t(j) & 1u) ^ 1u);   // the LN group has read the previous block's statistics
-            ln_stats[r_in_tile] = make_float2(ln_shift + ms, rsqrtf(var + args.ln_eps));
-            if (storer) ptx::tma_store_wait<0>();                  // the block's rows are in L2 before the LN group re-reads them
-            ptx::mbar_arrive(lnready_bar);
+          // publish (mean, M2) of this row over the tile's columns, then count the tile in for its 128-row block
+          const float ms = ln_s * (1.0f / float(kBlockN));
+          args.ln_part[size_t(n_blk) * args.ln_mpad + row] = make_float2(ln_shift + ms, fmaxf(ln_q - ln_s * ms, 0.f));
+          __threadfence();
+          epi_bar_sync(0);
+          if (storer) {
+            int* flag = args.ln_cnt + (m_blk * kCtas + int(cta_rank));
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
+            // stores of the PREVIOUS tile are complete once at most this tile's eight are still in flight: no stall
+            ptx::tma_store_wait<kSlabsPerTile>();
+            *ln_done = it;
           }
         }
         if constexpr (kAct) {
@@ -785,7 +740,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     // all global writes of this CTA's TMA stores must be complete before the kernel ends
     if constexpr (!kDirect) {
-      if (storer && grp < kGroups) ptx::tma_store_wait<0>();
+      if (storer && grp < kGroups) {
+        ptx::tma_store_wait<0>();
+        if constexpr (kLn) {
+          __threadfence_block();
+          *ln_done = 0x7fffffff;   // every tile of this CTA is stored
+        }
+      }
     }
   }
 

@@ -53,6 +53,7 @@ struct Block {
 struct Workspace {
   uint16_t *xln, *qkv, *attn, *hid, *p_a, *p_b;
   float *x, *xpre, *down_part;
+  void* ln_scratch;   // fused LayerNorm (IIC_FUSE_LN): cross-CTA row statistics
   size_t total;
 };
 
@@ -104,7 +105,7 @@ struct iic_handle {
   int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
-  int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): LayerNorms ride in the residual GEMM that produces their input - measured slower, see gemm_sm100.cuh
+  int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): the next block's ln_1 rides in the c_proj GEMM - measured: no gain on the power-capped step
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
@@ -147,6 +148,7 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
+  w.ln_scratch = take(gemm_ln_scratch_bytes(int(M), int(d)));
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.total = off;
   return w;
@@ -190,8 +192,7 @@ struct LnFuse {
   const float* gamma = nullptr;
   const float* beta = nullptr;
   void* out = nullptr;
-  const float* lora_a = nullptr;
-  void* p_out = nullptr;
+  void* scratch = nullptr;
 };
 
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
@@ -202,7 +203,7 @@ int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N,
   g.out2 = out2;
   if (ln != nullptr && ln->out != nullptr) {
     g.ln_gamma = ln->gamma; g.ln_beta = ln->beta; g.ln_out = ln->out;
-    g.ln_lora_a = ln->lora_a; g.ln_p_out = ln->p_out; g.ln_p_ld = h->lora_pad;
+    g.ln_scratch = ln->scratch;
   }
   g.down_a = down_a;
   g.down_part = down_part;
@@ -284,11 +285,12 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const float eps = 1e-5f;
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
-  // A LayerNorm whose input is produced by a residual GEMM (ln_2 after attn.out_proj, the next block's ln_1 after mlp.c_proj)
-  // rides in that GEMM (kEpiBiasResF32Ln): possible when the width is a multiple of the 256-column tile and the LayerNorm's
-  // own LoRA down-projection is absent, of rank <= 4 (fused too) or large enough to run as a GEMM on the LayerNorm output.
+  // The next block's ln_1 rides in this block's c_proj GEMM (kEpiBiasResF32Ln; IIC_FUSE_LN): c_proj is compute-bound, so its
+  // second epilogue group has the time to re-read and normalise the tile.  Possible when the width is a multiple of the
+  // 256-column tile and ln_1 carries no rank <= 4 LoRA down-projection of its own (attn.in_proj LoRA: not in the reference).
+  // ln_2 stays a kernel: its producer attn.out_proj is HBM-bound and ln_2 carries the c_fc down-projection.
   auto ln_fusable = [&](const LoraSlot& l, bool via_gemm) {
-    return h->fuse_ln != 0 && d % 256 == 0 && (l.rank == 0 || via_gemm || l.r4 == 4);
+    return h->fuse_ln != 0 && d % 256 == 0 && d <= 2048 && (l.rank == 0 || via_gemm);
   };
   bool ln1_done = false;   // this block's ln_1 was already produced by the previous block's c_proj
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
@@ -311,18 +313,11 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
     if (l_out.rank) IIC_TRY(run_lora_down(h, w.attn, d, M, l_out.a, l_out.at16, l_out.r4, w.p_b, s));
     // x = x + c_proj(act(c_fc(ln_2(x))))   -- LoRALinear on both (main.py:42-43)
     const bool fc_gemm = l_fc.rank > 0 && l_fc.r4 > 4 && l_fc.at16 != nullptr;
-    LnFuse ln2;
-    if (ln_fusable(l_fc, fc_gemm)) {
-      ln2.gamma = b.ln2_g; ln2.beta = b.ln2_b; ln2.out = w.xln;
-      if (l_fc.rank && !fc_gemm) { ln2.lora_a = l_fc.a; ln2.p_out = w.p_a; }
-    }
-    IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s, nullptr, nullptr,
-                     kGemm, &ln2));
-    if (ln2.out == nullptr)
-      IIC_TRY(timed(h, kLayerNorm, s, [&] {
-        return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
-                                l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
-      }));
+    IIC_TRY(run_gemm(h, w.attn, d, b.w_out, M, d, d, &l_out, w.p_b, kEpiBiasResF32, b.b_out, w.x, w.x, d, 1, s));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.x, d, b.ln2_g, b.ln2_b, w.xln, nullptr, d, M, d, eps, (l_fc.rank && !fc_gemm) ? l_fc.a : nullptr,
+                              l_fc.r4, w.p_a, h->lora_pad, h->f16, s);
+    }));
     if (fc_gemm) IIC_TRY(run_lora_down(h, w.xln, d, M, l_fc.a, l_fc.at16, l_fc.r4, w.p_a, s));
     // c_proj's LoRA down-projection (h . A2) rides in the c_fc epilogue while h is still in registers (rank <= 4)
     const bool fuse_down = l_pr.rank > 0 && l_pr.r4 == 4;
@@ -342,8 +337,7 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
       const LoraSlot& n_in = nb.lora[IIC_LORA_IN_PROJ];
       const bool n_in_gemm = n_in.rank > 0 && n_in.r4 > 4 && n_in.at16 != nullptr;
       if (ln_fusable(n_in, n_in_gemm)) {
-        ln1n.gamma = nb.ln1_g; ln1n.beta = nb.ln1_b; ln1n.out = w.xln;
-        if (n_in.rank && !n_in_gemm) { ln1n.lora_a = n_in.a; ln1n.p_out = w.p_a; }
+        ln1n.gamma = nb.ln1_g; ln1n.beta = nb.ln1_b; ln1n.out = w.xln; ln1n.scratch = w.ln_scratch;
         ln1_done = true;
       }
     }
@@ -1094,8 +1088,7 @@ int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, i
 
 int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                        const void* lora_bt, int r_pad, int lora_ld, const float* bias, const float* residual, float* out,
-                       const float* gamma, const float* beta, void* ln_out, const float* ln_lora_a_scaled, void* ln_p_out,
-                       int ln_p_ld, int ctas, void* stream) {
+                       const float* gamma, const float* beta, void* ln_out, int ctas, void* stream) {
   if (!h || !a || !w || !out || !residual || !gamma || !beta || !ln_out) return fail(h, IIC_ERR_ARG, "iic_op_gemm_res_ln: null argument");
   GemmProblem g;
   g.a = a; g.lda = lda;
@@ -1107,9 +1100,14 @@ int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int
   g.r_pad = r_pad; g.lora_ld = lora_ld;
   g.epilogue = kEpiBiasResF32; g.bias = bias; g.residual = residual; g.out = out; g.ldc = N; g.group = 1;
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_out = ln_out;
-  g.ln_lora_a = ln_lora_a_scaled; g.ln_p_out = ln_p_out; g.ln_p_ld = ln_p_ld;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  if (cudaMalloc(&scratch, gemm_ln_scratch_bytes(M, N)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
+  g.ln_scratch = scratch;
   const char* e = nullptr;
-  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
+  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, s, &e);
+  cudaStreamSynchronize(s);
+  cudaFree(scratch);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
   return IIC_OK;
 }

@@ -105,16 +105,15 @@ struct GemmProblem {
   float* down_part = nullptr;
   void* out2 = nullptr;  // kEpiBiasActDualBf16: 16-bit [M, ldc] pre-activation output (out receives the activation)
   // optional, kEpiBiasResF32 only: also emit the LayerNorm of the output rows (the LayerNorm that consumes the new residual
-  // stream) as 16-bit ln_out [M, N] (pitch N), with its rank-4 LoRA down-projection ln_p_out [M, ln_p_ld] = y . ln_lora_a
-  // when ln_lora_a (f32 [N, 4]) is given.  Needs N % 256 == 0.
+  // stream) as 16-bit ln_out [M, N] (pitch N).  Needs N % 256 == 0 and ln_scratch of gemm_ln_scratch_bytes(M, N) bytes
+  // (cross-CTA row statistics + counters; the launcher zeroes the counters).
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
   void* ln_out = nullptr;
-  const float* ln_lora_a = nullptr;
-  void* ln_p_out = nullptr;
-  int ln_p_ld = 0;
+  void* ln_scratch = nullptr;
 };
+size_t gemm_ln_scratch_bytes(int M, int N);
 // ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);
 size_t gemm_smem_bytes(int ctas);

@@ -652,23 +652,22 @@ class Engine:
 
     def op_gemm_res_ln(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
                        gamma: torch.Tensor, beta: torch.Tensor, lora_p: Optional[torch.Tensor] = None,
-                       lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0, ln_lora_a_scaled: Optional[torch.Tensor] = None,
-                       p_ld: int = 16, ctas: int = 0, out: Optional[torch.Tensor] = None):
-        """x_new = a . w^T (+ LoRA) + bias + residual (fp32) and LayerNorm(x_new) (16-bit) from one launch; with
-        ln_lora_a_scaled [N, 4] also the LayerNorm consumer's LoRA down-projection.  Returns (x_new, ln_out[, p])."""
+                       lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0, ctas: int = 0,
+                       out: Optional[torch.Tensor] = None):
+        """x_new = a . w^T (+ LoRA) + bias + residual (fp32) and LayerNorm(x_new) (16-bit) from one launch.
+        Returns (x_new, ln_out)."""
         M, K = a.shape
         N = w.shape[0]
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32, device=self.device)
         ln_out = torch.empty(M, N, dtype=self.op_dtype, device=self.device)
-        p = torch.zeros(M, p_ld, dtype=self.op_dtype, device=self.device) if ln_lora_a_scaled is not None else None
         lora_ld = lora_p.stride(0) if lora_p is not None else 0
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_gemm_res_ln(
                 self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(lora_p), _ptr(lora_bt), r_pad,
                 lora_ld, _ptr(bias), residual.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                ln_out.data_ptr(), _ptr(ln_lora_a_scaled), _ptr(p), p_ld, ctas, _stream_ptr(self.device)), "iic_op_gemm_res_ln")
-        return (out, ln_out, p) if p is not None else (out, ln_out)
+                ln_out.data_ptr(), ctas, _stream_ptr(self.device)), "iic_op_gemm_res_ln")
+        return out, ln_out
 
     def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=None,
                      lora_a_scaled: Optional[torch.Tensor] = None, p_ld: int = 16):

@@ -223,14 +223,12 @@ int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, i
                          const void* lora_bt, int r_pad, int lora_ld, const float* bias, void* out_act, void* out_pre, int act,
                          int ctas, void* stream);
 /* out f32 [M,N] = A . W^T (+ LoRA) + bias + residual  AND  ln_out 16-bit [M,N] = LayerNorm(out rows; gamma, beta, eps 1e-5)
- * from the same launch (the LayerNorm group of the kernel re-reads the stored rows from L2): x = x + attn.out_proj(..);
- * ln_2(x), and x = x + mlp.c_proj(..); next block's ln_1(x) of clip/model.py ResidualAttentionBlock.forward (called through
- * main.py:204/444/503).  ln_lora_a_scaled f32 [N,4] (nullable): the LayerNorm consumer's rank-<=4 LoRA down-projection
- * (main.py:30-31), written to ln_p_out 16-bit [M, ln_p_ld] (zeros beyond column 3).  N % 256 == 0; out may alias residual. */
+ * from the same launch (the kernel's second epilogue group re-reads the stored tile from L2 once all column tiles of its rows
+ * have published their partial statistics): x = x + mlp.c_proj(..); next block's ln_1(x) of clip/model.py
+ * ResidualAttentionBlock.forward (called through main.py:204/444/503).  N % 256 == 0, N <= 2048; out may alias residual. */
 int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                        const void* lora_bt, int r_pad, int lora_ld, const float* bias, const float* residual, float* out,
-                       const float* gamma, const float* beta, void* ln_out, const float* ln_lora_a_scaled, void* ln_p_out,
-                       int ln_p_ld, int ctas, void* stream);
+                       const float* gamma, const float* beta, void* ln_out, int ctas, void* stream);
 int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const float* beta, void* out_bf16,
                      float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
                      void* stream);
