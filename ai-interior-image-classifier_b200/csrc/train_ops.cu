@@ -344,8 +344,9 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
 // ---- both LoRA gradients that read the same activation gradient, in one pass ---------------------------------------------
 // For Y = dOut [M, N] of a LoRALinear (main.py:42-43):  dB = P^T . Y  (P = s x A, [M, 16])  and  dP = Y . B^T  (B [16, N]).
 // CTA = R rows x C columns, 4 warps; warp w owns C/4 columns (kTW 64-column tiles) for all R rows: its dB accumulators
-// [16 x C/4] live in registers for the whole CTA, the [16 rows x 16] dP block of every 16-row step is added to a CTA-wide
-// fp32 buffer in shared memory (4-way contention at most).  Partials: part_db[row block][16][N], part_dp[column group][M][16].
+// [16 x C/4] live in registers for the whole CTA; the [16 rows x 16] dP blocks of the four warps of a 16-row step are summed
+// through shared memory in a fixed order (one barrier per step: deterministic, unlike atomics).
+// Partials: part_db[row block][16][N], part_dp[column group][M][16].
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -363,12 +364,13 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* bm_gen = dsm + 4 * kBwdStages * kStageBytes;              // [16 ranks][kCtaCols] 16-bit, 16-byte chunks XOR-swizzled
   float* dp_s = reinterpret_cast<float*>(bm_gen + 16 * kCtaCols * 2);   // [rows_per_cta][16]
+  float* dpw = dp_s + rows_per_cta * 16;                                // [2 step parities][4 warps][16 x 16]
   const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(dsm)) + uint32_t(warp * kBwdStages * kStageBytes);
   const uint32_t bm_s = static_cast<uint32_t>(__cvta_generic_to_shared(bm_gen));
   const int c_cta = blockIdx.x * kCtaCols, c_warp = c_cta + warp * kWarpCols;
   const int m_begin = blockIdx.y * rows_per_cta;
   const int m_end = min(M, m_begin + rows_per_cta);
-  const int steps = (m_end - m_begin + 15) / 16;
+  const int steps = (m_end - m_begin + 15) / 16;   // the same for the four warps (they meet at a barrier every step)
 
   auto issue = [&](int step, int stage) {
     const int m0 = m_begin + step * 16;
@@ -401,7 +403,6 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
     const uint4 v = *reinterpret_cast<const uint4*>(Bm + size_t(r) * N + c_cta + ch * 8);
     *reinterpret_cast<uint4*>(bm_gen + r * (kCtaCols * 2) + ((ch ^ (r & 7)) << 4)) = v;
   }
-  for (int i = threadIdx.x; i < rows_per_cta * 4; i += 128) reinterpret_cast<float4*>(dp_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   float acc[kTW * 8][4];
@@ -456,16 +457,20 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
       }
     }
     {
-      float* d0 = dp_s + (st * 16 + g) * 16 + 2 * t4;
+      float* d0 = dpw + ((st & 1) * 4 + warp) * 256 + g * 16 + 2 * t4;
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        atomicAdd(d0 + n * 8, dp[n][0] + dq[n][0]);
-        atomicAdd(d0 + n * 8 + 1, dp[n][1] + dq[n][1]);
-        atomicAdd(d0 + 128 + n * 8, dp[n][2] + dq[n][2]);
-        atomicAdd(d0 + 128 + n * 8 + 1, dp[n][3] + dq[n][3]);
+        *reinterpret_cast<float2*>(d0 + n * 8) = make_float2(dp[n][0] + dq[n][0], dp[n][1] + dq[n][1]);
+        *reinterpret_cast<float2*>(d0 + 128 + n * 8) = make_float2(dp[n][2] + dq[n][2], dp[n][3] + dq[n][3]);
       }
     }
-    __syncwarp();
+    __syncthreads();   // also: every lane of every warp is done with this step's stage buffers
+    {
+      const float* w0 = dpw + (st & 1) * 4 * 256;   // the other parity is being written by the next step: no second barrier
+#pragma unroll
+      for (int e = threadIdx.x; e < 256; e += 128)
+        dp_s[st * 256 + e] = ((w0[e] + w0[256 + e]) + w0[512 + e]) + w0[768 + e];
+    }
   }
   // dB partial of this row block: rank g / g + 8, columns 2 t4, 2 t4 + 1 of each 8-column tile
 #pragma unroll
@@ -572,7 +577,7 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
   const int row_blocks = (M + rows - 1) / rows, col_groups = N / cta_cols;
   float* part_db = scratch;
   float* part_dp = scratch + size_t(row_blocks) * 16 * N;
-  const size_t smem = size_t(4 * kBwdStages * (16 * tw * 128 + 512)) + size_t(16) * cta_cols * 2 + size_t(rows) * 64;
+  const size_t smem = size_t(4 * kBwdStages * (16 * tw * 128 + 512)) + size_t(16) * cta_cols * 2 + size_t(rows) * 64 + 2 * 4 * 256 * 4;
   const uint16_t* p = static_cast<const uint16_t*>(P);
   const uint16_t* y = static_cast<const uint16_t*>(Y);
   const uint16_t* bm = static_cast<const uint16_t*>(Bm);

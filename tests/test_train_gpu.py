@@ -113,6 +113,8 @@ def test_lora_bwd_fused(engine, rank, shape):
     # 16-bit output: 2^-9 relative
     assert torch.allclose(dp.float(), ref_dp, rtol=4e-3, atol=4e-3), (dp.float() - ref_dp).abs().max()
     assert rank == 16 or dp[:, rank:].abs().max() == 0
+    db2, dp2 = engine.op_lora_bwd(P, Y, Bm, rank, scale=0.5)     # fixed summation order: bit-reproducible
+    assert torch.equal(db, db2) and torch.equal(dp, dp2)
 
 
 @pytest.mark.parametrize("ctas", [1, 2], ids=["cta1", "cta2"])
