@@ -56,6 +56,7 @@ struct BwdParams {
   int xy_bytes;         // bytes of one X (or Y) buffer (TMA boxes may overshoot TP rows)
   int xy_box, xy_loads;
   float scale, scale_log2e;
+  int causal;   // text tower: P[q, k] = 0 for k > q (the saved log-sum-exp already covers the visible keys only)
 };
 
 __host__ __device__ constexpr uint32_t idesc(uint32_t m, uint32_t n, bool f16, bool b_mn) {
@@ -354,6 +355,13 @@ attention_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, cons
                   if (pass == 0) {                         // key columns beyond T hold another image's keys
                     p0 = c0 < T ? p0 : 0.f;
                     p1 = c0 + 1 < T ? p1 : 0.f;
+                    if (prm.causal) {                      // row = query, column = key: keys after the query are masked
+                      p0 = c0 <= row ? p0 : 0.f;
+                      p1 = c0 + 1 <= row ? p1 : 0.f;
+                    }
+                  } else if (prm.causal) {                 // row = key, column = query: queries before the key never saw it
+                    p0 = c0 >= row ? p0 : 0.f;
+                    p1 = c0 + 1 >= row ? p1 : 0.f;
                   }
                   const float ds0 = p0 * (__uint_as_float(dv[2 * e]) - dd0) * scale;
                   const float ds1 = p1 * (__uint_as_float(dv[2 * e + 1]) - dd1) * scale;
@@ -472,7 +480,8 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 
 // returns -3 when the shape is outside this kernel's envelope (caller falls back to the mma.sync kernel)
 int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum_scratch,
-                               void* dqkv, int B, int T, int H, int head_dim, int f16, int num_sms, cudaStream_t stream) {
+                               void* dqkv, int B, int T, int H, int head_dim, int f16, int causal, int num_sms,
+                               cudaStream_t stream) {
   if (B <= 0) return 0;
   if (head_dim != kHd || T < 1 || T > kVecFloats - 48 || dsum_scratch == nullptr) return -3;
   BwdParams p;
@@ -497,6 +506,7 @@ int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_o
   p.stages = fixed + 4 * p.xy_bytes <= kMaxSmem ? 2 : 1;
   const int smem = fixed + p.stages * 2 * p.xy_bytes;
   p.items = B * H;
+  p.causal = causal;
   p.T = T;
   p.H = H;
   p.lse = lse;

@@ -181,9 +181,10 @@ int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, 
 int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum,
                       void* dqkv, int B, int T, int H, int hd, cudaStream_t s) {
   if (h->attn_bwd_impl != 1 && dsum != nullptr) {
-    int rc = launch_attention_bwd_sm100(qkv, out, d_out, lse, dsum, dqkv, B, T, H, hd, h->f16, h->num_sms, s);
+    int rc = launch_attention_bwd_sm100(qkv, out, d_out, lse, dsum, dqkv, B, T, H, hd, h->f16, h->cfg.causal, h->num_sms, s);
     if (rc != -3) return rc;
   }
+  if (h->cfg.causal) return -1;   // the mma.sync fallback has no causal mask (text sequences are 77 tokens: never needed)
   return launch_attention_bwd(qkv, out, d_out, lse, dqkv, B, T, H, hd, h->f16, s);
 }
 
@@ -438,19 +439,27 @@ int copy_rows_async(void* dst, size_t dst_pitch, const void* src, size_t src_pit
 }
 
 // forward in training mode: same kernels as inference, per-layer activations kept
-int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace& w, float* x_cls_out, cudaStream_t s) {
+// vision tower: `patches` -> class-token rows.  Sequence (text) handles: x_tokens f32 [B*T, d] (token + positional embedding)
+// -> the rows row_index[b] (EOT) of the final residual stream.
+int run_train_forward(iic_handle* h, const void* patches, const float* x_tokens, const int32_t* row_index, int B,
+                      TrainWorkspace& w, float* x_cls_out, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const int gg = h->g * h->g;
   const float eps = 1e-5f;
   h->err.clear();
-  IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
-                   nullptr, h->pos, w.xpre, d, gg, s));
-  IIC_TRY(timed(h, kMisc, s, [&] { return launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s); }));
   // The residual stream is never copied: every residual epilogue writes straight into the buffer the backward pass will read
   // (block l: x_in(l) -> out_proj -> x_mid(l) -> c_proj -> x_in(l+1); the last block writes the workspace stream w.x).
-  IIC_TRY(timed(h, kLayerNorm, s, [&] {
-    return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.layers[0].x_in, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
-  }));
+  if (x_tokens != nullptr) {
+    if (cudaMemcpyAsync(w.layers[0].x_in, x_tokens, size_t(M) * d * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(h, IIC_ERR_CUDA, "copy failed");
+  } else {
+    IIC_TRY(run_gemm(h, patches, h->patch_kpad, h->conv_w, B * gg, d, h->patch_kpad, nullptr, nullptr, kEpiPosF32,
+                     nullptr, h->pos, w.xpre, d, gg, s));
+    IIC_TRY(timed(h, kMisc, s, [&] { return launch_fill_cls(w.xpre, h->cls, h->pos, B, T, d, s); }));
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
+      return launch_layernorm(w.xpre, d, h->lnpre_g, h->lnpre_b, nullptr, w.layers[0].x_in, d, M, d, eps, nullptr, 0, nullptr, 0, h->f16, s);
+    }));
+  }
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
   for (size_t li = 0; li < h->blocks.size(); ++li) {
     Block& b = h->blocks[li];
@@ -488,16 +497,24 @@ int run_train_forward(iic_handle* h, const void* patches, int B, TrainWorkspace&
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, t.p2, s));
     IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, t.p2, kEpiBiasResF32, b.b_proj, t.x_mid, x_next, d, 1, s));
   }
+  if (row_index != nullptr) {   // the EOT rows (input of ln_final)
+    Scope sc(h->prof, kMisc, s);
+    return launch_gather_rows(w.x, row_index, T, d, B, x_cls_out, s) ? fail(h, IIC_ERR_CUDA, "row gather launch failed") : 0;
+  }
   // class-token rows of the final residual stream (input of ln_post), [B, d] contiguous
   return copy_rows_async(x_cls_out, size_t(d) * 4, w.x, size_t(T) * d * 4, size_t(d) * 4, size_t(B), s) ? fail(h, IIC_ERR_CUDA, "copy failed") : 0;
 }
 
-int run_train_backward_begin(iic_handle* h, int B, TrainWorkspace& w, const float* dx_cls, cudaStream_t s) {
+int run_train_backward_begin(iic_handle* h, int B, TrainWorkspace& w, const float* dx_cls, const int32_t* row_index, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T;
   h->err.clear();
-  // dx = 0 except the class-token rows
+  // dx = 0 except the class-token rows (sequence handles: the rows row_index[b])
   if (cudaMemsetAsync(w.dx, 0, size_t(M) * d * 4, s) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "memset failed");
-  if (copy_rows_async(w.dx, size_t(T) * d * 4, dx_cls, size_t(d) * 4, size_t(d) * 4, size_t(B), s)) return fail(h, IIC_ERR_CUDA, "copy failed");
+  if (row_index != nullptr) {
+    if (launch_scatter_rows(dx_cls, row_index, T, d, B, w.dx, s)) return fail(h, IIC_ERR_CUDA, "row scatter launch failed");
+  } else if (copy_rows_async(w.dx, size_t(T) * d * 4, dx_cls, size_t(d) * 4, size_t(d) * 4, size_t(B), s)) {
+    return fail(h, IIC_ERR_CUDA, "copy failed");
+  }
   IIC_TRY(timed(h, kMisc, s, [&] { return launch_cast16(w.dx, w.g16, (long long)M * d, h->f16, s); }));
   return 0;
 }
@@ -964,7 +981,28 @@ int iic_train_forward(iic_handle* h, const void* patches, int B, void* workspace
   TrainWorkspace w;
   int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
-  return run_train_forward(h, patches, B, w, x_cls_out, static_cast<cudaStream_t>(stream));
+  if (h->cfg.seq_tokens > 0) return fail(h, IIC_ERR_STATE, "iic_train_forward: sequence handle, use iic_train_forward_sequence");
+  return run_train_forward(h, patches, nullptr, nullptr, B, w, x_cls_out, static_cast<cudaStream_t>(stream));
+}
+
+int iic_train_forward_sequence(iic_handle* h, const float* x_tokens, const int32_t* row_index, int B, void* workspace,
+                               size_t workspace_bytes, float* x_rows_out, void* stream) {
+  if (!h || !x_tokens || !row_index || !x_rows_out) return fail(h, IIC_ERR_ARG, "iic_train_forward_sequence: null argument");
+  if (h->cfg.seq_tokens <= 0) return fail(h, IIC_ERR_STATE, "iic_train_forward_sequence: handle was not created with iic_config.seq_tokens");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  return run_train_forward(h, nullptr, x_tokens, row_index, B, w, x_rows_out, static_cast<cudaStream_t>(stream));
+}
+
+int iic_train_backward_begin_sequence(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_rows,
+                                      const int32_t* row_index, void* stream) {
+  if (!h || !dx_rows || !row_index) return fail(h, IIC_ERR_ARG, "iic_train_backward_begin_sequence: null argument");
+  if (h->cfg.seq_tokens <= 0) return fail(h, IIC_ERR_STATE, "iic_train_backward_begin_sequence: not a sequence handle");
+  TrainWorkspace w;
+  int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  return run_train_backward_begin(h, B, w, dx_rows, row_index, static_cast<cudaStream_t>(stream));
 }
 
 int iic_train_backward(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream) {
@@ -972,7 +1010,7 @@ int iic_train_backward(iic_handle* h, int B, void* workspace, size_t workspace_b
   TrainWorkspace w;
   int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
-  rc = run_train_backward_begin(h, B, w, dx_cls, static_cast<cudaStream_t>(stream));
+  rc = run_train_backward_begin(h, B, w, dx_cls, nullptr, static_cast<cudaStream_t>(stream));
   for (int li = int(h->blocks.size()) - 1; li >= 0 && rc == 0; --li)
     rc = run_train_backward_layer(h, B, w, li, static_cast<cudaStream_t>(stream));
   return rc;
@@ -983,7 +1021,7 @@ int iic_train_backward_begin(iic_handle* h, int B, void* workspace, size_t works
   TrainWorkspace w;
   int rc = check_train_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
-  return run_train_backward_begin(h, B, w, dx_cls, static_cast<cudaStream_t>(stream));
+  return run_train_backward_begin(h, B, w, dx_cls, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int iic_train_backward_layer(iic_handle* h, int B, void* workspace, size_t workspace_bytes, int layer, void* stream) {

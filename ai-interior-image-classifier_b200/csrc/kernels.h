@@ -18,6 +18,7 @@ int launch_lora_down_bf16(const void* x, int K, int rows, const float* lora_a, i
 int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, int p_ld, int f16, cudaStream_t stream);
 // out[b, :] = x[b * T + row_index[b], :]   (f32, D % 4 == 0)
 int launch_gather_rows(const float* x, const int32_t* row_index, int T, int D, int B, float* out, cudaStream_t stream);
+int launch_scatter_rows(const float* rows, const int32_t* row_index, int T, int D, int B, float* x, cudaStream_t stream);
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream);
 // dtype: 0 = f32, 1 = bf16, 2 = f16
 int launch_chw_to_patches(const void* img, int dtype, void* patches, int B, int R, int P, int k_pad, int f16,
@@ -37,7 +38,8 @@ int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, co
 
 // tcgen05 / TMEM variant for T <= 592 (attention_bwd_sm100.cu); dsum_scratch f32 [B*H*T]; returns -3 outside its envelope
 int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum_scratch,
-                               void* dqkv, int B, int T, int H, int head_dim, int f16, int num_sms, cudaStream_t stream);
+                               void* dqkv, int B, int T, int H, int head_dim, int f16, int causal, int num_sms,
+                               cudaStream_t stream);
 
 // ---- train_ops.cu ----
 int launch_layernorm_bwd(const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows, int D,

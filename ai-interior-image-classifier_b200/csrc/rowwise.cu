@@ -345,6 +345,26 @@ int launch_gather_rows(const float* x, const int32_t* row_index, int T, int D, i
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// training of the text tower: dx[b * T + row_index[b], :] = d_rows[b, :] (dx zeroed by the caller)
+__global__ void scatter_rows_kernel(const float4* __restrict__ rows, const int32_t* __restrict__ row_index, int T, int D4, int B,
+                                    float4* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D4) return;
+  const int b = i / D4, c = i - b * D4;
+  int r = row_index[b];
+  r = r < 0 ? 0 : (r >= T ? T - 1 : r);
+  x[(size_t(b) * T + r) * D4 + c] = rows[i];
+}
+
+int launch_scatter_rows(const float* rows, const int32_t* row_index, int T, int D, int B, float* x, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if (D % 4 != 0) return -1;
+  const int n = B * (D / 4);
+  scatter_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float4*>(rows), row_index, T, D / 4, B,
+                                                            reinterpret_cast<float4*>(x));
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream) {
   const int n = B * D;
   if (n <= 0) return 0;

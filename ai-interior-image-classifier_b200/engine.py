@@ -477,8 +477,28 @@ class Engine:
                                                        x_cls.data_ptr(), _stream_ptr(self.device)), "iic_train_forward")
         return x_cls
 
-    def train_backward(self, dx_cls: torch.Tensor, layer_done=None, loss_scale: "float | str" = "auto") -> None:
-        """dx_cls f32 [B, width].  `layer_done(layer)` (optional) is called right after block `layer`'s backward has been
+    def train_forward_sequence(self, x: torch.Tensor, row_index: torch.Tensor) -> torch.Tensor:
+        """Text tower (sequence engine): x f32 [B, T, width] = token + positional embedding, row_index [B] = EOT positions ->
+        f32 [B, width]: those rows of the final residual stream (input of ln_final); activations are kept for train_backward."""
+        if self.arch.seq_tokens <= 0:
+            raise RuntimeError("train_forward_sequence needs an engine built with VisionArch(seq_tokens=...)")
+        B, T, d = x.shape
+        if T != self.arch.seq_tokens or d != self.arch.width:
+            raise ValueError(f"expected [B, {self.arch.seq_tokens}, {self.arch.width}], got {tuple(x.shape)}")
+        x = x.detach().to(self.device, torch.float32).contiguous()
+        idx = row_index.detach().to(self.device, torch.int32).contiguous()
+        out = torch.empty(B, d, dtype=torch.float32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            ws = self._train_ws(B)
+            L.check(self.h, self.lib.iic_train_forward_sequence(self.h, x.data_ptr(), idx.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                                                                out.data_ptr(), _stream_ptr(self.device)),
+                    "iic_train_forward_sequence")
+        return out
+
+    def train_backward(self, dx_cls: torch.Tensor, layer_done=None, loss_scale: "float | str" = "auto",
+                       row_index: Optional[torch.Tensor] = None) -> None:
+        """dx_cls f32 [B, width] (sequence engines: the gradient of the rows `row_index` that train_forward_sequence returned).
+        `layer_done(layer)` (optional) is called right after block `layer`'s backward has been
         enqueued - its LoRA gradients are final once the stream reaches that point (hook for the gradient all-reduce).
         loss_scale: power of two applied to the activation gradients and divided out of the LoRA gradients ("auto": chosen
         so that max |dx_cls| maps to 2^8, which keeps fp16 operands clear of both underflow and overflow)."""
@@ -498,16 +518,22 @@ class Engine:
         with self._lock, torch.cuda.device(self.device):
             ws = self._train_ws(B)
             s = _stream_ptr(self.device)
-            if layer_done is None:
+            if layer_done is None and row_index is None:
                 L.check(self.h, self.lib.iic_train_backward(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(), s),
                         "iic_train_backward")
                 return
-            L.check(self.h, self.lib.iic_train_backward_begin(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(), s),
-                    "iic_train_backward_begin")
+            if row_index is not None:
+                idx = row_index.detach().to(self.device, torch.int32).contiguous()
+                L.check(self.h, self.lib.iic_train_backward_begin_sequence(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(),
+                                                                           idx.data_ptr(), s), "iic_train_backward_begin_sequence")
+            else:
+                L.check(self.h, self.lib.iic_train_backward_begin(self.h, B, ws.data_ptr(), ws.numel(), dx_cls.data_ptr(), s),
+                        "iic_train_backward_begin")
             for layer in range(self.arch.layers - 1, -1, -1):
                 L.check(self.h, self.lib.iic_train_backward_layer(self.h, B, ws.data_ptr(), ws.numel(), layer, s),
                         "iic_train_backward_layer")
-                layer_done(layer)
+                if layer_done is not None:
+                    layer_done(layer)
 
     def op_attention_bwd(self, qkv: torch.Tensor, d_out: torch.Tensor, B: int, T: int, heads: int):
         out = torch.empty(B * T, heads * 64, dtype=self.op_dtype, device=self.device)

@@ -158,3 +158,143 @@ class VisionLoRATrainer:
         torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm)
         self.optimizer.step()
         return float(loss)
+
+
+class TextLoRATrainer:
+    """The step /root/reference/train_lora.py:231-252 actually runs: image features from the frozen vision tower under
+    no_grad, text features through the LoRA on the TEXT tower's MLPs (`_replace_text_linears_with_lora`, train_lora.py:62-100;
+    its attn.out_proj pairs are dead in nn.MultiheadAttention's forward and never receive a gradient), symmetric InfoNCE with
+    `logit_scale.exp()`, backward, clip_grad_norm_(1.0), AdamW(lr 1e-4, wd 0.01) over the parameters named '*lora*'.
+
+    The text tower runs on a sequence engine (77 tokens, causal attention): forward keeping activations, backward through
+    the frozen blocks with the causal tcgen05 attention backward, LoRA gradients by the same kernels as the vision trainer.
+    token_embedding + positional_embedding in front and ln_final / text_projection / loss behind stay in PyTorch (O(B x width)).
+    Data parallel exactly like VisionLoRATrainer: one all-reduce (average) per block, overlapped with the blocks below."""
+
+    def __init__(self, model: CLIP, lr: float = 1e-4, weight_decay: float = 0.01, max_grad_norm: float = 1.0,
+                 logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
+        self.model = model
+        self.logit_scale = float(logit_scale) if logit_scale is not None else float(model.logit_scale.exp())
+        self.max_grad_norm = max_grad_norm
+        self.pg = process_group
+        self.overlap = overlap
+        dev = model.token_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("TextLoRATrainer needs the model on a CUDA device (B200); there is no CPU fallback")
+        self.slots: List[Tuple[int, int, torch.nn.Module]] = []
+        for i, blk in enumerate(model.transformer.resblocks):
+            for which, mod in ((L.LORA_C_FC, blk.mlp.c_fc), (L.LORA_C_PROJ, blk.mlp.c_proj)):
+                if _is_lora_wrapped(mod):
+                    self.slots.append((i, which, mod))
+        if not self.slots:
+            raise RuntimeError("no LoRA-wrapped text mlp.c_fc / mlp.c_proj found: wrap the text tower first")
+        for p in model.parameters():
+            p.requires_grad_(False)
+        self.buckets: Dict[int, torch.Tensor] = {}
+        self.params: List[torch.nn.Parameter] = []
+        per_layer: Dict[int, List[torch.nn.Parameter]] = {}
+        for i, which, mod in self.slots:
+            for p in (mod.lora.lora_A, mod.lora.lora_B):
+                if p.device != dev or p.dtype != torch.float32:
+                    p.data = p.data.to(dev, torch.float32)
+                p.requires_grad_(True)
+                per_layer.setdefault(i, []).append(p)
+                self.params.append(p)
+        for i, ps in per_layer.items():
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.buckets[i] = flat
+        self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)   # train_lora.py:212
+        self.comm_stream = torch.cuda.Stream(device=dev) if process_group is not None or VisionLoRATrainer._dist_on() else None
+        self.eng = None
+        self._sig = None
+
+    def _sync(self) -> None:
+        m = self.model
+        if self.eng is None:
+            self.eng = m.sync_text_engine(force=True)
+            m._text_sig = None   # inference through model.encode_text re-uploads what the optimizer moved
+        eng = self.eng
+        if getattr(self, "_sd_cache", None) is None:
+            sd: Dict[str, torch.Tensor] = {}
+            for i, blk in enumerate(m.transformer.resblocks):
+                p = f"transformer.resblocks.{i}."
+                sd[p + "attn.in_proj_weight"] = blk.attn.in_proj_weight
+                for name, mod in (("attn.out_proj", blk.attn.out_proj), ("mlp.c_fc", blk.mlp.c_fc), ("mlp.c_proj", blk.mlp.c_proj)):
+                    sd[p + name + ".weight"] = mod.weight
+            self._sd_cache = sd
+        sd = self._sd_cache
+        sig = (tuple((k, t.data_ptr(), t._version) for k, t in sd.items()),
+               tuple((i, which, mod.lora.lora_A.data_ptr(), mod.lora.lora_B.data_ptr(), float(mod.lora.scaling),
+                      mod.lora.lora_A.grad.data_ptr(), mod.lora.lora_B.grad.data_ptr()) for i, which, mod in self.slots))
+        if sig == self._sig:
+            eng.refresh_lora()
+            return
+        eng.enable_training(sd)
+        for i, which, mod in self.slots:
+            lo = mod.lora
+            eng.set_lora(i, which, lo.lora_A, lo.lora_B, float(lo.scaling))      # also pairs whose B is still zero
+            eng.set_lora_train(i, which, lo.lora_A, lo.lora_B, float(lo.scaling), lo.lora_A.grad, lo.lora_B.grad)
+            eng.set_lora_source(i, which, lo.lora_A, lo.lora_B, float(lo.scaling))
+        self._sig = sig
+        m._text_sig = None
+
+    def head_and_loss(self, x_eot: torch.Tensor, image_features: torch.Tensor) -> torch.Tensor:
+        """ln_final -> @ text_projection -> L2 -> symmetric InfoNCE (train_lora.py:236-246), fp32."""
+        m = self.model
+        f = F.layer_norm(x_eot, (x_eot.shape[-1],), m.ln_final.weight.detach().float(), m.ln_final.bias.detach().float(), 1e-5)
+        f = f @ m.text_projection.detach().float()
+        f = f / f.norm(dim=-1, keepdim=True)
+        logits_per_image = (image_features @ f.t()) * self.logit_scale
+        labels = torch.arange(x_eot.shape[0], device=x_eot.device)
+        return (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_image.t(), labels)) / 2
+
+    def forward_backward(self, image_features: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+        """image_features [B, E] (L2-normalised, no gradient: train_lora.py:232-234), tokens [B, 77]."""
+        import torch.distributed as dist
+        self._sync()
+        eng, m = self.eng, self.model
+        tokens = tokens.to(eng.device)
+        with torch.no_grad():
+            x = m.token_embedding(tokens).float() + m.positional_embedding.float()
+        eot = tokens.argmax(dim=-1)
+        x_eot = eng.train_forward_sequence(x, eot).requires_grad_(True)
+        loss = self.head_and_loss(x_eot, image_features.detach().to(eng.device, torch.float32))
+        (dx,) = torch.autograd.grad(loss, x_eot)
+        works = []
+        distributed = VisionLoRATrainer._dist_on()
+
+        def layer_done(layer: int) -> None:
+            if not distributed or layer not in self.buckets:
+                return
+            if self.overlap:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(eng.device))
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    works.append(dist.all_reduce(self.buckets[layer], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            else:
+                works.append(dist.all_reduce(self.buckets[layer], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+
+        eng.train_backward(dx, layer_done=layer_done, row_index=eot)
+        for w in works:
+            w.wait()
+        if distributed and self.overlap:
+            torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
+        return loss.detach()
+
+    def step(self, images_or_features: torch.Tensor, tokens: torch.Tensor) -> float:
+        """One optimisation step.  `images_or_features`: a preprocessed image batch [B,3,R,R] (encoded by the frozen vision
+        tower on its engine under no_grad, as train_lora.py:232-234 does) or precomputed L2-normalised image features [B, E]."""
+        t = images_or_features
+        if t.dim() == 4:
+            with torch.no_grad():
+                f = self.model.encode_image(t).float()
+                t = f / f.norm(dim=-1, keepdim=True)
+        loss = self.forward_backward(t, tokens)
+        torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm)
+        self.optimizer.step()
+        return float(loss)

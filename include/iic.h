@@ -196,6 +196,15 @@ int iic_train_backward(iic_handle* h, int B, void* workspace, size_t workspace_b
  * are final when the call's work completes, so the caller can all-reduce them while the blocks below are still running. */
 int iic_train_backward_begin(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_cls, void* stream);
 int iic_train_backward_layer(iic_handle* h, int B, void* workspace, size_t workspace_bytes, int layer, void* stream);
+/* Text tower (handles created with iic_config.seq_tokens, causal = 1): the training step train_lora.py:236-252 actually runs -
+ * `lora_wrapper.clip_model.encode_text(texts)` through the LoRA on the text MLPs (train_lora.py:62-100), loss.backward().
+ * x_tokens f32 [B*T, width] = token_embedding(tokens) + positional_embedding; row_index [B] = tokens.argmax(-1) (EOT);
+ * x_rows_out f32 [B, width] = those rows of the final residual stream (input of ln_final).  The backward starts from
+ * dx_rows [B, width] scattered to the same rows; the blocks are then walked with iic_train_backward_layer. */
+int iic_train_forward_sequence(iic_handle* h, const float* x_tokens, const int32_t* row_index, int B, void* workspace,
+                               size_t workspace_bytes, float* x_rows_out, void* stream);
+int iic_train_backward_begin_sequence(iic_handle* h, int B, void* workspace, size_t workspace_bytes, const float* dx_rows,
+                                      const int32_t* row_index, void* stream);
 
 /* ---- measurement ----------------------------------------------------------------------------------------------
  * Kernel classes: 0 tcgen05 GEMM (all), 1 LayerNorm, 2 attention, 3 LoRA down-projection, 4 head, 5 preprocess, 6 misc,

@@ -52,6 +52,27 @@ def test_attention_backward(engine, engine_f16, mode, B, T, H):
     assert _rel(dq, gq) < tol and _rel(dk, gk) < tol and _rel(dv, gv) < tol, (_rel(dq, gq), _rel(dk, gk), _rel(dv, gv))
 
 
+@pytest.mark.parametrize("B,T", [(3, 77), (40, 77), (2, 200)])
+def test_attention_backward_causal(iic, B, T):
+    """the same kernel with the text tower's causal mask (engine created with causal=True): P[q, k] = 0 for k > q"""
+    H = 8
+    arch = iic.VisionArch(image_size=224, patch_size=16, width=512, layers=1, heads=H, embed_dim=512, seq_tokens=T, causal=True)
+    eng = iic.Engine(arch, "cuda:0", operand_dtype="bf16")
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(27)
+    qkv = (torch.randn(B * T, 3 * d, device="cuda", generator=g)).to(torch.bfloat16)
+    do = (torch.randn(B * T, d, device="cuda", generator=g)).to(torch.bfloat16)
+    out, dqkv, lse = eng.op_attention_bwd(qkv, do, B, T, H)
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = x.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True).permute(0, 2, 1, 3).reshape(B * T, d)
+    ref.backward(do.float())
+    assert _rel(out.float(), ref.detach()) < 1e-2
+    gq, gk, gv = x.grad.view(B * T, 3, d).unbind(1)
+    dq, dk, dv = dqkv.float().view(B * T, 3, d).unbind(1)
+    assert _rel(dq, gq) < 1.5e-2 and _rel(dk, gk) < 1.5e-2 and _rel(dv, gv) < 1.5e-2, (_rel(dq, gq), _rel(dk, gk), _rel(dv, gv))
+
+
 def test_layernorm_and_activation_backward(engine):
     g = torch.Generator(device="cuda").manual_seed(22)
     rows, D = 197 * 3 + 5, 768
@@ -208,6 +229,93 @@ def test_lora_gradients_match_oracle_autograd(iic, mode, rank):
     assert worst < (1e-2 if mode == "f16" else 2e-2), max(errs.items(), key=lambda kv: kv[1])
     # out_proj LoRA parameters get no gradient (dead in the reference's forward, F4)
     assert all(named[n].grad is None for n in named if ".attn.out_proj.lora." in n)
+
+
+def _text_tokens(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.zeros(B, 77, dtype=torch.long)
+    for b in range(B):
+        n = int(torch.randint(4, 76, (1,), generator=g))
+        tok[b, 0] = 49406
+        tok[b, 1:n] = torch.randint(1, 49405, (n - 1,), generator=g)
+        tok[b, n] = 49407                       # EOT = the largest id: encode_text takes the row at argmax
+    return tok
+
+
+@pytest.mark.parametrize("rank", [4, 16])
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+def test_text_lora_gradients_match_oracle_autograd(iic, mode, rank):
+    """train_lora.py's own step (text tower through LoRA, image features fixed): d loss / d lora_{A,B} of every text MLP
+    vs CPU fp32 autograd through the oracle - causal attention backward, sequence forward / backward of the engine"""
+    from oracle import ref_semantics as RS
+    B = 8
+    tokens = _text_tokens(B, seed=5)
+    g = torch.Generator().manual_seed(6)
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1)
+    om = copy.deepcopy(oracle_model())
+    RS.replace_linears_with_lora(om, rank=rank, alpha=2 * rank)
+    gen = torch.Generator().manual_seed(77)
+    for n, p in om.named_parameters():
+        p.requires_grad_(False)
+        if n.startswith("transformer.") and n.endswith("lora_A"):
+            p.data = torch.randn(p.shape, generator=gen) * 0.02
+        if n.startswith("transformer.") and n.endswith("lora_B"):
+            p.data = torch.randn(p.shape, generator=gen) * 0.004
+    lora = {n: p for n, p in om.named_parameters() if n.startswith("transformer.") and "lora" in n and ".mlp." in n}
+    for p in lora.values():
+        p.requires_grad_(True)
+    f = om.encode_text(tokens)
+    f = f / f.norm(dim=-1, keepdim=True)
+    logits = (img @ f.t()) * 100.0
+    labels = torch.arange(B)
+    loss_ref = (torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.cross_entropy(logits.t(), labels)) / 2
+    loss_ref.backward()
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype=mode)
+    iic.replace_linears_with_lora(model, rank=rank, alpha=2 * rank)
+    src = {n: p for n, p in om.named_parameters() if "lora" in n}
+    for n, p in model.named_parameters():
+        if n in src:
+            p.data = src[n].detach().clone().to(p.device)
+    trainer = iic.TextLoRATrainer(model, logit_scale=100.0)
+    loss = trainer.forward_backward(img.cuda(), tokens.cuda())
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 5e-3 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    named = dict(model.named_parameters())
+    errs = {n: _rel(named[n].grad.cpu(), p.grad) for n, p in lora.items()}
+    worst = max(errs.values())
+    print(f"\n[text {mode} r={rank}] loss {loss.item():.5f} (ref {loss_ref.item():.5f}); worst text-LoRA gradient relative error {worst:.2e} "
+          f"over {len(lora)} tensors")
+    _dump(f"text_{mode}_r{rank}", {"loss": loss.item(), "loss_ref": loss_ref.item(), "worst_rel": worst})
+    assert worst < (1e-2 if mode == "f16" else 2e-2), max(errs.items(), key=lambda kv: kv[1])
+    # a second call reproduces the gradients bit for bit, and the inference path still agrees with the trained parameters
+    g1 = {n: named[n].grad.clone() for n in lora}
+    trainer.forward_backward(img.cuda(), tokens.cuda())
+    assert all(torch.equal(g1[n], named[n].grad) for n in lora)
+
+
+def test_text_training_step_reduces_loss(iic):
+    """a few steps of the reference's real training step (text-side LoRA) lower the loss and move only text LoRA parameters"""
+    B = 8
+    tokens = _text_tokens(B, seed=8).cuda()
+    g = torch.Generator().manual_seed(9)
+    img = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).cuda()
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="bf16")
+    iic.replace_linears_with_lora(model, rank=16, alpha=32)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    trainer = iic.TextLoRATrainer(model, lr=1e-3)
+    losses = [trainer.step(img, tokens) for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.05, losses
+    moved = {n for n, p in model.named_parameters() if not torch.equal(p.detach(), before[n])}
+    assert moved and all(n.startswith("transformer.") and ".mlp." in n and "lora" in n for n in moved), sorted(moved)[:5]
+    # model.encode_text (inference path on the engine) sees the trained adapters
+    model.text_on_engine = True
+    with torch.no_grad():
+        f = model.encode_text(tokens).float()
+    f = f / f.norm(dim=-1, keepdim=True)
+    logits = (img @ f.t()) * float(model.logit_scale.exp())
+    labels = torch.arange(B, device="cuda")
+    l_inf = (torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.cross_entropy(logits.t(), labels)) / 2
+    assert abs(float(l_inf) - trainer.step(img, tokens)) < 0.05
 
 
 def test_training_step_reduces_loss(iic):
