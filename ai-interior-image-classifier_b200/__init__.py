@@ -6,7 +6,7 @@ the repo root.  Public surface (mirrors what /root/reference/main.py uses from `
 
     clip-like:   load, tokenize, available_models               (clip_compat.py)
     LoRA:        LoRALayer, LoRALinear, replace_linears_with_lora, save_lora_weights, load_lora_weights_to_model
-    training:    VisionLoRATrainer                                (train.py)
+    training:    VisionLoRATrainer, TextLoRATrainer               (train.py)
     analyzers:   InteriorImageDetector, CachedInteriorAnalyzer, DatabaseStyleRoomAnalyzer   (analyzer.py)
     engine:      Engine, VisionArch, VIT_B_16, VIT_L_14_336      (engine.py; the ctypes binding is _lib.py)
 """
