@@ -174,7 +174,7 @@ class TextLoRATrainer:
     def __init__(self, model: CLIP, lr: float = 1e-4, weight_decay: float = 0.01, max_grad_norm: float = 1.0,
                  logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
         self.model = model
-        self.logit_scale = float(logit_scale) if logit_scale is not None else float(model.logit_scale.exp())
+        self.logit_scale = float(logit_scale) if logit_scale is not None else float(model.logit_scale.detach().exp())
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
         self.overlap = overlap
