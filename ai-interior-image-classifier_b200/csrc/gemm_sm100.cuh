@@ -484,22 +484,36 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         const int img = row / args.group;
         const long long out_row = (long long)row + img + 1;
         const float* addend = args.residual + size_t(row - img * args.group + 1) * args.N;
+        // the positional-embedding values of the NEXT chunk are requested before this chunk's accumulator is read: with L1
+        // carved out as shared memory they come from L2 (one exposed round trip per chunk otherwise)
+        float4 pe[8], pe_next[8];
+        auto load_pe = [&](int c, float4 (&dst)[8]) {
+          const int col = col0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = (row_ok && col < args.N) ? __ldg(reinterpret_cast<const float4*>(addend + col) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        load_pe(grp, pe);
 #pragma unroll 1
         for (int c = grp; c < kBlockN / 32; c += kGroups) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), v);
+          if (c + kGroups < kBlockN / 32) load_pe(c + kGroups, pe_next);
           ptx::tmem_ld_wait();
           if (c + kGroups >= kBlockN / 32) release_tmem();
           const int col = col0 + c * 32;
-          if (!row_ok || col >= args.N) continue;
-          float* o = reinterpret_cast<float*>(args.out) + size_t(out_row) * args.ldc + col;
+          if (row_ok && col < args.N) {
+            float* o = reinterpret_cast<float*>(args.out) + size_t(out_row) * args.ldc + col;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 r = *reinterpret_cast<const float4*>(addend + col + i);
-            *reinterpret_cast<float4*>(o + i) =
-                make_float4(__uint_as_float(v[i]) + r.x, __uint_as_float(v[i + 1]) + r.y,
-                            __uint_as_float(v[i + 2]) + r.z, __uint_as_float(v[i + 3]) + r.w);
+            for (int i = 0; i < 8; ++i) {
+              const float4 r = pe[i];
+              *reinterpret_cast<float4*>(o + 4 * i) =
+                  make_float4(__uint_as_float(v[4 * i]) + r.x, __uint_as_float(v[4 * i + 1]) + r.y,
+                              __uint_as_float(v[4 * i + 2]) + r.z, __uint_as_float(v[4 * i + 3]) + r.w);
+            }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pe[i] = pe_next[i];
         }
       } else {
         uint64_t dacc01 = 0ull, dacc23 = 0ull;   // packed partial sums of the consumer's LoRA down-projection
