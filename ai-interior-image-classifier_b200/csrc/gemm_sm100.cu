@@ -125,6 +125,11 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     if (err) *err = e_shape;
     return -1;
   }
+  // 5-7 are variants the launcher selects itself (deep-K ring, fused LayerNorm): not valid as a request
+  if (p.epilogue < 0 || p.epilogue > kEpiBiasActDualBf16 || (p.epilogue >= kEpiBiasResF32DeepK && p.epilogue <= kEpiBiasResF32LnDeepK)) {
+    if (err) *err = "gemm: unknown epilogue";
+    return -1;
+  }
   const bool lora = p.lora_p != nullptr && p.lora_bt != nullptr && p.r_pad > 0;
   if (lora && (p.r_pad % 16 != 0 || p.r_pad > 64)) {
     if (err) *err = e_lora;
