@@ -31,7 +31,7 @@ class VisionLoRATrainer:
                  max_grad_norm: float = 1.0, logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
         self.visual: VisionTransformer = model.visual if hasattr(model, "visual") else model
         self.logit_scale = float(logit_scale) if logit_scale is not None else (
-            float(model.logit_scale.exp()) if hasattr(model, "logit_scale") else 100.0)
+            float(model.logit_scale.detach().exp()) if hasattr(model, "logit_scale") else 100.0)
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
         self.overlap = overlap

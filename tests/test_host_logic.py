@@ -104,6 +104,13 @@ def test_no_cpu_fallback(iic, product_cpu):
         from PIL import Image
         with pytest.raises(RuntimeError, match="CUDA"):
             pre(Image.new("RGB", (300, 260)))
+    # the trainers refuse a CPU model as well (text side: at construction; vision side: when the engine is created)
+    wrapped = copy.deepcopy(model)
+    iic.replace_linears_with_lora(wrapped, rank=4, alpha=8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        iic.TextLoRATrainer(wrapped)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        iic.VisionLoRATrainer(wrapped)
 
 
 def test_c_abi_header_library_and_binding_agree(iic):
