@@ -766,17 +766,36 @@ int iic_refresh_lora(iic_handle* h, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = h->cfg.width, mlp = h->cfg.mlp_dim;
   const int dims[4][2] = {{d, 3 * d}, {d, d}, {d, mlp}, {mlp, d}};   // (in, out) of in_proj, out_proj, c_fc, c_proj
+  // up to 16 slots per launch: the operand buffers are caller-owned device memory registered through iic_set_lora / _train /
+  // _operands16
+  LoraRefreshBatch batch;
+  batch.n = 0;
+  batch.pad = h->lora_pad;
+  auto flush = [&]() -> int {
+    if (batch.n == 0) return 0;
+    Scope sc(h->prof, kMisc, st);
+    int rc = launch_lora_refresh_batch(batch, h->f16, st);
+    batch.n = 0;
+    return rc;
+  };
   for (Block& b : h->blocks)
     for (int which = 0; which < 4; ++which) {
       LoraSlot& s = b.lora[which];
       if (s.rank <= 0 || s.src_a == nullptr || s.src_b == nullptr) continue;
-      Scope sc(h->prof, kMisc, st);
-      // the operand buffers are caller-owned device memory registered through iic_set_lora / _train / _operands16
-      int rc = launch_lora_refresh(s.src_a, s.src_b, dims[which][0], dims[which][1], s.rank, s.r4, h->lora_pad, s.scaling,
-                                   const_cast<float*>(s.a), const_cast<void*>(s.bt), const_cast<void*>(s.a16),
-                                   const_cast<float*>(s.bt32), const_cast<void*>(s.at16), const_cast<void*>(s.b16), h->f16, st);
-      if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "iic_refresh_lora: launch failed");
+      LoraRefreshSlot& q = batch.slot[batch.n++];
+      q.A = s.src_a; q.B = s.src_b;
+      q.a = const_cast<float*>(s.a); q.bt = const_cast<void*>(s.bt); q.a16 = const_cast<void*>(s.a16);
+      q.bt32 = const_cast<float*>(s.bt32); q.at16 = const_cast<void*>(s.at16); q.b16 = const_cast<void*>(s.b16);
+      q.in = dims[which][0]; q.out = dims[which][1]; q.rank = s.rank; q.r4 = s.r4; q.scaling = s.scaling;
+      if (batch.n == 16) {
+        int rc = flush();
+        if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "iic_refresh_lora: launch failed");
+      }
     }
+  {
+    int rc = flush();
+    if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "iic_refresh_lora: launch failed");
+  }
   return IIC_OK;
 }
 

@@ -60,6 +60,24 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
 // derived operands of one LoRA slot from its fp32 parameters A [in, rank], B [rank, out] (see train_ops.cu); null outputs skipped
 int launch_lora_refresh(const float* A, const float* B, int in, int out, int rank, int r4, int pad, float scaling, float* a,
                         void* bt, void* a16, float* bt32, void* at16, void* b16, int f16, cudaStream_t stream);
+// the same for up to 16 slots in ONE launch (the per-step refresh of a 12-block model is 24 slots: two launches, not 24)
+struct LoraRefreshSlot {
+  const float* A;   // f32 [in, rank]
+  const float* B;   // f32 [rank, out]
+  float* a;         // destinations as in launch_lora_refresh (null: skipped)
+  void* bt;
+  void* a16;
+  float* bt32;
+  void* at16;
+  void* b16;
+  int in, out, rank, r4;
+  float scaling;
+};
+struct LoraRefreshBatch {
+  LoraRefreshSlot slot[16];
+  int n, pad;
+};
+int launch_lora_refresh_batch(const LoraRefreshBatch& batch, int f16, cudaStream_t stream);
 
 // ---- head.cu ----
 int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,

@@ -687,6 +687,50 @@ __global__ void lora_refresh_kernel(const float* __restrict__ A, const float* __
   (void)sizeof(T);
 }
 
+template <bool kF16>
+__global__ void lora_refresh_batch_kernel(const __grid_constant__ LoraRefreshBatch b) {
+  using T = typename Act<kF16>::T;
+  const LoraRefreshSlot& q = b.slot[blockIdx.y];
+  const int in = q.in, out = q.out, rank = q.rank, r4 = q.r4, pad = b.pad;
+  T* bt = static_cast<T*>(q.bt);
+  T* a16 = static_cast<T*>(q.a16);
+  T* at16 = static_cast<T*>(q.at16);
+  T* b16 = static_cast<T*>(q.b16);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < in) {
+    for (int c = 0; c < pad; ++c) {
+      const float v = c < rank ? q.A[size_t(i) * rank + c] * q.scaling : 0.f;
+      if (c < r4 && q.a != nullptr) q.a[size_t(i) * r4 + c] = v;
+      if (a16 != nullptr) a16[size_t(i) * pad + c] = Act<kF16>::from_float(v);
+      if (at16 != nullptr) at16[size_t(c) * in + i] = Act<kF16>::from_float(v);
+    }
+  }
+  if (i < out) {
+    for (int c = 0; c < pad; ++c) {
+      const float v = c < rank ? q.B[size_t(c) * out + i] : 0.f;
+      if (bt != nullptr) bt[size_t(i) * pad + c] = Act<kF16>::from_float(v);
+      if (c < r4 && q.bt32 != nullptr) q.bt32[size_t(i) * r4 + c] = v;
+      if (b16 != nullptr) b16[size_t(c) * out + i] = Act<kF16>::from_float(v);
+    }
+  }
+}
+
+int launch_lora_refresh_batch(const LoraRefreshBatch& batch, int f16, cudaStream_t stream) {
+  if (batch.n <= 0) return 0;
+  if (batch.n > 16) return -1;
+  int n_max = 0;
+  for (int k = 0; k < batch.n; ++k) {
+    const LoraRefreshSlot& q = batch.slot[k];
+    if (q.A == nullptr || q.B == nullptr || q.rank <= 0 || q.rank > batch.pad || q.in <= 0 || q.out <= 0) return -1;
+    n_max = n_max > q.in ? n_max : q.in;
+    n_max = n_max > q.out ? n_max : q.out;
+  }
+  const dim3 grid = dim3(static_cast<unsigned>((n_max + 127) / 128), static_cast<unsigned>(batch.n), 1u);
+  if (f16) lora_refresh_batch_kernel<true><<<grid, 128, 0, stream>>>(batch);
+  else lora_refresh_batch_kernel<false><<<grid, 128, 0, stream>>>(batch);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int launch_lora_refresh(const float* A, const float* B, int in, int out, int rank, int r4, int pad, float scaling, float* a,
                         void* bt, void* a16, float* bt32, void* at16, void* b16, int f16, cudaStream_t stream) {
   if (A == nullptr || B == nullptr || rank <= 0 || rank > pad || in <= 0 || out <= 0) return -1;
