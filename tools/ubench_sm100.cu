@@ -5,6 +5,8 @@
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/ubench_sm100 tools/ubench_sm100.cu
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -153,7 +155,128 @@ __global__ void __launch_bounds__(256, 1) k_fma2(long long* out, float* sink, in
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) out[warp] = t1 - t0;
 }
 
-int main() {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mixed-format probe: does tcgen05.mma kind::f16 accept A = f16 with B = bf16 (separate format fields of the instruction
+// descriptor)?  One 128 x 64 x 64 product from hand-swizzled (SWIZZLE_128B, K-major) shared memory, checked on the host.
+//   fmt_a / fmt_b: 0 = f16, 1 = bf16
+// ---------------------------------------------------------------------------------------------------------------------
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cmath>
+#include <vector>
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFFu);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+__global__ void __launch_bounds__(128, 1) k_mixed(const uint16_t* a_bits, const uint16_t* b_bits, float* out, int fmt_a, int fmt_b) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint32_t slot;
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* sa = smem;                // 128 rows x 128 B
+  uint8_t* sb = smem + 128 * 128;    // 64 rows x 128 B
+  const int t = threadIdx.x;
+  // row r, 16-byte chunk c -> physical chunk c ^ (r & 7)
+  for (int i = t; i < 128 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(a_bits + r * 64 + c * 8);
+  }
+  for (int i = t; i < 64 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(b_bits + r * 64 + c * 8);
+  }
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (t == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+  if (t < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = slot;
+  if (t == 0) {
+    const uint32_t idesc = (1u << 4) | (uint32_t(fmt_a) << 7) | (uint32_t(fmt_b) << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sa), b0 = (uint32_t)__cvta_generic_to_shared(sb);
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t da = sw128_desc(a0 + k * 32), db = sw128_desc(b0 + k * 32);
+      const uint32_t acc = k ? 1u : 0u;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                   ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+  }
+  {
+    uint32_t ok = 0; long long t0 = clock64();
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(bar_addr), "r"(0u) : "memory");
+      if (clock64() - t0 > 2000000000ll) { __trap(); }
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int warp = t >> 5;
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t v[32];
+    ld32(tb + (uint32_t(warp * 32) << 16) + c, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 32; ++j) out[t * 64 + c + j] = __uint_as_float(v[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(64u) : "memory");
+}
+
+static float bits_to_float(uint16_t b, int fmt) {
+  if (fmt == 1) { uint32_t u = uint32_t(b) << 16; float f; memcpy(&f, &u, 4); return f; }
+  __half h; memcpy(&h, &b, 2); return __half2float(h);
+}
+static uint16_t float_to_bits(float f, int fmt) {
+  if (fmt == 1) { __nv_bfloat16 h = __float2bfloat16(f); uint16_t b; memcpy(&b, &h, 2); return b; }
+  __half h = __float2half(f); uint16_t b; memcpy(&b, &h, 2); return b;
+}
+static void run_mixed_probe(int only_fa, int only_fb) {
+  uint16_t *da, *db; float* dout;
+  cudaMalloc(&da, 128 * 64 * 2); cudaMalloc(&db, 64 * 64 * 2); cudaMalloc(&dout, 128 * 64 * 4);
+  cudaFuncSetAttribute(k_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+  for (int fa = 0; fa < 2; ++fa)
+    for (int fb = 0; fb < 2; ++fb) {
+      if (fa != only_fa || fb != only_fb) continue;   // one pair per process: a rejected pair poisons the context
+      std::vector<uint16_t> ha(128 * 64), hb(64 * 64);
+      std::vector<float> fa_(128 * 64), fb_(64 * 64), ho(128 * 64);
+      uint32_t s = 12345u + fa * 7 + fb * 13;
+      auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float((s >> 8) & 0xFFFF) / 65536.0f - 0.5f) * 2.7f; };
+      // values with more mantissa bits than bf16 keeps, so "A silently read as bf16" would be visible
+      for (int i = 0; i < 128 * 64; ++i) { ha[i] = float_to_bits(rnd(), fa); fa_[i] = bits_to_float(ha[i], fa); }
+      for (int i = 0; i < 64 * 64; ++i) { hb[i] = float_to_bits(rnd(), fb); fb_[i] = bits_to_float(hb[i], fb); }
+      cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
+      cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+      cudaMemset(dout, 0xff, 128 * 64 * 4);
+      k_mixed<<<1, 128, 32768>>>(da, db, dout, fa, fb);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mixed probe A=%s B=%s: LAUNCH FAILED: %s\n", fa ? "bf16" : "f16", fb ? "bf16" : "f16", cudaGetErrorString(e)); return; }
+      cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost);
+      double worst = 0, ref_max = 0;
+      for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 64; ++n) {
+          double r = 0;
+          for (int k = 0; k < 64; ++k) r += double(fa_[m * 64 + k]) * double(fb_[n * 64 + k]);
+          worst = fmax(worst, fabs(r - double(ho[m * 64 + n]))); ref_max = fmax(ref_max, fabs(r));
+        }
+      printf("mixed probe A=%s B=%s: max |err| %.3e (max |ref| %.2f) -> %s\n", fa ? "bf16" : "f16", fb ? "bf16" : "f16", worst, ref_max,
+             worst < 1e-4 * ref_max ? "EXACT PRODUCT (format pair accepted)" : "WRONG");
+    }
+}
+
+int main(int argc, char** argv) {
+  // `ubench_sm100 mixed <fmt_a> <fmt_b>` (0 = f16, 1 = bf16): the mixed-format probe alone
+  if (argc >= 4 && !strcmp(argv[1], "mixed")) { run_mixed_probe(atoi(argv[2]), atoi(argv[3])); return 0; }
   long long* d; float* sink;
   cudaMalloc(&d, 2048 * sizeof(long long)); cudaMalloc(&sink, 16);
   long long h[16];
