@@ -158,8 +158,9 @@ class InteriorImageDetector:
         device-to-host copy per batch.  Decision rule: main.py:208-222."""
         out = []
         for i in range(0, len(images), batch_size):
-            eng = self._engine()
-            with eng._lock:
+            # sync (weights / LoRA / labels) + classify as ONE critical section of the engine: no other thread's upload can
+            # interleave (main.py:345-346 calls the detector from a 4-thread pool)
+            with self.model.visual.engine()._lock:
                 eng = self._engine()
                 u8 = [clip.Preprocess._to_u8(im, eng.device) for im in images[i:i + batch_size]]
                 r = eng.classify(u8, want_embedding=False)
@@ -286,8 +287,7 @@ class CachedInteriorAnalyzer:
         """PIL list -> (topk_val, topk_idx, split_sum, probs-of-detector) on the host, one D2H per batch."""
         tvs, tis, sss, nons = [], [], [], []
         for i in range(0, len(images), batch_size):
-            eng, names = self._engine(with_detector)
-            with eng._lock:
+            with self.model.visual.engine()._lock:      # sync + labels + classify: one critical section
                 eng, names = self._engine(with_detector)
                 u8 = [clip.Preprocess._to_u8(im, eng.device) for im in images[i:i + batch_size]]
                 r = eng.classify(u8, want_embedding=False)
@@ -395,8 +395,7 @@ class CachedInteriorAnalyzer:
 
     def _analyze_image_tensor_fast(self, image_input: torch.Tensor):
         """image_input: preprocessed float tensor [1,3,R,R] (what the reference passes, main.py:489, 500)."""
-        eng, names = self._engine(False)
-        with eng._lock:
+        with self.model.visual.engine()._lock:
             eng, names = self._engine(False)
             r = eng.classify_patches(eng.patchify(image_input.to(eng.device)), image_input.shape[0], want_embedding=False)
             tv, ti = r.topk_val.cpu(), r.topk_idx.cpu()
@@ -427,8 +426,7 @@ class DatabaseStyleRoomAnalyzer:
     def _analyze_styles_batch(self, images, batch_size: int = 16):
         out = []
         for i in range(0, len(images), batch_size):
-            eng = self.model.visual.sync_engine()
-            with eng._lock:
+            with self.model.visual.engine()._lock:
                 eng = self.model.visual.sync_engine()
                 eng.set_labels(self.style_features, [len(self.styles)], None, topk=1, logit_scale=100.0)
                 eng._labels_owner = None

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 import math
 import os
+import threading
+import warnings
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple, Union
 
@@ -39,6 +41,11 @@ _MODELS = {
                            transformer_heads=12, transformer_layers=12, file="ViT-L-14-336px.pt"),
 }
 _SOT, _EOT = 49406, 49407
+_ENGINE_CREATE_LOCK = threading.Lock()
+
+
+def _opted_in(flag: Optional[bool], env: str) -> bool:
+    return bool(flag) if flag is not None else os.environ.get(env, "0") == "1"
 
 
 def available_models() -> List[str]:
@@ -111,10 +118,12 @@ class VisionTransformer(nn.Module):
         # Reference parity: nn.MultiheadAttention never calls out_proj(x), so a LoRA hanging off
         # attn.out_proj has no effect in the reference.  Set True to apply it anyway (generic slot of the kernel).
         self.apply_out_proj_lora = False
-        # 16-bit operand format of the engine: "bf16" (BASELINE's named dtype) or "f16" (upstream CLIP's GPU dtype).
-        self.operand_dtype = os.environ.get("IIC_OPERAND_DTYPE", "bf16")
+        # 16-bit operand format of the engine: "f16" (the default, _lib.DEFAULT_OPERAND_DTYPE: upstream CLIP's own GPU
+        # dtype) or "bf16" (explicit non-default arm).
+        self.operand_dtype = L.operand_dtype_name(None)
         self._engine: Optional[Engine] = None
         self._sig = None
+        self._zero_b: Dict[int, Tuple[int, int, bool]] = {}   # id(lora_B) -> (data_ptr, _version, "is all zero")
 
     # -- engine plumbing ------------------------------------------------------------------------------------
     def engine(self) -> Engine:
@@ -123,11 +132,23 @@ class VisionTransformer(nn.Module):
             raise RuntimeError(
                 "the iic-b200 vision tower only runs on a CUDA device (B200); move the model with .to('cuda'). "
                 "There is deliberately no CPU fallback.")
-        want = torch.float16 if str(self.operand_dtype).lower() in ("f16", "fp16", "float16", "torch.float16") else torch.bfloat16
-        if self._engine is None or self._engine.device != dev or self._engine.op_dtype != want:
-            self._engine = Engine(self.arch, dev, operand_dtype=want)
-            self._sig = None
-        return self._engine
+        want = torch.float16 if L.operand_dtype_name(self.operand_dtype) == "f16" else torch.bfloat16
+        with _ENGINE_CREATE_LOCK:
+            if self._engine is None or self._engine.device != dev or self._engine.op_dtype != want:
+                self._engine = Engine(self.arch, dev, operand_dtype=want)
+                self._sig = None
+            return self._engine
+
+    def _b_is_zero(self, b: torch.Tensor) -> bool:
+        """lora_B == 0 (fresh wrap / tensor missing from the checkpoint: the delta is exactly zero).  The answer
+        needs a device-to-host sync, so it is cached per tensor on (data_ptr, _version): steady-state calls make none."""
+        key = id(b)
+        hit = self._zero_b.get(key)
+        if hit is not None and hit[0] == b.data_ptr() and hit[1] == b._version:
+            return hit[2]
+        z = not bool((b != 0).any())
+        self._zero_b[key] = (b.data_ptr(), b._version, z)
+        return z
 
     def _tensors(self, keep_zero_lora: bool = False) -> Tuple[Dict[str, torch.Tensor], Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, float]]]:
         sd: Dict[str, torch.Tensor] = {
@@ -147,7 +168,7 @@ class VisionTransformer(nn.Module):
                 sd[p + name + ".weight"], sd[p + name + ".bias"] = mod.weight, mod.bias  # proxies on a LoRALinear
                 if _is_lora_wrapped(mod) and (which != L.LORA_OUT_PROJ or self.apply_out_proj_lora):
                     scaling = float(getattr(mod.lora, "scaling", 1.0))
-                    if keep_zero_lora or bool((mod.lora.lora_B != 0).any()):  # B == 0 (fresh / missing in ckpt): delta is exactly 0
+                    if keep_zero_lora or not self._b_is_zero(mod.lora.lora_B):  # B == 0 (fresh / missing in ckpt): delta is exactly 0
                         lora[(i, which)] = (mod.lora.lora_A, mod.lora.lora_B, scaling)
         return sd, lora
 
@@ -155,6 +176,12 @@ class VisionTransformer(nn.Module):
         """(Re)upload whatever changed since the last call (optimizer step, checkpoint load, `.data` swap).
         use_lora=False runs the frozen base tower (the reference's detector owns an un-LoRA'd copy, main.py:238)."""
         eng = self.engine()
+        # the whole comparison + upload holds the engine lock (re-entrant): a concurrent classify on another thread can never
+        # see a half-switched LoRA configuration (the reference calls its detector from a 4-thread pool, main.py:345-346)
+        with eng._lock:
+            return self._sync_locked(eng, force, use_lora, keep_zero_lora)
+
+    def _sync_locked(self, eng: Engine, force: bool, use_lora: bool, keep_zero_lora: bool) -> Engine:
         sd, lora = self._tensors(keep_zero_lora)
         if not use_lora:
             lora = {}
@@ -233,11 +260,17 @@ class CLIP(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("text_on_engine needs the model on a CUDA device (B200); there is no CPU fallback for the engine")
         v = self.visual
-        want = torch.float16 if str(v.operand_dtype).lower() in ("f16", "fp16", "float16", "torch.float16") else torch.bfloat16
-        if self._text_engine is None or self._text_engine.device != dev or self._text_engine.op_dtype != want:
-            self._text_engine = Engine(self._text_arch, dev, operand_dtype=want)
-            self._text_sig = None
-        eng = self._text_engine
+        want = torch.float16 if L.operand_dtype_name(v.operand_dtype) == "f16" else torch.bfloat16
+        with _ENGINE_CREATE_LOCK:
+            if self._text_engine is None or self._text_engine.device != dev or self._text_engine.op_dtype != want:
+                self._text_engine = Engine(self._text_arch, dev, operand_dtype=want)
+                self._text_sig = None
+            eng = self._text_engine
+        with eng._lock:
+            return self._sync_text_locked(eng, force)
+
+    def _sync_text_locked(self, eng: Engine, force: bool) -> Engine:
+        v = self.visual
         sd: Dict[str, torch.Tensor] = {"ln_final.weight": self.ln_final.weight, "ln_final.bias": self.ln_final.bias,
                                        "text_projection": self.text_projection}
         lora: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor, float]] = {}
@@ -250,7 +283,7 @@ class CLIP(nn.Module):
                                      (L.LORA_C_FC, "mlp.c_fc", blk.mlp.c_fc), (L.LORA_C_PROJ, "mlp.c_proj", blk.mlp.c_proj)):
                 sd[p + name + ".weight"], sd[p + name + ".bias"] = mod.weight, mod.bias  # proxies on a LoRALinear
                 # an attn.out_proj LoRA is dead in the reference's forward (F4): never applied
-                if _is_lora_wrapped(mod) and which != L.LORA_OUT_PROJ and bool((mod.lora.lora_B != 0).any()):
+                if _is_lora_wrapped(mod) and which != L.LORA_OUT_PROJ and not v._b_is_zero(mod.lora.lora_B):
                     lora[(i, which)] = (mod.lora.lora_A, mod.lora.lora_B, float(getattr(mod.lora, "scaling", 1.0)))
         sig_w = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
         sig_l = tuple((k, a.data_ptr(), a._version, b.data_ptr(), b._version, s) for k, (a, b, s) in sorted(lora.items()))
@@ -337,16 +370,29 @@ def _find_bpe() -> Optional[str]:
     return None
 
 
-def tokenize(texts: Union[str, List[str]], context_length: int = 77, truncate: bool = False) -> torch.Tensor:
+def tokenize(texts: Union[str, List[str]], context_length: int = 77, truncate: bool = False,
+             allow_standin: Optional[bool] = None) -> torch.Tensor:
     """clip.tokenize contract: LongTensor[N, 77] = [SOT] ids... [EOT] zero-padded; raises when too long.
-    With the genuine `clip` package importable its tokenizer is used; otherwise (this image: no BPE vocabulary, no
-    network) a deterministic byte-level stand-in keeps the same framing so `argmax` finds EOT."""
+    With the genuine `clip` package importable its BPE tokenizer is used.  Without it (this image: no BPE vocabulary, no
+    network) the call RAISES, like the reference's would - unless the caller opts in (allow_standin=True or
+    IIC_ALLOW_STANDIN_TOKENIZER=1: tests, benches) to a deterministic byte-level stand-in that keeps the same framing so
+    `argmax` finds EOT.  The stand-in is only meaningful with seeded weights: with real weights it yields garbage features."""
+    real = None
     try:
         import clip as _real
-        if getattr(_real, "__file__", None) and _find_bpe():
-            return _real.tokenize(texts, context_length=context_length, truncate=truncate)
-    except Exception:
-        pass
+        # the genuine package ships its BPE vocabulary next to its sources; anything else named `clip` in sys.modules
+        # (this module installed as a drop-in, a test stub) is not a tokenizer to delegate to
+        if getattr(_real, "__file__", None) and _find_bpe() and getattr(_real, "tokenize", None) is not tokenize:
+            real = _real
+    except ImportError:
+        real = None
+    if real is not None:
+        return real.tokenize(texts, context_length=context_length, truncate=truncate)
+    if not _opted_in(allow_standin, "IIC_ALLOW_STANDIN_TOKENIZER"):
+        raise RuntimeError(
+            "clip.tokenize: the OpenAI `clip` package (BPE vocabulary) is not installed. Install it, or opt in to the "
+            "byte-level stand-in tokenizer with tokenize(..., allow_standin=True) / IIC_ALLOW_STANDIN_TOKENIZER=1 "
+            "(seeded-weight tests and benches only: with real weights it produces meaningless text features).")
     if isinstance(texts, str):
         texts = [texts]
     out = torch.zeros(len(texts), context_length, dtype=torch.long)
@@ -404,31 +450,53 @@ def build_visual(name: str = "ViT-B/16", seed: int = 0) -> VisionTransformer:
     return v.eval()
 
 
-def _checkpoint_state_dict(path: str) -> Optional[Dict[str, torch.Tensor]]:
+def _checkpoint_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """OpenAI checkpoint (TorchScript archive) or a plain state dict.  Parse errors PROPAGATE: a corrupt or partly
+    written file must not silently turn into random weights."""
     try:
+        return torch.jit.load(path, map_location="cpu").state_dict()
+    except RuntimeError as jit_err:
         try:
-            return torch.jit.load(path, map_location="cpu").state_dict()
-        except RuntimeError:
             sd = torch.load(path, map_location="cpu")
-            return sd.get("state_dict", sd) if isinstance(sd, dict) else None
-    except Exception:
-        return None
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f"cannot read CLIP checkpoint {path}: not a TorchScript archive ({jit_err}) and torch.load "
+                               f"failed ({e})") from e
+    if isinstance(sd, dict):
+        sd = sd.get("state_dict", sd)
+    if not isinstance(sd, dict) or not sd:
+        raise RuntimeError(f"CLIP checkpoint {path} does not contain a state dict")
+    return sd
 
 
 def load(name: str = "ViT-B/16", device: Union[str, torch.device, None] = None, jit: bool = False,
          download_root: Optional[str] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-         operand_dtype: Optional[str] = None):
+         operand_dtype: Optional[str] = None, allow_random_init: Optional[bool] = None):
     """clip.load contract: returns (model.eval(), preprocess).
 
     Weights: `state_dict` if given; else the OpenAI checkpoint at `download_root or ~/.cache/clip/<file>` if it is
-    on disk (nothing is ever downloaded); else seeded random initialisation with the upstream init scales.
-    Parameters stay fp32 (master copy); the engine rounds matmul weights to bf16 on upload.  `jit` is ignored."""
+    on disk (nothing is ever downloaded; a file that is there but cannot be parsed RAISES).  With neither, the call
+    raises like the reference's `clip.load` would when its download fails - unless the caller opts in
+    (allow_random_init=True or IIC_ALLOW_RANDOM_INIT=1: tests, benches) to a seeded random initialisation with the
+    upstream init scales, which is announced with a warning.  A misconfigured deployment therefore never serves
+    classifications from random weights silently.
+    Parameters stay fp32 (master copy); the engine converts matmul weights to the 16-bit operand dtype on upload
+    (`operand_dtype`: "f16" default | "bf16").  `jit` is ignored."""
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
-    if state_dict is None and name in _MODELS:
+    if name not in _MODELS:
+        raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
+    if state_dict is None:
         path = os.path.join(download_root or os.path.expanduser("~/.cache/clip"), _MODELS[name]["file"])
         if os.path.isfile(path):
             state_dict = _checkpoint_state_dict(path)
+        elif _opted_in(allow_random_init, "IIC_ALLOW_RANDOM_INIT"):
+            warnings.warn(f"clip.load({name!r}): no checkpoint at {path}; using SEEDED RANDOM weights "
+                          f"(allow_random_init) - outputs are meaningless outside tests and benches", stacklevel=2)
+        else:
+            raise RuntimeError(
+                f"clip.load({name!r}): checkpoint {path} not found and nothing is downloaded (no network). Put the OpenAI "
+                f"checkpoint there, pass state_dict=..., or opt in to seeded random weights with allow_random_init=True / "
+                f"IIC_ALLOW_RANDOM_INIT=1 (tests and benches only).")
     model = build_model(name, state_dict).to(device)
     if operand_dtype is not None:
         model.visual.operand_dtype = operand_dtype

@@ -225,14 +225,14 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H
   const int TP = (T + 15) / 16 * 16;
   const size_t smem = size_t(TP) * 128 * 2;
   if (smem > 227 * 1024) return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess ||
         cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
             cudaSuccess)
       return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(head_dim));
   const uint16_t* q = static_cast<const uint16_t*>(qkv);

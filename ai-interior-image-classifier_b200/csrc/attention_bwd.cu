@@ -268,12 +268,12 @@ int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, co
   const int TP = (T + 15) / 16 * 16;
   const size_t smem = size_t(TP) * 128 * 4 + size_t(TP) * 8;
   if (smem > 227 * 1024) return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const float scale = 1.0f / sqrtf(float(head_dim));
   const float scale_log2e = 1.4426950408889634f * scale;

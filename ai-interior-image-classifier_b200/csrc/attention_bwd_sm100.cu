@@ -530,12 +530,12 @@ int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_o
   if (!make_map(&tqf, qkv, rows, uint64_t(3 * d), uint32_t(p.xy_box), h16) || !make_map(&tqt, qkv, rows, uint64_t(3 * d), 128, h16) ||
       !make_map(&tdf, d_out, rows, uint64_t(d), uint32_t(p.xy_box), h16) || !make_map(&tdt, d_out, rows, uint64_t(d), 128, h16))
     return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(attention_bwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
         cudaFuncSetAttribute(attention_bwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
       return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const int grid = p.items < num_sms ? p.items : num_sms;
   if (f16)

@@ -685,14 +685,14 @@ int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T,
   const uint64_t rows = uint64_t(B) * T;
   if (!make_map(&tq, qkv, rows, uint64_t(3 * d), 128, f16 != 0) || !make_map(&tkv, qkv, rows, uint64_t(3 * d), uint32_t(p.kv_box), f16 != 0))
     return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(attention_sm100_kernel<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
         cudaFuncSetAttribute(attention_sm100_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
         cudaFuncSetAttribute(attention_sm100_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess ||
         cudaFuncSetAttribute(attention_sm100_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem) != cudaSuccess)
       return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const int grid = p.items < num_sms ? p.items : num_sms;
   if (max_units == 6) {

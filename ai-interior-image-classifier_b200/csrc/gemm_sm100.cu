@@ -54,10 +54,10 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
                cudaStream_t stream) {
   using S = GemmSmem<kCtas, kBlockN, kEpi>;
   auto kern = gemm_bf16_tn_kernel<kCtas, kBlockN, kEpi, kF16>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const int tile_m = kBlockM * kCtas;
   const int m_tiles = (args.M + tile_m - 1) / tile_m;

@@ -208,11 +208,11 @@ int launch_head(const float* x, long long x_img_stride, const float* ln_g, const
   if (topk > kMaxTopk || topk < 0) return -1;
   const size_t smem = sizeof(float) * (size_t(kImgs) * (W + E + L) + 64);
   if (smem > 200 * 1024) return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return -2;
-    attr_done = true;
+    attr_done.mark();
   }
   const int blocks = (B + kImgs - 1) / kImgs;
   head_kernel<<<blocks, kThreads, smem, stream>>>(x, x_img_stride, ln_g, ln_b, eps, proj, W, E, text, L, group_off,

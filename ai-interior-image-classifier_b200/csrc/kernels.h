@@ -6,7 +6,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace iic {
+
+// One-time per-DEVICE opt-in guard.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only, so
+// a process-wide "done" flag would leave a second engine on another GPU of the same process without the opt-in.  One bit per
+// device ordinal; two threads racing on the first call both set the (idempotent) attribute, which is harmless.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0ull};
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool need() const { return ((done.load(std::memory_order_acquire) >> device()) & 1ull) == 0ull; }
+  void mark() { done.fetch_or(1ull << device(), std::memory_order_release); }
+};
 
 // ---- rowwise.cu ----
 int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta,

@@ -591,10 +591,10 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
 #define IIC_LB(F16, TW)                                                                                                   \
   {                                                                                                                       \
     auto kern = lora_bwd_kernel<F16, TW>;                                                                                 \
-    static bool attr = false;                                                                                             \
-    if (!attr) {                                                                                                          \
+    static PerDeviceOnce attr;                                                                                            \
+    if (attr.need()) {                                                                                                    \
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) return -2;  \
-      attr = true;                                                                                                        \
+      attr.mark();                                                                                                        \
     }                                                                                                                     \
     kern<<<grid, 128, smem, stream>>>(p, p_ld, y, N, M, bm, rows, rank, part_db, part_dp);                                    \
   }

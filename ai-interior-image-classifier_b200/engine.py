@@ -83,13 +83,8 @@ class Engine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.arch = arch
-        if operand_dtype is None:
-            operand_dtype = os.environ.get("IIC_OPERAND_DTYPE", "bf16")
-        if isinstance(operand_dtype, str):
-            operand_dtype = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "f16": torch.float16,
-                             "fp16": torch.float16, "float16": torch.float16}[operand_dtype.lower()]
-        if operand_dtype not in (torch.bfloat16, torch.float16):
-            raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
+        # None -> IIC_OPERAND_DTYPE or _lib.DEFAULT_OPERAND_DTYPE (fp16): ONE default for engine, bench, smoke and tests
+        operand_dtype = torch.float16 if L.operand_dtype_name(operand_dtype) == "f16" else torch.bfloat16
         self.op_dtype = operand_dtype
         cfg = L.IicConfig(arch.image_size, arch.patch_size, arch.width, arch.layers, arch.heads, arch.mlp_dim,
                           arch.embed_dim, arch.activation, self.device.index, gemm_ctas,
@@ -138,7 +133,7 @@ class Engine:
 
     def load_visual_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
         """`sd`: OpenAI-CLIP `visual.*` tensors keyed WITHOUT the `visual.` prefix (fp32, any device).
-        Linear / conv weights are rounded to bf16 here (the compute dtype), everything else stays fp32."""
+        Linear / conv weights are converted to the 16-bit operand dtype here, everything else stays fp32."""
         a = self.arch
         f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
         bf16 = lambda t: t.detach().to(self.device, torch.float32).to(self.op_dtype).contiguous()
@@ -505,17 +500,30 @@ class Engine:
         dx_cls = dx_cls.detach().to(self.device, torch.float32).contiguous()
         B = dx_cls.shape[0]
         if loss_scale == "auto":
-            # max |dx_cls| of the PREVIOUS step picks the scale (the value is long since on the host: no pipeline stall);
-            # the 2^8 target leaves 2^8 of headroom below fp16's maximum for step-to-step drift
-            prev = getattr(self, "_amax_prev", None)
-            amax = float(prev) if prev is not None else float(dx_cls.abs().max())
-            self._amax_prev = dx_cls.abs().max().to("cpu", non_blocking=True)
+            # max |dx_cls| of the PREVIOUS step picks the scale (no pipeline stall): it is copied into a PINNED buffer and an
+            # event marks the copy, which is synchronised before the value is read - back-to-back forward_backward calls
+            # (gradient accumulation, benches) therefore never read a half-written number.  The 2^8 target leaves 2^8 of
+            # headroom below fp16's maximum for step-to-step drift; `loss_scale_backoff` (<= 1, halved by the trainers when a
+            # step produced non-finite gradients, recovered slowly) is applied on top.
+            with torch.cuda.device(self.device):
+                if getattr(self, "_amax_pin", None) is None:
+                    self._amax_pin = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+                    self._amax_event = None
+                if self._amax_event is not None:
+                    self._amax_event.synchronize()
+                    amax = float(self._amax_pin[0])
+                else:
+                    amax = float(dx_cls.abs().max())
+                self._amax_pin.copy_(dx_cls.abs().max().reshape(1), non_blocking=True)
+                self._amax_event = torch.cuda.Event()
+                self._amax_event.record(torch.cuda.current_stream(self.device))
             loss_scale = 2.0 ** math.floor(math.log2(256.0 / amax)) if amax > 0 and math.isfinite(amax) else 1.0
+            loss_scale *= float(getattr(self, "loss_scale_backoff", 1.0))
         loss_scale = float(loss_scale)
         if loss_scale != 1.0:
             dx_cls = dx_cls * loss_scale
-        L.check(self.h, self.lib.iic_train_set_loss_scale(self.h, loss_scale), "iic_train_set_loss_scale")
         with self._lock, torch.cuda.device(self.device):
+            L.check(self.h, self.lib.iic_train_set_loss_scale(self.h, loss_scale), "iic_train_set_loss_scale")
             ws = self._train_ws(B)
             s = _stream_ptr(self.device)
             if layer_done is None and row_index is None:

@@ -26,6 +26,44 @@ from . import _lib as L
 from .clip_compat import CLIP, VisionTransformer, _is_lora_wrapped
 
 
+def _broadcast_lora(params: List[torch.nn.Parameter], process_group=None) -> None:
+    """Every rank must start from rank 0's adapters: lora_A comes from the unseeded global RNG (main.py:26), so without this
+    the replicas would average gradients but apply them to different parameters and drift apart silently.  One flat
+    bucket, one broadcast (what torch DDP does at construction)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1):
+        return
+    with torch.no_grad():
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        dist.broadcast(flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+        off = 0
+        for p in params:
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+
+def _guarded_step(trainer, loss: torch.Tensor) -> float:
+    """clip_grad_norm_(1.0) + AdamW step (train_lora.py:249-252), skipped when the gradients are not finite (an fp16 overflow
+    of an activation gradient): the step is dropped, the engine's loss scale backs off by 2 and recovers by 2 every 200 good
+    steps - one overflow must not poison the AdamW moments and the parameters for good.  One host sync per step (the loss
+    read the reference makes anyway), taken before the optimizer launches."""
+    total = torch.nn.utils.clip_grad_norm_(trainer.params, max_norm=trainer.max_grad_norm)
+    loss_v, total_v = torch.stack([loss.detach().float().reshape(()), total.detach().float().reshape(())]).tolist()
+    eng = trainer.eng
+    if total_v != total_v or total_v in (float("inf"), float("-inf")):
+        trainer.skipped_steps = getattr(trainer, "skipped_steps", 0) + 1
+        trainer._good_steps = 0
+        eng.loss_scale_backoff = max(getattr(eng, "loss_scale_backoff", 1.0) * 0.5, 2.0 ** -16)
+        for p in trainer.params:
+            p.grad.zero_()
+        return loss_v
+    trainer._good_steps = getattr(trainer, "_good_steps", 0) + 1
+    if trainer._good_steps % 200 == 0 and getattr(eng, "loss_scale_backoff", 1.0) < 1.0:
+        eng.loss_scale_backoff = min(1.0, eng.loss_scale_backoff * 2.0)
+    trainer.optimizer.step()
+    return loss_v
+
+
 class VisionLoRATrainer:
     def __init__(self, model: "CLIP | VisionTransformer", lr: float = 1e-4, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
@@ -65,6 +103,7 @@ class VisionLoRATrainer:
                 p.grad = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             self.buckets[i] = flat
+        _broadcast_lora(self.params, process_group)      # identical adapters on every rank before the optimizer state exists
         self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)   # train_lora.py:212
         self.comm_stream = torch.cuda.Stream(device=dev) if process_group is not None or self._dist_on() else None
         self._training_weights_sig = None
@@ -155,9 +194,7 @@ class VisionLoRATrainer:
     def step(self, images: torch.Tensor, text_features: torch.Tensor) -> float:
         """train_lora.py:249-252: backward, clip_grad_norm_(1.0), optimizer.step()."""
         loss = self.forward_backward(images, text_features)
-        torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm)
-        self.optimizer.step()
-        return float(loss)
+        return _guarded_step(self, loss)
 
 
 class TextLoRATrainer:
@@ -207,6 +244,7 @@ class TextLoRATrainer:
                 p.grad = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             self.buckets[i] = flat
+        _broadcast_lora(self.params, process_group)
         self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)   # train_lora.py:212
         self.comm_stream = torch.cuda.Stream(device=dev) if process_group is not None or VisionLoRATrainer._dist_on() else None
         self.eng = None
@@ -295,6 +333,4 @@ class TextLoRATrainer:
                 f = self.model.encode_image(t).float()
                 t = f / f.norm(dim=-1, keepdim=True)
         loss = self.forward_backward(t, tokens)
-        torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm)
-        self.optimizer.step()
-        return float(loss)
+        return _guarded_step(self, loss)

@@ -24,7 +24,7 @@ def analyzer(iic, tmp_path_factory):
     os.makedirs(root / "dataset_images", exist_ok=True)
     for f, c in zip(files, crops["crops"]):
         Image.fromarray(c).save(root / (os.path.splitext(f)[0] + ".png"))   # lossless 224x224: resize is the identity
-    model, pre = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="f16")
+    model, pre = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict())     # default operand dtype
     a = iic.CachedInteriorAnalyzer(use_lora=True, lora_weights_path=None, lora_rank=4, lora_alpha=8, device="cuda",
                                    json_path=os.path.join(GOLDEN, "interior_dataset_fixture.json"), model=model,
                                    preprocess=pre)
@@ -69,6 +69,103 @@ def test_analyze_images_batch_matches_reference(analyzer):
             assert got["reason"] == want["reason"]
             assert abs(got["interior_confidence"] - want["interior_confidence"]) < 5e-3
             _same_analysis(got["analysis"], want["analysis"])
+
+
+def _expected_from_reference(ref, top5, i, filter_interiors):
+    """what /root/reference/main.py:371-469 returns for image i, from the reference's own per-image outputs (ref_shipped.npz:
+    detector triples main.py:191-222, top-5 lists main.py:500-510; gen_golden.py checked batch == per-image on 12 images)"""
+    if filter_interiors and not bool(ref["det_is"][i]):
+        cat, conf = str(ref["det_cat"][i]), float(ref["det_conf"][i])
+        return {"is_interior": False, "interior_confidence": conf, "detected_category": cat, "analysis": {},
+                "reason": f"Nie wnętrze: {cat} (confidence: {conf:.3f})"}
+    return {"is_interior": True, "interior_confidence": float(ref["det_conf"][i]) if filter_interiors else 1.0,
+            "detected_category": "interior", "analysis": top5[i], "reason": "Success - interior image analyzed"}
+
+
+def _compare_result(got, want, tol=5e-3):
+    assert got["is_interior"] == want["is_interior"] and got["detected_category"] == want["detected_category"], (got, want)
+    assert abs(got["interior_confidence"] - want["interior_confidence"]) < tol
+    if want["is_interior"]:
+        assert got["reason"] == want["reason"]
+    else:   # the reason string embeds the confidence with 3 decimals: compare its text part
+        assert got["reason"].split("(")[0] == want["reason"].split("(")[0]
+    if want["analysis"]:
+        _same_analysis(got["analysis"], want["analysis"], tol)
+    else:
+        assert got["analysis"] == {}
+
+
+def _only_tie_swaps(got, want, ref_logits_row, tol=2e-2):
+    lab = golden_json("labels.json")
+    col, c0 = {}, len(lab["detector"])
+    for g in lab["group_order"]:
+        for k, name in enumerate(lab["groups"][g]):
+            col[(g, name)] = c0 + k
+        c0 += len(lab["groups"][g])
+    for g, pairs in want.items():
+        gl, wl = [l for l, _ in got[g]], [l for l, _ in pairs]
+        if gl == wl:
+            continue
+        thr = min(float(ref_logits_row[col[(g, l)]]) for l in wl)          # the reference's rank-5 logit
+        for a_, b_ in zip(gl, wl):                                           # positions that differ: both labels inside the tie band
+            if a_ != b_ and max(abs(float(ref_logits_row[col[(g, a_)]]) - float(ref_logits_row[col[(g, b_)]])),
+                                0.0) > tol:
+                return False
+        if any(abs(float(ref_logits_row[col[(g, l)]]) - thr) > tol for l in set(gl) ^ set(wl)):
+            return False
+    return True
+
+
+def test_analyze_images_batch_all_151_images(analyzer):
+    """config 2 through the public entry point: all 150 dataset images + interior_sample.jpg, both filter settings, default
+    operand dtype, against the reference's own outputs; >= 99 % of the images must agree in every field (label order of all
+    five top-5 lists included)"""
+    ref = golden_npz("ref_shipped.npz")
+    top5 = json.loads(str(ref["top5"]))
+    paths = [_png(analyzer, f) for f in analyzer.files]
+    for flt in (True, False):
+        res = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=flt)
+        assert set(res) == set(paths)
+        bad, ties = [], 0
+        for i, p in enumerate(paths):
+            want = _expected_from_reference(ref, top5, i, flt)
+            try:
+                _compare_result(res[p], want)
+            except AssertionError as e:
+                # The fixture's weights are seeded, so rank 5 / rank 6 of a group are now and then closer than the logit
+                # tolerance itself.  Such a swap is not a disagreement: every label that differs must sit within 2e-2 of the
+                # REFERENCE's own rank-5 logit (ref_shipped.npz holds all 437 reference logits), everything else must match.
+                if want["is_interior"] and res[p]["is_interior"] and _only_tie_swaps(res[p]["analysis"], want["analysis"], ref["logits"][i]):
+                    ties += 1
+                else:
+                    bad.append((analyzer.files[i], str(e)[:160]))
+        n_same = len(paths) - len(bad) - ties
+        print(f"\n[analyze_images_batch filter={flt}] {n_same}/{len(paths)} images identical to the reference in every field, "
+              f"{ties} differ only by a rank-5/6 swap inside the 2e-2 logit tolerance, {len(bad)} disagree")
+        assert len(bad) <= len(paths) // 100, bad[:3]
+        assert n_same >= 0.97 * len(paths)
+
+
+def test_analyze_images_batch_native_sizes(analyzer, tmp_path):
+    """arbitrary-size image file -> Pillow-exact resize kernels -> encoder -> result dict, in ONE entry-point call: ten dataset
+    photos at their native sizes (256x256 ... 1024x768, stored lossless so the decoded pixels are the reference's)"""
+    from PIL import Image
+    raw = golden_npz("raw_subset.npz")
+    ref = golden_npz("ref_shipped.npz")
+    top5 = json.loads(str(ref["top5"]))
+    names = [str(n) for n in raw["names"]]
+    paths, sizes = [], set()
+    for j, n in enumerate(names):
+        p = str(tmp_path / (os.path.splitext(os.path.basename(n))[0] + ".png"))
+        Image.fromarray(raw[f"img{j}"]).save(p)
+        sizes.add(raw[f"img{j}"].shape[:2])
+        paths.append(p)
+    assert len(sizes) >= 8 and any(s != (224, 224) for s in sizes)        # the general resize path, not the identity
+    idx = [analyzer.files.index(n) for n in names]
+    for flt in (True, False):
+        res = analyzer.analyze_images_batch(paths, batch_size=4, filter_interiors=flt)
+        for p, i in zip(paths, idx):
+            _compare_result(res[p], _expected_from_reference(ref, top5, i, flt))
 
 
 def test_detector_matches_reference_on_all_images(analyzer):

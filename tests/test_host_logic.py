@@ -79,6 +79,30 @@ def test_text_tower_and_tokenizer_match_oracle(iic, product_cpu):
     assert abs(product_cpu[0].logit_scale.exp().item() - 100.0) < 1e-3
 
 
+def test_load_and_tokenize_refuse_silent_standins(iic, monkeypatch, tmp_path):
+    """a deployment without the checkpoint / BPE vocabulary must fail loudly, like the reference's clip.load /
+    clip.tokenize would, instead of serving classifications from random weights; a corrupt checkpoint propagates its error;
+    the stand-ins exist only behind an explicit opt-in (argument or environment variable set by tests and benches)."""
+    monkeypatch.delenv("IIC_ALLOW_RANDOM_INIT", raising=False)
+    monkeypatch.delenv("IIC_ALLOW_STANDIN_TOKENIZER", raising=False)
+    with pytest.raises(RuntimeError, match="not found"):
+        iic.load("ViT-B/16", device="cpu", download_root=str(tmp_path))
+    with pytest.raises(RuntimeError, match="BPE|clip"):
+        iic.tokenize(["salon"])
+    with pytest.warns(UserWarning, match="RANDOM"):
+        model, _ = iic.load("ViT-B/16", device="cpu", download_root=str(tmp_path), allow_random_init=True)
+    assert model.visual.proj.shape == (768, 512)
+    assert iic.tokenize(["salon"], allow_standin=True).shape == (1, 77)
+    (tmp_path / "ViT-B-16.pt").write_bytes(b"this is not a checkpoint")
+    with pytest.raises(Exception, match="checkpoint|pickle|load|archive|invalid"):
+        iic.load("ViT-B/16", device="cpu", download_root=str(tmp_path), allow_random_init=True)
+    # the one default operand dtype of engine, bench, smoke and tests
+    assert iic._lib.DEFAULT_OPERAND_DTYPE == "f16" and iic._lib.operand_dtype_name(None) == "f16"
+    assert iic._lib.operand_dtype_name(torch.bfloat16) == "bf16" and model.visual.operand_dtype == "f16"
+    with pytest.raises(ValueError):
+        iic._lib.operand_dtype_name("fp8")
+
+
 def test_label_schema_known_answers(iic):
     """interior_dataset.json schema: 151 entries / 150 files, group sizes 20/12/299/36/30."""
     data = golden_json("interior_dataset_fixture.json")["training_data"]
@@ -156,9 +180,21 @@ items = [f"interior{{i}}.jpg" for i in range(151)]
 mine = dp.shard(items, rank, world)
 local = [(p, len(p) * 7 % 13) for p in mine]                  # stand-in for per-image results
 allr = dp.gather_in_order(local)
+# trainers broadcast rank 0's LoRA parameters at construction (ranks initialise lora_A from different RNG states)
+train = import_module("ai-interior-image-classifier_b200.train")
+torch.manual_seed(100 + rank)
+ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+train._broadcast_lora(ps)
+chk = torch.cat([p.detach().reshape(-1) for p in ps]).double()
+both = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(both, chk)
+same_params = bool(torch.equal(both[0], both[1]))
+torch.manual_seed(100)
+want = torch.cat([torch.randn(5, 3).reshape(-1), torch.randn(7)]).double()
+same_params = same_params and bool(torch.equal(both[0], want))
 t = torch.tensor([10.0 + rank], dtype=torch.float64)          # bench.py: max over ranks of the step time
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-ok = [p for p, _ in allr] == items and t.item() == 11.0 and len(mine) in (75, 76)
+ok = [p for p, _ in allr] == items and t.item() == 11.0 and len(mine) in (75, 76) and same_params
 dist.barrier(); dist.destroy_process_group()
 print(json.dumps({{"rank": rank, "ok": bool(ok), "n": len(mine)}}))
 sys.exit(0 if ok else 1)

@@ -3,8 +3,11 @@ oracle/gen_golden.py from /root/reference/main.py on the repo's 150 dataset imag
 
 Bars (BASELINE.json north_star / BASELINE.md section 4):
     embedding cosine similarity >= 0.999
-    per-label logits (100 * cos, 437 labels) within 2e-2 absolute     <- bf16 tensor-core path vs fp32 CPU reference
+    per-label logits (100 * cos, 437 labels) within 2e-2 absolute     <- 16-bit tensor-core path vs fp32 CPU reference
     identical top-1 style and top-5 label sets on >= 99 % of images; identical detector decision
+These bars are asserted on the DEFAULT operand dtype - the one `Engine()`, `load()`, bench.py and smoke() run (fp16,
+_lib.DEFAULT_OPERAND_DTYPE).  bf16 is an explicit non-default arm (`operand_dtype="bf16"`): `test_bf16_arm_*` below runs it
+against what an 8-bit mantissa can deliver and records the numbers; it certifies nothing about the default path.
 
 Top-5 SETS and near ties.  The fixture's weights are seeded, not pretrained, so the 299 "characteristics" logits of an
 image are densely packed and rank 5 / rank 6 are often closer than the logit error itself (fp16: max 0.004).  Two
@@ -26,33 +29,32 @@ pytestmark = pytest.mark.gpu
 COS_BAR = 0.999
 LOGIT_BAR = 2e-2
 AGREE_BAR = 0.99
-STRICT_SETS = 0.95   # strict equality: near-tie flips allowed on at most 5 % of images (see module docstring)
-# bf16 operands (8-bit mantissa) cannot reach the 2e-2 max-norm logit bar on this fixture: rounding the GEMM A operands
-# alone costs 0.023 (tools/error_budget.py emulates it inside the fp32 oracle: ln 0.019, gelu 0.016, attn_out 0.011,
-# qkv 0.006, in quadrature 0.028; measured on the B200: max 0.029, p99.9 0.019, rms 0.007).  With near-tied random-weight
-# labels that also flips rank 5/6 in ~3 % of images.  The bf16 bars below are therefore the ones bf16 can meet; the
-# fp16-operand instantiation of the SAME kernels (upstream CLIP's own GPU dtype) is held to the north-star bars.
-BF16_LOGIT_MAX, BF16_LOGIT_P999, BF16_SETS = 4e-2, 3e-2, 0.95
+STRICT_SETS = 0.97   # strict set equality of all five groups, near-tie flips included (the 99 % bar is on the tie-aware count)
 
 
-@pytest.fixture(scope="module", params=["f16", "bf16"])
-def product(request, iic):
-    model, preprocess = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(),
-                                 operand_dtype=request.param)
-    model.mode = request.param
+@pytest.fixture(scope="module")
+def product(iic):
+    """the product exactly as a user gets it: no operand dtype named -> the default"""
+    model, preprocess = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict())
+    model.mode = iic._lib.operand_dtype_name(model.visual.operand_dtype)
+    assert model.mode == iic._lib.DEFAULT_OPERAND_DTYPE == "f16"
+    return model, preprocess
+
+
+@pytest.fixture(scope="module")
+def product_bf16(iic):
+    model, preprocess = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="bf16")
+    model.mode = "bf16"
     return model, preprocess
 
 
 def _check(mode, cos, dl, style, sets, det):
+    """north-star bars, no per-dtype exceptions"""
     sets, sets_tie = sets
     assert cos.min().item() >= COS_BAR
     assert style >= AGREE_BAR and det >= AGREE_BAR
-    if mode == "f16":
-        assert dl.max().item() <= LOGIT_BAR
-        assert sets_tie >= AGREE_BAR and sets >= STRICT_SETS
-    else:
-        assert dl.max().item() <= BF16_LOGIT_MAX and dl.flatten().quantile(0.999).item() <= BF16_LOGIT_P999
-        assert sets >= BF16_SETS - 0.05 and sets_tie >= BF16_SETS
+    assert dl.max().item() <= LOGIT_BAR
+    assert sets_tie >= AGREE_BAR and sets >= STRICT_SETS
 
 
 def _report(name, emb, emb_ref, logits, logits_ref):
@@ -220,3 +222,13 @@ def test_batch_invariance_and_determinism(product, iic):
     perm = torch.randperm(1024, device="cuda", generator=g)
     r2 = eng.classify_same_size(big[perm])
     assert torch.equal(r2.logits, l1[perm]) and torch.equal(r2.topk_idx, ti[idx][perm])
+
+
+def test_bf16_arm_dataset_parity(product_bf16, iic):
+    """NON-DEFAULT arm (operand_dtype="bf16"), recorded for comparison: an 8-bit mantissa on the GEMM A operands alone costs
+    ~0.026 on a 100 * cos logit (tools/error_budget.py emulates it inside the fp32 oracle: LayerNorm outputs 0.019, GELU
+    outputs 0.016, attention outputs 0.011, QKV 0.006), so this arm is held to what bf16 can deliver - embedding cosine and
+    top-1 / detector agreement at the north-star values, logits within 4e-2 - and NOT claimed to meet the 2e-2 logit bar."""
+    cos, dl, style, (sets, sets_tie), det = _run(product_bf16, iic, "ref_shipped.npz", vision_lora=False)
+    assert cos.min().item() >= COS_BAR and style >= AGREE_BAR and det >= AGREE_BAR
+    assert dl.max().item() <= 4e-2 and sets_tie >= 0.95

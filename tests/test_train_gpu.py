@@ -173,8 +173,12 @@ def test_gemm_training_epilogues(iic, engine, ctas, act):
     assert torch.allclose(du.float(), uf.grad, rtol=6e-3, atol=2e-3), (du.float() - uf.grad).abs().max()
 
 
+GRAD_BAR = 1e-2          # north star: LoRA gradients within 1e-2 relative - asserted on the default operand dtype
+BF16_ARM_GRAD_BAR = 3e-2  # explicit non-default arm: gradients evaluated at activations that carry the 8-bit forward error
+
+
 @pytest.mark.parametrize("rank", [4, 16])
-@pytest.mark.parametrize("mode", ["f16", "bf16"])
+@pytest.mark.parametrize("mode", ["default", "bf16_arm"])
 def test_lora_gradients_match_oracle_autograd(iic, mode, rank):
     """whole encoder, batch 8: d loss / d lora_{A,B} of every vision MLP vs CPU fp32 autograd through the oracle
     (rank 4: main.py's adapters, down-projections fused into LayerNorm / the c_fc epilogue; rank 16: train_lora.py's,
@@ -202,7 +206,8 @@ def test_lora_gradients_match_oracle_autograd(iic, mode, rank):
     loss_ref = (torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.cross_entropy(logits.t(), labels)) / 2
     loss_ref.backward()
     # ---- product ----
-    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype=mode)
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(),
+                        operand_dtype=None if mode == "default" else "bf16")
     iic.replace_linears_with_lora(model, rank=rank, alpha=2 * rank)
     src = {n: p for n, p in om.named_parameters() if "lora" in n}
     for n, p in model.named_parameters():
@@ -222,11 +227,11 @@ def test_lora_gradients_match_oracle_autograd(iic, mode, rank):
     by_layer = [max(v for k, v in errs.items() if f"resblocks.{i}." in k) for i in range(12)]
     print(f"\n[{mode} r={rank}] loss {loss.item():.5f} (ref {loss_ref.item():.5f}); worst LoRA-gradient relative error {worst:.2e} over "
           f"{len(lora)} tensors; per block: " + " ".join(f"{e:.1e}" for e in by_layer))
-    _dump(f"{mode}_r{rank}", {"loss": loss.item(), "loss_ref": loss_ref.item(), "worst_rel": worst, "per_block_worst_rel": by_layer})
-    # north star: LoRA gradients within 1e-2 relative.  fp16 operands (+ power-of-two loss scaling) are held to it (measured
-    # 2e-3).  With bf16 operands the gradient is evaluated at activations that already carry the 8-bit-mantissa forward
-    # error (every block, including the last, sits at ~1e-2: it is not an accumulation effect), measured worst 1.3e-2.
-    assert worst < (1e-2 if mode == "f16" else 2e-2), max(errs.items(), key=lambda kv: kv[1])
+    _dump(f"{'f16' if mode == 'default' else 'bf16'}_r{rank}", {"loss": loss.item(), "loss_ref": loss_ref.item(), "worst_rel": worst, "per_block_worst_rel": by_layer})
+    # north star: LoRA gradients within 1e-2 relative, asserted on the default dtype (fp16 operands + power-of-two loss
+    # scaling; measured 2e-3).  The explicit bf16 arm evaluates the gradient at activations that already carry the
+    # 8-bit-mantissa forward error (every block sits at ~1e-2: not an accumulation effect; measured worst 1.3e-2).
+    assert worst < (GRAD_BAR if mode == "default" else BF16_ARM_GRAD_BAR), max(errs.items(), key=lambda kv: kv[1])
     # out_proj LoRA parameters get no gradient (dead in the reference's forward, F4)
     assert all(named[n].grad is None for n in named if ".attn.out_proj.lora." in n)
 
@@ -243,7 +248,7 @@ def _text_tokens(B, seed):
 
 
 @pytest.mark.parametrize("rank", [4, 16])
-@pytest.mark.parametrize("mode", ["f16", "bf16"])
+@pytest.mark.parametrize("mode", ["default", "bf16_arm"])
 def test_text_lora_gradients_match_oracle_autograd(iic, mode, rank):
     """train_lora.py's own step (text tower through LoRA, image features fixed): d loss / d lora_{A,B} of every text MLP
     vs CPU fp32 autograd through the oracle - causal attention backward, sequence forward / backward of the engine"""
@@ -270,7 +275,8 @@ def test_text_lora_gradients_match_oracle_autograd(iic, mode, rank):
     labels = torch.arange(B)
     loss_ref = (torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.cross_entropy(logits.t(), labels)) / 2
     loss_ref.backward()
-    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype=mode)
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(),
+                        operand_dtype=None if mode == "default" else "bf16")
     iic.replace_linears_with_lora(model, rank=rank, alpha=2 * rank)
     src = {n: p for n, p in om.named_parameters() if "lora" in n}
     for n, p in model.named_parameters():
@@ -285,10 +291,10 @@ def test_text_lora_gradients_match_oracle_autograd(iic, mode, rank):
     worst = max(errs.values())
     print(f"\n[text {mode} r={rank}] loss {loss.item():.5f} (ref {loss_ref.item():.5f}); worst text-LoRA gradient relative error {worst:.2e} "
           f"over {len(lora)} tensors")
-    _dump(f"text_{mode}_r{rank}", {"loss": loss.item(), "loss_ref": loss_ref.item(), "worst_rel": worst})
-    # fp16 operands are held to the north star's 1e-2; bf16 operands carry the 8-bit-mantissa forward error into every block's
-    # gradient (vision tower: 1.3e-2; the 77-token text tower with its near-uniform initial loss: 2.0e-2 measured)
-    assert worst < (1e-2 if mode == "f16" else 3e-2), max(errs.items(), key=lambda kv: kv[1])
+    _dump(f"text_{'f16' if mode == 'default' else 'bf16'}_r{rank}", {"loss": loss.item(), "loss_ref": loss_ref.item(), "worst_rel": worst})
+    # the default dtype is held to the north star's 1e-2; the explicit bf16 arm carries the 8-bit-mantissa forward error into
+    # every block's gradient (vision tower: 1.3e-2; the 77-token text tower with its near-uniform initial loss: 2.0e-2)
+    assert worst < (GRAD_BAR if mode == "default" else BF16_ARM_GRAD_BAR), max(errs.items(), key=lambda kv: kv[1])
     # a second call reproduces the gradients bit for bit, and the inference path still agrees with the trained parameters
     g1 = {n: named[n].grad.clone() for n in lora}
     trainer.forward_backward(img.cuda(), tokens.cuda())
@@ -301,7 +307,7 @@ def test_text_training_step_reduces_loss(iic):
     tokens = _text_tokens(B, seed=8).cuda()
     g = torch.Generator().manual_seed(9)
     img = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).cuda()
-    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="bf16")
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict())
     iic.replace_linears_with_lora(model, rank=16, alpha=32)
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
     trainer = iic.TextLoRATrainer(model, lr=1e-3)
@@ -325,7 +331,7 @@ def test_training_step_reduces_loss(iic):
     B = 8
     crops = torch.from_numpy(golden_npz("crops_u8.npz")["crops"][:B]).cuda()
     text = torch.from_numpy(golden_npz("text_features.npz")["text"][40:40 + B]).cuda()
-    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict(), operand_dtype="bf16")
+    model, _ = iic.load("ViT-B/16", device="cuda", state_dict=oracle_state_dict())
     iic.replace_linears_with_lora(model, rank=4, alpha=8)            # fresh LoRA: lora_B == 0 (main.py:27)
     frozen = {n: p.detach().clone() for n, p in model.named_parameters() if "lora" not in n and n.startswith("visual.")}
     trainer = iic.VisionLoRATrainer(model, lr=1e-3, logit_scale=100.0)
