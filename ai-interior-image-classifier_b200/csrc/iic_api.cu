@@ -101,7 +101,8 @@ struct iic_handle {
   std::string err;
   const void* conv_w = nullptr;
   int f16 = 0;  // 16-bit operand format of activations and matmul weights: 0 = bf16, 1 = fp16
-  int attn_impl = 0;  // 0 auto (tcgen05 kernel inside its envelope), 1 mma.sync kernel, 2 tcgen05 kernel
+  int attn_impl = 0;  // 0 auto (whole-row tcgen05 kernel for T <= 208 unmasked, else the block-wise tcgen05 kernel inside its
+                      // envelope), 1 mma.sync kernel, 2 block-wise tcgen05 kernel, 3 whole-row tcgen05 kernel (IIC_ATTN_IMPL)
   int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
@@ -169,6 +170,12 @@ bool check_ready(iic_handle* h) {
 // lse (nullable): log2-domain log-sum-exp per (image, head, query), kept by the training forward for the backward pass.
 int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, int T, int H, int hd, int impl, cudaStream_t s) {
   if (impl == 0) impl = h->attn_impl;
+  // impl: 0 auto, 1 mma.sync kernel, 2 block-wise tcgen05 kernel (online softmax), 3 whole-row tcgen05 kernel (T <= 208, no mask)
+  if ((impl == 0 || impl == 3) && !h->cfg.causal) {
+    int rc = launch_attention_row_sm100(qkv, out, lse, B, T, H, hd, h->f16, h->num_sms, s);
+    if (rc != -3 || impl == 3) return rc == -3 ? -1 : rc;
+  }
+  if (impl == 3) return -1;
   if (impl != 1) {
     int rc = launch_attention_sm100(qkv, out, lse, B, T, H, hd, h->f16, h->cfg.causal != 0, h->num_sms, s);
     if (rc != -3 || impl == 2) return rc == -3 ? -1 : rc;

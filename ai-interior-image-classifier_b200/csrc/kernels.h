@@ -48,6 +48,10 @@ int launch_attention(const void* qkv, void* out, float* lse, int B, int T, int H
 // returns -3 if the shape is outside its envelope
 int launch_attention_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, bool causal,
                            int num_sms, cudaStream_t stream);
+// whole-row tcgen05 kernel for short, unmasked sequences (attention_row_sm100.cu): T <= 208, head_dim 64; the score row of a
+// query is complete in TMEM before the softmax reads it (exact maximum, no online rescale).  Returns -3 outside its envelope.
+int launch_attention_row_sm100(const void* qkv, void* out, float* lse, int B, int T, int H, int head_dim, int f16, int num_sms,
+                               cudaStream_t stream);
 // dqkv[M, 3d] (16-bit) from d_out[M, d], the saved qkv / out / lse.  T <= 432 (everything of one head lives in smem).
 int launch_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int T,
                          int H, int head_dim, int f16, cudaStream_t stream);

@@ -731,7 +731,8 @@ class Engine:
         return p
 
     def op_attention(self, qkv: torch.Tensor, B: int, T: int, heads: int, impl: int = 0) -> torch.Tensor:
-        """impl: 0 = encoder default, 1 = mma.sync kernel, 2 = tcgen05 kernel (T <= ~760)"""
+        """impl: 0 = encoder default, 1 = mma.sync kernel, 2 = block-wise tcgen05 kernel (T <= ~760), 3 = whole-row tcgen05 kernel
+        (unmasked, T <= 208)"""
         out = torch.empty(B * T, heads * 64, dtype=self.op_dtype, device=self.device)
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_attention(self.h, qkv.data_ptr(), out.data_ptr(), B, T, heads, impl,

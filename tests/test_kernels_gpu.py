@@ -210,6 +210,51 @@ def test_attention(engine, T, B, H, impl):
     assert _rel(out.float(), ref) < 8e-3
 
 
+@pytest.mark.parametrize("mode", ["bf16", "f16"])
+@pytest.mark.parametrize("T,B,H", [(197, 3, 12), (197, 40, 12), (197, 1024, 12), (193, 2, 12), (192, 6, 12), (129, 5, 12), (128, 7, 12), (50, 2, 12),
+                                   (16, 1, 12), (1, 2, 12), (77, 9, 8), (208, 3, 4), (145, 13, 12), (177, 150, 12)])
+def test_attention_whole_row(engine, engine_f16, mode, T, B, H):
+    """whole-row tcgen05 kernel (attention_row_sm100.cu, impl 3; the encoder's default for unmasked T <= 208): one / two query
+    tiles, odd and even unit counts, padding keys in the last unit, single-unit rows, batches that make every SM walk many
+    items; against fp32 SDPA on the same 16-bit operands.  The large batch is the BASELINE configs[2] shape."""
+    eng = engine if mode == "bf16" else engine_f16
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(60 + T)
+    qkv = (torch.randn(B * T, 3 * d, device="cuda", generator=g) * 1.5).to(eng.op_dtype)
+    out = eng.op_attention(qkv, B, T, H, impl=3)
+    ref = torch.empty(B * T, d, device="cuda")
+    for b0 in range(0, B, 64):      # chunked: the fp32 reference of 1024 images would need 6 GB of scores
+        b1 = min(B, b0 + 64)
+        q, k, v = qkv[b0 * T:b1 * T].float().view(b1 - b0, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+        ref[b0 * T:b1 * T] = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape((b1 - b0) * T, d)
+    assert torch.isfinite(out.float()).all()
+    assert torch.allclose(out.float(), ref, rtol=2 ** -6, atol=2e-2), (out.float() - ref).abs().max()
+    assert _rel(out.float(), ref) < (8e-3 if mode == "bf16" else 1.5e-3)
+    # a second launch gives the same bits, and the default dispatch (impl 0) picks this kernel for unmasked T <= 208
+    assert torch.equal(out, eng.op_attention(qkv, B, T, H, impl=3)) and torch.equal(out, eng.op_attention(qkv, B, T, H, impl=0))
+
+
+def test_attention_whole_row_extreme_scores(engine_f16):
+    """rows whose scores span hundreds of units (exact maximum: no rescale path to get wrong), rows that are constant, and one
+    dominant key per row: p must stay finite and normalised"""
+    eng = engine_f16
+    B, T, H = 2, 197, 12
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(16)
+    qkv = torch.randn(B, T, 3, H, 64, device="cuda", generator=g)
+    ramp = torch.arange(T, device="cuda", dtype=torch.float32)
+    qkv[:, :, 0, :, 0] = 4.0
+    qkv[:, :, 1, 0::3, 0] = (0.5 * ramp)[None, :, None]                    # steadily rising scores (max at the last key)
+    qkv[:, :, 1, 1::3, 0] = (-0.5 * ramp)[None, :, None]                   # falling: max at key 0
+    qkv[:, :, 1, 2::3, :] = 0.0                                            # all scores equal: uniform attention
+    qkv = qkv.reshape(B * T, 3 * d).to(torch.float16)
+    out = eng.op_attention(qkv, B, T, H, impl=3)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert torch.isfinite(out.float()).all()
+    assert torch.allclose(out.float(), ref, rtol=2 ** -8, atol=4e-3), (out.float() - ref).abs().max()
+
+
 @pytest.mark.parametrize("T,B,H", [(197, 2, 12), (577, 1, 16)])
 def test_attention_rising_scores(engine, T, B, H):
     """Scores that grow along the key axis force the tcgen05 kernel's running maximum to move in every key block

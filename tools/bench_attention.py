@@ -13,10 +13,10 @@ def _timeit(fn, warmup, iters):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
 eng = iic_b200.Engine(iic_b200.VIT_B_16, "cuda:0")
-impls = [(1, "mma.sync"), (2, "tcgen05")]
+impls = [(1, "mma.sync"), (2, "tcgen05-blocks"), (3, "tcgen05-row")]
 if len(sys.argv) > 1: impls = [i for i in impls if str(i[0]) in sys.argv[1:]]
 for B, T, H in ((1024, 197, 12), (256, 577, 16)):
-    qkv = torch.randn(B * T, 3 * H * 64, device="cuda").bfloat16()
+    qkv = torch.randn(B * T, 3 * H * 64, device="cuda").to(eng.op_dtype)
     for impl, name in impls:
         try:
             t = timeit(lambda: eng.op_attention(qkv, B, T, H, impl=impl))
