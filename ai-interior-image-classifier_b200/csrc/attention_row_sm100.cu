@@ -4,30 +4,43 @@
 //   ResidualAttentionBlock, reached through model.encode_image at /root/reference/main.py:204, 444, 503]
 //
 // One persistent CTA per SM walks (image, head) items; K and V of two items are resident in 128B-swizzled smem.  Queries form
-// 128-row tiles; tile j of the CTA goes to one of two TMEM REGIONS (256 columns each) and its softmax GROUP:
+// 128-row tiles; the two tiles of a 197-token item go to the two TMEM REGIONS (256 columns each), each served by its own
+// softmax GROUP of 8 warps and its own MMA issuer warp:
 //
 //   S = Q K^T              ONE tcgen05.mma chain (4 k-steps, N = all keys rounded up to 16: 208 at T = 197) into region
 //                          columns [0, N): the score row of a query is complete in TMEM before the softmax touches it.
-//   softmax                exact row maximum first (pass 1: tcgen05.ld + FMNMX3, nothing else), then p = exp2(s*c - m*c)
-//                          (pass 2) - no online rescale, no speculative exponentials, no redo path.  TWO threads per query
-//                          row (column halves A / B, in different warps of the same TMEM lane quadrant): 16 softmax warps =
-//                          4 per scheduler, so TMEM / MUFU latencies hide behind other warps instead of behind 80-element
-//                          register blocks (96-104 registers per thread).  The halves meet twice per TILE (row
-//                          maximum through smem + a 64-thread named barrier; row sum through smem, read in the epilogue).
-//                          P (16 bit) is written IN PLACE over the S columns its own thread has already consumed:
-//                          half A -> columns [0, 8 ua), half B -> [16 ua, 16 ua + 8 ub)   (ua / ub = 16-key units per half).
+//   softmax                exact row maximum first (pass 1), then p = exp2(s*c - m*c) (pass 2): no online rescale, no
+//                          speculative exponentials, no redo path.  TWO threads per query row (column halves A / B, in
+//                          different warps of the same TMEM lane quadrant): 16 softmax warps = 4 per scheduler.  Every
+//                          tcgen05.wait::ld costs ~100+ cycles, so a half reads its scores in three loads per tile: its
+//                          lower <= 4 units (pass 1), its top <= 3 units (pass 1; they stay in registers for pass 2), the
+//                          lower units again (pass 2).  The halves meet through smem + a 64-thread named barrier (row
+//                          maximum, then row sum).  P (16 bit) is written IN PLACE: P(u) into the first 8 columns of unit u's
+//                          own S columns, except unit 12, whose columns are O's: into the second half of unit 11's.
 //   O = P V                tcgen05.mma with A = P from TMEM (one k-step per 16 keys), B = V in its natural [key][dim]
 //                          layout (MN-major), accumulator in region columns [192, 256) - S columns that are dead by then.
-//   epilogue               O row * 1 / sum -> 16 bit -> global (each half stores 32 of the 64 dims); optional log2-domain
-//                          LSE for the backward pass.
+//                          Each half releases its P in two chunks (top units, lower units); half B's first chunk holds unit
+//                          12, so the first MMA (which overwrites O's columns) waits for it.
+//   epilogue               O row * 1 / sum -> 16 bit -> 64B-swizzled smem slab -> ONE TMA store per warp (32 rows x 32 dims;
+//                          rows >= T are clipped by the [B][T][d] tensor map); optional log2-domain LSE for the backward pass.
 //
-//   warp 0  TMA producer (K, V per item; Q tile per group)     warp 1 / 2  MMA issuer of group 0 / 1 (blocking waits:
-//   no polling loops competing for issue slots)     warp 2 also owns the TMEM allocation     warps 4-19  softmax:
-//   (warp - 4) & 3 = lane quadrant, bit 2 = group, bit 3 = column half.
+//   warp 0  TMA producer (K, V per item; Q tile per group)     warp 1 / 2  MMA issuer of group 0 / 1     warp 2 also owns
+//   the TMEM allocation     warps 4-19  softmax: (warp - 4) & 3 = lane quadrant, bit 2 = group, bit 3 = column half.
 //
-// The MUFU pipe (16 ex2 / clk / SM) bounds the kernel: a quarter of the exponentials run as a degree-3 polynomial on the
-// FMA pipe (same scheme and constants as attention_sm100.cu).  Longer sequences (ViT-L/14 @ 336: 577 keys) and the causal
-// text tower stay on attention_sm100.cu (online softmax over 80-key blocks).  All waits are bounded (trap, never hang).
+// Measured at B = 1024, T = 197, H = 12 (12288 items, 83 per SM): 0.357 ms against 0.423 ms for the block-wise kernel
+// (attention_sm100.cu).  Floors of the launch: HBM 1.24 GB = 0.19 ms; MUFU 0.12-0.16 ms; tensor pipe ~0.16 ms (S 4 x ~130 clk
+// + P.V 13 x 58-77 clk per tile: consecutive MMAs into one accumulator serialise).  Ablations on the same box
+// (tools/build_variant.sh): TMA loads + barriers only 0.140 ms (the HBM read floor), + both MMA chains 0.204, exponentials
+// +0.045, pass 1 + exchange +0.04.  What bounds it is the serial chain of a tile (S -> pass 1 -> pass 2 -> P.V -> epilogue,
+// ~8000 clk per item with ~100-250 clk per hop) and issue slots, not a pipe: running a share of the exponentials as a
+// polynomial on the FMA pipe (the block-wise kernel's trick) makes it SLOWER here (0.383 / 0.398 / 0.408 ms for 2 / 3 / 4 of 8
+// pairs).  Tried and dropped, each measured: one thread per row x two passes of x16 double-buffered loads (0.387); all 16
+// warps on one tile with four threads per row, scores read once and kept in registers, the previous tile's epilogue deferred
+// into the next tile's body (0.411 - every phase runs in lock-step and nothing fills the gaps); two O accumulators for
+// alternating units, densely packed P, two-stage release (0.48-0.56); the MMA issuer on the scheduler of the mostly idle lane
+// quadrant 3 (no change); a staggered start of the two groups (no change); mbarrier.try_wait with a suspend hint (no change,
+// kept: fewer polling instructions).  Longer sequences (ViT-L/14 @ 336: 577 keys) and the causal text tower stay on
+// attention_sm100.cu (online softmax over 80-key blocks).  All waits are bounded (trap, never hang).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -117,7 +130,9 @@ __device__ __forceinline__ float ex2f(float x) {
   return r;
 }
 #ifndef IIC_ATTN_ROW_POLY_MASK
-#define IIC_ATTN_ROW_POLY_MASK 0x24   // pairs 2 and 5 of the 8 pairs of a 16-column unit run on the FMA pipe
+#define IIC_ATTN_ROW_POLY_MASK 0x00   // bit e: pair e of the 8 pairs of a 16-column unit runs its exponentials as a polynomial on the FMA
+                                      // pipe.  Measured at B = 1024, T = 197: 0x00 0.357 ms, 0x24 (2 of 8) 0.383, 0x94 (3 of 8) 0.398,
+                                      // 0x55 (4 of 8) 0.408 - this kernel is bound by issue slots and latency, not by the MUFU pipe
 #endif
 
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
@@ -200,9 +215,6 @@ __device__ __forceinline__ void exp_unit(const uint32_t* v, uint32_t* pk, uint64
   for (int e = 0; e < 8; ++e) {
     const uint64_t xx = ffma2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), c2, nm2);
     float e0, e1;
-#ifdef ABL_NO_EXP
-    upk2(xx, e0, e1);
-#else
     if ((IIC_ATTN_ROW_POLY_MASK >> e) & 1) {
       ex2_poly_pair(xx, e0, e1);
     } else {
@@ -211,7 +223,6 @@ __device__ __forceinline__ void exp_unit(const uint32_t* v, uint32_t* pk, uint64
       e0 = ex2f(x0);
       e1 = ex2f(x1);
     }
-#endif
     if (e & 1) acc1 = fadd2(acc1, pk2(e0, e1)); else acc0 = fadd2(acc0, pk2(e0, e1));
     pk[e] = Act<kF16>::pack(e0, e1);
   }
@@ -344,11 +355,9 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         if (ptx::elect_one()) {
           const uint64_t dq = ptx::make_kmajor_sw128_desc(q_s + uint32_t(g) * kQTileBytes);
           const uint64_t dk = ptx::make_kmajor_sw128_desc(ks);
-#ifndef ABL_NO_S
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             ptx::umma_f16<1>(region, dq + uint64_t(2 * kk), dk + uint64_t(2 * kk), id_s, kk != 0 ? 1u : 0u);
-#endif
           ptx::umma_commit<1>(s_full(g));
           ptx::umma_commit<1>(q_empty(g));
         }
@@ -372,11 +381,7 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
           const int count = ch ? hi_h - lo_h - keep_h : keep_h;
           ptx::mbar_wait(p_done(g, hf, ch), par);
           ptx::tcgen05_fence_after();
-#ifdef ABL_NO_PV
-          if (false) {
-#else
           if (ptx::elect_one()) {
-#endif
             for (int k = 0; k < count; ++k) {
               const int u = ch ? lo_h + k : hi_h - 1 - k;
               const uint32_t pa = region + uint32_t(u == 12 ? 16 * 11 + 8 : 16 * u);
@@ -444,29 +449,17 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       uint32_t kv[48];
       float m = -INFINITY;
       uint64_t acc0 = 0ull, acc1 = 0ull;
-#ifdef ABL_NO_PASS1
-      if (false) {
-#else
       if (live && my_units > 0) {
-#endif
         // ---- pass 1: exact row maximum of this half ----
         if (n_rest > 0) {
           uint32_t rv[64];
 #pragma unroll
-#ifdef ABL_P1_NOLOAD
-          for (int j = 0; j < 64; ++j) rv[j] = uint32_t(j + lane);
-#else
           for (int j = 0; j < 4; ++j)   // unconditional loads (slots past n_rest re-read the last unit): the array stays in registers
             ld16(region + uint32_t(16 * (lo + (j < n_rest ? j : n_rest - 1))), rv + 16 * j);
           ptx::tmem_ld_wait();
-#endif
           TRACE(2);
-#ifdef ABL_P1_NOMAX
-          m = __uint_as_float(rv[0] ^ rv[17] ^ rv[35] ^ rv[50]);
-#else
 #pragma unroll
           for (int j = 0; j < 4; ++j) m = max_regs<16>(rv + 16 * j, m);
-#endif
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i)     // slots past n_keep re-read the lowest kept unit
@@ -481,11 +474,9 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       }
       xchg[((0 * 2 + int(par)) * 2 + g) * 256 + half * 128 + r] = m;
       TRACE(4);
-#ifndef ABL_P1_NOXCHG
       named_barrier(bar_id, 64);
       TRACE(5);
       m = fmaxf(m, xchg[((0 * 2 + int(par)) * 2 + g) * 256 + (half ^ 1) * 128 + r]);
-#endif
       // ---- pass 2: exponentials, P in place, two releases per half (kept set, rest set) to the P.V issuer ----
       if (live && my_units > 0) {
         // P(u) goes into the first 8 columns of the unit's own S columns; unit 12 (whose columns are O's) into the second half
@@ -546,11 +537,7 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
       // ---- epilogue: this half's 32 of the 64 output dims -> swizzled smem slab -> one TMA store per warp ----
       ptx::mbar_wait(o_full(g), par);
       ptx::tcgen05_fence_after();
-#ifdef ABL_NO_EPI
-      if (false) {
-#else
       if (live) {
-#endif
         uint32_t o[32];
         ld32(region + uint32_t(kOCol + 32 * half), o);
         ptx::tmem_ld_wait();
