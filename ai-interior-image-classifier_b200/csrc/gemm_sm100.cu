@@ -92,8 +92,6 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
   switch (epi) {
     case kEpiActGradBf16: return launch_one<kCtas, 256, kEpiActGradBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasActDualBf16: return launch_one<kCtas, 256, kEpiBiasActDualBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
-    case kEpiBiasResF32Ln: return launch_one<kCtas, 256, kEpiBiasResF32Ln, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
-    case kEpiBiasResF32LnDeepK: return launch_one<kCtas, 256, kEpiBiasResF32LnDeepK, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasBf16: return launch_one<kCtas, 256, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasGeluBf16: return launch_one<kCtas, 256, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasResF32: return launch_one<kCtas, 256, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
@@ -105,11 +103,6 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 }  // namespace
-
-size_t gemm_ln_scratch_bytes(int M, int N) {
-  const size_t m_pad = (size_t(M) + 255) / 256 * 256;   // covers 128- and 256-row tiles
-  return ((m_pad / 128) * sizeof(int) + 1023) / 1024 * 1024 + size_t((N + 255) / 256) * m_pad * sizeof(float2);
-}
 
 size_t gemm_smem_bytes(int ctas) {
   return ctas == 2 ? GemmSmem<2, 256, kEpiBiasBf16>::kTotal : GemmSmem<1, 256, kEpiBiasBf16>::kTotal;
@@ -125,8 +118,8 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     if (err) *err = e_shape;
     return -1;
   }
-  // 5-7 are variants the launcher selects itself (deep-K ring, fused LayerNorm): not valid as a request
-  if (p.epilogue < 0 || p.epilogue > kEpiBiasActDualBf16 || (p.epilogue >= kEpiBiasResF32DeepK && p.epilogue <= kEpiBiasResF32LnDeepK)) {
+  // 5 is a variant the launcher selects itself (deep-K ring); 6 and 7 are retired: not valid as a request
+  if (p.epilogue < 0 || p.epilogue > kEpiBiasActDualBf16 || (p.epilogue >= kEpiBiasResF32DeepK && p.epilogue < kEpiActGradBf16)) {
     if (err) *err = "gemm: unknown epilogue";
     return -1;
   }
@@ -164,19 +157,10 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     if (p.residual == nullptr) ok = false;
     else ok = make_tile_map_kind(&tres, p.residual, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f16 ? 1 : 0);
   }
-  const bool ln = p.ln_out != nullptr;
-  CUtensorMap tln = ta;
+  CUtensorMap tln = ta;   // second output (kEpiBiasActDualBf16: the kept pre-activation)
   if (ok && p.epilogue == kEpiBiasActDualBf16) {
     if (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 15) != 0) ok = false;
     else ok = make_tile_map_kind(&tln, p.out2, uint64_t(p.M), uint64_t(p.N), uint64_t(p.ldc), kBlockM, f16 ? 1 : 0);
-  }
-  if (ln) {
-    static const char* e_ln = "gemm: fused LayerNorm needs the fp32 residual epilogue, N % 256 == 0 (<= 2048), gamma/beta and ln_scratch";
-    if (p.epilogue != kEpiBiasResF32 || p.N % 256 != 0 || p.N > 2048 || p.ln_gamma == nullptr || p.ln_beta == nullptr || p.ln_scratch == nullptr) {
-      if (err) *err = e_ln;
-      return -1;
-    }
-    ok = ok && make_tile_map_kind(&tln, p.ln_out, uint64_t(p.M), uint64_t(p.N), uint64_t(p.N), kBlockM, f16 ? 1 : 0);
   }
   if (!ok) {
     if (err) *err = e_map;
@@ -194,29 +178,10 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   args.group = p.group > 0 ? p.group : 1;
   args.down_a = p.down_a;
   args.down_part = p.down_part;
-  args.ln_gamma = p.ln_gamma;
-  args.ln_beta = p.ln_beta;
-  args.ln_eps = p.ln_eps;
-  args.ln_out = p.ln_out;
-  args.ln_part = nullptr;
-  args.ln_cnt = nullptr;
-  args.ln_mpad = 0;
-  if (ln) {
-    // [counters: one per 128-row block][(mean, M2) partials: N/256 x rows padded to whole 256-row tiles]
-    const int m_tiles = (p.M + kBlockM * ctas - 1) / (kBlockM * ctas);
-    const size_t cnt_bytes = (size_t(m_tiles) * ctas * sizeof(int) + 1023) & ~size_t(1023);
-    args.ln_cnt = static_cast<int*>(p.ln_scratch);
-    args.ln_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(p.ln_scratch) + cnt_bytes);
-    args.ln_mpad = m_tiles * kBlockM * ctas;
-    if (cudaMemsetAsync(args.ln_cnt, 0, cnt_bytes, stream) != cudaSuccess) {
-      if (err) *err = e_launch;
-      return -2;
-    }
-  }
   // long reductions get the deep-ring variant of the residual epilogue (measured: c_proj 1268 -> 1322 TFLOP/s; the short-K
   // out_proj is bound by its fp32 residual traffic and prefers the 4-slab residual ring)
   const bool deep = p.epilogue == kEpiBiasResF32 && p.K >= 2048;
-  const int epi = ln ? int(deep ? kEpiBiasResF32LnDeepK : kEpiBiasResF32Ln) : (deep ? int(kEpiBiasResF32DeepK) : p.epilogue);
+  const int epi = deep ? int(kEpiBiasResF32DeepK) : p.epilogue;
   int rc;
   if (f16)
     rc = ctas == 2 ? dispatch_epi<2, true>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)

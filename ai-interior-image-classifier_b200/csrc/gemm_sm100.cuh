@@ -45,16 +45,8 @@ enum GemmEpilogue : int {
   kEpiGeluExactBf16 = 4, // out 16-bit = gelu_erf(acc + bias)              (non-OpenAI checkpoints)
   kEpiBiasResF32DeepK = 5,  // kEpiBiasResF32 with a deeper operand ring and a shorter residual ring: chosen by the
                             // launcher for long reductions (K >= 2048: mlp.c_proj), where TMA look-ahead matters more
-  // kEpiBiasResF32 + the LayerNorm that consumes the new residual stream (ln_2 after attn.out_proj, the next block's ln_1
-  // after mlp.c_proj) in the same launch.  Tile schedule unchanged.  The
-  // accumulate group gathers per-row (mean, M2) of its 256 columns while acc + bias + residual passes through its registers
-  // and publishes them to global memory (counter per 128-row block, release/acquire); the otherwise idle second epilogue
-  // group waits until all column tiles of its row block have published and its own tile's TMA stores are complete, combines
-  // the partial statistics (Chan), re-reads its tile from L2 by TMA, normalises and writes the 16-bit LayerNorm output: the
-  // LayerNorm costs no HBM read of the residual stream and no launch.  OPT-IN (IIC_FUSE_LN=1): measured on the B200 the fused
-  // c_proj is 0.83 ms against 0.74 + 0.14 ms, but the power-capped step does not get faster; history and numbers in DESIGN.md.
-  kEpiBiasResF32Ln = 6,
-  kEpiBiasResF32LnDeepK = 7,
+  // (6, 7: the LayerNorm fused behind the residual GEMM - built in three versions in round 1, parity-tested, measured, never a
+  // win on the power-capped step, removed in round 2; history in DESIGN.md)
   // training: out 16-bit = acc * act'(u), u = the forward's pre-activation tile, TMA-loaded (16-bit, through tm_res) into the
   // staging slab ahead of the epilogue: dU = (dY . W2 + dP2 . A2^T) o act'(U) without a round trip of dH through HBM.
   // GemmArgs.group = activation (1 QuickGELU, 2 erf GELU).
@@ -77,14 +69,6 @@ struct GemmArgs {
   // activation epilogues: per-tile partial of the consumer's LoRA down-projection, part[n_blk][row][0..3] (see kernels.h)
   const float* down_a;
   float* down_part;
-  // fused LayerNorm of the output rows (kEpiBiasResF32Ln*): y = (x - mean) * rstd * gamma + beta over all N columns
-  const float* ln_gamma;
-  const float* ln_beta;
-  float ln_eps;
-  void* ln_out;             // 16-bit [M, N] (pitch N)
-  float2* ln_part;          // [n_tiles][ln_mpad]: (mean, M2) of each row over the tile's columns
-  int* ln_cnt;              // [m_tiles * kCtas], zeroed before the launch: column tiles of the 128-row block published so far
-  int ln_mpad;
 };
 
 constexpr int kBlockM = 128;  // rows per CTA (TMEM lanes)
@@ -94,9 +78,8 @@ constexpr int kSlabBytes = kBlockM * 128;  // epilogue staging slab: 128 rows x 
 
 template <int kCtas, int kBlockN, int kEpi>
 struct GemmSmem {
-  static constexpr bool kLn = kEpi == kEpiBiasResF32Ln || kEpi == kEpiBiasResF32LnDeepK;
-  static constexpr bool kDeepK = kEpi == kEpiBiasResF32DeepK || kEpi == kEpiBiasResF32LnDeepK;
-  static constexpr bool kResidual = kEpi == kEpiBiasResF32 || kEpi == kEpiBiasResF32DeepK || kLn;
+  static constexpr bool kDeepK = kEpi == kEpiBiasResF32DeepK;
+  static constexpr bool kResidual = kEpi == kEpiBiasResF32 || kEpi == kEpiBiasResF32DeepK;
   static constexpr bool kActGrad = kEpi == kEpiActGradBf16;
   static constexpr bool kDual = kEpi == kEpiBiasActDualBf16;
   static constexpr bool kSlabLoad = kResidual || kActGrad;   // warp 3 TMA-loads a tile of a second input into the staging slabs
@@ -111,18 +94,16 @@ struct GemmSmem {
   static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect || kActGrad || kDual) ? 2 : 1;
   static constexpr int kSlabs =   // staging ring depth
       kDirect ? 0 : (kResidual ? (kDeepK ? 3 : 4) : ((kActGrad || kDual) ? 4 : 2));
-  // fused LayerNorm tail: fp32 input slabs (re-read of the stored rows) and one 16-bit output slab
-  static constexpr int kLnSlabs = 0;   // the LayerNorm group re-reads its tile with plain (L2) loads into registers
   static constexpr int kBufPerGroup = kDirect ? 1 : kSlabs / kGroups;
   static constexpr int kRingBudget =
       (kDeepK ? 208 : 192) * 1024 - kSlabs * kSlabBytes;
   static constexpr int kStages = kRingBudget / kStageBytes;  // 2 CTA: 6 / 5 / 4;  1 CTA: 4 / 3 / 2 ... see static_assert
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * kBlockN;  // 512 when kBlockN = 256
-  static constexpr int kBarBytes = kLn ? 2048 : 1024;   // LN: + the (scale, shift) of the tile's 128 rows
+  static constexpr int kBarBytes = 1024;
   // consumer LoRA-A slice of the current tile [kBlockN][4] fp32 + the tile's bias slice [kBlockN] fp32 (activation epilogues)
   static constexpr int kDownBytes = kBlockN * 20;
-  static constexpr int kTotal = kStages * kStageBytes + (kSlabs + kLnSlabs) * kSlabBytes + kBarBytes + kDownBytes +
+  static constexpr int kTotal = kStages * kStageBytes + kSlabs * kSlabBytes + kBarBytes + kDownBytes +
                                 1024 /*alignment slack*/;
   static_assert(kStages >= 2, "smem ring too shallow");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
@@ -152,14 +133,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_al, const __grid_constant__ CUtensorMap tm_bl,
                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
-                    const __grid_constant__ CUtensorMap tm_ln, const GemmArgs args) {
+                    const __grid_constant__ CUtensorMap tm_out2, const GemmArgs args) {
   using S = GemmSmem<kCtas, kBlockN, kEpi>;
   constexpr int kStages = S::kStages;
   constexpr int kSlabs = S::kSlabs;
   constexpr int kTileM = kBlockM * kCtas;
   constexpr bool kResidual = S::kResidual;
   constexpr bool kDirect = S::kDirect;
-  constexpr bool kLn = S::kLn;
   constexpr bool kActGrad = S::kActGrad;
   constexpr bool kDual = S::kDual;
   constexpr bool kAct = kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDual;
@@ -171,7 +151,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t slab_base = smem_base + kStages * S::kStageBytes;
-  const uint32_t bar_base = slab_base + (kSlabs + S::kLnSlabs) * kSlabBytes;
+  const uint32_t bar_base = slab_base + kSlabs * kSlabBytes;
   auto smem_a = [&](int s) { return smem_base + s * S::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * S::kStageBytes + S::kABytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -182,10 +162,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 * S::kAccStages + 4 + b); };
   constexpr int kTmemSlotOff = 8 * (2 * kStages + 2 * S::kAccStages + 12);
   const uint32_t tmem_slot = bar_base + kTmemSlotOff;
-  uint8_t* bar_gen = smem_gen + kStages * S::kStageBytes + (kSlabs + S::kLnSlabs) * kSlabBytes;
-  // kLn: number of this CTA's tiles whose TMA stores are complete (accumulate group's storer -> LayerNorm group)
-  volatile int* ln_done = reinterpret_cast<volatile int*>(bar_gen + kTmemSlotOff + 8);
-  float2* ln_ss = reinterpret_cast<float2*>(bar_gen + 1024);   // kLn only (kBarBytes = 2048)
+  uint8_t* bar_gen = smem_gen + kStages * S::kStageBytes + kSlabs * kSlabBytes;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(bar_gen + kTmemSlotOff);
   float4* down_s = reinterpret_cast<float4*>(bar_gen + S::kBarBytes);
   float* bias_s = reinterpret_cast<float*>(bar_gen + S::kBarBytes + kBlockN * 16);
@@ -205,7 +182,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     if constexpr (!kDirect) ptx::prefetch_tensormap(&tm_out);
     if constexpr (S::kSlabLoad) ptx::prefetch_tensormap(&tm_res);
-    if constexpr (kLn || kDual) ptx::prefetch_tensormap(&tm_ln);
+    if constexpr (kDual) ptx::prefetch_tensormap(&tm_out2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -220,7 +197,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       ptx::mbar_init(rfull_bar(b), 1);   // residual producer's arrive.expect_tx
       ptx::mbar_init(rempty_bar(b), 1);  // the storing epilogue thread, once the TMA store has read the slab
     }
-    if constexpr (kLn) *ln_done = 0;
     ptx::fence_mbar_init();
   }
   if constexpr (kCtas > 1) ptx::cluster_sync();  // peer barriers exist before anybody signals them / allocs TMEM
@@ -338,108 +314,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const bool storer = (threadIdx.x & 127) == 0;  // first thread of each group issues that group's TMA stores
     int my_slab = grp;                   // running index (over the whole kernel) of the next slab this group handles
     int m_blk = 0, n_blk = 0;
-    // LayerNorm statistics of this thread's row over the tile's 256 columns: sums of (x - shift) and (x - shift)^2 with
-    // shift = mean of the tile's first 32 columns (one pass without cancellation trouble)
-    float ln_shift = 0.f, ln_s = 0.f, ln_q = 0.f;
-    if constexpr (kLn) {
-      if (grp == 1) {
-        // ======================= fused LayerNorm tail (second epilogue group) =======================
-        // Thread t owns the 16-byte column chunk (t & 7) of eight rows of every 32-column input slab, so gamma / beta / the
-        // LoRA-A rows of its four columns are a handful of loads per slab (with ~all of L1 carved out as shared memory, a
-        // one-thread-per-row layout's 48 L2-latency loads per slab made this group the kernel's bottleneck).
-        const int t = threadIdx.x & 127;
-        const bool tstorer = t == 0;
-        const int chunk = t & 7;
-        const int rsel = t >> 3;   // rows i * 16 + rsel
-        const float4* g4 = reinterpret_cast<const float4*>(args.ln_gamma);
-        const float4* b4 = reinterpret_cast<const float4*>(args.ln_beta);
-        uint16_t* ln_out = static_cast<uint16_t*>(args.ln_out);
-        const float* xnew = static_cast<const float*>(args.out);
-        const float inv_tiles = 1.0f / float(n_tiles), inv_n = 1.0f / float(args.N);
-        for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
-          const int row0 = m_blk * kTileM + int(cta_rank) * kBlockM;
-          const int col0 = n_blk * kBlockN;
-          if (tstorer) {
-            // (1) this tile's rows are stored (complete, not merely read); (2) every column tile of the 128-row block has
-            // published its partial statistics.  Both waits are bounded like the mbarrier waits (trap, not hang).
-            uint32_t spins = 0;
-            while (*ln_done <= it) {
-              __nanosleep(64);
-              if (++spins > (1u << 24)) __trap();
-            }
-            const int* flag = args.ln_cnt + (m_blk * kCtas + int(cta_rank));
-            int seen;
-            do {
-              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-              if (seen < n_tiles) {
-                __nanosleep(128);
-                if (++spins > (1u << 24)) __trap();
-              }
-            } while (seen < n_tiles);
-            ptx::fence_proxy_async_global();
-          }
-          epi_bar_sync(1);   // the statistics and the stored rows are visible to the whole group (acquire above + barrier)
-          // the re-read of the tile: thread = 16-byte chunk `chunk` of rows i * 16 + rsel of each 32-column slab (8 lanes cover
-          // 128 contiguous bytes of a row), one slab ahead in registers.  Plain L2 loads rather than TMA: a TMA load queues
-          // behind the operand ring's requests (measured 5-7 us per slab).
-          const float* xb = xnew + size_t(row0 + rsel) * args.N + col0 + chunk * 4;
-          auto load_slab = [&](int q, float4 (&dst)[8]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = (row0 + i * 16 + rsel < args.M) ? __ldcg(reinterpret_cast<const float4*>(xb + size_t(i) * 16 * args.N + q * 32))
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          };
-          float4 cur[8], nxt[8];
-          load_slab(0, cur);
-          {
-            // thread t combines the partial statistics of row t (independent loads, one L2 round trip) ...
-            const float2* pp = args.ln_part + (row0 + t);
-            float2 st[8];
-#pragma unroll
-            for (int n = 0; n < 8; ++n)
-              if (n < n_tiles) st[n] = __ldcg(pp + size_t(n) * args.ln_mpad);
-            float msum = 0.f;
-#pragma unroll
-            for (int n = 0; n < 8; ++n)
-              if (n < n_tiles) msum += st[n].x;
-            const float mean = msum * inv_tiles;
-            float m2 = 0.f;
-#pragma unroll
-            for (int n = 0; n < 8; ++n)
-              if (n < n_tiles) {
-                const float dm = st[n].x - mean;
-                m2 += st[n].y + float(kBlockN) * dm * dm;
-              }
-            const float rstd = rsqrtf(m2 * inv_n + args.ln_eps);
-            ln_ss[t] = make_float2(rstd, -mean * rstd);
-          }
-          epi_bar_sync(1);
-          // ... y = (x * sc + sh) * gamma + beta with (sc, sh) = (rstd, -mean * rstd) read back per row (registers are short)
-#pragma unroll 1
-          for (int q = 0; q < kBlockN / 32; ++q) {
-            if (q + 1 < kBlockN / 32) load_slab(q + 1, nxt);
-            const int c4 = (col0 >> 2) + q * 8 + chunk;   // float4 index of this thread's four columns
-            const float4 g = __ldg(g4 + c4), be = __ldg(b4 + c4);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 16 + rsel;
-              float4 x = cur[i];
-              const float2 ss = ln_ss[r];
-              x.x = fmaf(fmaf(x.x, ss.x, ss.y), g.x, be.x);
-              x.y = fmaf(fmaf(x.y, ss.x, ss.y), g.y, be.y);
-              x.z = fmaf(fmaf(x.z, ss.x, ss.y), g.z, be.z);
-              x.w = fmaf(fmaf(x.w, ss.x, ss.y), g.w, be.w);
-              // eight chunk lanes write 64 contiguous bytes of the row: full 32-byte sectors
-              if (row0 + r < args.M)
-                *reinterpret_cast<uint2*>(ln_out + size_t(row0 + r) * args.N + c4 * 4) =
-                    make_uint2(Act<kF16>::pack(x.x, x.y), Act<kF16>::pack(x.z, x.w));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-          }
-        }
-      }
-    }
     for (int it = 0; grp < kGroups && tile_at(it, m_blk, n_blk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -541,32 +415,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               r.z += __uint_as_float(v[4 * j + 2]) + bb.z;
               r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
               *p = r;
-              if constexpr (kLn) {
-                if (s == 0) {
-                  v[4 * j] = __float_as_uint(r.x); v[4 * j + 1] = __float_as_uint(r.y);   // keep: the shift comes first
-                  v[4 * j + 2] = __float_as_uint(r.z); v[4 * j + 3] = __float_as_uint(r.w);
-                } else {
-                  const float d0 = r.x - ln_shift, d1 = r.y - ln_shift, d2 = r.z - ln_shift, d3 = r.w - ln_shift;
-                  ln_s += (d0 + d1) + (d2 + d3);
-                  ln_q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-                }
-              }
-            }
-            if constexpr (kLn) {
-              if (s == 0) {
-                float t = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) t += __uint_as_float(v[i]);
-                ln_shift = t * (1.0f / 32.0f);
-                ln_s = 0.f;
-                ln_q = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float d = __uint_as_float(v[i]) - ln_shift;
-                  ln_s += d;
-                  ln_q += d * d;
-                }
-              }
             }
             ptx::fence_proxy_async_smem();
             epi_bar_sync(grp);
@@ -711,7 +559,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               ptx::fence_proxy_async_smem();
               epi_bar_sync(grp);
               if (storer) {
-                ptx::tma_store_2d(&tm_ln, slab_base + grp * kSlabBytes, col, row0);          // pre-activation
+                ptx::tma_store_2d(&tm_out2, slab_base + grp * kSlabBytes, col, row0);        // pre-activation
                 ptx::tma_store_2d(&tm_out, slab_base + (grp + 2) * kSlabBytes, col, row0);   // activation
                 ptx::tma_store_commit();
               }
@@ -730,20 +578,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             }
           }
         }
-        if constexpr (kLn) {
-          // publish (mean, M2) of this row over the tile's columns, then count the tile in for its 128-row block
-          const float ms = ln_s * (1.0f / float(kBlockN));
-          args.ln_part[size_t(n_blk) * args.ln_mpad + row] = make_float2(ln_shift + ms, fmaxf(ln_q - ln_s * ms, 0.f));
-          __threadfence();
-          epi_bar_sync(0);
-          if (storer) {
-            int* flag = args.ln_cnt + (m_blk * kCtas + int(cta_rank));
-            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(flag) : "memory");
-            // stores of the PREVIOUS tile are complete once at most this tile's eight are still in flight: no stall
-            ptx::tma_store_wait<kSlabsPerTile>();
-            *ln_done = it;
-          }
-        }
         if constexpr (kAct) {
           // one partial per (column tile, epilogue group): part[2 * n_blk + grp][row][0..3]
           if (args.down_a != nullptr && row_ok)
@@ -756,10 +590,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if constexpr (!kDirect) {
       if (storer && grp < kGroups) {
         ptx::tma_store_wait<0>();
-        if constexpr (kLn) {
-          __threadfence_block();
-          *ln_done = 0x7fffffff;   // every tile of this CTA is stored
-        }
       }
     }
   }

@@ -76,28 +76,40 @@ head_kernel(const float* __restrict__ x, long long x_img_stride, const float* __
   __syncthreads();
 
   // ---- 2. projection: emb[i][e] = sum_k xln[i][k] * proj[k][e]   (proj row-major [W, E], coalesced over e) ----
+  // Summation order (shared with the small-batch path below, so that an image's result does not depend on the batch it travels
+  // in): K is cut into 16 chunks of ceil(W / 16) rows, each chunk is a sequential fmaf chain in k order, the 16 partial sums
+  // are added left to right.
   for (int e = tid; e < E && emb_in == nullptr; e += kThreads) {
-    float acc[kImgs];
+    float tot[kImgs];
 #pragma unroll
-    for (int i = 0; i < kImgs; ++i) acc[i] = 0.f;
-    // 16 projection rows in flight per thread: each CTA streams the whole [W, E] matrix from L2 exactly once, so the loop is
-    // bound by load latency, not bandwidth (4 in flight: 0.5 ms per 1024 images; same summation order, same bits)
-    for (int k0 = 0; k0 < W; k0 += 16) {
-      float wv[16];
+    for (int i = 0; i < kImgs; ++i) tot[i] = 0.f;
+    const int kw = (W + 15) / 16;
+    for (int c = 0; c < 16; ++c) {
+      const int k_lo = c * kw, k_hi = min(W, k_lo + kw);
+      float acc[kImgs];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) wv[j] = (k0 + j < W) ? __ldg(proj + size_t(k0 + j) * E + e) : 0.f;
+      for (int i = 0; i < kImgs; ++i) acc[i] = 0.f;
+      // 16 projection rows in flight per thread: each CTA streams the whole [W, E] matrix from L2 exactly once, so the loop is
+      // bound by load latency, not bandwidth
+      for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+        float wv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (k0 + j < W) {
+        for (int j = 0; j < 16; ++j) wv[j] = (k0 + j < k_hi) ? __ldg(proj + size_t(k0 + j) * E + e) : 0.f;
 #pragma unroll
-          for (int i = 0; i < kImgs; ++i) acc[i] = fmaf(s_x[i * W + k0 + j], wv[j], acc[i]);
+        for (int j = 0; j < 16; ++j) {
+          if (k0 + j < k_hi) {
+#pragma unroll
+            for (int i = 0; i < kImgs; ++i) acc[i] = fmaf(s_x[i * W + k0 + j], wv[j], acc[i]);
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < kImgs; ++i) tot[i] += acc[i];
     }
 #pragma unroll
     for (int i = 0; i < kImgs; ++i) {
-      s_e[i * E + e] = acc[i];
-      if (i < n_img && emb_out != nullptr) emb_out[size_t(img0 + i) * E + e] = acc[i];
+      s_e[i * E + e] = tot[i];
+      if (i < n_img && emb_out != nullptr) emb_out[size_t(img0 + i) * E + e] = tot[i];
     }
   }
   __syncthreads();
@@ -199,13 +211,213 @@ head_kernel(const float* __restrict__ x, long long x_img_stride, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Small batches (B <= kSmallB: the single-image calls of main.py:191-222, 472-510): the work of head_kernel spread over
+// many CTAs in three short launches.  One CTA of 256 threads walking [W, E] and [L, E] for <= 4 images is ~0.29 ms of pure load
+// latency - a quarter of the batch-1 latency of the whole path.  Same arithmetic in the same summation ORDER per output as
+// head_kernel (16 K-chunks for the projection, the lane / shuffle-tree order for norms and logits), so a small batch gives
+// the SAME BITS as the same images inside a large one (tests/test_parity_gpu.py::test_batch_invariance_and_determinism).
+//   head_small_proj:   ln_post(CLS) per CTA (cheap, recomputed), then 32 output columns per CTA: lane = column, the 16 warps
+//                      split K (all of a thread's projection rows in flight at once), cross-warp sum through smem
+//   head_small_logits: row norm per CTA (recomputed), then one label per warp, lanes split E
+//   head_small_groups: softmax / top-k / leading-span sum, one warp per (image, group)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kSmallB = 16;
+constexpr int kSmallThreads = 512;
+
+__global__ void __launch_bounds__(kSmallThreads)
+head_small_proj_kernel(const float* __restrict__ x, long long x_img_stride, const float* __restrict__ ln_g,
+                       const float* __restrict__ ln_b, float eps, const float* __restrict__ proj, int W, int E, int B,
+                       float* __restrict__ emb_out) {
+  extern __shared__ float sm[];
+  float* s_x = sm;                       // [B][W] normalised class-token rows
+  float* s_p = s_x + size_t(B) * W;      // [16 warps][B][32] partial sums
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < B; i += kSmallThreads / 32) {
+    const float* xr = x + size_t(i) * x_img_stride;
+    float s = 0.f;
+    for (int k = lane; k < W; k += 32) s += xr[k];
+    const float mean = warp_sum(s) / W;
+    float q = 0.f;
+    for (int k = lane; k < W; k += 32) { const float dlt = xr[k] - mean; q += dlt * dlt; }
+    const float rstd = rsqrtf(warp_sum(q) / W + eps);
+    for (int k = lane; k < W; k += 32) s_x[i * W + k] = (xr[k] - mean) * rstd * ln_g[k] + ln_b[k];
+  }
+  __syncthreads();
+  const int e = blockIdx.x * 32 + lane;
+  const int kw = (W + 15) / 16;          // projection rows per warp
+  const int k0 = warp * kw, k1 = min(W, k0 + kw);
+  float acc[kSmallB];
+#pragma unroll
+  for (int i = 0; i < kSmallB; ++i) acc[i] = 0.f;
+  for (int kb = k0; kb < k1; kb += 16) {
+    float wv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) wv[j] = (kb + j < k1 && e < E) ? __ldg(proj + size_t(kb + j) * E + e) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (kb + j < k1) {
+#pragma unroll
+        for (int i = 0; i < kSmallB; ++i)
+          if (i < B) acc[i] = fmaf(s_x[i * W + kb + j], wv[j], acc[i]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < kSmallB; ++i)
+    if (i < B) s_p[(warp * B + i) * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int o = tid; o < B * 32; o += kSmallThreads) {
+    const int i = o >> 5, l = o & 31;
+    float v = 0.f;
+    for (int w = 0; w < 16; ++w) v += s_p[(w * B + i) * 32 + l];   // fixed order: bit-reproducible
+    if (blockIdx.x * 32 + l < E) emb_out[size_t(i) * E + blockIdx.x * 32 + l] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+head_small_logits_kernel(const float* __restrict__ emb, int E, const float* __restrict__ text, int L, float logit_scale, int B,
+                         float* __restrict__ logits_out) {
+  extern __shared__ float sm[];
+  float* s_e = sm;                       // [B][E] L2-normalised embeddings
+  float* s_r = s_e + size_t(B) * E;      // [B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < B * E; i += kSmallThreads) s_e[i] = emb[i];
+  __syncthreads();
+  for (int i = warp; i < B; i += kSmallThreads / 32) {
+    float q = 0.f;
+    for (int k = lane; k < E; k += 32) { const float v = s_e[i * E + k]; q += v * v; }
+    q = warp_sum(q);
+    if (lane == 0) s_r[i] = rsqrtf(q);   // no epsilon, as the reference (main.py:205)
+  }
+  __syncthreads();
+  const int l = blockIdx.x * (kSmallThreads / 32) + warp;
+  if (l >= L) return;
+  const float* tr = text + size_t(l) * E;
+  float acc[kSmallB];
+#pragma unroll
+  for (int i = 0; i < kSmallB; ++i) acc[i] = 0.f;
+  for (int e0 = lane; e0 < E; e0 += 32 * 16) {
+    float tv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tv[j] = (e0 + 32 * j < E) ? __ldg(tr + e0 + 32 * j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int e = e0 + 32 * j;
+      if (e < E) {
+#pragma unroll
+        for (int i = 0; i < kSmallB; ++i)
+          if (i < B) acc[i] = fmaf(s_e[i * E + e] * s_r[i], tv[j], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSmallB; ++i)
+    if (i < B) {
+      const float v = warp_sum(acc[i]) * logit_scale;
+      if (lane == 0) logits_out[size_t(i) * L + l] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+head_small_groups_kernel(const float* __restrict__ logits, int L, const int* __restrict__ group_off,
+                         const int* __restrict__ group_split, int G, int topk, int B, float* __restrict__ probs_out,
+                         float* __restrict__ topk_val, int* __restrict__ topk_idx, float* __restrict__ split_sum,
+                         float* __restrict__ scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + warp;
+  if (pair >= B * G) return;
+  const int i = pair / G, gidx = pair - i * G;
+  const int lo = group_off[gidx], hi = group_off[gidx + 1];
+  const float* lg = logits + size_t(i) * L;
+  float* pr = scratch + size_t(i) * L;      // probabilities (working copy: entries are knocked out by the top-k rounds)
+  float mx = -CUDART_INF_F;
+  for (int l = lo + lane; l < hi; l += 32) mx = fmaxf(mx, lg[l]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int l = lo + lane; l < hi; l += 32) sum += expf(lg[l] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  const int split = group_split != nullptr ? group_split[gidx] : 0;
+  float ssum = 0.f;
+  for (int l = lo + lane; l < hi; l += 32) {
+    const float p = expf(lg[l] - mx) * inv;
+    pr[l] = p;
+    if (probs_out != nullptr) probs_out[size_t(i) * L + l] = p;
+    if (l - lo < split) ssum += p;
+  }
+  ssum = warp_sum(ssum);
+  if (lane == 0 && split_sum != nullptr) split_sum[size_t(i) * G + gidx] = ssum;
+  __syncwarp();
+  const int kk = min(topk, hi - lo);
+  for (int r = 0; r < topk; ++r) {
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    if (r < kk) {
+      for (int l = lo + lane; l < hi; l += 32) {
+        const float p = pr[l];
+        if (p > bv) { bv = p; bi = l; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+    }
+    if (lane == 0) {
+      const size_t oidx = (size_t(i) * G + gidx) * topk + r;
+      if (r < kk) {
+        topk_val[oidx] = bv;
+        topk_idx[oidx] = bi - lo;
+        pr[bi] = -2.f;
+      } else {
+        topk_val[oidx] = 0.f;
+        topk_idx[oidx] = -1;
+      }
+    }
+    __syncwarp();
+  }
+}
+}  // namespace
+
+size_t head_small_scratch_bytes(int B, int E, int L) {
+  return (B > 0 && B <= kSmallB) ? sizeof(float) * (size_t(B) * E + 2 * size_t(B) * L) : 0;
+}
+
 int launch_head(const float* x, long long x_img_stride, const float* ln_g, const float* ln_b, float eps,
                 const float* proj, int W, int E, const float* text, int L, const int* group_off,
                 const int* group_split, int G, int topk, float logit_scale, int B, float* emb_out, float* logits_out,
                 float* probs_out, float* topk_val, int* topk_idx, float* split_sum, const float* emb_in,
-                cudaStream_t stream) {
+                float* small_scratch, cudaStream_t stream) {
   if (B <= 0) return 0;
   if (topk > kMaxTopk || topk < 0) return -1;
+  if (B <= kSmallB && small_scratch != nullptr && W <= 2048) {
+    // ---- latency path: three short, wide launches ----
+    float* emb = emb_out != nullptr ? emb_out : small_scratch;                       // [B, E]
+    float* logits = logits_out != nullptr ? logits_out : small_scratch + size_t(B) * E;   // [B, L]
+    float* pwork = small_scratch + size_t(B) * E + size_t(B) * L;                    // [B, L]
+    static PerDeviceOnce attr_small;
+    if (attr_small.need()) {
+      if (cudaFuncSetAttribute(head_small_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(head_small_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return -2;
+      attr_small.mark();
+    }
+    if (emb_in == nullptr) {
+      const size_t smem = sizeof(float) * (size_t(B) * W + size_t(16) * B * 32);
+      head_small_proj_kernel<<<(E + 31) / 32, kSmallThreads, smem, stream>>>(x, x_img_stride, ln_g, ln_b, eps, proj, W, E, B, emb);
+    } else {
+      emb = const_cast<float*>(emb_in);
+    }
+    if (text == nullptr || L <= 0) return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    const size_t smem2 = sizeof(float) * (size_t(B) * E + 64);
+    head_small_logits_kernel<<<(L + kSmallThreads / 32 - 1) / (kSmallThreads / 32), kSmallThreads, smem2, stream>>>(
+        emb, E, text, L, logit_scale, B, logits);
+    head_small_groups_kernel<<<(B * G + 7) / 8, 256, 0, stream>>>(logits, L, group_off, group_split, G, topk, B, probs_out, topk_val,
+                                                                 topk_idx, split_sum, pwork);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   const size_t smem = sizeof(float) * (size_t(kImgs) * (W + E + L) + 64);
   if (smem > 200 * 1024) return -1;
   static PerDeviceOnce attr_done;

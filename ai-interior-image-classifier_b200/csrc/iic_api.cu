@@ -52,8 +52,7 @@ struct Block {
 
 struct Workspace {
   uint16_t *xln, *qkv, *attn, *hid, *p_a, *p_b;
-  float *x, *xpre, *down_part;
-  void* ln_scratch;   // fused LayerNorm (IIC_FUSE_LN): cross-CTA row statistics
+  float *x, *xpre, *down_part, *head_small;
   size_t total;
 };
 
@@ -106,7 +105,6 @@ struct iic_handle {
   int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
-  int fuse_ln = 0;        // 1 (IIC_FUSE_LN=1): the next block's ln_1 rides in the c_proj GEMM - measured: no gain on the power-capped step
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
@@ -149,7 +147,11 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
-  w.ln_scratch = take(gemm_ln_scratch_bytes(int(M), int(d)));
+  // small batches: scratch of the multi-CTA head path (launch_head) - embedding, logits and a probability working copy
+  {
+    const int Bs = B < 16 ? B : 16, Lcap = h->L > 1024 ? h->L : 1024;
+    w.head_small = static_cast<float*>(take(head_small_scratch_bytes(Bs, h->cfg.embed_dim, Lcap)));
+  }
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.total = off;
   return w;
@@ -195,24 +197,12 @@ int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const voi
   return launch_attention_bwd(qkv, out, d_out, lse, dqkv, B, T, H, hd, h->f16, s);
 }
 
-// LayerNorm fused behind a residual GEMM: y = LN(out rows) -> 16-bit `out` [M, N], optional rank-4 down-projection into p_out
-struct LnFuse {
-  const float* gamma = nullptr;
-  const float* beta = nullptr;
-  void* out = nullptr;
-  void* scratch = nullptr;
-};
-
 int run_gemm(iic_handle* h, const void* a, int lda, const void* w, int M, int N, int K,
              const LoraSlot* lora, const void* p, int epi, const float* bias, const float* residual, void* out,
              int ldc, int group, cudaStream_t s, const float* down_a = nullptr, float* down_part = nullptr,
-             int prof_class = kGemm, const LnFuse* ln = nullptr, void* out2 = nullptr) {
+             int prof_class = kGemm, void* out2 = nullptr) {
   GemmProblem g;
   g.out2 = out2;
-  if (ln != nullptr && ln->out != nullptr) {
-    g.ln_gamma = ln->gamma; g.ln_beta = ln->beta; g.ln_out = ln->out;
-    g.ln_scratch = ln->scratch;
-  }
   g.down_a = down_a;
   g.down_part = down_part;
   g.a = a; g.lda = lda; g.w = w; g.ldw = K; g.M = M; g.N = N; g.K = K;
@@ -293,14 +283,6 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
   const int d = h->cfg.width, T = h->T, M = B * T, mlp = h->cfg.mlp_dim, H = h->cfg.heads;
   const float eps = 1e-5f;
   const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
-  // The next block's ln_1 rides in this block's c_proj GEMM (kEpiBiasResF32Ln; IIC_FUSE_LN): c_proj is compute-bound, so its
-  // second epilogue group has the time to re-read and normalise the tile.  Possible when the width is a multiple of the
-  // 256-column tile and ln_1 carries no rank <= 4 LoRA down-projection of its own (attn.in_proj LoRA: not in the reference).
-  // ln_2 stays a kernel: its producer attn.out_proj is HBM-bound and ln_2 carries the c_fc down-projection.
-  auto ln_fusable = [&](const LoraSlot& l, bool via_gemm) {
-    return h->fuse_ln != 0 && d % 256 == 0 && d <= 2048 && (l.rank == 0 || via_gemm);
-  };
-  bool ln1_done = false;   // this block's ln_1 was already produced by the previous block's c_proj
   for (size_t bi = 0; bi < h->blocks.size(); ++bi) {
     Block& b = h->blocks[bi];
     const LoraSlot& l_in = b.lora[IIC_LORA_IN_PROJ];
@@ -310,8 +292,7 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
     // x = x + attn(ln_1(x))
     // LoRA down-projections of rank <= 4 ride inside the LayerNorm; larger ranks go through the GEMM (run_lora_down)
     const bool in_gemm = l_in.rank > 0 && l_in.r4 > 4 && l_in.at16 != nullptr;
-    if (!ln1_done)
-      IIC_TRY(timed(h, kLayerNorm, s, [&] {
+    IIC_TRY(timed(h, kLayerNorm, s, [&] {
         return launch_layernorm(w.x, d, b.ln1_g, b.ln1_b, w.xln, nullptr, d, M, d, eps, (l_in.rank && !in_gemm) ? l_in.a : nullptr,
                                 l_in.r4, w.p_a, h->lora_pad, h->f16, s);
       }));
@@ -337,26 +318,13 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
       }));
     else if (l_pr.rank)
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, w.p_b, s));
-    // the next block's ln_1 (its input is this GEMM's output); xln and p_a are free again: c_fc has consumed them
-    LnFuse ln1n;
-    ln1_done = false;
-    if (bi + 1 < h->blocks.size()) {
-      Block& nb = h->blocks[bi + 1];
-      const LoraSlot& n_in = nb.lora[IIC_LORA_IN_PROJ];
-      const bool n_in_gemm = n_in.rank > 0 && n_in.r4 > 4 && n_in.at16 != nullptr;
-      if (ln_fusable(n_in, n_in_gemm)) {
-        ln1n.gamma = nb.ln1_g; ln1n.beta = nb.ln1_b; ln1n.out = w.xln; ln1n.scratch = w.ln_scratch;
-        ln1_done = true;
-      }
-    }
-    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s, nullptr, nullptr,
-                     kGemm, &ln1n));
+    IIC_TRY(run_gemm(h, w.hid, mlp, b.w_proj, M, d, mlp, &l_pr, w.p_b, kEpiBiasResF32, b.b_proj, w.x, w.x, d, 1, s));
   }
   return 0;
 }
 
 int run_head(iic_handle* h, const float* x_cls, long long x_img_stride, const float* emb_in, int B, float* emb_out,
-             const iic_head_out* out, cudaStream_t s) {
+             const iic_head_out* out, cudaStream_t s, float* small_scratch = nullptr) {
   const bool scores = out != nullptr;
   if (scores && (h->text == nullptr || h->G <= 0)) return fail(h, IIC_ERR_STATE, "iic_set_labels has not been called");
   if (scores && (out->topk_val == nullptr || out->topk_idx == nullptr))
@@ -366,7 +334,8 @@ int run_head(iic_handle* h, const float* x_cls, long long x_img_stride, const fl
                        scores ? h->text : nullptr, scores ? h->L : 0, h->d_group_off,
                        h->has_split ? h->d_group_split : nullptr, scores ? h->G : 0, h->topk, h->logit_scale, B, emb_out,
                        scores ? out->logits : nullptr, scores ? out->probs : nullptr, scores ? out->topk_val : nullptr,
-                       scores ? out->topk_idx : nullptr, scores ? out->split_sum : nullptr, emb_in, s);
+                       scores ? out->topk_idx : nullptr, scores ? out->split_sum : nullptr, emb_in,
+                       B <= 16 ? small_scratch : nullptr, s);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "head kernel launch failed");
   return 0;
 }
@@ -492,7 +461,7 @@ int run_train_forward(iic_handle* h, const void* patches, const float* x_tokens,
     if (h->train_fused)   // h -> hid (c_proj operand), u -> kept for the backward
       IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, kEpiBiasActDualBf16, b.b_fc, nullptr, w.hid, mlp,
                        act_epi == kEpiGeluExactBf16 ? 2 : 1, s, fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr,
-                       kGemm, nullptr, t.u));
+                       kGemm, t.u));
     else
       IIC_TRY(run_gemm(h, t.y2, d, b.w_fc, M, mlp, d, &l_fc, t.p1, act_epi, b.b_fc, nullptr, w.hid, mlp, 1, s,
                        fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
@@ -636,7 +605,6 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
   if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
   if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
-  if (const char* e = getenv("IIC_FUSE_LN")) h->fuse_ln = atoi(e);
   if (const char* e = getenv("IIC_TRAIN_FUSED")) h->train_fused = atoi(e);
   if (const char* e = getenv("IIC_LORA_BWD_FUSED")) h->lora_bwd_fused = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
@@ -893,7 +861,7 @@ int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
-  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, nullptr, s);
+  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, nullptr, s, w.head_small);
 }
 
 int iic_encode_sequence(iic_handle* h, const float* x_in, const int32_t* row_index, int B, void* workspace,
@@ -916,7 +884,7 @@ int iic_encode_sequence(iic_handle* h, const float* x_in, const int32_t* row_ind
     Scope sc(h->prof, kMisc, s);
     if (launch_gather_rows(w.x, row_index, T, d, B, rows, s) != 0) return fail(h, IIC_ERR_CUDA, "row gather launch failed");
   }
-  return run_head(h, rows, (long long)d, nullptr, B, emb_out, nullptr, s);
+  return run_head(h, rows, (long long)d, nullptr, B, emb_out, nullptr, s, w.head_small);
 }
 
 int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, void* stream) {
@@ -933,7 +901,7 @@ int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, siz
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rc = run_encoder(h, patches, B, w, s);
   if (rc) return rc;
-  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, out, s);
+  return run_head(h, w.x, (long long)h->T * h->cfg.width, nullptr, B, emb_out, out, s, w.head_small);
 }
 
 int iic_profile(iic_handle* h, int enable) {
@@ -1084,26 +1052,24 @@ int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act,
   return IIC_OK;
 }
 
+size_t iic_op_lora_scratch_bytes(int N, int M) { return (N > 0 && M > 0) ? lora_outer_scratch_bytes(N, M) : 0; }
+
 int iic_op_lora_bwd(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale,
-                    float* out_db, void* out_dp16, void* stream) {
-  if (!h || !P || !Y || !Bm || !out_db || !out_dp16) return fail(h, IIC_ERR_ARG, "iic_op_lora_bwd: null argument");
-  float* scratch = nullptr;
-  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, M)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
-  int rc = launch_lora_bwd(P, p_ld, Y, N, M, Bm, rank, scale, out_db, out_dp16, scratch, h->f16, static_cast<cudaStream_t>(stream));
-  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-  cudaFree(scratch);
+                    float* out_db, void* out_dp16, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!h || !P || !Y || !Bm || !out_db || !out_dp16 || !scratch) return fail(h, IIC_ERR_ARG, "iic_op_lora_bwd: null argument");
+  if (scratch_bytes < lora_outer_scratch_bytes(N, M)) return fail(h, IIC_ERR_ARG, "iic_op_lora_bwd: scratch too small (iic_op_lora_scratch_bytes)");
+  int rc = launch_lora_bwd(P, p_ld, Y, N, M, Bm, rank, scale, out_db, out_dp16, static_cast<float*>(scratch), h->f16,
+                           static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -2 ? IIC_ERR_CUDA : IIC_ERR_ARG, rc == -3 ? "lora_bwd: needs N % 256 == 0 and p_ld == 16" : "lora_bwd failed");
   return IIC_OK;
 }
 
 int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale,
-                      int transpose, float* out, void* stream) {
-  if (!h || !P || !Y || !out) return fail(h, IIC_ERR_ARG, "iic_op_lora_outer: null argument");
-  float* scratch = nullptr;
-  if (cudaMalloc(&scratch, lora_outer_scratch_bytes(N, M)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
-  int rc = launch_lora_outer(P, p_ld, Y, N, M, act, rank, scale, transpose, out, scratch, h->f16, static_cast<cudaStream_t>(stream));
-  cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-  cudaFree(scratch);
+                      int transpose, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!h || !P || !Y || !out || !scratch) return fail(h, IIC_ERR_ARG, "iic_op_lora_outer: null argument");
+  if (scratch_bytes < lora_outer_scratch_bytes(N, M)) return fail(h, IIC_ERR_ARG, "iic_op_lora_outer: scratch too small (iic_op_lora_scratch_bytes)");
+  int rc = launch_lora_outer(P, p_ld, Y, N, M, act, rank, scale, transpose, out, static_cast<float*>(scratch), h->f16,
+                             static_cast<cudaStream_t>(stream));
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, "lora_outer failed");
   return IIC_OK;
 }
@@ -1146,32 +1112,6 @@ int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, i
   g.group = act == IIC_ACT_GELU_ERF ? 2 : 1;
   const char* e = nullptr;
   int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, static_cast<cudaStream_t>(stream), &e);
-  if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
-  return IIC_OK;
-}
-
-int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
-                       const void* lora_bt, int r_pad, int lora_ld, const float* bias, const float* residual, float* out,
-                       const float* gamma, const float* beta, void* ln_out, int ctas, void* stream) {
-  if (!h || !a || !w || !out || !residual || !gamma || !beta || !ln_out) return fail(h, IIC_ERR_ARG, "iic_op_gemm_res_ln: null argument");
-  GemmProblem g;
-  g.a = a; g.lda = lda;
-  g.w = w; g.ldw = ldw;
-  g.M = M; g.N = N; g.K = K;
-  g.lora_p = lora_p;
-  g.lora_bt = lora_bt;
-  g.f16 = h->f16;
-  g.r_pad = r_pad; g.lora_ld = lora_ld;
-  g.epilogue = kEpiBiasResF32; g.bias = bias; g.residual = residual; g.out = out; g.ldc = N; g.group = 1;
-  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_out = ln_out;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  void* scratch = nullptr;
-  if (cudaMalloc(&scratch, gemm_ln_scratch_bytes(M, N)) != cudaSuccess) return fail(h, IIC_ERR_CUDA, "scratch alloc failed");
-  g.ln_scratch = scratch;
-  const char* e = nullptr;
-  int rc = launch_gemm(g, ctas == 1 ? 1 : (ctas == 2 ? 2 : h->ctas), h->num_sms, s, &e);
-  cudaStreamSynchronize(s);
-  cudaFree(scratch);
   if (rc != 0) return fail(h, rc == -1 ? IIC_ERR_ARG : IIC_ERR_CUDA, e ? e : "gemm failed");
   return IIC_OK;
 }

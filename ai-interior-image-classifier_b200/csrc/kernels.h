@@ -104,7 +104,9 @@ int launch_head(const float* x, long long x_img_stride, const float* ln_g, const
                 const float* proj, int W, int E, const float* text, int L, const int* group_off,
                 const int* group_split, int G, int topk, float logit_scale, int B, float* emb_out, float* logits_out,
                 float* probs_out, float* topk_val, int* topk_idx, float* split_sum, const float* emb_in,
-                cudaStream_t stream);
+                float* small_scratch, cudaStream_t stream);
+// device scratch (floats: B*E + 2*B*L) that switches launch_head to its small-batch latency path (B <= 16); 0 otherwise
+size_t head_small_scratch_bytes(int B, int E, int L);
 
 // ---- preprocess.cu ----
 struct PreprocessPlan;  // opaque: host-side coefficient tables + device scratch, owned by the engine handle
@@ -144,16 +146,7 @@ struct GemmProblem {
   const float* down_a = nullptr;
   float* down_part = nullptr;
   void* out2 = nullptr;  // kEpiBiasActDualBf16: 16-bit [M, ldc] pre-activation output (out receives the activation)
-  // optional, kEpiBiasResF32 only: also emit the LayerNorm of the output rows (the LayerNorm that consumes the new residual
-  // stream) as 16-bit ln_out [M, N] (pitch N).  Needs N % 256 == 0 and ln_scratch of gemm_ln_scratch_bytes(M, N) bytes
-  // (cross-CTA row statistics + counters; the launcher zeroes the counters).
-  const float* ln_gamma = nullptr;
-  const float* ln_beta = nullptr;
-  float ln_eps = 1e-5f;
-  void* ln_out = nullptr;
-  void* ln_scratch = nullptr;
 };
-size_t gemm_ln_scratch_bytes(int M, int N);
 // ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);
 size_t gemm_smem_bytes(int ctas);

@@ -570,20 +570,22 @@ class Engine:
         M, N = Y.shape
         db = torch.zeros(rank, N, dtype=torch.float32, device=self.device)
         dp = torch.zeros(M, 16, dtype=self.op_dtype, device=self.device)
+        scratch = torch.empty(int(self.lib.iic_op_lora_scratch_bytes(N, M)), dtype=torch.uint8, device=self.device)   # caller-owned
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_lora_bwd(self.h, P.data_ptr(), P.stride(0), Y.data_ptr(), N, M, Bm.data_ptr(), rank,
-                                                     float(scale), db.data_ptr(), dp.data_ptr(), _stream_ptr(self.device)),
-                    "iic_op_lora_bwd")
+                                                     float(scale), db.data_ptr(), dp.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                                     _stream_ptr(self.device)), "iic_op_lora_bwd")
         return db, dp
 
     def op_lora_outer(self, P: torch.Tensor, Y: torch.Tensor, rank: int, act: int = 0, scale: float = 1.0,
                       transpose: bool = False) -> torch.Tensor:
         M, N = Y.shape
         out = torch.zeros((N, rank) if transpose else (rank, N), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(int(self.lib.iic_op_lora_scratch_bytes(N, M)), dtype=torch.uint8, device=self.device)   # caller-owned
         with self._lock, torch.cuda.device(self.device):
             L.check(self.h, self.lib.iic_op_lora_outer(self.h, P.data_ptr(), P.stride(0), Y.data_ptr(), N, M, act, rank, float(scale),
-                                                       1 if transpose else 0, out.data_ptr(), _stream_ptr(self.device)),
-                    "iic_op_lora_outer")
+                                                       1 if transpose else 0, out.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                                       _stream_ptr(self.device)), "iic_op_lora_outer")
         return out
 
     # ------------------------------------------------------------------ measurement
@@ -683,25 +685,6 @@ class Engine:
                 self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(lora_p), _ptr(lora_bt), r_pad,
                 lora_ld, _ptr(bias), out.data_ptr(), pre.data_ptr(), act, ctas, _stream_ptr(self.device)), "iic_op_gemm_act_dual")
         return out, pre
-
-    def op_gemm_res_ln(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
-                       gamma: torch.Tensor, beta: torch.Tensor, lora_p: Optional[torch.Tensor] = None,
-                       lora_bt: Optional[torch.Tensor] = None, r_pad: int = 0, ctas: int = 0,
-                       out: Optional[torch.Tensor] = None):
-        """x_new = a . w^T (+ LoRA) + bias + residual (fp32) and LayerNorm(x_new) (16-bit) from one launch.
-        Returns (x_new, ln_out)."""
-        M, K = a.shape
-        N = w.shape[0]
-        if out is None:
-            out = torch.empty(M, N, dtype=torch.float32, device=self.device)
-        ln_out = torch.empty(M, N, dtype=self.op_dtype, device=self.device)
-        lora_ld = lora_p.stride(0) if lora_p is not None else 0
-        with self._lock, torch.cuda.device(self.device):
-            L.check(self.h, self.lib.iic_op_gemm_res_ln(
-                self.h, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _ptr(lora_p), _ptr(lora_bt), r_pad,
-                lora_ld, _ptr(bias), residual.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                ln_out.data_ptr(), ctas, _stream_ptr(self.device)), "iic_op_gemm_res_ln")
-        return out, ln_out
 
     def op_layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype=None,
                      lora_a_scaled: Optional[torch.Tensor] = None, p_ld: int = 16):

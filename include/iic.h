@@ -13,8 +13,10 @@
  * Conventions
  *   - All data pointers are DEVICE pointers unless a parameter says "host".
  *   - The caller owns every input / output / workspace buffer and keeps weight buffers alive for the life of
- *     the handle (weights are borrowed, not copied).  The library owns only a few KB of descriptors plus the
- *     grow-only resampling scratch used by iic_preprocess.
+ *     the handle (weights are borrowed, not copied).  The library owns only a few KB of descriptors (label group offsets,
+ *     TMA maps are built per call on the host) and ONE documented exception: the grow-only resampling scratch of the
+ *     general-size iic_preprocess (intermediate rows + coefficient tables, sized by the largest batch seen; the
+ *     same-size fast path and every other entry point allocate nothing and never synchronise the stream).
  *   - All work is enqueued on the caller's stream (cudaStream_t passed as void*); calls are asynchronous.
  *   - Return value: 0 = IIC_OK, negative = error; iic_last_error(h) describes the last failure.
  *   - A handle is not re-entrant: serialise calls per handle (one handle per GPU per process for data parallel).
@@ -231,13 +233,6 @@ int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, i
 int iic_op_gemm_act_dual(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
                          const void* lora_bt, int r_pad, int lora_ld, const float* bias, void* out_act, void* out_pre, int act,
                          int ctas, void* stream);
-/* out f32 [M,N] = A . W^T (+ LoRA) + bias + residual  AND  ln_out 16-bit [M,N] = LayerNorm(out rows; gamma, beta, eps 1e-5)
- * from the same launch (the kernel's second epilogue group re-reads the stored tile from L2 once all column tiles of its rows
- * have published their partial statistics): x = x + mlp.c_proj(..); next block's ln_1(x) of clip/model.py
- * ResidualAttentionBlock.forward (called through main.py:204/444/503).  N % 256 == 0, N <= 2048; out may alias residual. */
-int iic_op_gemm_res_ln(iic_handle* h, const void* a, int lda, const void* w, int ldw, int M, int N, int K, const void* lora_p,
-                       const void* lora_bt, int r_pad, int lora_ld, const float* bias, const float* residual, float* out,
-                       const float* gamma, const float* beta, void* ln_out, int ctas, void* stream);
 int iic_op_layernorm(iic_handle* h, const float* x, const float* gamma, const float* beta, void* out_bf16,
                      float* out_f32, int rows, int D, const float* lora_a_scaled, int r4, void* p_out, int p_ld,
                      void* stream);
@@ -258,9 +253,12 @@ int iic_op_act_bwd(iic_handle* h, void* dh, const void* u, long long n, int act,
  * out_db f32 [rank, N] = scale * P^T . Y with P 16-bit [M, p_ld = 16] the forward's s * x . A, and out_dp16 16-bit [M, 16] =
  * Y . Bm^T with Bm 16-bit [16, N] = lora_B (rows >= rank zero).  N % 256 == 0. */
 int iic_op_lora_bwd(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale,
-                    float* out_db, void* out_dp16, void* stream);
+                    float* out_db, void* out_dp16, void* scratch, size_t scratch_bytes, void* stream);
 int iic_op_lora_outer(iic_handle* h, const void* P, int p_ld, const void* Y, int N, int M, int act, int rank, float scale,
-                      int transpose, float* out, void* stream);
+                      int transpose, float* out, void* scratch, size_t scratch_bytes, void* stream);
+/* Bytes of caller-owned device scratch the two LoRA gradient operators above need for an [M, N] gradient (deterministic
+ * two-stage reduction: per-row-block partials).  The operators allocate nothing and do not synchronise the stream. */
+size_t iic_op_lora_scratch_bytes(int N, int M);
 
 #ifdef __cplusplus
 }
