@@ -262,6 +262,7 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   const uint32_t tmem_slot = bar + 256;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + xchg_off + kXchgBytes + 256);
 
+  ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = prm.T, H = prm.H, nq = prm.nq, U = prm.U, items = prm.items;
   const int d = H * kHd;
@@ -292,6 +293,7 @@ attention_row_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::pdl_wait();   // set-up done: from here on the previous kernel's output (qkv) is read
 
   // tile t of the CTA's n-th item belongs to group t ^ (n & 1) (two tiles) or n & 1 (one tile): the group that gets the short
   // second tile of a 197-token sequence alternates from item to item
@@ -656,8 +658,8 @@ int launch_attention_row_sm100(const void* qkv, void* out, float* lse, int B, in
   cudaMemsetAsync(d_trace, 0, 20 * 32 * 8 * sizeof(long long), stream);
   p.trace = d_trace;
 #endif
-  if (f16) attention_row_sm100_kernel<true><<<grid, kThreads, smem, stream>>>(tq, tkv, tout, p);
-  else attention_row_sm100_kernel<false><<<grid, kThreads, smem, stream>>>(tq, tkv, tout, p);
+  if (f16) launch_k(attention_row_sm100_kernel<true>, dim3(grid), dim3(kThreads), size_t(smem), stream, tq, tkv, tout, p);
+  else launch_k(attention_row_sm100_kernel<false>, dim3(grid), dim3(kThreads), size_t(smem), stream, tq, tkv, tout, p);
 #ifdef IIC_ATTN_TRACE
   if (const char* path = getenv("IIC_ATTN_TRACE_OUT")) {
     static long long h_trace[20 * 32 * 8];

@@ -168,6 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   float* bias_s = reinterpret_cast<float*>(bar_gen + S::kBarBytes + kBlockN * 16);
   uint8_t* slab_gen = smem_gen + kStages * S::kStageBytes;
 
+  ptx::pdl_launch_dependents();   // the next kernel of the stream may start its prologue (PDL launches only)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (kCtas == 1) ? 0u : ptx::cluster_ctarank();
@@ -205,6 +206,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if constexpr (kCtas > 1) ptx::cluster_sync(); else __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // barriers, TMEM and descriptors are set up: from here on global memory written by the previous kernel is read
+  ptx::pdl_wait();
 
   const int m_tiles = (args.M + kTileM - 1) / kTileM;
   const int n_tiles = (args.N + kBlockN - 1) / kBlockN;

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#include "ptx_sm100.cuh"
 
 namespace iic {
 
@@ -42,6 +43,8 @@ head_kernel(const float* __restrict__ x, long long x_img_stride, const float* __
             int G, int topk, float logit_scale, int B, float* __restrict__ emb_out, float* __restrict__ logits_out,
             float* __restrict__ probs_out, float* __restrict__ topk_val, int* __restrict__ topk_idx,
             float* __restrict__ split_sum, const float* __restrict__ emb_in) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float sm[];
   float* s_x = sm;
   float* s_e = s_x + kImgs * W;
@@ -230,6 +233,8 @@ __global__ void __launch_bounds__(kSmallThreads)
 head_small_proj_kernel(const float* __restrict__ x, long long x_img_stride, const float* __restrict__ ln_g,
                        const float* __restrict__ ln_b, float eps, const float* __restrict__ proj, int W, int E, int B,
                        float* __restrict__ emb_out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float sm[];
   float* s_x = sm;                       // [B][W] normalised class-token rows
   float* s_p = s_x + size_t(B) * W;      // [16 warps][B][32] partial sums
@@ -278,6 +283,8 @@ head_small_proj_kernel(const float* __restrict__ x, long long x_img_stride, cons
 __global__ void __launch_bounds__(kSmallThreads)
 head_small_logits_kernel(const float* __restrict__ emb, int E, const float* __restrict__ text, int L, float logit_scale, int B,
                          float* __restrict__ logits_out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float sm[];
   float* s_e = sm;                       // [B][E] L2-normalised embeddings
   float* s_r = s_e + size_t(B) * E;      // [B]
@@ -324,6 +331,8 @@ head_small_groups_kernel(const float* __restrict__ logits, int L, const int* __r
                          const int* __restrict__ group_split, int G, int topk, int B, float* __restrict__ probs_out,
                          float* __restrict__ topk_val, int* __restrict__ topk_idx, float* __restrict__ split_sum,
                          float* __restrict__ scratch) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 8 + warp;
   if (pair >= B * G) return;
@@ -406,16 +415,16 @@ int launch_head(const float* x, long long x_img_stride, const float* ln_g, const
     }
     if (emb_in == nullptr) {
       const size_t smem = sizeof(float) * (size_t(B) * W + size_t(16) * B * 32);
-      head_small_proj_kernel<<<(E + 31) / 32, kSmallThreads, smem, stream>>>(x, x_img_stride, ln_g, ln_b, eps, proj, W, E, B, emb);
+      launch_k(head_small_proj_kernel, dim3((E + 31) / 32), dim3(kSmallThreads), smem, stream, x, x_img_stride, ln_g, ln_b, eps, proj, W, E, B, emb);
     } else {
       emb = const_cast<float*>(emb_in);
     }
     if (text == nullptr || L <= 0) return cudaGetLastError() == cudaSuccess ? 0 : -2;
     const size_t smem2 = sizeof(float) * (size_t(B) * E + 64);
-    head_small_logits_kernel<<<(L + kSmallThreads / 32 - 1) / (kSmallThreads / 32), kSmallThreads, smem2, stream>>>(
-        emb, E, text, L, logit_scale, B, logits);
-    head_small_groups_kernel<<<(B * G + 7) / 8, 256, 0, stream>>>(logits, L, group_off, group_split, G, topk, B, probs_out, topk_val,
-                                                                 topk_idx, split_sum, pwork);
+    launch_k(head_small_logits_kernel, dim3((L + kSmallThreads / 32 - 1) / (kSmallThreads / 32)), dim3(kSmallThreads), smem2, stream,
+             static_cast<const float*>(emb), E, text, L, logit_scale, B, logits);
+    launch_k(head_small_groups_kernel, dim3((B * G + 7) / 8), dim3(256), 0, stream, static_cast<const float*>(logits), L, group_off,
+             group_split, G, topk, B, probs_out, topk_val, topk_idx, split_sum, pwork);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   const size_t smem = sizeof(float) * (size_t(kImgs) * (W + E + L) + 64);

@@ -15,6 +15,10 @@
 
 using namespace iic;
 
+namespace iic {
+thread_local int g_pdl = 0;
+}
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -105,6 +109,7 @@ struct iic_handle {
   int train_fused = 1;    // 1: the training forward keeps the c_fc pre-activation (dual-output epilogue) and the c_proj dX GEMM
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
+  int pdl_max_batch = 16;  // batches up to this size launch their kernels with programmatic dependent launch (IIC_PDL_MAX_BATCH; 0 = off)
   int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
@@ -120,6 +125,12 @@ struct iic_handle {
 };
 
 namespace {
+
+// programmatic dependent launch for the duration of one small-batch call on this thread (kernels.h: g_pdl)
+struct PdlScope {
+  PdlScope(const iic_handle* h, int B) { g_pdl = (h && h->pdl_max_batch > 0 && B > 0 && B <= h->pdl_max_batch) ? 1 : 0; }
+  ~PdlScope() { g_pdl = 0; }
+};
 
 int fail(iic_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -605,6 +616,7 @@ int iic_create(iic_handle** out, const iic_config* cfg) {
   h->f16 = cfg->operand_dtype == IIC_DTYPE_F16 ? 1 : 0;
   if (const char* e = getenv("IIC_ATTN_IMPL")) h->attn_impl = atoi(e);
   if (const char* e = getenv("IIC_ATTN_BWD_IMPL")) h->attn_bwd_impl = atoi(e);
+  if (const char* e = getenv("IIC_PDL_MAX_BATCH")) h->pdl_max_batch = atoi(e);
   if (const char* e = getenv("IIC_TRAIN_FUSED")) h->train_fused = atoi(e);
   if (const char* e = getenv("IIC_LORA_BWD_FUSED")) h->lora_bwd_fused = atoi(e);
   if (const char* e = getenv("IIC_GEMM_CTAS")) { if (atoi(e) == 1) h->ctas = 1; else if (atoi(e) == 2) h->ctas = 2; }
@@ -815,6 +827,7 @@ int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int
 int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* out, int out_layout, void* stream) {
   if (!h || !imgs || !out || B < 0 || out_layout < 0 || out_layout > 2)
     return fail(h, IIC_ERR_ARG, "iic_preprocess_same_size: bad argument");
+  PdlScope pdl(h, B);
   Scope sc(h->prof, kPreprocess, static_cast<cudaStream_t>(stream));
   int rc = launch_preprocess_fast(h->pre, imgs, B, h->cfg.image_size, h->cfg.patch_size, h->patch_kpad, out, out_layout,
                                   h->f16, static_cast<cudaStream_t>(stream));
@@ -855,6 +868,7 @@ static int check_ws(iic_handle* h, int B, void* workspace, size_t bytes, Workspa
 int iic_encode(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
                void* stream) {
   if (!h || !patches || !emb_out) return fail(h, IIC_ERR_ARG, "iic_encode: null argument");
+  PdlScope pdl(h, B);
   Workspace w;
   int rc = check_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;
@@ -895,6 +909,7 @@ int iic_head(iic_handle* h, const float* emb, int B, const iic_head_out* out, vo
 int iic_classify(iic_handle* h, const void* patches, int B, void* workspace, size_t workspace_bytes, float* emb_out,
                  const iic_head_out* out, void* stream) {
   if (!h || !patches || !out) return fail(h, IIC_ERR_ARG, "iic_classify: null argument");
+  PdlScope pdl(h, B);
   Workspace w;
   int rc = check_ws(h, B, workspace, workspace_bytes, &w);
   if (rc) return rc;

@@ -24,6 +24,25 @@ struct PerDeviceOnce {
   void mark() { done.fetch_or(1ull << device(), std::memory_order_release); }
 };
 
+// Programmatic dependent launch for the small-batch (latency) path: the ~100 dependent launches of a batch-1 pass overlap
+// each kernel's launch latency and prologue with its predecessor's tail.  Set per call by the engine (iic_api.cu) on the calling
+// thread; kernels on that path start with ptx::pdl_launch_dependents() and call ptx::pdl_wait() before their first global read.
+extern thread_local int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- rowwise.cu ----
 int launch_layernorm(const float* x, long long x_row_stride, const float* gamma, const float* beta,
                      void* out_bf16, float* out_f32, long long out_row_stride, int rows, int D, float eps,

@@ -26,6 +26,7 @@
 
 #include "act_types.cuh"
 #include "kernels.h"
+#include "ptx_sm100.cuh"
 
 namespace iic {
 
@@ -194,9 +195,11 @@ template <bool kF16>
 __global__ void __launch_bounds__(256)
 preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut,
                            uint16_t* __restrict__ out, int B, int R, int k_pad) {
+  ptx::pdl_launch_dependents();
   __shared__ float s_lut[768];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];   // constant table: may precede the dependency wait
   __syncthreads();
+  ptx::pdl_wait();
   const int g = R / 16;
   const long long total = (long long)B * R * g;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,6 +238,8 @@ preprocess_fast_p16_kernel(const uint8_t* __restrict__ img, const float* __restr
 __global__ void __launch_bounds__(256)
 preprocess_same_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut, void* out, int out_mode, int f16,
                        int B, int R, int P, int k_pad) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long total = (long long)B * R * R;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -312,15 +317,15 @@ int launch_preprocess_fast(PreprocessPlan* plan, const uint8_t* imgs, int B, int
   if (out_mode == 0 && P == 16 && (reinterpret_cast<uintptr_t>(imgs) & 15) == 0 && k_pad % 8 == 0) {
     const long long total = (long long)B * R * (R / 16);
     if (f16)
-      preprocess_fast_p16_kernel<true><<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-          imgs, plan->d_lut, reinterpret_cast<uint16_t*>(out), B, R, k_pad);
+      launch_k(preprocess_fast_p16_kernel<true>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, stream, imgs, plan->d_lut,
+               reinterpret_cast<uint16_t*>(out), B, R, k_pad);
     else
-      preprocess_fast_p16_kernel<false><<<unsigned((total + 255) / 256), 256, 0, stream>>>(
-          imgs, plan->d_lut, reinterpret_cast<uint16_t*>(out), B, R, k_pad);
+      launch_k(preprocess_fast_p16_kernel<false>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, stream, imgs, plan->d_lut,
+               reinterpret_cast<uint16_t*>(out), B, R, k_pad);
   } else {
     const long long total = (long long)B * R * R;
-    preprocess_same_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(imgs, plan->d_lut, out, out_mode, f16, B,
-                                                                            R, P, k_pad);
+    launch_k(preprocess_same_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, stream, imgs, plan->d_lut, out, out_mode, f16,
+             B, R, P, k_pad);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -40,6 +40,14 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and its
+// memory is visible (a no-op for ordinary launches), pdl_launch_dependents() lets the NEXT kernel start its prologue now.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------------------
 // cluster
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

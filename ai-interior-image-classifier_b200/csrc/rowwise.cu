@@ -12,6 +12,7 @@
 
 #include "act_types.cuh"
 #include "kernels.h"
+#include "ptx_sm100.cuh"
 
 namespace iic {
 
@@ -35,6 +36,8 @@ layernorm_kernel(const float* __restrict__ x, long long x_row_stride, const floa
                  long long out_row_stride, int rows, float eps, const float* __restrict__ lora_a, int r4,
                  uint16_t* __restrict__ p_out, int p_ld) {
   constexpr int D = kVec * 128;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -202,6 +205,8 @@ lora_down_bf16_kernel(const uint16_t* __restrict__ x, int K, int rows, const flo
 template <bool kF16>
 __global__ void __launch_bounds__(256)
 lora_reduce_kernel(const float* __restrict__ part, int n_tiles, int rows, uint16_t* __restrict__ p_out, int p_ld) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,6 +225,8 @@ lora_reduce_kernel(const float* __restrict__ part, int n_tiles, int rows, uint16
 // x_pre[b*T + 0, :] = class_embedding + positional_embedding[0]
 __global__ void fill_cls_kernel(float* __restrict__ x_pre, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int B, int T, int D) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
@@ -261,13 +268,13 @@ static int layernorm_launch(const float* x, long long xs, const float* gamma, co
   const int need = (rows + wpb - 1) / wpb;
   if (la == nullptr) {
     const int blocks = need < sms * 8 ? need : sms * 8;   // <= 8 resident CTAs/SM worth of warps, grid-stride beyond
-    layernorm_kernel<kVec, kF16, 0><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
+    launch_k(layernorm_kernel<kVec, kF16, 0>, dim3(blocks), dim3(threads), 0, stream, x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
   } else if (r4 == 4) {
     const int blocks = need < sms ? need : sms;           // A slice lives in registers (1 CTA/SM): few, long-lived warps
-    layernorm_kernel<kVec, kF16, 1><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
+    launch_k(layernorm_kernel<kVec, kF16, 1>, dim3(blocks), dim3(threads), 0, stream, x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
   } else {
     const int blocks = need < sms * 8 ? need : sms * 8;
-    layernorm_kernel<kVec, kF16, 2><<<blocks, threads, 0, stream>>>(x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
+    launch_k(layernorm_kernel<kVec, kF16, 2>, dim3(blocks), dim3(threads), 0, stream, x, xs, gamma, beta, ob, of, ors, rows, eps, la, r4, po, pld);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -320,9 +327,9 @@ int launch_lora_reduce(const float* part, int n_tiles, int rows, void* p_out, in
   if (p_ld % 4 != 0 || p_ld < 4) return -1;
   const int blocks = (rows + 255) / 256;
   if (f16)
-    lora_reduce_kernel<true><<<blocks, 256, 0, stream>>>(part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
+    launch_k(lora_reduce_kernel<true>, dim3(blocks), dim3(256), 0, stream, part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
   else
-    lora_reduce_kernel<false><<<blocks, 256, 0, stream>>>(part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
+    launch_k(lora_reduce_kernel<false>, dim3(blocks), dim3(256), 0, stream, part, n_tiles, rows, static_cast<uint16_t*>(p_out), p_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -368,7 +375,7 @@ int launch_scatter_rows(const float* rows, const int32_t* row_index, int T, int 
 int launch_fill_cls(float* x_pre, const float* cls, const float* pos, int B, int T, int D, cudaStream_t stream) {
   const int n = B * D;
   if (n <= 0) return 0;
-  fill_cls_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x_pre, cls, pos, B, T, D);
+  launch_k(fill_cls_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, x_pre, cls, pos, B, T, D);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
