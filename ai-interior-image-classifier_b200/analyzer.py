@@ -344,8 +344,73 @@ class CachedInteriorAnalyzer:
                               "analysis": {}, "reason": f"Nie wnętrze: {category} (confidence: {interior:.3f})"}
         return results
 
+    # -- data parallel inside one process (images are independent, weights replicated, no collective) ------------
+    @staticmethod
+    def _cuda_device(device) -> torch.device:
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise RuntimeError(f"analyze_images_batch(devices=...): {dev} is not a CUDA device (there is no CPU path)")
+        return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _make_replica(self, dev: torch.device) -> "CachedInteriorAnalyzer":
+        """This analyzer bound to `dev`: a deep copy of the model (hence its own engine and workspace) with the cached label
+        matrices moved over; label schema, categories and settings are shared."""
+        import copy
+        r = copy.copy(self)                       # shallow: shares training_data / all_categories
+        r.__dict__.pop("_replicas", None)
+        r.device = str(dev)
+        r.model = copy.deepcopy(self.model).to(dev)
+        r.model.visual._engine, r.model.visual._sig, r.model.visual._zero_b = None, None, {}   # a fresh engine on `dev`
+        if hasattr(r.model, "_text_engine"):
+            r.model._text_engine, r.model._text_sig = None, None
+        r.preprocess = clip.Preprocess(r.model.visual)
+        r.detector = copy.copy(self.detector)
+        r.detector.device, r.detector.model, r.detector.preprocess = str(dev), r.model, r.preprocess
+        r.detector.text_features = self.detector.text_features.to(dev)
+        r.text_features_cache = {g: t.to(dev) for g, t in self.text_features_cache.items()}
+        return r
+
+    def _analyze_data_parallel(self, image_paths, devices, **kw):
+        """Contiguous shards of `image_paths`, one feeder thread per entry of `devices`; every thread runs the ordinary
+        single-device entry point on its replica (ctypes releases the GIL, so the engines run concurrently).  The merged dict
+        equals the single-device result: an image's result does not depend on the batch it travels in.  A device may be named
+        more than once (several engines on one GPU)."""
+        from .dp import shard_bounds
+        paths = list(image_paths)
+        devs = [self._cuda_device(d) for d in devices]
+        cache = self.__dict__.setdefault("_replicas", {})
+        own = self._cuda_device(self.device)
+        reps = []
+        for slot, dev in enumerate(devs):
+            if dev == own and self not in reps:
+                reps.append(self)
+                continue
+            key = (slot, str(dev))
+            if key not in cache:
+                cache[key] = self._make_replica(dev)
+            reps.append(cache[key])
+        spans = [shard_bounds(len(paths), k, len(reps)) for k in range(len(reps))]
+
+        def work(k):
+            lo, hi = spans[k]
+            if lo == hi:
+                return {}
+            with torch.cuda.device(torch.device(reps[k].device)):
+                return reps[k].analyze_images_batch(paths[lo:hi], **kw)
+        with ThreadPoolExecutor(max_workers=len(reps)) as ex:
+            parts = list(ex.map(work, range(len(reps))))
+        merged = {}
+        for part in parts:
+            merged.update(part)
+        return merged
+
     def analyze_images_batch(self, image_paths, batch_size: int = 16, filter_interiors: bool = True,
-                             confidence_threshold: float = 0.3):
+                             confidence_threshold: float = 0.3, devices: Optional[Sequence] = None):
+        """main.py:371-469.  `devices` (new, optional): a list of CUDA devices, e.g. range(8) - the paths are sharded over them
+        (one engine + one feeder thread per device); the returned dict is the same as on one device."""
+        if devices is not None and len(list(devices)) > 1:
+            return self._analyze_data_parallel(image_paths, list(devices), batch_size=batch_size, filter_interiors=filter_interiors,
+                                               confidence_threshold=confidence_threshold)
         results, valid_images, image_metadata = {}, [], []
         if filter_interiors and self.share_detector_encoder:
             return self._analyze_shared(image_paths, batch_size, confidence_threshold)

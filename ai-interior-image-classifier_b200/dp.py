@@ -28,3 +28,19 @@ def gather_in_order(local_results: List, group=None) -> List:
     bucket = [None] * dist.get_world_size(group)
     dist.all_gather_object(bucket, list(local_results), group=group)
     return [r for part in bucket for r in part]
+
+
+def analyze_distributed(analyzer, image_paths: Sequence[str], group=None, **kw) -> dict:
+    """`CachedInteriorAnalyzer.analyze_images_batch` under torchrun (one process per GPU): every rank analyses its contiguous
+    shard of `image_paths` on its own engine - no data-path collective - and the per-path result dicts are gathered on the
+    host, so every rank returns the same dict the single-process call returns (/root/reference/main.py:371-469)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return analyzer.analyze_images_batch(list(image_paths), **kw)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = list(shard(list(image_paths), rank, world))
+    local = analyzer.analyze_images_batch(mine, **kw) if mine else {}
+    merged = {}
+    for path, res in gather_in_order([(p, local[p]) for p in mine if p in local], group):
+        merged[path] = res
+    return merged

@@ -111,6 +111,11 @@ class Engine:
         self._profiling = False
         self.graph_max_batch = int(os.environ.get("IIC_GRAPH_MAX_BATCH", "16"))
 
+    def __deepcopy__(self, memo):
+        """An engine is bound to one device handle: a deep-copied model gets None here and builds its own engine on first use
+        (clip_compat.VisionTransformer.engine), e.g. the per-device replicas of analyzer.analyze_images_batch(devices=...)."""
+        return None
+
     def __del__(self):
         try:
             if getattr(self, "h", None):

@@ -66,7 +66,11 @@ def _guarded_step(trainer, loss: torch.Tensor) -> float:
 
 class VisionLoRATrainer:
     def __init__(self, model: "CLIP | VisionTransformer", lr: float = 1e-4, weight_decay: float = 0.01,
-                 max_grad_norm: float = 1.0, logit_scale: Optional[float] = None, process_group=None, overlap: bool = True):
+                 max_grad_norm: float = 1.0, logit_scale: Optional[float] = None, process_group=None, overlap: bool = True,
+                 distributed: Optional[bool] = None):
+        """distributed: None = data parallel whenever torch.distributed is initialised with more than one rank; False = this
+        rank alone (no broadcast, no all-reduce: local gradients)."""
+        self.distributed = distributed
         self.visual: VisionTransformer = model.visual if hasattr(model, "visual") else model
         self.logit_scale = float(logit_scale) if logit_scale is not None else (
             float(model.logit_scale.detach().exp()) if hasattr(model, "logit_scale") else 100.0)
@@ -103,7 +107,8 @@ class VisionLoRATrainer:
                 p.grad = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             self.buckets[i] = flat
-        _broadcast_lora(self.params, process_group)      # identical adapters on every rank before the optimizer state exists
+        if distributed is not False:
+            _broadcast_lora(self.params, process_group)  # identical adapters on every rank before the optimizer state exists
         self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)   # train_lora.py:212
         self.comm_stream = torch.cuda.Stream(device=dev) if process_group is not None or self._dist_on() else None
         self._training_weights_sig = None
@@ -170,7 +175,7 @@ class VisionLoRATrainer:
         loss = self.head_and_loss(x_cls, text_features.detach().to(eng.device, torch.float32))
         (dx_cls,) = torch.autograd.grad(loss, x_cls)
         works = []
-        distributed = self._dist_on()
+        distributed = self._dist_on() and self.distributed is not False
 
         def layer_done(layer: int) -> None:
             if not distributed or layer not in self.buckets:

@@ -250,3 +250,20 @@ def test_gpu_jpeg_ingest(analyzer, tmp_path):
         same_style += hs[0][0] == ds[0][0]
         assert abs(hs[0][1] - ds[0][1]) < 2e-2
     assert same_style >= len(paths) - 2
+
+
+def test_analyze_images_batch_data_parallel(analyzer):
+    """analyze_images_batch(devices=[...]): shards over one engine + feeder thread per device; the merged dict equals the
+    single-device result field by field (bit-equal probabilities: an image's result does not depend on its batch).  With one
+    GPU the two replicas share the device (two engines in one process: also the per-device attribute opt-in of ADVICE r1)."""
+    paths = [_png(analyzer, f) for f in analyzer.files[:61]]
+    one = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=True)
+    ndev = torch.cuda.device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    two = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=True, devices=devices)
+    assert list(two) == list(one) or set(two) == set(one)
+    for p in paths:
+        assert two[p] == one[p], (p, two[p], one[p])
+    three = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=False, devices=devices + [0])
+    ref = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=False)
+    assert all(three[p] == ref[p] for p in paths)
