@@ -302,7 +302,22 @@ class CLIP(nn.Module):
         self._text_sig = (sig_w, sig_l)
         return eng
 
+    def _adopt_stray_lora(self) -> None:
+        """/root/reference/main.py:26-27 creates its LoRA parameters on the CPU and never moves them: on a CUDA
+        model `x @ self.lora_A` inside the text tower then fails on the device.  Any LoRA parameter of the text tower that lives
+        on another device than the tower is moved over in place (what `model.to(device)` after the wrap would have done); the
+        vision tower needs nothing - the engine uploads its operands itself."""
+        dev = self.token_embedding.weight.device
+        for mod in self.transformer.modules():
+            lo = getattr(mod, "lora", None)
+            if lo is None or not _is_lora_wrapped(mod):
+                continue
+            for prm in lo.parameters():
+                if prm.device != dev:
+                    prm.data = prm.data.to(dev)
+
     def encode_text(self, text: torch.Tensor) -> torch.Tensor:
+        self._adopt_stray_lora()
         if self.text_on_engine:
             eng = self.sync_text_engine()
             with torch.no_grad():
