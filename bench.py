@@ -379,9 +379,11 @@ def main():
         timgs = torch.randint(0, 256, (TB, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
         ttext = torch.nn.functional.normalize(torch.randn(TB, 512, device=dev, generator=g), dim=-1)
         tr_out = {}
-        for overlap in (True, False):
-            tr = iic_b200.VisionLoRATrainer(vis, logit_scale=100.0, overlap=overlap)
-            for _ in range(3):
+        # three arms of the same step: eager launches with the per-block all-reduce overlapped with the backward / not
+        # overlapped, and the whole forward + loss + backward replayed as ONE CUDA graph (all-reduce of the flat buffer after it)
+        for arm, kw in (("ms_overlap", dict(overlap=True)), ("ms_no_overlap", dict(overlap=False)), ("ms_graph", dict(use_graph=True))):
+            tr = iic_b200.VisionLoRATrainer(vis, logit_scale=100.0, **kw)
+            for _ in range(4):
                 tr.step(timgs, ttext)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -391,7 +393,7 @@ def main():
             e1.record()
             barrier()
             (ms,) = max_over_ranks(e0.elapsed_time(e1) / tsteps)
-            tr_out["ms_overlap" if overlap else "ms_no_overlap"] = ms
+            tr_out[arm] = ms
         tr.forward_backward(timgs, ttext)
         flat = torch.cat([b for _, b in sorted(tr.buckets.items())])
         pflat = torch.cat([p.detach().reshape(-1) for p in tr.params])
@@ -406,13 +408,14 @@ def main():
                     same_g = bool(ok.item() == 1.0)
                 else:
                     same_p = bool(ok.item() == 1.0)
-        extra["train"] = {"ms_per_step": tr_out["ms_overlap"], "images_s": world * TB / (tr_out["ms_overlap"] * 1e-3), "batch_per_gpu": TB,
+        best = min(tr_out["ms_overlap"], tr_out["ms_graph"])
+        extra["train"] = {"ms_per_step": best, "images_s": world * TB / (best * 1e-3), "batch_per_gpu": TB, "ms_graph": tr_out["ms_graph"],
                           "lora_rank": args.lora_rank, "steps": tsteps, "loss": float(loss), "allreduce_bytes": int(flat.numel() * 4) if world > 1 else 0,
                           "ms_overlap": tr_out["ms_overlap"], "ms_no_overlap": tr_out["ms_no_overlap"],
                           "ranks_identical_grads": same_g, "ranks_identical_params_after_steps": same_p,
                           "skipped_steps": int(getattr(tr, "skipped_steps", 0)),
-                          "train_tflops": 72.1e9 * TB / (tr_out["ms_overlap"] * 1e-3) / 1e12,
-                          "frac_of_sustained_peak": 72.1e9 * TB / (tr_out["ms_overlap"] * 1e-3) / 1e12 / peaks["tflops"],
+                          "train_tflops": 72.1e9 * TB / (best * 1e-3) / 1e12,
+                          "frac_of_sustained_peak": 72.1e9 * TB / (best * 1e-3) / 1e12 / peaks["tflops"],
                           "what": "VisionLoRATrainer.step: fwd + bwd through the frozen blocks + LoRA-only grads + clip_grad_norm_ + AdamW "
                                   "(train_lora.py:227-252 on the vision MLPs); one NCCL all-reduce(avg) per block on a side stream"}
         del tr, vis, timgs
