@@ -121,6 +121,49 @@ __device__ __forceinline__ float quick_gelu(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// (o0, o1) = (a0 + b0, a1 + b1) as one FADD2 (same rounding as two FADDs)
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  uint64_t a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(a));
+}
+// Two QuickGELUs on the packed fp32 pipe (FMUL2, FMUL2, FFMA2 + two MUFU.TANH): 2.5 issue slots per element instead of 4.
+// mul/fma.rn.f32x2 round each lane exactly like the scalar forms, so the result is bit-identical to quick_gelu().
+__device__ __forceinline__ void quick_gelu2(float& a, float& b) {
+  uint64_t x, z, hx, t;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(0x3F59DB233F59DB23ull));   // 0.851f in both lanes
+  float z0, z1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(z));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(0x3F0000003F000000ull));  // 0.5f
+  asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(x) : "l"(hx), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x));
+}
+// (a, b) *= QuickGELU'(u0), QuickGELU'(u1) on the packed pipe; lane arithmetic and rounding order identical to
+//   s = fmaf(0.5, tanh(0.851 u), 0.5);  g = fmaf((1.702 u) s, 1 - s, s);  a *= g
+__device__ __forceinline__ void quick_gelu_grad_mul2(float& a, float& b, float u0, float u1) {
+  uint64_t u, z, t, sg, w, om, g, ab;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(u0), "f"(u1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(u), "l"(0x3F59DB233F59DB23ull));    // 0.851f
+  float z0, z1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(z));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(sg) : "l"(0x3F0000003F000000ull), "l"(t));            // 0.5 t + 0.5
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w) : "l"(u), "l"(0x3FD9DB233FD9DB23ull));    // 1.702f u
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w) : "l"(w), "l"(sg));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(om) : "l"(sg), "l"(0xBF800000BF800000ull), "l"(0x3F8000003F800000ull));   // 1 - s (exact as in the scalar form)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(g) : "l"(w), "l"(om), "l"(sg));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(a), "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ab) : "l"(ab), "l"(g));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(ab));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 constexpr int kGemmThreads = 384;
@@ -413,10 +456,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               float4 r = *p;
               float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
               bb = reinterpret_cast<const float4*>(bias_s + s * 32)[j];
-              r.x += __uint_as_float(v[4 * j]) + bb.x;
-              r.y += __uint_as_float(v[4 * j + 1]) + bb.y;
-              r.z += __uint_as_float(v[4 * j + 2]) + bb.z;
-              r.w += __uint_as_float(v[4 * j + 3]) + bb.w;
+              float t0, t1, t2, t3;   // r += (acc + bias), as packed FADD2s (same rounding order as the scalar form)
+              add2(t0, t1, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), bb.x, bb.y);
+              add2(t2, t3, __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), bb.z, bb.w);
+              add2(r.x, r.y, r.x, r.y, t0, t1);
+              add2(r.z, r.w, r.z, r.w, t2, t3);
               *p = r;
             }
             ptx::fence_proxy_async_smem();
@@ -461,7 +505,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int c = j * 8 + 2 * e;
                 const float a0 = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]);
                 const float a1 = __uint_as_float(c < 32 ? v0[(c + 1) & 31] : v1[(c + 1) & 31]);
-                pu[e] = Act<kF16>::pack(a0 * grad(u2.x), a1 * grad(u2.y));
+                if (erf_act) {
+                  pu[e] = Act<kF16>::pack(a0 * grad(u2.x), a1 * grad(u2.y));
+                } else {
+                  float o0 = a0, o1 = a1;
+                  quick_gelu_grad_mul2(o0, o1, u2.x, u2.y);
+                  pu[e] = Act<kF16>::pack(o0, o1);
+                }
               }
               *p = uu;
             }
@@ -502,10 +552,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = bb[i >> 2];
-                f[i] = __uint_as_float(half == 0 ? v0[i] : v1[i]) + b4.x;
-                f[i + 1] = __uint_as_float(half == 0 ? v0[i + 1] : v1[i + 1]) + b4.y;
-                f[i + 2] = __uint_as_float(half == 0 ? v0[i + 2] : v1[i + 2]) + b4.z;
-                f[i + 3] = __uint_as_float(half == 0 ? v0[i + 3] : v1[i + 3]) + b4.w;
+                add2(f[i], f[i + 1], __uint_as_float(half == 0 ? v0[i] : v1[i]), __uint_as_float(half == 0 ? v0[i + 1] : v1[i + 1]), b4.x, b4.y);
+                add2(f[i + 2], f[i + 3], __uint_as_float(half == 0 ? v0[i + 2] : v1[i + 2]), __uint_as_float(half == 0 ? v0[i + 3] : v1[i + 3]), b4.z,
+                     b4.w);
               }
               if constexpr (kDual) {
                 uint8_t* u_row = slab_gen + grp * kSlabBytes + r_in_tile * 128;
@@ -523,11 +572,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                   for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+                  for (int i = 0; i < 32; i += 2) quick_gelu2(f[i], f[i + 1]);
                 }
               } else if constexpr (kEpi == kEpiBiasGeluBf16) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+                for (int i = 0; i < 32; i += 2) quick_gelu2(f[i], f[i + 1]);
               } else if constexpr (kEpi == kEpiGeluExactBf16) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
