@@ -393,7 +393,12 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   w.dp1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
-  w.outer_scratch = static_cast<float*>(take(lora_outer_scratch_bytes(int(mlp), int(M))));
+  {   // one scratch for every LoRA gradient reduction of the step: the CTA shapes (and so the partial counts) depend on N
+    size_t sc = lora_outer_scratch_bytes(int(mlp), int(M));
+    for (size_t n : {d, 3 * d})
+      if (lora_outer_scratch_bytes(int(n), int(M)) > sc) sc = lora_outer_scratch_bytes(int(n), int(M));
+    w.outer_scratch = static_cast<float*>(take(sc));
+  }
   w.attn_d = static_cast<float*>(take(size_t(B) * H * h->T * 4));   // D = rowsum(dO o O) of the attention backward
   w.xpre = reinterpret_cast<float*>(w.hid);
   w.layers.resize(h->blocks.size());

@@ -245,13 +245,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   }
 }
 
-constexpr int kOuterRowsPerCta = 512;   // 4 warps x 128 rows
 constexpr int kOuterStages = 4;
 
 template <bool kF16>
 __global__ void __launch_bounds__(128)
 lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __restrict__ Y, int N, int M, int act,
-                      float* __restrict__ part) {
+                      int rank, int rows_per_warp, float* __restrict__ part) {
   // per warp: kOuterStages x (Y slice 16 x 128 B = 2 KB, P slice 16 x 32 B = 512 B) - three slices in flight per warp keep
   // the kernel on the HBM roofline; the CTA-wide reduction buffer red[4][16][65] aliases the stage buffers after the loop
   __shared__ __align__(128) uint8_t sbuf[4][kOuterStages][2560];
@@ -259,8 +258,8 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
   float (*red)[16][65] = reinterpret_cast<float (*)[16][65]>(&sbuf[0][0][0]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 64;
-  const int m_begin = blockIdx.y * kOuterRowsPerCta + warp * 128;
-  const int m_end = min(M, m_begin + 128);
+  const int m_begin = (blockIdx.y * 4 + warp) * rows_per_warp;
+  const int m_end = min(M, m_begin + rows_per_warp);
   const uint32_t sb = static_cast<uint32_t>(__cvta_generic_to_shared(&sbuf[warp][0][0]));
   float acc[8][4];
 #pragma unroll
@@ -340,7 +339,8 @@ lora_outer_mma_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* 
     red[warp][g + 8][8 * j + 2 * t + 1] = acc[j][3];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * 64; i += 128) {
+  const int used = (rank + 3) & ~3;   // the reduction reads rows c < rank only
+  for (int i = threadIdx.x; i < used * 64; i += 128) {
     const int c = i >> 6, n = i & 63;
     if (n0 + n < N)
       part[(size_t(blockIdx.y) * 16 + c) * N + n0 + n] = (red[0][c][n] + red[1][c][n]) + (red[2][c][n] + red[3][c][n]);
@@ -482,8 +482,9 @@ lora_bwd_kernel(const uint16_t* __restrict__ P, int p_ld, const uint16_t* __rest
 #pragma unroll
   for (int j = 0; j < kTW * 8; ++j) {
     const int col = c_warp + j * 8 + 2 * t4;
-    *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g) * N + col) = make_float2(acc[j][0], acc[j][1]);
-    *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g + 8) * N + col) = make_float2(acc[j][2], acc[j][3]);
+    if (g < rank) *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g) * N + col) = make_float2(acc[j][0], acc[j][1]);
+    if (g + 8 < rank)
+      *reinterpret_cast<float2*>(part_db + (size_t(blockIdx.y) * 16 + g + 8) * N + col) = make_float2(acc[j][2], acc[j][3]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < (m_end - m_begin) * 4; i += 128)
@@ -504,20 +505,44 @@ lora_dp_reduce_kernel(const float* __restrict__ part, int groups, int M, uint16_
   reinterpret_cast<uint2*>(out)[i] = make_uint2(Act<kF16>::pack(s.x, s.y), Act<kF16>::pack(s.z, s.w));
 }
 
-// out = scale * sum_split part[split][c][n], c < rc (4 or 16 columns per pass)
-// written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r))
+// out = scale * sum_split part[split][c][n], c < rc (4 or 16 columns per pass; only the c0 + c < rank rows are touched)
+// written either as [c0+c][n] (dB: (r, out)) or [n][c0+c] (dA: (in, r)).  CTA = 32 consecutive n x 8 split lanes: lane j
+// adds splits j, j + 8, ... (independent loads, four in flight), the eight partial sums are added in lane order - a fixed
+// summation tree, so the result is deterministic; ~2 memory round trips instead of one per split.
 __global__ void __launch_bounds__(256)
 lora_outer_reduce_kernel(const float* __restrict__ part, int splits, int N, int rank, int c0, int rc, float scale, int transpose,
                          float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rc * N) return;
-  const int c = i / N, n = i - c * N;
-  if (c0 + c >= rank) return;
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int n_chunks = (N + 31) / 32;
+  const int c = blockIdx.x / n_chunks, n = (blockIdx.x - c * n_chunks) * 32 + lane;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += part[(size_t(sp) * rc + c) * N + n];
-  s *= scale;
-  if (transpose) out[size_t(n) * rank + c0 + c] = s;
-  else out[size_t(c0 + c) * N + n] = s;
+  if (n < N) {
+    const float* p = part + size_t(c) * N + n;
+    const size_t stride = size_t(rc) * N;
+    for (int sp = j; sp < splits; sp += 32) {
+      const float v0 = p[size_t(sp) * stride];
+      const float v1 = sp + 8 < splits ? p[size_t(sp + 8) * stride] : 0.f;
+      const float v2 = sp + 16 < splits ? p[size_t(sp + 16) * stride] : 0.f;
+      const float v3 = sp + 24 < splits ? p[size_t(sp + 24) * stride] : 0.f;
+      s = (((s + v0) + v1) + v2) + v3;
+    }
+  }
+  red[j][lane] = s;
+  __syncthreads();
+  if (j != 0 || n >= N) return;
+  float t = red[0][lane];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) t += red[k][lane];
+  t *= scale;
+  if (transpose) out[size_t(n) * rank + c0 + c] = t;
+  else out[size_t(c0 + c) * N + n] = t;
+}
+static void launch_outer_reduce(const float* part, int splits, int N, int rank, int c0, int rc, float scale, int transpose, float* out,
+                                cudaStream_t stream) {
+  const int used = rank - c0 < rc ? rank - c0 : rc;
+  if (used <= 0) return;
+  lora_outer_reduce_kernel<<<used * ((N + 31) / 32), 256, 0, stream>>>(part, splits, N, rank, c0, rc, scale, transpose, out);
 }
 
 }  // namespace
@@ -564,12 +589,51 @@ int launch_act_bwd(void* dh, const void* u, long long n, int act, int f16, cudaS
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-// fused dB + dP pass (lora_bwd_kernel): 512 x 512 CTAs when N % 512 == 0 and there are enough of them, else 256 x 256
+// SMs of the current device (grid shaping only; 148 when there is no device to ask)
+static int sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+// rows per CTA (a multiple of `step`, <= max_rows) that minimise  waves x (rows + fixed cost of a CTA, ~48 rows' worth:
+// pipeline fill, B slice, partial write-out)  for `col_groups` CTAs per row block - these kernels stream Y once, so a nearly
+// empty last wave (300 CTAs on 296 slots: what 512-row CTAs gave at M = 25216) costs a whole CTA time.
+// smem_of(rows) = dynamic + static shared memory of one CTA.  Ties go to the larger CTA (fewer partials).
+template <class SmemOf>
+static int rows_for_whole_waves(int M, int col_groups, int step, int min_rows, int max_rows, SmemOf smem_of) {
+  const int sms = sm_count();
+  long long best_cost = -1;
+  int best = max_rows;
+  for (int rows = min_rows; rows <= max_rows; rows += step) {
+    long long per_sm = (228 * 1024) / (long long)(smem_of(rows) + 1024);
+    if (per_sm < 1) continue;
+    if (per_sm > 16) per_sm = 16;
+    const long long ctas = (long long)col_groups * ((M + rows - 1) / rows), slots = per_sm * sms;
+    const long long cost = ((ctas + slots - 1) / slots) * (rows + 48);
+    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = rows; }
+  }
+  return best;
+}
+static size_t lora_bwd_smem(int tw, int rows) {
+  return size_t(4 * kBwdStages * (16 * tw * 128 + 512)) + size_t(16) * (256 * tw) * 2 + size_t(rows) * 64 + 2 * 4 * 256 * 4;
+}
+// fused dB + dP pass (lora_bwd_kernel): 512-column CTAs when N % 512 == 0 and there are enough of them, else 256 columns;
+// the row count fills whole waves (M = 25216: 528 x 512 -> 288 CTAs on 296 slots; 128 x 256 -> 591 on 592)
 static void lora_bwd_geometry(int N, int M, int* tw, int* rows, int* cta_cols) {
   const bool big = N % 512 == 0 && (long long)(N / 512) * ((M + 511) / 512) >= 2 * 148;
   *tw = big ? 2 : 1;
-  *rows = big ? 512 : 256;
   *cta_cols = big ? 512 : 256;
+  const int t = *tw;
+  *rows = rows_for_whole_waves(M, N / *cta_cols, 16, 64, big ? 528 : 512, [t](int r) { return lora_bwd_smem(t, r); });
+}
+// lora_outer_mma_kernel: rows per warp (x 4 warps per CTA of 64 columns; 40 KB of static shared memory)
+static int lora_outer_rows_per_warp(int N, int M) {
+  return rows_for_whole_waves(M, (N + 63) / 64, 64, 256, 2048, [](int) { return size_t(4 * kOuterStages * 2560); }) / 4;
 }
 
 int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const void* Bm, int rank, float scale, float* out_db,
@@ -583,7 +647,7 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
   const int row_blocks = (M + rows - 1) / rows, col_groups = N / cta_cols;
   float* part_db = scratch;
   float* part_dp = scratch + size_t(row_blocks) * 16 * N;
-  const size_t smem = size_t(4 * kBwdStages * (16 * tw * 128 + 512)) + size_t(16) * cta_cols * 2 + size_t(rows) * 64 + 2 * 4 * 256 * 4;
+  const size_t smem = lora_bwd_smem(tw, rows);
   const uint16_t* p = static_cast<const uint16_t*>(P);
   const uint16_t* y = static_cast<const uint16_t*>(Y);
   const uint16_t* bm = static_cast<const uint16_t*>(Bm);
@@ -601,7 +665,7 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
   if (f16) { if (tw == 2) IIC_LB(true, 2) else IIC_LB(true, 1) }
   else { if (tw == 2) IIC_LB(false, 2) else IIC_LB(false, 1) }
 #undef IIC_LB
-  lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(part_db, row_blocks, N, rank, 0, 16, scale, 0, out_db);
+  launch_outer_reduce(part_db, row_blocks, N, rank, 0, 16, scale, 0, out_db, stream);
   if (f16) lora_dp_reduce_kernel<true><<<(M * 4 + 255) / 256, 256, 0, stream>>>(part_dp, col_groups, M, static_cast<uint16_t*>(out_dp16));
   else lora_dp_reduce_kernel<false><<<(M * 4 + 255) / 256, 256, 0, stream>>>(part_dp, col_groups, M, static_cast<uint16_t*>(out_dp16));
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -609,7 +673,8 @@ int launch_lora_bwd(const void* P, int p_ld, const void* Y, int N, int M, const 
 
 int lora_outer_splits(int M) { return (M + 63) / 64; }   // 64 rows per split
 size_t lora_outer_scratch_bytes(int N, int M) {   // the largest partial buffer of the three reduction kernels
-  const size_t rows = size_t(lora_outer_splits(M)) * 4, rows_mma = size_t((M + 511) / 512) * 16, rows16 = size_t((M + 255) / 256) * 16;
+  const int rpc = 4 * lora_outer_rows_per_warp(N, M);
+  const size_t rows = size_t(lora_outer_splits(M)) * 4, rows_mma = size_t((M + rpc - 1) / rpc) * 16, rows16 = size_t((M + 255) / 256) * 16;
   size_t bytes = (rows > rows_mma ? (rows > rows16 ? rows : rows16) : (rows_mma > rows16 ? rows_mma : rows16)) * N * sizeof(float);
   if (N % 256 == 0) {   // lora_bwd_kernel: dB partials per row block + dP partials per column group
     int tw, r, c;
@@ -629,11 +694,11 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
   static const int impl = [] { const char* e = getenv("IIC_LORA_OUTER_IMPL"); return e ? atoi(e) : 0; }();   // 1: CUDA-core kernels
   if (impl == 0 && rank <= 16 && p_ld >= 16 && (reinterpret_cast<uintptr_t>(P) & 15) == 0 && (p_ld % 8) == 0) {
     // tensor-core reduction: one pass over Y for every rank; one partial per 512-row CTA
-    const int splits = (M + kOuterRowsPerCta - 1) / kOuterRowsPerCta;
+    const int rpw = lora_outer_rows_per_warp(N, M), splits = (M + 4 * rpw - 1) / (4 * rpw);
     dim3 grid(unsigned((N + 63) / 64), unsigned(splits));
-    if (f16) lora_outer_mma_kernel<true><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, scratch);
-    else lora_outer_mma_kernel<false><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, scratch);
-    lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, 0, 16, scale, transpose, out);
+    if (f16) lora_outer_mma_kernel<true><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, rank, rpw, scratch);
+    else lora_outer_mma_kernel<false><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, act, rank, rpw, scratch);
+    launch_outer_reduce(scratch, splits, N, rank, 0, 16, scale, transpose, out, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   if (rank > 4 && rank <= 16 && p_ld >= 16) {
@@ -642,7 +707,7 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
     dim3 grid(unsigned((N + 255) / 256), unsigned(splits));
     if (f16) lora_outer16_kernel<true><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, rps, act, scratch);
     else lora_outer16_kernel<false><<<grid, 128, 0, stream>>>(p, p_ld, y, N, M, rps, act, scratch);
-    lora_outer_reduce_kernel<<<(16 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, 0, 16, scale, transpose, out);
+    launch_outer_reduce(scratch, splits, N, rank, 0, 16, scale, transpose, out, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   const int splits = lora_outer_splits(M);
@@ -651,7 +716,7 @@ int launch_lora_outer(const void* P, int p_ld, const void* Y, int N, int M, int 
   for (int c0 = 0; c0 < rank; c0 += 4) {   // 4 LoRA columns per pass over Y (rank 4: one pass)
     if (f16) lora_outer_kernel<true><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
     else lora_outer_kernel<false><<<grid, 128, 0, stream>>>(p + c0, p_ld, y, N, M, rps, act, scratch);
-    lora_outer_reduce_kernel<<<(4 * N + 255) / 256, 256, 0, stream>>>(scratch, splits, N, rank, c0, 4, scale, transpose, out);
+    launch_outer_reduce(scratch, splits, N, rank, c0, 4, scale, transpose, out, stream);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

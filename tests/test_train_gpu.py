@@ -97,27 +97,30 @@ def test_layernorm_and_activation_backward(engine):
 
 
 @pytest.mark.parametrize("rank", [4, 16])
-def test_lora_gradient_reductions(engine, rank):
+@pytest.mark.parametrize("shape", [(197 * 9 + 3, 3072), (197 * 128, 3072), (197 * 128, 768), (70, 64)])
+def test_lora_gradient_reductions(engine, rank, shape):
     g = torch.Generator(device="cuda").manual_seed(23)
-    M, N = 197 * 9 + 3, 3072
+    M, N = shape      # the full-size shapes exercise the whole-wave CTA geometry (rows per CTA depend on M, N and the SM count)
     P = torch.zeros(M, 16, device="cuda", dtype=torch.bfloat16)
     P[:, :rank] = torch.randn(M, rank, device="cuda", generator=g).to(torch.bfloat16)
     Y = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
     dB = engine.op_lora_outer(P, Y, rank)                                       # [r, N] = P^T Y
     ref = P[:, :rank].float().t() @ Y.float()
-    assert torch.allclose(dB, ref, rtol=1e-3, atol=2e-2), (dB - ref).abs().max()
+    tol = max(1.0, (M / 1776) ** 0.5)
+    assert torch.allclose(dB, ref, rtol=1e-3, atol=2e-2 * tol), (dB - ref).abs().max()
     dA = engine.op_lora_outer(P, Y, rank, act=1, scale=2.0, transpose=True)     # [N, r] = 2 * gelu(Y)^T P
     yf = Y.float()
     # the tensor-core reduction feeds gelu(Y) rounded to the operand type - the same value the forward's c_proj GEMM consumed
     h = (yf * torch.sigmoid(1.702 * yf)).to(torch.bfloat16).float()
     ref = 2.0 * h.t() @ P[:, :rank].float()
-    assert torch.allclose(dA, ref, rtol=1e-3, atol=3e-2), (dA - ref).abs().max()
+    assert torch.allclose(dA, ref, rtol=1e-3, atol=3e-2 * tol), (dA - ref).abs().max()
+    assert torch.equal(dA, engine.op_lora_outer(P, Y, rank, act=1, scale=2.0, transpose=True))      # fixed summation order
     ref32 = 2.0 * (yf * torch.sigmoid(1.702 * yf)).t() @ P[:, :rank].float()
     assert (dA - ref32).abs().max() < 1e-2 * ref32.abs().max()      # vs un-rounded gelu: the operand rounding, 2^-9 relative per term
 
 
 @pytest.mark.parametrize("rank", [4, 16])
-@pytest.mark.parametrize("shape", [(197 * 9 + 3, 3072), (197 * 9 + 3, 768), (197 * 128, 3072), (577 * 2, 1024), (40, 256)])
+@pytest.mark.parametrize("shape", [(197 * 9 + 3, 3072), (197 * 9 + 3, 768), (197 * 128, 3072), (197 * 128, 768), (577 * 2, 1024), (40, 256)])
 def test_lora_bwd_fused(engine, rank, shape):
     """dB = P^T . Y and dP = Y . B^T from one pass over Y, against fp32 products of the same bf16 operands"""
     M, N = shape

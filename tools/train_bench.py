@@ -18,7 +18,7 @@ lora = import_module("ai-interior-image-classifier_b200.lora")
 def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     B = int(os.environ.get("TRAIN_B", "128")); steps = int(os.environ.get("STEPS", "10")); r = int(os.environ.get("RANK_LORA", "4"))
-    mode = os.environ.get("IIC_OPERAND_DTYPE", "bf16")
+    mode = iic_b200._lib.operand_dtype_name()                # the one default operand dtype (IIC_OPERAND_DTYPE overrides)
     name = os.environ.get("MODEL", "ViT-B/16")              # or "ViT-L/14@336px" (BASELINE configs[4])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
