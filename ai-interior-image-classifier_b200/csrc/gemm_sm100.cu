@@ -83,14 +83,33 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   return e == cudaSuccess ? 0 : -2;
 }
 
+template <int kCtas, int kBlockN, bool kF16>
+int dispatch_narrow(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
+                    const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
+                    cudaStream_t stream) {
+  switch (epi) {
+    case kEpiBiasBf16: return launch_one<kCtas, kBlockN, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasGeluBf16: return launch_one<kCtas, kBlockN, kEpiBiasGeluBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiGeluExactBf16: return launch_one<kCtas, kBlockN, kEpiGeluExactBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasResF32: return launch_one<kCtas, kBlockN, kEpiBiasResF32, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiBiasResF32DeepK: return launch_one<kCtas, kBlockN, kEpiBiasResF32DeepK, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    case kEpiPosF32: return launch_one<kCtas, kBlockN, kEpiPosF32, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    default: return -1;
+  }
+}
+
 template <int kCtas, bool kF16>
-int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
+int dispatch_epi(int epi, int tile_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal, const CUtensorMap& tbl,
                  const CUtensorMap& tout, const CUtensorMap& tres, const CUtensorMap& tln, const GemmArgs& args, int num_sms,
                  cudaStream_t stream) {
   // skinny outputs (the LoRA down-projection GEMMs, N = 16): a 64-column tile - the 256-wide MMAs on a zero-filled weight tile
   // were what bounded them (K = 3072: 13 us of tensor time per 256-row tile for 16 useful columns)
-  if (epi == kEpiBiasBf16 && args.N <= 64)
+  if (epi == kEpiBiasBf16 && tile_n == 64)
     return launch_one<kCtas, 64, kEpiBiasBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+  if constexpr (kCtas == 2) {   // small-batch path (gemm_tile_n)
+    if (tile_n == 64) return dispatch_narrow<2, 64, kF16>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    if (tile_n == 128) return dispatch_narrow<2, 128, kF16>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+  }
   switch (epi) {
     case kEpiActGradBf16: return launch_one<kCtas, 256, kEpiActGradBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
     case kEpiBiasActDualBf16: return launch_one<kCtas, 256, kEpiBiasActDualBf16, kF16>(ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
@@ -105,6 +124,23 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 }  // namespace
+
+int gemm_tile_n(int M, int N, int epilogue, int ctas, int num_sms) {
+  if (epilogue == kEpiBiasBf16 && N <= 64) return 64;
+  static const int narrow_max = [] { const char* e = getenv("IIC_GEMM_NARROW"); return e ? atoi(e) : 1; }();   // 0: always 256
+  const bool inference_epi = epilogue == kEpiBiasBf16 || epilogue == kEpiBiasGeluBf16 || epilogue == kEpiGeluExactBf16 ||
+                             epilogue == kEpiBiasResF32 || epilogue == kEpiPosF32;
+  if (ctas != 2 || !inference_epi || narrow_max == 0 || M <= 0 || N <= 0) return 256;
+  const int clusters = num_sms / 2;
+  const int tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
+  if (tiles256 * 4 <= clusters) return 64;
+  if (tiles256 * 2 <= clusters) return 128;
+  return 256;
+}
+int gemm_down_parts(int M, int N, int epilogue, int ctas, int num_sms) {
+  const int tn = gemm_tile_n(M, N, epilogue, ctas, num_sms);
+  return (tn >= 128 ? 2 : 1) * ((N + tn - 1) / tn);
+}
 
 size_t gemm_smem_bytes(int ctas) {
   return ctas == 2 ? GemmSmem<2, 256, kEpiBiasBf16>::kTotal : GemmSmem<1, 256, kEpiBiasBf16>::kTotal;
@@ -130,7 +166,8 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
     if (err) *err = e_lora;
     return -1;
   }
-  const uint32_t box_b = uint32_t(((p.epilogue == kEpiBiasBf16 && p.N <= 64) ? 64 : 256) / ctas);
+  const int tile_n = p.tile_n == 256 ? ((p.epilogue == kEpiBiasBf16 && p.N <= 64) ? 64 : 256) : gemm_tile_n(p.M, p.N, p.epilogue, ctas, num_sms);
+  const uint32_t box_b = uint32_t(tile_n / ctas);
   CUtensorMap ta, tb, tal, tbl;
   const bool f16 = p.f16 != 0;
   bool ok = make_tile_map(&ta, p.a, uint64_t(p.M), uint64_t(p.K), uint64_t(p.lda), kBlockM, f16) &&
@@ -186,11 +223,11 @@ int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream
   const int epi = deep ? int(kEpiBiasResF32DeepK) : p.epilogue;
   int rc;
   if (f16)
-    rc = ctas == 2 ? dispatch_epi<2, true>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
-                   : dispatch_epi<1, true>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, true>(epi, tile_n, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
+                   : dispatch_epi<1, true>(epi, tile_n, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
   else
-    rc = ctas == 2 ? dispatch_epi<2, false>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
-                   : dispatch_epi<1, false>(epi, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
+    rc = ctas == 2 ? dispatch_epi<2, false>(epi, tile_n, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream)
+                   : dispatch_epi<1, false>(epi, tile_n, ta, tb, tal, tbl, tout, tres, tln, args, num_sms, stream);
   if (rc != 0 && err) *err = rc == -1 ? e_shape : e_launch;
   return rc;
 }

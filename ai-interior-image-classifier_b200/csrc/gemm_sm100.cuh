@@ -91,7 +91,10 @@ struct GemmSmem {
   // epilogue warp groups working on alternate slabs of a tile: 2 for the MUFU-heavy activation epilogues (one group's
   // MUFU / TMEM latency hides under the other's ALU work), 1 otherwise (measured: a second group only adds contention
   // for the bias-only and the residual epilogues)
-  static constexpr int kGroups = (kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kDirect || kActGrad || kDual) ? 2 : 1;
+  // (narrow tiles of the small-batch path: a group needs at least one staging slab of the tile)
+  static constexpr int kSlabsPerTile = kBlockN / (kResidual ? 32 : 64);
+  static constexpr int kGroups =
+      ((kEpi == kEpiBiasGeluBf16 || kEpi == kEpiGeluExactBf16 || kActGrad || kDual) && kSlabsPerTile >= 2) || kDirect ? 2 : 1;
   static constexpr int kSlabs =   // staging ring depth
       kDirect ? 0 : (kResidual ? (kDeepK ? 3 : 4) : ((kActGrad || kDual) ? 4 : 2));
   static constexpr int kBufPerGroup = kDirect ? 1 : kSlabs / kGroups;
@@ -372,20 +375,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // stage this tile's bias slice (and, activation epilogues, its slice of the consumer's LoRA-A) while the MMAs of the tile
         // are still running: with ~all of L1 carved out as shared memory a __ldg in the slab loop is an exposed L2 round trip
         // per 32 columns (c_fc in-step 0.93 -> 0.81 ms)
-        static_assert(!kAct || (kGroups == 2 && kBlockN == 256), "one staged LoRA-A row per epilogue thread");
+        static_assert(!kAct || 128 * kGroups >= kBlockN, "one staged LoRA-A row per epilogue thread");
         constexpr int kEpiThreads = 128 * kGroups;
         const int t = threadIdx.x - 128;  // 0..kEpiThreads-1
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
         float bv0 = 0.f, bv1 = 0.f;
         if constexpr (kAct) {
-          if (args.down_a != nullptr && col0 + t < args.N) v0 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + t);
+          if (args.down_a != nullptr && t < kBlockN && col0 + t < args.N) v0 = __ldg(reinterpret_cast<const float4*>(args.down_a) + col0 + t);
         }
         if (args.bias != nullptr && t < kBlockN && col0 + t < args.N) bv0 = __ldg(args.bias + col0 + t);
         if (args.bias != nullptr && t + kEpiThreads < kBlockN && col0 + t + kEpiThreads < args.N)
           bv1 = __ldg(args.bias + col0 + t + kEpiThreads);
         // previous tile's readers are done with the buffers
         if constexpr (kGroups == 2) epi_bar_sync_all(); else epi_bar_sync(0);
-        if constexpr (kAct) down_s[t] = v0;
+        if constexpr (kAct) { if (t < kBlockN) down_s[t] = v0; }
         if (t < kBlockN) bias_s[t] = bv0;
         if (t + kEpiThreads < kBlockN) bias_s[t + kEpiThreads] = bv1;
         if constexpr (kGroups == 2) epi_bar_sync_all(); else epi_bar_sync(0);
@@ -631,9 +634,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           }
         }
         if constexpr (kAct) {
-          // one partial per (column tile, epilogue group): part[2 * n_blk + grp][row][0..3]
+          // one partial per (column tile, epilogue group): part[kGroups * n_blk + grp][row][0..3]
           if (args.down_a != nullptr && row_ok)
-            *reinterpret_cast<ulonglong2*>(args.down_part + (size_t(2 * n_blk + grp) * args.M + row) * 4) =
+            *reinterpret_cast<ulonglong2*>(args.down_part + (size_t(kGroups * n_blk + grp) * args.M + row) * 4) =
                 make_ulonglong2(dacc01, dacc23);
         }
       }

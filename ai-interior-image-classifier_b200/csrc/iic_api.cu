@@ -157,7 +157,11 @@ Workspace carve(const iic_handle* h, int B, void* base) {
   w.hid = static_cast<uint16_t*>(take(M * mlp * 2));  // also hosts x_pre (f32 [M, d]) before ln_pre: mlp*2 >= d*4
   w.p_a = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.p_b = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
-  w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
+  {
+    const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
+    const int parts_wide = 2 * int((mlp + 255) / 256), parts = gemm_down_parts(int(M), int(mlp), act_epi, h->ctas, h->num_sms);
+    w.down_part = static_cast<float*>(take(size_t(parts > parts_wide ? parts : parts_wide) * M * 16));
+  }
   // small batches: scratch of the multi-CTA head path (launch_head) - embedding, logits and a probability working copy
   {
     const int Bs = B < 16 ? B : 16, Lcap = h->L > 1024 ? h->L : 1024;
@@ -325,7 +329,7 @@ int run_blocks(iic_handle* h, int B, const Workspace& w, cudaStream_t s) {
                      fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
     if (fuse_down)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, w.p_b, h->lora_pad, h->f16, s);
+        return launch_lora_reduce(w.down_part, gemm_down_parts(M, mlp, act_epi, h->ctas, h->num_sms), M, w.p_b, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, w.p_b, s));
@@ -392,7 +396,11 @@ TrainWorkspace carve_train(const iic_handle* h, int B, void* base) {
   w.da = static_cast<uint16_t*>(take(M * d * 2));
   w.dp1 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
   w.dp2 = static_cast<uint16_t*>(take(M * h->lora_pad * 2 + 4096));
-  w.down_part = static_cast<float*>(take(size_t(2 * ((mlp + 255) / 256)) * M * 16));
+  {
+    const int act_epi = h->cfg.activation == IIC_ACT_GELU_ERF ? kEpiGeluExactBf16 : kEpiBiasGeluBf16;
+    const int parts_wide = 2 * int((mlp + 255) / 256), parts = gemm_down_parts(int(M), int(mlp), act_epi, h->ctas, h->num_sms);
+    w.down_part = static_cast<float*>(take(size_t(parts > parts_wide ? parts : parts_wide) * M * 16));
+  }
   {   // one scratch for every LoRA gradient reduction of the step: the CTA shapes (and so the partial counts) depend on N
     size_t sc = lora_outer_scratch_bytes(int(mlp), int(M));
     for (size_t n : {d, 3 * d})
@@ -483,7 +491,8 @@ int run_train_forward(iic_handle* h, const void* patches, const float* x_tokens,
                        fuse_down ? l_pr.a : nullptr, fuse_down ? w.down_part : nullptr));
     if (fuse_down)
       IIC_TRY(timed(h, kLoraDown, s, [&] {
-        return launch_lora_reduce(w.down_part, 2 * ((mlp + 255) / 256), M, t.p2, h->lora_pad, h->f16, s);
+        return launch_lora_reduce(w.down_part, gemm_down_parts(M, mlp, h->train_fused ? int(kEpiBiasActDualBf16) : act_epi, h->ctas, h->num_sms), M,
+                                  t.p2, h->lora_pad, h->f16, s);
       }));
     else if (l_pr.rank)
       IIC_TRY(run_lora_down(h, w.hid, mlp, M, l_pr.a, l_pr.at16, l_pr.r4, t.p2, s));
@@ -1102,6 +1111,7 @@ int iic_op_gemm(iic_handle* h, const void* a, int lda, const void* w, int ldw, i
   GemmProblem g;
   g.down_a = down_a;
   g.down_part = down_part;
+  if (down_part != nullptr) g.tile_n = 256;   // the caller sized down_part for the wide tile (include/iic.h)
   g.a = a; g.lda = lda;
   g.w = w; g.ldw = ldw;
   g.M = M; g.N = N; g.K = K;

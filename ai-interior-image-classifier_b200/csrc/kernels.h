@@ -160,14 +160,20 @@ struct GemmProblem {
   int group;
   int f16;  // 16-bit operand format: 0 = bf16, 1 = fp16
   // optional, activation epilogues only: fuse the NEXT projection's LoRA down-projection (rank <= 4) into this epilogue.
-  // down_a f32 [N, 4] = scaling * lora_A of the consumer; down_part f32 [2*ceil(N/256)][M][4] receives per-tile partials
-  // (two per column tile: one from each epilogue warp group).
+  // down_a f32 [N, 4] = scaling * lora_A of the consumer; down_part f32 [gemm_down_parts(...)][M][4] receives per-tile
+  // partials (one per column tile and epilogue warp group).
   const float* down_a = nullptr;
   float* down_part = nullptr;
   void* out2 = nullptr;  // kEpiBiasActDualBf16: 16-bit [M, ldc] pre-activation output (out receives the activation)
+  int tile_n = 0;        // 0: gemm_tile_n() decides; 256: force the wide tile (callers that sized down_part for it)
 };
 // ctas: 1 or 2 (tcgen05 cta_group).  num_sms: SM count of the device.
 int launch_gemm(const GemmProblem& p, int ctas, int num_sms, cudaStream_t stream, const char** err);
+// Output-tile width the launcher picks: 256 columns per CTA pair, except that problems whose 256-wide tiles would leave
+// most SMs idle (the single-image path: M = 197 rows) are cut into 128- or 64-column tiles (inference epilogues, ctas == 2).
+int gemm_tile_n(int M, int N, int epilogue, int ctas, int num_sms);
+// number of partial slots the fused LoRA down-projection of an activation epilogue writes for this problem
+int gemm_down_parts(int M, int N, int epilogue, int ctas, int num_sms);
 size_t gemm_smem_bytes(int ctas);
 
 }  // namespace iic

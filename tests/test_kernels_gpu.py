@@ -134,6 +134,95 @@ def test_gemm_lora_fused(engine, ctas, rank):
     assert _rel(out.float(), full) < 6e-3
 
 
+# rows of 1 / 2 / 4 / 8 images: the launcher cuts these into 64- or 128-column tiles (gemm_tile_n) so that the single-image path
+# does not leave most SMs idle; the last one is wide again
+NARROW_M = [197, 2 * 197, 4 * 197, 8 * 197, 77, 33]
+
+
+@pytest.mark.parametrize("M", NARROW_M)
+def test_gemm_narrow_tiles(engine, M):
+    """every inference epilogue at small row counts (narrow output tiles): same fp32 references and tolerances as the wide-tile tests"""
+    g = torch.Generator(device="cuda").manual_seed(100 + M)
+    d, mlp = 768, 3072
+    x = _bf16(torch.randn(M, d, device="cuda", generator=g))
+    for N, K in ((3 * d, d), (d, d), (mlp, d)):
+        w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+        bias = torch.randn(N, device="cuda", generator=g) * 0.1
+        a = x if K == d else None
+        ref = a.float() @ w.float().t() + bias
+        out = engine.op_gemm(a, w, L.EPI_BIAS_BF16, bias=bias)
+        assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=2e-2), (N, K, (out.float() - ref).abs().max())
+        out = engine.op_gemm(a, w, L.EPI_BIAS_GELU_BF16, bias=bias)
+        assert torch.allclose(out.float(), quick_gelu(ref), rtol=2 ** -7, atol=1e-2), (N, K)
+        out = engine.op_gemm(a, w, L.EPI_GELU_ERF_BF16, bias=bias)
+        assert torch.allclose(out.float(), torch.nn.functional.gelu(ref), rtol=2 ** -7, atol=1e-2), (N, K)
+    # residual epilogues, in place on the fp32 stream: short and long reduction (the latter takes the deep operand ring)
+    for K in (d, mlp):
+        a = _bf16(torch.randn(M, K, device="cuda", generator=g))
+        w = _bf16(torch.randn(d, K, device="cuda", generator=g) * K ** -0.5)
+        bias = torch.randn(d, device="cuda", generator=g) * 0.1
+        xs = torch.randn(M, d, device="cuda", generator=g)
+        ref = xs + a.float() @ w.float().t() + bias
+        engine.op_gemm(a, w, L.EPI_BIAS_RES_F32, bias=bias, residual=xs, out=xs)
+        assert torch.allclose(xs, ref, rtol=1e-4, atol=2e-4), (K, (xs - ref).abs().max())
+    # LoRA k-step into the same accumulator
+    rank = 4
+    w = _bf16(torch.randn(mlp, d, device="cuda", generator=g) * d ** -0.5)
+    bias = torch.randn(mlp, device="cuda", generator=g) * 0.1
+    p = torch.zeros(M, 16, device="cuda", dtype=torch.bfloat16)
+    p[:, :rank] = _bf16(torch.randn(M, rank, device="cuda", generator=g))
+    bt = torch.zeros(mlp, 16, device="cuda", dtype=torch.bfloat16)
+    bt[:, :rank] = _bf16(torch.randn(mlp, rank, device="cuda", generator=g) * 0.3)
+    out = engine.op_gemm(x, w, L.EPI_BIAS_GELU_BF16, bias=bias, lora_p=p, lora_bt=bt, r_pad=16)
+    base = x.float() @ w.float().t() + bias
+    ref = quick_gelu(base + p.float() @ bt.float().t())
+    assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=2e-2), (out.float() - ref).abs().max()
+    assert (out.float() - quick_gelu(base)).abs().mean() > 10 * (out.float() - ref).abs().mean()
+
+
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_gemm_narrow_patch_embed(engine, B):
+    G, N, K = 196, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(3 + B)
+    a = _bf16(torch.randn(B * G, K, device="cuda", generator=g))
+    w = _bf16(torch.randn(N, K, device="cuda", generator=g) * K ** -0.5)
+    pos = torch.randn(G + 1, N, device="cuda", generator=g)
+    out = torch.full((B * (G + 1), N), 7.0, device="cuda")
+    engine.op_gemm(a, w, L.EPI_POS_F32, residual=pos, out=out, group=G)
+    ref = (a.float() @ w.float().t()).view(B, G, N) + pos[1:]
+    got = out.view(B, G + 1, N)
+    assert torch.allclose(got[:, 1:], ref, rtol=1e-4, atol=2e-4)
+    assert (got[:, 0] == 7.0).all()
+
+
+def test_small_batch_lora_matches_large_batch(engine):
+    """a LoRA-adapted model (rank 4 on c_fc / c_proj: the c_proj down-projection rides in the c_fc epilogue as per-tile partials) gives
+    the same embedding for an image alone (narrow tiles, more partial slots) and inside a batch of 40 (wide tiles): the frozen
+    products accumulate in the same order, only the grouping of the partials differs (fp32, far below the 16-bit operand rounding)"""
+    from importlib import import_module
+    clipc = import_module("ai-interior-image-classifier_b200.clip_compat")
+    lora = import_module("ai-interior-image-classifier_b200.lora")
+    vis = clipc.build_visual("ViT-B/16", seed=0).cuda()
+    for blk in vis.transformer.resblocks:
+        blk.mlp.c_fc = lora.LoRALinear(blk.mlp.c_fc, rank=4, alpha=8)
+        blk.mlp.c_proj = lora.LoRALinear(blk.mlp.c_proj, rank=4, alpha=8)
+    gen = torch.Generator().manual_seed(5)
+    for n, p_ in vis.named_parameters():
+        if n.endswith("lora_B"):
+            p_.data.copy_(torch.randn(p_.shape, generator=gen) * 0.02)
+    eng = vis.sync_engine()
+    text = torch.nn.functional.normalize(torch.randn(60, 512, generator=gen), dim=-1).cuda()
+    eng.set_labels(text, [40, 20], [11, 0], topk=5, logit_scale=100.0)
+    imgs = torch.randint(0, 256, (40, 224, 224, 3), dtype=torch.uint8, generator=gen).cuda()
+    big = eng.classify_same_size(imgs)
+    for B in (1, 2, 4):
+        small = eng.classify_same_size(imgs[:B].clone(), use_graph=False)
+        err = (small.embedding - big.embedding[:B]).abs().max().item()
+        assert err <= 2e-3 * big.embedding.abs().max().item(), (B, err)
+        assert (small.logits - big.logits[:B]).abs().max().item() < 2e-3
+
+
+
 @pytest.mark.parametrize("D", [768, 1024])
 def test_layernorm(engine, D):
     rows = 197 * 4 + 1
