@@ -69,7 +69,7 @@ def load_image(path_or_url: str, timeout: int = 30):
 
 
 class DeviceImage:
-    """An image that was decoded ON the GPU (nvJPEG): uint8 HWC tensor, ready for the preprocess kernel - no PIL object,
+    """An image that was decoded ON the GPU (jpeg.py): uint8 HWC tensor, ready for the preprocess kernel - no PIL object,
     no host copy of the pixels.  Quacks enough like a PIL image for the code that only forwards it (`.size`, `.convert`)."""
 
     def __init__(self, hwc_u8: torch.Tensor):
@@ -83,39 +83,23 @@ class DeviceImage:
 
 
 def load_images(paths: Sequence[str], device=None, gpu_decode: bool = False, timeout: int = 30):
-    """Batch version of `load_image` (image ingest, main.py:322-346, 404-417).  With gpu_decode, local
-    JPEG files are read as bytes and decoded in ONE batched nvJPEG call on `device` (torchvision.io.decode_jpeg), so
-    the pixels never exist on the host and the preprocess kernel reads them where they were decoded; everything else (URLs,
-    PNG, CMYK JPEGs, a decode error) goes through `load_image` on a small thread pool, exactly like the reference."""
+    """Batch version of `load_image` (image ingest, main.py:322-346, 404-417).  With gpu_decode, the BYTES of
+    local JPEG files are read into one pinned buffer and decoded on `device` by the engine's own decoder (csrc/jpeg.cu, jpeg.py:
+    bit-identical to Pillow), so the pixels never exist on the host and the preprocess kernel reads them where they were decoded;
+    everything else (URLs, PNG, progressive / CMYK JPEGs, an unreadable file) goes through `load_image` on a small thread pool,
+    exactly like the reference."""
     out: List[object] = [None] * len(paths)
     rest = list(range(len(paths)))
     if gpu_decode and device is not None and torch.device(device).type == "cuda":
-        try:
-            from torchvision.io import ImageReadMode, decode_jpeg
-            idx, blobs = [], []
-            for i, p in enumerate(paths):
-                if isinstance(p, str) and not p.startswith("http") and p.lower().endswith((".jpg", ".jpeg")) and os.path.isfile(p):
-                    with open(p, "rb") as f:
-                        b = f.read()
-                    if b[:2] == b"\xff\xd8":
-                        idx.append(i)
-                        blobs.append(torch.frombuffer(bytearray(b), dtype=torch.uint8))
-            if blobs:
-                try:
-                    dec = decode_jpeg(blobs, device=device, mode=ImageReadMode.RGB)
-                except Exception:  # noqa: BLE001 - one bad file must not take the batch down: decode one by one
-                    dec = []
-                    for b in blobs:
-                        try:
-                            dec.append(decode_jpeg(b, device=device, mode=ImageReadMode.RGB))
-                        except Exception:  # noqa: BLE001
-                            dec.append(None)
-                for i, t in zip(idx, dec):
-                    if t is not None and t.dim() == 3 and t.shape[0] == 3:
-                        out[i] = DeviceImage(t.permute(1, 2, 0).contiguous())
-                rest = [i for i in rest if out[i] is None]
-        except ImportError:
-            pass
+        from .jpeg import decode_jpeg_files
+        idx = [i for i, p in enumerate(paths)
+               if isinstance(p, str) and not p.startswith("http") and p.lower().endswith((".jpg", ".jpeg")) and os.path.isfile(p)]
+        if idx:
+            imgs, _ = decode_jpeg_files([paths[i] for i in idx], device)
+            for i, t in zip(idx, imgs):
+                if t is not None:
+                    out[i] = DeviceImage(t)
+            rest = [i for i in rest if out[i] is None]
     if rest:
         with ThreadPoolExecutor(max_workers=4) as ex:   # host-side fetch/decode, as the reference does (main.py:345-346)
             for i, im in zip(rest, ex.map(lambda q: load_image(q, timeout), [paths[i] for i in rest])):

@@ -1,0 +1,714 @@
+// Baseline-JPEG decode on the GPU: row N2 of the hot-path scope table (image ingest).
+//
+// Reference semantics: `Image.open(path).convert("RGB")` (/root/reference/main.py:330-334 load_image; callers main.py:165, 412),
+// i.e. Pillow on libjpeg-turbo with its defaults (JDCT_ISLOW, fancy upsampling, YCbCr -> RGB).  The result is BIT-IDENTICAL to
+// Pillow's for every file inside the envelope below (oracle: oracle/jpeg_ref.py, pinned against Pillow itself):
+//
+//   envelope   SOF0 / SOF1 (sequential Huffman, 8-bit), one interleaved scan, 1 component (grayscale) or 3 components YCbCr with
+//              luma sampling 1x1 (4:4:4), 2x1 (4:2:2) or 2x2 (4:2:0) and 1x1 chroma, Huffman table ids 0 / 1, restart intervals.
+//              Everything else (progressive, arithmetic, CMYK, RGB-coded, 4:4:0 ...) is reported per file by the plan
+//              (IIC_JPEG_UNSUPPORTED) and stays on the caller's host path, as PNG / URL inputs do.
+//
+// Stages (one launch each for the whole batch, all on the caller's stream):
+//   host   iic_jpeg_plan_create   marker parsing (jdmarker.c), Huffman look-up tables (jdhuff.c jpeg_make_d_derived_tbl), layout
+//   1      jpeg_huffman_kernel    entropy decoding is inherently serial inside a scan, so the parallelism is ACROSS the images of the
+//                                 batch: one warp per image, lane 0 walks the bit stream (64-bit accumulator, 4 bytes per refill
+//                                 when no 0xFF is among them, 10-bit look-ahead table, canonical-code walk for longer codes), the
+//                                 whole warp writes every finished 8x8 block (zig-zag already undone) as one 128-byte store
+//   2      jpeg_idct_kernel       dequantisation + jpeg_idct_islow (jidctint.c) incl. the range-limit table; 8 threads per block
+//   3      jpeg_color_kernel      fancy (triangle) upsampling of the chroma planes (jdsample.c, context rows as jdmainct.c) and
+//                                 ycc_rgb_convert (jdcolor.c) -> uint8 HWC RGB at the image's own size, one thread per pixel
+// The decoded pixels never exist on the host: iic_preprocess reads them where they were written.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/iic.h"
+#include "kernels.h"
+
+namespace iic {
+
+namespace {
+
+constexpr int kLutBits = 10;
+constexpr int kLutSize = 1 << kLutBits;
+
+struct HuffTable {            // device view of one Huffman table
+  uint16_t lut[kLutSize];     // (code length << 8) | symbol for codes of <= kLutBits bits; 0: longer code
+  int32_t maxcode[18];        // largest code of each length (as an integer of that many bits), -1: none
+  int32_t valoff[18];         // index of the first symbol of that length minus its smallest code
+  uint8_t vals[256];
+};
+static_assert(sizeof(HuffTable) % 8 == 0, "tables are laid out back to back");
+
+struct alignas(16) JpegComp {
+  uint16_t qt[64];            // quantisation table, natural order
+  unsigned long long coef_off;    // byte offsets into the scratch buffer
+  unsigned long long plane_off;
+  int h, v;                   // sampling factors (1 x 1 for a lone component)
+  int bw, bh;                 // block grid (padded to whole MCUs)
+  int dw, dh;                 // real samples of the component (downsampled_width / height)
+  int pitch;                  // bytes per plane row = 8 bw
+  int td, ta;                 // Huffman table slots (0 / 1)
+  int pad_[3];
+};
+static_assert(sizeof(JpegComp) == 192, "layout shared by host and device");
+
+struct alignas(16) JpegImage {
+  unsigned long long data_off;    // first entropy-coded byte inside the blob
+  unsigned long long tab_off;     // 4 HuffTable: DC0, DC1, AC0, AC1
+  unsigned char* out;             // uint8 [height][width][3]
+  unsigned int data_len;          // bytes from data_off to the end of the file
+  int width, height, ncomp, hmax, vmax, mcux, mcuy, restart_interval;
+  int pad_;
+  JpegComp comp[3];
+};
+static_assert(sizeof(JpegImage) == 64 + 3 * 192, "layout shared by host and device");
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ------------------------------------------------------------------------------------------------ entropy decoding
+struct BitReader {
+  const uint8_t* p;     // next unread byte
+  const uint8_t* end;
+  uint64_t acc;         // MSB-aligned bit accumulator
+  int n;                // valid bits in acc
+  int marker;           // a marker has been reached: zeros are fed from here on (jdhuff.c jpeg_fill_bit_buffer)
+};
+
+__device__ __forceinline__ uint32_t load_be32(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t lo = __ldg(w), hi = __ldg(w + 1);                  // the blob is readable 8 bytes past its end
+  const uint32_t le = __funnelshift_r(lo, hi, uint32_t(a & 3) * 8);
+  return __byte_perm(le, 0, 0x0123);
+}
+
+__device__ __forceinline__ void refill(BitReader& br) {
+  while (br.n <= 32) {
+    if (!br.marker && br.p + 4 <= br.end) {
+      const uint32_t w = load_be32(br.p);
+      if (((~w - 0x01010101u) & w & 0x80808080u) == 0u) {          // no 0xFF among the four bytes: no stuffing, no marker
+        br.acc |= uint64_t(w) << (32 - br.n);
+        br.n += 32;
+        br.p += 4;
+        continue;
+      }
+    }
+    uint32_t b = 0;
+    if (!br.marker && br.p < br.end) {
+      b = *br.p++;
+      if (b == 0xFF) {
+        uint32_t b2 = br.p < br.end ? *br.p : 0xD9u;
+        while (b2 == 0xFF && br.p < br.end) {                       // fill bytes
+          ++br.p;
+          b2 = br.p < br.end ? *br.p : 0xD9u;
+        }
+        ++br.p;
+        if (b2 == 0) b = 0xFF;
+        else { br.marker = int(b2); b = 0; }
+      }
+    }
+    br.acc |= uint64_t(b) << (56 - br.n);
+    br.n += 8;
+  }
+}
+
+// byte-align and step over the RSTn marker (jdhuff.c process_restart / jdmarker.c read_restart_marker)
+__device__ __forceinline__ void restart(BitReader& br) {
+  br.acc = 0;
+  br.n = 0;
+  if (!br.marker) {
+    while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] != 0 && br.p[1] != 0xFF)) ++br.p;
+    br.p += 2;
+  }
+  br.marker = 0;
+}
+
+__device__ __forceinline__ int decode_symbol(BitReader& br, const HuffTable* __restrict__ t) {
+  const uint32_t e = __ldg(&t->lut[uint32_t(br.acc >> (64 - kLutBits))]);
+  if (e != 0) {
+    const int len = int(e >> 8);
+    br.acc <<= len;
+    br.n -= len;
+    return int(e & 255u);
+  }
+  const int code16 = int(br.acc >> 48);
+#pragma unroll 1
+  for (int l = kLutBits + 1; l <= 16; ++l) {
+    const int c = code16 >> (16 - l);
+    if (c <= __ldg(&t->maxcode[l])) {
+      br.acc <<= l;
+      br.n -= l;
+      return int(__ldg(&t->vals[(c + __ldg(&t->valoff[l])) & 255]));
+    }
+  }
+  br.acc <<= 16;   // corrupt stream: libjpeg warns and returns 0
+  br.n -= 16;
+  return 0;
+}
+
+__device__ __forceinline__ int receive_extend(BitReader& br, int s) {   // HUFF_EXTEND
+  const int v = int(br.acc >> (64 - s));
+  br.acc <<= s;
+  br.n -= s;
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+__device__ void decode_block(BitReader& br, const HuffTable* __restrict__ dc, const HuffTable* __restrict__ ac, int& pred,
+                             int16_t* blk) {
+  if (br.n <= 32) refill(br);
+  int s = decode_symbol(br, dc) & 15;
+  if (s) pred += receive_extend(br, s);
+  blk[0] = int16_t(pred);
+  int k = 1;
+#pragma unroll 1
+  while (k < 64) {
+    if (br.n <= 32) refill(br);
+    const int rs = decode_symbol(br, ac);
+    const int r = rs >> 4;
+    s = rs & 15;
+    if (s) {
+      k += r;
+      const int v = receive_extend(br, s);
+      if (k < 64) blk[c_zigzag[k]] = int16_t(v);
+      ++k;
+    } else {
+      if (r != 15) break;
+      k += 16;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ order,
+                                                          const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch) {
+  const JpegImage& im = imgs[order[blockIdx.x]];
+  __shared__ __align__(16) int16_t blk[64];
+  const int lane = threadIdx.x;
+  reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
+  __syncwarp();
+  BitReader br;
+  br.p = blob + im.data_off;
+  br.end = br.p + im.data_len;
+  br.acc = 0;
+  br.n = 0;
+  br.marker = 0;
+  const HuffTable* tabs = reinterpret_cast<const HuffTable*>(scratch + im.tab_off);
+  int pred[3] = {0, 0, 0};
+  int todo = im.restart_interval;
+  const int ncomp = im.ncomp;
+  for (int my = 0; my < im.mcuy; ++my) {
+    for (int mx = 0; mx < im.mcux; ++mx) {
+      if (lane == 0 && im.restart_interval) {
+        if (todo == 0) {
+          restart(br);
+          pred[0] = pred[1] = pred[2] = 0;
+          todo = im.restart_interval;
+        }
+        --todo;
+      }
+#pragma unroll 1
+      for (int ci = 0; ci < ncomp; ++ci) {
+        const JpegComp& cp = im.comp[ci];
+        int16_t* coef = reinterpret_cast<int16_t*>(scratch + cp.coef_off);
+        for (int by = 0; by < cp.v; ++by) {
+          for (int bx = 0; bx < cp.h; ++bx) {
+            if (lane == 0) decode_block(br, tabs + cp.td, tabs + 2 + cp.ta, pred[ci], blk);
+            __syncwarp();
+            const size_t b = size_t(my * cp.v + by) * cp.bw + size_t(mx * cp.h + bx);
+            reinterpret_cast<uint32_t*>(coef + b * 64)[lane] = reinterpret_cast<uint32_t*>(blk)[lane];
+            reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dequantisation + IDCT
+// one pass of jpeg_idct_islow over 8 values (jidctint.c; 13-bit constants)
+__device__ __forceinline__ void idct8(const int (&in)[8], int (&out)[8], int descale) {
+  int z2 = in[2], z3 = in[6];
+  int z1 = (z2 + z3) * 4433;
+  int tmp2 = z1 + z3 * (-15137);
+  int tmp3 = z1 + z2 * 6270;
+  z2 = in[0];
+  z3 = in[4];
+  int tmp0 = (z2 + z3) << 13;
+  int tmp1 = (z2 - z3) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = in[7];
+  tmp1 = in[5];
+  tmp2 = in[3];
+  tmp3 = in[1];
+  z1 = tmp0 + tmp3;
+  z2 = tmp1 + tmp2;
+  z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * 9633;
+  tmp0 *= 2446;
+  tmp1 *= 16819;
+  tmp2 *= 25172;
+  tmp3 *= 12299;
+  z1 *= -7373;
+  z2 *= -20995;
+  z3 = z3 * (-16069) + z5;
+  z4 = z4 * (-3196) + z5;
+  tmp0 += z1 + z3;
+  tmp1 += z2 + z4;
+  tmp2 += z2 + z3;
+  tmp3 += z1 + z4;
+  const int rnd = 1 << (descale - 1);
+  out[0] = (tmp10 + tmp3 + rnd) >> descale;
+  out[7] = (tmp10 - tmp3 + rnd) >> descale;
+  out[1] = (tmp11 + tmp2 + rnd) >> descale;
+  out[6] = (tmp11 - tmp2 + rnd) >> descale;
+  out[2] = (tmp12 + tmp1 + rnd) >> descale;
+  out[5] = (tmp12 - tmp1 + rnd) >> descale;
+  out[3] = (tmp13 + tmp0 + rnd) >> descale;
+  out[4] = (tmp13 - tmp0 + rnd) >> descale;
+}
+
+// post-IDCT range limit: sample_range_limit[(x & RANGE_MASK) + CENTERJSAMPLE] of jdmaster.c prepare_range_limit_table
+__device__ __forceinline__ uint32_t range_limit(int x) {
+  const int i = x & 1023;
+  return uint32_t(i < 128 ? i + 128 : (i < 512 ? 255 : (i < 896 ? 0 : i - 896)));
+}
+
+__device__ __forceinline__ int find_unit(const int* __restrict__ start, int n, int cta) {   // last u with start[u] <= cta
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&start[mid]) <= cta) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// units = (image, component) pairs; cta_start[u] = first CTA of unit u (32 blocks per CTA), cta_start[n_units] = grid size
+__global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restrict__ imgs, const int2* __restrict__ units,
+                                                        const int* __restrict__ cta_start, int n_units,
+                                                        uint8_t* __restrict__ scratch) {
+  __shared__ int ws[32][8][9];
+  const int u = find_unit(cta_start, n_units, int(blockIdx.x));
+  const int2 un = units[u];
+  const JpegComp& cp = imgs[un.x].comp[un.y];
+  const int lb = threadIdx.x >> 3, r = threadIdx.x & 7;
+  const long long nblocks = (long long)cp.bw * cp.bh;
+  const long long b = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 32 + lb;
+  const bool valid = b < nblocks;
+  {
+    int4 raw = make_int4(0, 0, 0, 0);
+    if (valid) raw = *reinterpret_cast<const int4*>(scratch + cp.coef_off + size_t(b) * 128 + r * 16);
+    const uint4 q = *reinterpret_cast<const uint4*>(cp.qt + r * 8);
+    const int16_t* c16 = reinterpret_cast<const int16_t*>(&raw);
+    const uint16_t* q16 = reinterpret_cast<const uint16_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[lb][r][j] = int(c16[j]) * int(q16[j]);
+  }
+  __syncthreads();
+  {
+    int in[8], out[8];                                  // pass 1: column r of the block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) in[i] = ws[lb][i][r];
+    idct8(in, out, 13 - 2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ws[lb][i][r] = out[i];
+  }
+  __syncthreads();
+  {
+    int in[8], out[8];                                  // pass 2: row r
+#pragma unroll
+    for (int j = 0; j < 8; ++j) in[j] = ws[lb][r][j];
+    idct8(in, out, 13 + 2 + 3);
+    if (valid) {
+      const uint32_t lo = range_limit(out[0]) | (range_limit(out[1]) << 8) | (range_limit(out[2]) << 16) | (range_limit(out[3]) << 24);
+      const uint32_t hi = range_limit(out[4]) | (range_limit(out[5]) << 8) | (range_limit(out[6]) << 16) | (range_limit(out[7]) << 24);
+      const int by = int(b / cp.bw), bx = int(b - (long long)by * cp.bw);
+      *reinterpret_cast<uint2*>(scratch + cp.plane_off + size_t(by * 8 + r) * cp.pitch + bx * 8) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsampling + colour
+__device__ __forceinline__ int upsample(const uint8_t* __restrict__ plane, const JpegComp& cp, int hmax, int vmax, int x, int y) {
+  if (cp.h == hmax && cp.v == vmax) return plane[size_t(y) * cp.pitch + x];
+  const int cx = x >> 1;
+  if (cp.v == vmax) {                                   // h2v1
+    const uint8_t* row = plane + size_t(y) * cp.pitch;
+    const int p = row[cx];
+    if (cp.dw <= 2) return p;                           // jinit_upsampler: box replication for very narrow components
+    const int nb = (x & 1) ? min(cx + 1, cp.dw - 1) : max(cx - 1, 0);
+    return (3 * p + row[nb] + ((x & 1) ? 2 : 1)) >> 2;
+  }
+  const int cy = y >> 1;                                // h2v2
+  const uint8_t* r0 = plane + size_t(cy) * cp.pitch;
+  if (cp.dw <= 2) return r0[cx];
+  const int oy = (y & 1) ? min(cy + 1, cp.dh - 1) : max(cy - 1, 0);   // context rows replicate the first / last real row
+  const uint8_t* r1 = plane + size_t(oy) * cp.pitch;
+  const int nb = (x & 1) ? min(cx + 1, cp.dw - 1) : max(cx - 1, 0);
+  const int cs = 3 * r0[cx] + r1[cx], cn = 3 * r0[nb] + r1[nb];
+  return (3 * cs + cn + ((x & 1) ? 7 : 8)) >> 4;
+}
+
+__device__ __forceinline__ uint8_t clamp255(int v) { return uint8_t(min(max(v, 0), 255)); }
+
+// cta_start[i] = first CTA of image i (256 pixels per CTA)
+__global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ image_of,
+                                                         const int* __restrict__ cta_start, int n,
+                                                         const uint8_t* __restrict__ scratch) {
+  const int u = find_unit(cta_start, n, int(blockIdx.x));
+  const JpegImage& im = imgs[image_of[u]];
+  const long long pix = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 256 + threadIdx.x;
+  if (pix >= (long long)im.width * im.height) return;
+  const int y = int(pix / im.width), x = int(pix - (long long)y * im.width);
+  const int Y = scratch[im.comp[0].plane_off + size_t(y) * im.comp[0].pitch + x];
+  uint8_t* o = im.out + size_t(pix) * 3;
+  if (im.ncomp == 1) {
+    o[0] = o[1] = o[2] = uint8_t(Y);
+    return;
+  }
+  const int cb = upsample(scratch + im.comp[1].plane_off, im.comp[1], im.hmax, im.vmax, x, y) - 128;
+  const int cr = upsample(scratch + im.comp[2].plane_off, im.comp[2], im.hmax, im.vmax, x, y) - 128;
+  // jdcolor.c build_ycc_rgb_table: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554
+  o[0] = clamp255(Y + ((91881 * cr + 32768) >> 16));
+  o[1] = clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+  o[2] = clamp255(Y + ((116130 * cb + 32768) >> 16));
+}
+
+// ------------------------------------------------------------------------------------------------ host: headers and layout
+const uint8_t kZigzagHost[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HostTable {
+  bool present = false;
+  uint8_t bits[16];
+  uint8_t vals[256];
+  int count = 0;
+};
+
+struct Parsed {
+  int status = IIC_JPEG_CORRUPT;
+  std::string why;
+  JpegImage img;               // offsets filled in by the layout pass
+  HostTable tab[2][2];         // [class][id]
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void build_table(const HostTable& t, HuffTable* out) {
+  std::memset(out, 0, sizeof(HuffTable));
+  for (int l = 0; l < 18; ++l) out->maxcode[l] = -1;
+  std::memcpy(out->vals, t.vals, size_t(t.count));
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; ++l) {
+    const int cnt = t.bits[l - 1];
+    out->valoff[l] = k - code;
+    for (int i = 0; i < cnt; ++i, ++k, ++code) {
+      if (l <= kLutBits && code < (1 << l)) {
+        const int first = code << (kLutBits - l);
+        for (int f = 0; f < (1 << (kLutBits - l)); ++f) out->lut[first + f] = uint16_t((l << 8) | t.vals[k]);
+      }
+    }
+    out->maxcode[l] = cnt ? code - 1 : -1;
+    code <<= 1;
+  }
+  out->maxcode[17] = 0x7fffffff;
+}
+
+// marker segments up to the first SOS (jdmarker.c read_markers); fills p.img geometry, quantisation tables and Huffman tables
+void parse_one(const uint8_t* d, size_t n, Parsed& p) {
+  auto corrupt = [&](const char* w) { p.status = IIC_JPEG_CORRUPT; p.why = w; };
+  auto unsupported = [&](const char* w) { p.status = IIC_JPEG_UNSUPPORTED; p.why = w; };
+  std::memset(&p.img, 0, sizeof(p.img));
+  if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return corrupt("not a JPEG (no SOI)");
+  uint16_t qt[4][64];
+  bool have_qt[4] = {false, false, false, false};
+  int comp_id[3] = {0, 0, 0}, comp_tq[3] = {0, 0, 0}, comp_h[3] = {1, 1, 1}, comp_v[3] = {1, 1, 1};
+  bool have_sof = false, jfif = false;
+  int adobe = -1;
+  size_t pos = 2;
+  for (;;) {
+    while (pos < n && d[pos] != 0xFF) ++pos;
+    while (pos < n && d[pos] == 0xFF) ++pos;
+    if (pos >= n) return corrupt("no SOS marker");
+    const int m = d[pos++];
+    if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+    if (m == 0xD9) return corrupt("EOI before SOS");
+    if (pos + 2 > n) return corrupt("truncated marker segment");
+    const size_t seglen = (size_t(d[pos]) << 8) | d[pos + 1];
+    if (seglen < 2 || pos + seglen > n) return corrupt("truncated marker segment");
+    const uint8_t* seg = d + pos + 2;
+    const size_t sl = seglen - 2;
+    if (m == 0xDB) {
+      size_t q = 0;
+      while (q < sl) {
+        const int pq = seg[q] >> 4, tq = seg[q] & 15;
+        ++q;
+        if (tq > 3 || pq > 1 || q + size_t(64 * (pq + 1)) > sl) return corrupt("bad DQT");
+        for (int i = 0; i < 64; ++i) {
+          qt[tq][kZigzagHost[i]] = pq ? uint16_t((seg[q] << 8) | seg[q + 1]) : uint16_t(seg[q]);
+          q += size_t(pq + 1);
+        }
+        have_qt[tq] = true;
+      }
+    } else if (m == 0xC0 || m == 0xC1) {
+      if (have_sof) return corrupt("two SOF markers");
+      if (sl < 6) return corrupt("bad SOF");
+      if (seg[0] != 8) return unsupported("sample precision other than 8 bits");
+      p.img.height = (seg[1] << 8) | seg[2];
+      p.img.width = (seg[3] << 8) | seg[4];
+      p.img.ncomp = seg[5];
+      if (p.img.width <= 0 || p.img.height <= 0) return unsupported("zero image dimension (DNL)");
+      if (p.img.ncomp != 1 && p.img.ncomp != 3) return unsupported("component count other than 1 or 3 (CMYK / YCCK)");
+      if (sl < size_t(6 + 3 * p.img.ncomp)) return corrupt("bad SOF");
+      for (int c = 0; c < p.img.ncomp; ++c) {
+        comp_id[c] = seg[6 + 3 * c];
+        comp_h[c] = seg[7 + 3 * c] >> 4;
+        comp_v[c] = seg[7 + 3 * c] & 15;
+        comp_tq[c] = seg[8 + 3 * c];
+        if (comp_tq[c] > 3 || comp_h[c] < 1 || comp_h[c] > 4 || comp_v[c] < 1 || comp_v[c] > 4) return corrupt("bad SOF component");
+      }
+      have_sof = true;
+    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return unsupported(m == 0xC2 ? "progressive JPEG" : "lossless / hierarchical / arithmetic JPEG");
+    } else if (m == 0xCC) {
+      return unsupported("arithmetic coding");
+    } else if (m == 0xC4) {
+      size_t q = 0;
+      while (q < sl) {
+        if (q + 17 > sl) return corrupt("bad DHT");
+        const int tc = seg[q] >> 4, th = seg[q] & 15;
+        if (tc > 1 || th > 3) return corrupt("bad DHT");
+        int cnt = 0;
+        for (int i = 0; i < 16; ++i) cnt += seg[q + 1 + i];
+        if (cnt > 256 || q + 17 + size_t(cnt) > sl) return corrupt("bad DHT");
+        if (th <= 1) {
+          HostTable& t = p.tab[tc][th];
+          std::memcpy(t.bits, seg + q + 1, 16);
+          std::memcpy(t.vals, seg + q + 17, size_t(cnt));
+          t.count = cnt;
+          t.present = true;
+        }
+        q += 17 + size_t(cnt);
+      }
+    } else if (m == 0xDD) {
+      if (sl < 2) return corrupt("bad DRI");
+      p.img.restart_interval = (seg[0] << 8) | seg[1];
+    } else if (m == 0xE0) {
+      if (sl >= 5 && std::memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
+    } else if (m == 0xEE) {
+      if (sl >= 12 && std::memcmp(seg, "Adobe", 5) == 0) adobe = seg[11];
+    } else if (m == 0xDA) {
+      if (!have_sof) return corrupt("SOS before SOF");
+      if (sl < 1 || sl < size_t(1 + 2 * seg[0] + 3)) return corrupt("bad SOS");
+      const int ns = seg[0];
+      if (ns != p.img.ncomp) return unsupported("multi-scan sequential JPEG");
+      int hmax = 1, vmax = 1;
+      for (int c = 0; c < p.img.ncomp; ++c) { hmax = std::max(hmax, comp_h[c]); vmax = std::max(vmax, comp_v[c]); }
+      if (p.img.ncomp == 3) {
+        // jdapimin.c default_decompress_parms: JFIF -> YCbCr; else Adobe transform 0 -> RGB; else ids 'R','G','B' -> RGB
+        const bool rgb_ids = comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B';
+        if (!jfif && (adobe == 0 || (adobe < 0 && rgb_ids))) return unsupported("RGB-coded JPEG");
+        if (comp_h[1] != 1 || comp_v[1] != 1 || comp_h[2] != 1 || comp_v[2] != 1 ||
+            !((hmax == 1 && vmax == 1) || (hmax == 2 && vmax == 1) || (hmax == 2 && vmax == 2)))
+          return unsupported("chroma sampling other than 4:4:4 / 4:2:2 / 4:2:0");
+      } else {
+        hmax = vmax = 1;
+        comp_h[0] = comp_v[0] = 1;      // a lone component is decoded block by block whatever its factors say (jdinput.c)
+      }
+      p.img.hmax = hmax;
+      p.img.vmax = vmax;
+      p.img.mcux = (p.img.width + 8 * hmax - 1) / (8 * hmax);
+      p.img.mcuy = (p.img.height + 8 * vmax - 1) / (8 * vmax);
+      for (int s = 0; s < ns; ++s) {
+        const int cs = seg[1 + 2 * s], tt = seg[2 + 2 * s];
+        if (cs != comp_id[s]) return unsupported("scan component order differs from the frame's");
+        const int td = tt >> 4, ta = tt & 15;
+        if (td > 1 || ta > 1) return unsupported("Huffman table id above 1");
+        if (!p.tab[0][td].present || !p.tab[1][ta].present) return corrupt("scan refers to a missing Huffman table");
+        if (!have_qt[comp_tq[s]]) return corrupt("component refers to a missing quantisation table");
+        JpegComp& cp = p.img.comp[s];
+        cp.h = comp_h[s];
+        cp.v = comp_v[s];
+        cp.td = td;
+        cp.ta = ta;
+        cp.bw = p.img.mcux * cp.h;
+        cp.bh = p.img.mcuy * cp.v;
+        cp.dw = (p.img.width * cp.h + hmax - 1) / hmax;
+        cp.dh = (p.img.height * cp.v + vmax - 1) / vmax;
+        cp.pitch = cp.bw * 8;
+        std::memcpy(cp.qt, qt[comp_tq[s]], sizeof(cp.qt));
+      }
+      const size_t start = pos + seglen;
+      p.img.data_off = start;          // relative to the file; the layout pass adds the file's offset in the blob
+      p.img.data_len = unsigned(std::min<size_t>(n - start, 0xffffffffu));
+      p.status = IIC_JPEG_OK;
+      return;
+    }
+    pos += seglen;
+  }
+}
+
+}  // namespace
+}  // namespace iic
+
+struct iic_jpeg_plan {
+  std::vector<iic::Parsed> files;
+  std::vector<int> ok;                 // indices of the files inside the envelope, longest entropy segment first
+  size_t desc_bytes = 0;               // descriptor region = staging size: images, tables, unit tables
+  size_t off_tables = 0, off_order = 0, off_units = 0, off_idct_start = 0, off_color_img = 0, off_color_start = 0;
+  size_t scratch_bytes = 0;
+  int idct_ctas = 0, color_ctas = 0, n_units = 0;
+  std::string err;
+};
+
+extern "C" {
+
+int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic_jpeg_plan** out) {
+  using namespace iic;
+  if (out == nullptr) return IIC_ERR_ARG;
+  *out = nullptr;
+  if (blob == nullptr || offsets == nullptr || n < 0) return IIC_ERR_ARG;
+  iic_jpeg_plan* pl = new (std::nothrow) iic_jpeg_plan();
+  if (pl == nullptr) return IIC_ERR_ARG;
+  pl->files.resize(size_t(n));
+  for (int i = 0; i < n; ++i) {
+    Parsed& p = pl->files[size_t(i)];
+    if (offsets[i + 1] < offsets[i]) { p.status = IIC_JPEG_CORRUPT; p.why = "negative file size"; continue; }
+    parse_one(blob + offsets[i], size_t(offsets[i + 1] - offsets[i]), p);
+    if (p.status == IIC_JPEG_OK) {
+      p.img.data_off += uint64_t(offsets[i]);
+      pl->ok.push_back(i);
+    }
+  }
+  std::stable_sort(pl->ok.begin(), pl->ok.end(),
+                   [&](int a, int b) { return pl->files[size_t(a)].img.data_len > pl->files[size_t(b)].img.data_len; });
+  // descriptor region: [JpegImage x m][HuffTable x 4m][order m][units 3m int2][idct_start 3m+1][color_img m][color_start m+1]
+  const size_t m = pl->ok.size();
+  size_t off = 0;
+  off += align_up(m * sizeof(JpegImage), 256);
+  pl->off_tables = off;
+  off += align_up(m * 4 * sizeof(HuffTable), 256);
+  pl->off_order = off;
+  off += align_up(m * sizeof(int), 256);
+  pl->off_units = off;
+  off += align_up(3 * m * sizeof(int2), 256);
+  pl->off_idct_start = off;
+  off += align_up((3 * m + 1) * sizeof(int), 256);
+  pl->off_color_img = off;
+  off += align_up(m * sizeof(int), 256);
+  pl->off_color_start = off;
+  off += align_up((m + 1) * sizeof(int), 256);
+  pl->desc_bytes = off;
+  // coefficient blocks and sample planes behind it
+  long long idct_ctas = 0, color_ctas = 0;
+  int units = 0;
+  for (size_t j = 0; j < m; ++j) {
+    Parsed& p = pl->files[size_t(pl->ok[j])];
+    p.img.tab_off = pl->off_tables + j * 4 * sizeof(HuffTable);
+    for (int c = 0; c < p.img.ncomp; ++c) {
+      JpegComp& cp = p.img.comp[c];
+      const size_t blocks = size_t(cp.bw) * size_t(cp.bh);
+      cp.coef_off = off;
+      off += align_up(blocks * 128, 256);
+      cp.plane_off = off;
+      off += align_up(blocks * 64, 256);
+      idct_ctas += (long long)((blocks + 31) / 32);
+      ++units;
+    }
+    color_ctas += ((long long)p.img.width * p.img.height + 255) / 256;
+  }
+  if (idct_ctas > 0x7fffffffLL || color_ctas > 0x7fffffffLL) {
+    delete pl;
+    return IIC_ERR_ARG;
+  }
+  pl->scratch_bytes = off + 256;
+  pl->idct_ctas = int(idct_ctas);
+  pl->color_ctas = int(color_ctas);
+  pl->n_units = units;
+  *out = pl;
+  return IIC_OK;
+}
+
+void iic_jpeg_plan_destroy(iic_jpeg_plan* plan) { delete plan; }
+
+int iic_jpeg_plan_info(const iic_jpeg_plan* plan, int i, int* width, int* height, int* status) {
+  if (plan == nullptr || i < 0 || size_t(i) >= plan->files.size()) return IIC_ERR_ARG;
+  const iic::Parsed& p = plan->files[size_t(i)];
+  if (status) *status = p.status;
+  if (width) *width = p.status == IIC_JPEG_OK ? p.img.width : 0;
+  if (height) *height = p.status == IIC_JPEG_OK ? p.img.height : 0;
+  return IIC_OK;
+}
+
+const char* iic_jpeg_plan_reason(const iic_jpeg_plan* plan, int i) {
+  if (plan == nullptr || i < 0 || size_t(i) >= plan->files.size()) return "";
+  return plan->files[size_t(i)].why.c_str();
+}
+
+size_t iic_jpeg_plan_staging_bytes(const iic_jpeg_plan* plan) { return plan ? plan->desc_bytes : 0; }
+size_t iic_jpeg_plan_scratch_bytes(const iic_jpeg_plan* plan) { return plan ? plan->scratch_bytes : 0; }
+
+int iic_jpeg_decode(const iic_jpeg_plan* plan, const uint8_t* dev_blob, uint8_t* const* out_rgb, void* staging, void* scratch,
+                    void* stream) {
+  using namespace iic;
+  if (plan == nullptr || dev_blob == nullptr || out_rgb == nullptr || staging == nullptr || scratch == nullptr) return IIC_ERR_ARG;
+  const size_t m = plan->ok.size();
+  if (m == 0) return IIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* st = static_cast<uint8_t*>(staging);
+  JpegImage* imgs = reinterpret_cast<JpegImage*>(st);
+  HuffTable* tabs = reinterpret_cast<HuffTable*>(st + plan->off_tables);
+  int* order = reinterpret_cast<int*>(st + plan->off_order);
+  int2* units = reinterpret_cast<int2*>(st + plan->off_units);
+  int* idct_start = reinterpret_cast<int*>(st + plan->off_idct_start);
+  int* color_img = reinterpret_cast<int*>(st + plan->off_color_img);
+  int* color_start = reinterpret_cast<int*>(st + plan->off_color_start);
+  int u = 0, ic = 0, cc = 0, m_out = 0;
+  for (size_t j = 0; j < m; ++j) {
+    const int fi = plan->ok[j];
+    const Parsed& p = plan->files[size_t(fi)];
+    imgs[j] = p.img;
+    imgs[j].out = out_rgb[fi];
+    for (int tc = 0; tc < 2; ++tc)
+      for (int th = 0; th < 2; ++th) {
+        if (p.tab[tc][th].present) build_table(p.tab[tc][th], &tabs[j * 4 + size_t(tc * 2 + th)]);
+        else std::memset(&tabs[j * 4 + size_t(tc * 2 + th)], 0, sizeof(HuffTable));
+      }
+    if (out_rgb[fi] == nullptr) continue;     // the caller skips this file
+    order[m_out] = int(j);
+    for (int c = 0; c < p.img.ncomp; ++c) {
+      units[u] = make_int2(int(j), c);
+      idct_start[u] = ic;
+      ic += int((size_t(p.img.comp[c].bw) * size_t(p.img.comp[c].bh) + 31) / 32);
+      ++u;
+    }
+    color_img[m_out] = int(j);
+    color_start[m_out] = cc;
+    cc += int(((long long)p.img.width * p.img.height + 255) / 256);
+    ++m_out;
+  }
+  idct_start[u] = ic;
+  color_start[m_out] = cc;
+  if (m_out == 0) return IIC_OK;
+  uint8_t* sc = static_cast<uint8_t*>(scratch);
+  if (cudaMemcpyAsync(sc, st, plan->desc_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return IIC_ERR_CUDA;
+  const JpegImage* d_imgs = reinterpret_cast<const JpegImage*>(sc);
+  jpeg_huffman_kernel<<<m_out, 32, 0, s>>>(d_imgs, reinterpret_cast<const int*>(sc + plan->off_order), dev_blob, sc);
+  jpeg_idct_kernel<<<ic, 256, 0, s>>>(d_imgs, reinterpret_cast<const int2*>(sc + plan->off_units),
+                                      reinterpret_cast<const int*>(sc + plan->off_idct_start), u, sc);
+  jpeg_color_kernel<<<cc, 256, 0, s>>>(d_imgs, reinterpret_cast<const int*>(sc + plan->off_color_img),
+                                       reinterpret_cast<const int*>(sc + plan->off_color_start), m_out, sc);
+  return cudaGetLastError() == cudaSuccess ? IIC_OK : IIC_ERR_CUDA;
+}
+
+}  // extern "C"

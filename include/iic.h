@@ -142,6 +142,36 @@ int iic_preprocess(iic_handle* h, const uint8_t* const* imgs, const int* hw, int
                    void* stream);
 /* Fast path: one contiguous uint8 [B, R, R, 3] buffer already at the model resolution (no resampling). */
 int iic_preprocess_same_size(iic_handle* h, const uint8_t* imgs, int B, void* out, int out_layout, void* stream);
+/* ---- image ingest: baseline-JPEG decode on the device ----------------------------------------------
+ * Replaces `Image.open(path).convert("RGB")` (/root/reference/main.py:330-334 load_image, called from main.py:165 and
+ * main.py:412) for local JPEG files: the decoded uint8 HWC pixels are written where iic_preprocess reads them and are
+ * bit-identical to Pillow / libjpeg-turbo (islow IDCT, fancy upsampling, fixed-point YCbCr -> RGB).  Envelope: sequential
+ * Huffman JPEG (SOF0 / SOF1, 8 bit), grayscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0, restart intervals; files outside it are
+ * reported by the plan and stay on the caller's host path (as PNG files and URLs do).
+ *
+ * A PLAN is a host-only object (no CUDA call): it parses the headers of n files laid back to back in `blob` (file i =
+ * bytes [offsets[i], offsets[i+1])) and lays out the device scratch.  The caller then provides
+ *   dev_blob   the same bytes on the device, readable for 8 bytes past offsets[n]
+ *   out_rgb    HOST array of n DEVICE pointers, out_rgb[i] -> uint8 [height_i][width_i][3]; NULL skips file i (required for
+ *              files whose status is not IIC_JPEG_OK)
+ *   staging    iic_jpeg_plan_staging_bytes() of PINNED host memory (the descriptors are built there and copied to the device
+ *              on the stream; it must stay untouched until that copy has run)
+ *   scratch    iic_jpeg_plan_scratch_bytes() of device memory, 256-byte aligned (descriptors, Huffman tables, coefficient
+ *              blocks, sample planes)
+ * and iic_jpeg_decode enqueues one copy and three kernels on `stream`.  Nothing is allocated or synchronised inside. */
+#define IIC_JPEG_OK 0
+#define IIC_JPEG_UNSUPPORTED 1 /* a valid JPEG outside the envelope (progressive, CMYK, arithmetic, ...) */
+#define IIC_JPEG_CORRUPT 2     /* not a JPEG / broken header                                              */
+typedef struct iic_jpeg_plan iic_jpeg_plan;
+int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic_jpeg_plan** out);
+void iic_jpeg_plan_destroy(iic_jpeg_plan* plan);
+int iic_jpeg_plan_info(const iic_jpeg_plan* plan, int i, int* width, int* height, int* status);
+const char* iic_jpeg_plan_reason(const iic_jpeg_plan* plan, int i); /* why file i is outside the envelope ("" if it is not) */
+size_t iic_jpeg_plan_staging_bytes(const iic_jpeg_plan* plan);
+size_t iic_jpeg_plan_scratch_bytes(const iic_jpeg_plan* plan);
+int iic_jpeg_decode(const iic_jpeg_plan* plan, const uint8_t* dev_blob, uint8_t* const* out_rgb, void* staging, void* scratch,
+                    void* stream);
+
 /* [B,3,R,R] float tensor (what reference code feeds encode_image) -> patch matrix. */
 int iic_patchify(iic_handle* h, const void* chw, int dtype, int B, void* patches_out, void* stream);
 

@@ -152,3 +152,89 @@ def test_restatement_equals_reference_code():
         for n in ("transformer.resblocks.0.mlp.c_fc.lora.lora_A", "transformer.resblocks.11.mlp.c_proj.lora.lora_B"):
             assert torch.equal(dict(a.named_parameters())[n], dict(b.named_parameters())[n])
         assert torch.equal(a.encode_text(tok), b.encode_text(tok))
+
+
+# ---------------------------------------------------------------------------------------------- JPEG ingest (row N2)
+def _jpeg_fixtures():
+    import json
+    import numpy as np
+    d = os.path.join(GOLDEN, "jpeg")
+    meta = json.load(open(os.path.join(d, "meta.json")))["files"]
+    exp = np.load(os.path.join(d, "expected.npz"))
+    return d, meta, exp
+
+
+def test_jpeg_oracle_matches_pillow_on_fixtures():
+    """oracle/jpeg_ref.py == the committed Pillow outputs == Pillow on this box, bit for bit, on every fixture of the envelope;
+    files outside it raise Unsupported"""
+    import io
+    import numpy as np
+    from PIL import Image
+    from oracle import jpeg_ref as J
+    d, meta, exp = _jpeg_fixtures()
+    seen = 0
+    for name, m in meta.items():
+        data = open(os.path.join(d, name + ".jpg"), "rb").read()
+        live = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        assert np.array_equal(live, exp[name]), name          # the committed vectors are what Pillow produces here too
+        if m["in_envelope"]:
+            got = J.decode_rgb(data)
+            assert got.shape == exp[name].shape and np.array_equal(got, exp[name]), name
+            seen += 1
+        else:
+            with pytest.raises(J.Unsupported):
+                J.decode_rgb(data)
+    assert seen >= 8
+
+
+def test_jpeg_oracle_matches_pillow_on_fresh_encodes():
+    """files Pillow encodes on the fly: every sampling layout, narrow / odd sizes (the box-replication rule for components of
+    width <= 2), restart intervals, optimised Huffman tables, extreme qualities"""
+    import io
+    import numpy as np
+    from PIL import Image
+    from oracle import jpeg_ref as J
+    rng = np.random.default_rng(7)
+    n = 0
+    for (h, w) in ((1, 1), (2, 5), (8, 8), (9, 17), (16, 3), (31, 33), (40, 4)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for sub in (0, 1, 2):
+            for kw in (dict(quality=92), dict(quality=15, optimize=True), dict(quality=100, restart_marker_blocks=2)):
+                buf = io.BytesIO()
+                Image.fromarray(img).save(buf, "JPEG", subsampling=sub, **kw)
+                data = buf.getvalue()
+                ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+                assert np.array_equal(J.decode_rgb(data), ref), (h, w, sub, kw)
+                n += 1
+    assert n == 63
+
+
+def test_jpeg_oracle_pinned_on_reference_dataset():
+    """oracle/pin_jpeg.py ran over the reference's own 151 files in the build container: 140 baseline files bit-exact with Pillow,
+    11 progressive files outside the envelope, no mismatch"""
+    import json
+    pin = json.load(open(os.path.join(GOLDEN, "jpeg_pin.json")))["summary"]
+    assert pin["files"] == 151 and pin["mismatch"] == 0 and pin["bit_exact"] == 140 and pin["outside_envelope"] == 11
+
+
+def test_jpeg_plan_parses_headers_without_a_gpu():
+    """the C-ABI plan object is host-only: sizes / status of every fixture agree with Pillow, and the layout sizes are sane"""
+    import numpy as np
+    import torch
+    from importlib import import_module
+    jp = import_module("ai-interior-image-classifier_b200.jpeg")
+    d, meta, exp = _jpeg_fixtures()
+    names = sorted(meta)
+    files = [open(os.path.join(d, n + ".jpg"), "rb").read() for n in names] + [b"", b"\xff\xd8\xff", b"not a jpeg at all"]
+    offsets = np.zeros(len(files) + 1, dtype=np.int64)
+    np.cumsum([len(f) for f in files], out=offsets[1:])
+    blob = torch.frombuffer(bytearray(b"".join(files) + bytes(64)), dtype=torch.uint8)
+    plan = jp.JpegPlan(blob, offsets)
+    for i, n in enumerate(names):
+        if meta[n]["in_envelope"]:
+            assert plan.status[i] == jp.JPEG_OK and plan.sizes[i] == exp[n].shape[:2], n
+        else:
+            assert plan.status[i] == jp.JPEG_UNSUPPORTED and plan.sizes[i] == (0, 0) and plan.reasons[i], n
+    assert plan.status[-3:] == [jp.JPEG_CORRUPT] * 3
+    assert plan.scratch_bytes > plan.staging_bytes > 8 * 4 * 2048
+    plan.close()
