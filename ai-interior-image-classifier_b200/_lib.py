@@ -78,6 +78,7 @@ PROTOTYPES = {
     "iic_jpeg_plan_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p)]),
     "iic_jpeg_plan_destroy": (None, [C.c_void_p]),
     "iic_jpeg_plan_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "iic_jpeg_plan_infos": (C.c_int, [C.c_void_p, C.c_void_p]),
     "iic_jpeg_plan_reason": (C.c_char_p, [C.c_void_p, C.c_int]),
     "iic_jpeg_plan_staging_bytes": (C.c_size_t, [C.c_void_p]),
     "iic_jpeg_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),

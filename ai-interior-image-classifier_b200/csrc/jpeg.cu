@@ -13,8 +13,8 @@
 //   host   iic_jpeg_plan_create   marker parsing (jdmarker.c), Huffman look-up tables (jdhuff.c jpeg_make_d_derived_tbl), layout
 //   1      jpeg_huffman_kernel    entropy decoding is inherently serial inside a scan, so the parallelism is ACROSS the images of the
 //                                 batch: one warp per image, lane 0 walks the bit stream (64-bit accumulator, 4 bytes per refill
-//                                 when no 0xFF is among them, 10-bit look-ahead table, canonical-code walk for longer codes), the
-//                                 whole warp writes every finished 8x8 block (zig-zag already undone) as one 128-byte store
+//                                 when no 0xFF is among them; one shared-memory look-up per AC symbol for code + value bits <= 11, canonical-code walk otherwise), the
+//                                 whole warp writes every finished 8x8 block (still in zig-zag order) as one 128-byte store
 //   2      jpeg_idct_kernel       dequantisation + jpeg_idct_islow (jidctint.c) incl. the range-limit table; 8 threads per block
 //   3      jpeg_color_kernel      fancy (triangle) upsampling of the chroma planes (jdsample.c, context rows as jdmainct.c) and
 //                                 ycc_rgb_convert (jdcolor.c) -> uint8 HWC RGB at the image's own size, one thread per pixel
@@ -46,6 +46,16 @@ struct HuffTable {            // device view of one Huffman table
 };
 static_assert(sizeof(HuffTable) % 8 == 0, "tables are laid out back to back");
 
+// AC symbols whose code AND value bits fit the look-ahead (code length + size <= kFastBits) decode with ONE look-up and no
+// data-dependent branch:  entry = value << 16 | advance << 8 | total bits  (0: not covered), where `advance` is what the symbol
+// adds to the zig-zag position: run + 1 for a coefficient, 16 for ZRL, 64 for EOB (ends the block through the loop condition).
+// One table per distinct AC table of the batch; a warp copies the two of its image into shared memory.
+constexpr int kFastBits = 11;
+constexpr int kFastSize = 1 << kFastBits;
+struct FastAc {
+  int32_t e[kFastSize];
+};
+
 struct alignas(16) JpegComp {
   uint16_t qt[64];            // quantisation table, natural order
   unsigned long long coef_off;    // byte offsets into the scratch buffer
@@ -61,10 +71,10 @@ static_assert(sizeof(JpegComp) == 192, "layout shared by host and device");
 
 struct alignas(16) JpegImage {
   unsigned long long data_off;    // first entropy-coded byte inside the blob
-  unsigned long long tab_off;     // 4 HuffTable: DC0, DC1, AC0, AC1
   unsigned char* out;             // uint8 [height][width][3]
   unsigned int data_len;          // bytes from data_off to the end of the file
   int width, height, ncomp, hmax, vmax, mcux, mcuy, restart_interval;
+  short tab[4];                   // DC0, DC1, AC0, AC1: index into the batch's table array (identical tables are stored once)
   int pad_;
   JpegComp comp[3];
 };
@@ -162,36 +172,79 @@ __device__ __forceinline__ int receive_extend(BitReader& br, int s) {   // HUFF_
   return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
 }
 
-__device__ void decode_block(BitReader& br, const HuffTable* __restrict__ dc, const HuffTable* __restrict__ ac, int& pred,
-                             int16_t* blk) {
+// one 8x8 block: blk receives the quantised coefficients in ZIG-ZAG order (the IDCT kernel undoes it on load).
+// After a refill the accumulator holds > 32 bits, enough for THREE one-look-up symbols (<= 11 bits each) before the next check;
+// the common path falls through every branch (a lone warp pays ~20 cycles for each taken one).
+__device__ __forceinline__ void decode_block(BitReader& br, const HuffTable* __restrict__ dc, const HuffTable* __restrict__ ac,
+                                             const int32_t* __restrict__ fast, int& pred, int16_t* blk) {
   if (br.n <= 32) refill(br);
   int s = decode_symbol(br, dc) & 15;
   if (s) pred += receive_extend(br, s);
   blk[0] = int16_t(pred);
   int k = 1;
+  auto fast_step = [&](int e) {
+    const int len = e & 255, pos = k + ((e >> 8) & 255) - 1;
+    br.acc <<= len;
+    br.n -= len;
+    if (pos < 64) blk[pos] = int16_t(e >> 16);          // ZRL writes a zero into a still-zero slot; EOB lands beyond the block
+    k = pos + 1;
+  };
 #pragma unroll 1
   while (k < 64) {
-    if (br.n <= 32) refill(br);
-    const int rs = decode_symbol(br, ac);
-    const int r = rs >> 4;
-    s = rs & 15;
-    if (s) {
-      k += r;
-      const int v = receive_extend(br, s);
-      if (k < 64) blk[c_zigzag[k]] = int16_t(v);
-      ++k;
-    } else {
-      if (r != 15) break;
-      k += 16;
+    if (__builtin_expect(br.n <= 32, 0)) refill(br);
+    int e = fast[uint32_t(br.acc >> (64 - kFastBits))];
+    if (__builtin_expect((e & 255) == 0, 0)) {          // long code or large value: canonical walk + receive / extend
+      const int rs = decode_symbol(br, ac);
+      s = rs & 15;
+      int v = 0;
+      if (s) v = receive_extend(br, s);
+      const int pos = k + (s ? (rs >> 4) + 1 : ((rs >> 4) == 15 ? 16 : 64)) - 1;
+      if (pos < 64) blk[pos] = int16_t(v);
+      k = pos + 1;
+      continue;
     }
+    fast_step(e);
+    if (k >= 64) break;
+    e = fast[uint32_t(br.acc >> (64 - kFastBits))];
+    if (__builtin_expect((e & 255) == 0, 0)) continue;
+    fast_step(e);
+    if (k >= 64) break;
+    e = fast[uint32_t(br.acc >> (64 - kFastBits))];
+    if (__builtin_expect((e & 255) == 0, 0)) continue;
+    fast_step(e);
   }
 }
 
-__global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ order,
-                                                          const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch) {
-  const JpegImage& im = imgs[order[blockIdx.x]];
-  __shared__ __align__(16) int16_t blk[64];
-  const int lane = threadIdx.x;
+// kHuffWarps images per CTA, one warp each.  The one-look-up tables of the CTA's FIRST image sit in shared memory; the host orders
+// the images by AC table pair, so the other warps nearly always use the same pair and read them there too (a warp whose image
+// has different tables reads its own from global memory / L1 instead).
+constexpr int kHuffWarps = 4;
+__global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ order,
+                                                                       int n_images, const HuffTable* __restrict__ tables,
+                                                                       const FastAc* __restrict__ fast_tables,
+                                                                       const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch) {
+  __shared__ __align__(16) int16_t blk_s[kHuffWarps][64];
+  __shared__ __align__(16) int32_t fast_s[2][kFastSize];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int first = blockIdx.x * kHuffWarps;
+  {
+    const JpegImage& im0 = imgs[order[first]];
+    for (int t = 0; t < 2; ++t) {
+      const uint4* src = reinterpret_cast<const uint4*>(fast_tables[im0.tab[2 + t]].e);
+      uint4* dst = reinterpret_cast<uint4*>(fast_s[t]);
+      for (int i = threadIdx.x; i < kFastSize / 4; i += 32 * kHuffWarps) dst[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+  if (first + warp >= n_images) return;
+  const JpegImage& im = imgs[order[first + warp]];
+  int16_t* blk = blk_s[warp];
+  const int32_t* fast[2];
+  {
+    const JpegImage& im0 = imgs[order[first]];
+    for (int t = 0; t < 2; ++t)
+      fast[t] = im.tab[2 + t] == im0.tab[2 + t] ? fast_s[t] : fast_tables[im.tab[2 + t]].e;
+  }
   reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
   __syncwarp();
   BitReader br;
@@ -200,7 +253,8 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
   br.acc = 0;
   br.n = 0;
   br.marker = 0;
-  const HuffTable* tabs = reinterpret_cast<const HuffTable*>(scratch + im.tab_off);
+  const HuffTable* dc_tab[2] = {tables + im.tab[0], tables + im.tab[1]};
+  const HuffTable* ac_tab[2] = {tables + im.tab[2], tables + im.tab[3]};
   int pred[3] = {0, 0, 0};
   int todo = im.restart_interval;
   const int ncomp = im.ncomp;
@@ -220,7 +274,7 @@ __global__ void __launch_bounds__(32) jpeg_huffman_kernel(const JpegImage* __res
         int16_t* coef = reinterpret_cast<int16_t*>(scratch + cp.coef_off);
         for (int by = 0; by < cp.v; ++by) {
           for (int bx = 0; bx < cp.h; ++bx) {
-            if (lane == 0) decode_block(br, tabs + cp.td, tabs + 2 + cp.ta, pred[ci], blk);
+            if (lane == 0) decode_block(br, dc_tab[cp.td], ac_tab[cp.ta], fast[cp.ta], pred[ci], blk);
             __syncwarp();
             const size_t b = size_t(my * cp.v + by) * cp.bw + size_t(mx * cp.h + bx);
             reinterpret_cast<uint32_t*>(coef + b * 64)[lane] = reinterpret_cast<uint32_t*>(blk)[lane];
@@ -297,6 +351,9 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restr
                                                         const int* __restrict__ cta_start, int n_units,
                                                         uint8_t* __restrict__ scratch) {
   __shared__ int ws[32][8][9];
+  __shared__ __align__(16) int16_t raw[32][64];            // the CTA's 32 blocks as stored: zig-zag order
+  __shared__ uint8_t unzig[64];                           // natural index -> zig-zag position
+  if (threadIdx.x < 64) unzig[c_zigzag[threadIdx.x]] = uint8_t(threadIdx.x);
   const int u = find_unit(cta_start, n_units, int(blockIdx.x));
   const int2 un = units[u];
   const JpegComp& cp = imgs[un.x].comp[un.y];
@@ -305,13 +362,14 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restr
   const long long b = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 32 + lb;
   const bool valid = b < nblocks;
   {
-    int4 raw = make_int4(0, 0, 0, 0);
-    if (valid) raw = *reinterpret_cast<const int4*>(scratch + cp.coef_off + size_t(b) * 128 + r * 16);
+    int4 in = make_int4(0, 0, 0, 0);
+    if (valid) in = *reinterpret_cast<const int4*>(scratch + cp.coef_off + size_t(b) * 128 + r * 16);
+    *reinterpret_cast<int4*>(&raw[lb][r * 8]) = in;
+    __syncthreads();
     const uint4 q = *reinterpret_cast<const uint4*>(cp.qt + r * 8);
-    const int16_t* c16 = reinterpret_cast<const int16_t*>(&raw);
     const uint16_t* q16 = reinterpret_cast<const uint16_t*>(&q);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ws[lb][r][j] = int(c16[j]) * int(q16[j]);
+    for (int j = 0; j < 8; ++j) ws[lb][r][j] = int(raw[lb][unzig[r * 8 + j]]) * int(q16[j]);
   }
   __syncthreads();
   {
@@ -360,27 +418,47 @@ __device__ __forceinline__ int upsample(const uint8_t* __restrict__ plane, const
 
 __device__ __forceinline__ uint8_t clamp255(int v) { return uint8_t(min(max(v, 0), 255)); }
 
-// cta_start[i] = first CTA of image i (256 pixels per CTA)
+// cta_start[i] = first CTA of image i; a thread converts 4 horizontally adjacent pixels (a CTA: 1024 pixel slots, rows padded to 4)
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ image_of,
                                                          const int* __restrict__ cta_start, int n,
                                                          const uint8_t* __restrict__ scratch) {
   const int u = find_unit(cta_start, n, int(blockIdx.x));
   const JpegImage& im = imgs[image_of[u]];
-  const long long pix = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 256 + threadIdx.x;
-  if (pix >= (long long)im.width * im.height) return;
-  const int y = int(pix / im.width), x = int(pix - (long long)y * im.width);
-  const int Y = scratch[im.comp[0].plane_off + size_t(y) * im.comp[0].pitch + x];
-  uint8_t* o = im.out + size_t(pix) * 3;
+  const int qpr = (im.width + 3) >> 2;                    // pixel quads per row
+  const long long q = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 256 + threadIdx.x;
+  if (q >= (long long)qpr * im.height) return;
+  const int y = int(q / qpr), x0 = int(q - (long long)y * qpr) * 4;
+  const int nx = min(4, im.width - x0);
+  const uint8_t* yrow = scratch + im.comp[0].plane_off + size_t(y) * im.comp[0].pitch + x0;
+  const uint32_t y4 = *reinterpret_cast<const uint32_t*>(yrow);      // plane rows are padded to whole blocks: always readable
+  uint8_t rgb[12];
   if (im.ncomp == 1) {
-    o[0] = o[1] = o[2] = uint8_t(Y);
-    return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = uint8_t(y4 >> (8 * i));
+  } else {
+    const uint8_t* pcb = scratch + im.comp[1].plane_off;
+    const uint8_t* pcr = scratch + im.comp[2].plane_off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = min(x0 + i, im.width - 1);
+      const int Y = int((y4 >> (8 * i)) & 255u);
+      const int cb = upsample(pcb, im.comp[1], im.hmax, im.vmax, x, y) - 128;
+      const int cr = upsample(pcr, im.comp[2], im.hmax, im.vmax, x, y) - 128;
+      // jdcolor.c build_ycc_rgb_table: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554
+      rgb[3 * i] = clamp255(Y + ((91881 * cr + 32768) >> 16));
+      rgb[3 * i + 1] = clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+      rgb[3 * i + 2] = clamp255(Y + ((116130 * cb + 32768) >> 16));
+    }
   }
-  const int cb = upsample(scratch + im.comp[1].plane_off, im.comp[1], im.hmax, im.vmax, x, y) - 128;
-  const int cr = upsample(scratch + im.comp[2].plane_off, im.comp[2], im.hmax, im.vmax, x, y) - 128;
-  // jdcolor.c build_ycc_rgb_table: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554
-  o[0] = clamp255(Y + ((91881 * cr + 32768) >> 16));
-  o[1] = clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
-  o[2] = clamp255(Y + ((116130 * cb + 32768) >> 16));
+  uint8_t* o = im.out + (size_t(y) * im.width + x0) * 3;
+  if (nx == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+      o32[w] = uint32_t(rgb[4 * w]) | (uint32_t(rgb[4 * w + 1]) << 8) | (uint32_t(rgb[4 * w + 2]) << 16) | (uint32_t(rgb[4 * w + 3]) << 24);
+  } else {
+    for (int i = 0; i < 3 * nx; ++i) o[i] = rgb[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host: headers and layout
@@ -422,6 +500,28 @@ void build_table(const HostTable& t, HuffTable* out) {
     code <<= 1;
   }
   out->maxcode[17] = 0x7fffffff;
+}
+
+// the one-look-up AC table (see FastAc) from the canonical look-ahead table
+void build_fast_ac(const HostTable& t, FastAc* out) {
+  std::memset(out, 0, sizeof(FastAc));
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; ++l) {
+    for (int i = 0; i < t.bits[l - 1]; ++i, ++k, ++code) {
+      const int rs = t.vals[k], r = rs >> 4, sz = rs & 15;
+      const int tot = l + sz;
+      if (tot > kFastBits || code >= (1 << l)) continue;
+      const int adv = sz ? r + 1 : (r == 15 ? 16 : 64);
+      for (int vb = 0; vb < (1 << sz); ++vb) {
+        int v = 0;
+        if (sz) v = vb < (1 << (sz - 1)) ? vb - (1 << sz) + 1 : vb;
+        const int first = ((code << sz) | vb) << (kFastBits - tot);
+        const int32_t e = int32_t((uint32_t(v) << 16) | uint32_t(adv << 8) | uint32_t(tot));
+        for (int f = 0; f < (1 << (kFastBits - tot)); ++f) out->e[first + f] = e;
+      }
+    }
+    code <<= 1;
+  }
 }
 
 // marker segments up to the first SOS (jdmarker.c read_markers); fills p.img geometry, quantisation tables and Huffman tables
@@ -563,6 +663,9 @@ void parse_one(const uint8_t* d, size_t n, Parsed& p) {
 
 struct iic_jpeg_plan {
   std::vector<iic::Parsed> files;
+  std::vector<iic::HuffTable> tables;  // the distinct Huffman tables of the batch, built once
+  std::vector<iic::FastAc> fast;       // one-look-up companion of every table (only those of AC tables are read)
+  size_t off_fast = 0;
   std::vector<int> ok;                 // indices of the files inside the envelope, longest entropy segment first
   size_t desc_bytes = 0;               // descriptor region = staging size: images, tables, unit tables
   size_t off_tables = 0, off_order = 0, off_units = 0, off_idct_start = 0, off_color_img = 0, off_color_start = 0;
@@ -590,14 +693,54 @@ int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic
       pl->ok.push_back(i);
     }
   }
-  std::stable_sort(pl->ok.begin(), pl->ok.end(),
-                   [&](int a, int b) { return pl->files[size_t(a)].img.data_len > pl->files[size_t(b)].img.data_len; });
-  // descriptor region: [JpegImage x m][HuffTable x 4m][order m][units 3m int2][idct_start 3m+1][color_img m][color_start m+1]
+
+  // the distinct Huffman tables of the batch (most encoders emit the Annex K tables: a handful per batch, L1-resident on the device)
   const size_t m = pl->ok.size();
+  {
+    std::vector<const HostTable*> seen;
+    for (size_t j = 0; j < m; ++j) {
+      Parsed& p = pl->files[size_t(pl->ok[j])];
+      for (int tc = 0; tc < 2; ++tc)
+        for (int th = 0; th < 2; ++th) {
+          const HostTable& t = p.tab[tc][th];
+          int idx = 0;
+          if (t.present) {
+            idx = -1;
+            for (size_t k = 0; k < seen.size() && idx < 0; ++k)
+              if (seen[k]->count == t.count && std::memcmp(seen[k]->bits, t.bits, 16) == 0 &&
+                  std::memcmp(seen[k]->vals, t.vals, size_t(t.count)) == 0)
+                idx = int(k);
+            if (idx < 0) {
+              if (seen.size() >= 32000) { delete pl; return IIC_ERR_ARG; }
+              idx = int(seen.size());
+              seen.push_back(&t);
+              pl->tables.emplace_back();
+              build_table(t, &pl->tables.back());
+              pl->fast.emplace_back();
+              if (tc == 1) build_fast_ac(t, &pl->fast.back());
+              else std::memset(&pl->fast.back(), 0, sizeof(FastAc));
+            }
+          }
+          p.img.tab[tc * 2 + th] = short(idx);
+        }
+    }
+    if (pl->tables.empty()) { pl->tables.emplace_back(); pl->fast.emplace_back(); }
+  }
+  // launch order: images with the same AC table pair side by side (they share the CTA's shared-memory copy), the longest
+  // entropy-coded segment of a group first
+  std::stable_sort(pl->ok.begin(), pl->ok.end(), [&](int a, int b) {
+    const JpegImage& x = pl->files[size_t(a)].img;
+    const JpegImage& y = pl->files[size_t(b)].img;
+    const int kx = (int(x.tab[2]) << 16) | int(x.tab[3]), ky = (int(y.tab[2]) << 16) | int(y.tab[3]);
+    return kx != ky ? kx < ky : x.data_len > y.data_len;
+  });
+  // descriptor region: [JpegImage x m][HuffTable x distinct][order m][units 3m int2][idct_start 3m+1][color_img m][color_start m+1]
   size_t off = 0;
   off += align_up(m * sizeof(JpegImage), 256);
   pl->off_tables = off;
-  off += align_up(m * 4 * sizeof(HuffTable), 256);
+  off += align_up(pl->tables.size() * sizeof(HuffTable), 256);
+  pl->off_fast = off;
+  off += align_up(pl->fast.size() * sizeof(FastAc), 256);
   pl->off_order = off;
   off += align_up(m * sizeof(int), 256);
   pl->off_units = off;
@@ -614,7 +757,6 @@ int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic
   int units = 0;
   for (size_t j = 0; j < m; ++j) {
     Parsed& p = pl->files[size_t(pl->ok[j])];
-    p.img.tab_off = pl->off_tables + j * 4 * sizeof(HuffTable);
     for (int c = 0; c < p.img.ncomp; ++c) {
       JpegComp& cp = p.img.comp[c];
       const size_t blocks = size_t(cp.bw) * size_t(cp.bh);
@@ -625,7 +767,7 @@ int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic
       idct_ctas += (long long)((blocks + 31) / 32);
       ++units;
     }
-    color_ctas += ((long long)p.img.width * p.img.height + 255) / 256;
+    color_ctas += ((long long)((p.img.width + 3) / 4) * p.img.height + 255) / 256;
   }
   if (idct_ctas > 0x7fffffffLL || color_ctas > 0x7fffffffLL) {
     delete pl;
@@ -647,6 +789,18 @@ int iic_jpeg_plan_info(const iic_jpeg_plan* plan, int i, int* width, int* height
   if (status) *status = p.status;
   if (width) *width = p.status == IIC_JPEG_OK ? p.img.width : 0;
   if (height) *height = p.status == IIC_JPEG_OK ? p.img.height : 0;
+  return IIC_OK;
+}
+
+int iic_jpeg_plan_infos(const iic_jpeg_plan* plan, int* whs) {
+  if (plan == nullptr || whs == nullptr) return IIC_ERR_ARG;
+  for (size_t i = 0; i < plan->files.size(); ++i) {
+    const iic::Parsed& p = plan->files[i];
+    const bool ok = p.status == IIC_JPEG_OK;
+    whs[3 * i] = ok ? p.img.width : 0;
+    whs[3 * i + 1] = ok ? p.img.height : 0;
+    whs[3 * i + 2] = p.status;
+  }
   return IIC_OK;
 }
 
@@ -679,11 +833,6 @@ int iic_jpeg_decode(const iic_jpeg_plan* plan, const uint8_t* dev_blob, uint8_t*
     const Parsed& p = plan->files[size_t(fi)];
     imgs[j] = p.img;
     imgs[j].out = out_rgb[fi];
-    for (int tc = 0; tc < 2; ++tc)
-      for (int th = 0; th < 2; ++th) {
-        if (p.tab[tc][th].present) build_table(p.tab[tc][th], &tabs[j * 4 + size_t(tc * 2 + th)]);
-        else std::memset(&tabs[j * 4 + size_t(tc * 2 + th)], 0, sizeof(HuffTable));
-      }
     if (out_rgb[fi] == nullptr) continue;     // the caller skips this file
     order[m_out] = int(j);
     for (int c = 0; c < p.img.ncomp; ++c) {
@@ -694,16 +843,21 @@ int iic_jpeg_decode(const iic_jpeg_plan* plan, const uint8_t* dev_blob, uint8_t*
     }
     color_img[m_out] = int(j);
     color_start[m_out] = cc;
-    cc += int(((long long)p.img.width * p.img.height + 255) / 256);
+    cc += int(((long long)((p.img.width + 3) / 4) * p.img.height + 255) / 256);
     ++m_out;
   }
   idct_start[u] = ic;
   color_start[m_out] = cc;
   if (m_out == 0) return IIC_OK;
+  std::memcpy(tabs, plan->tables.data(), plan->tables.size() * sizeof(HuffTable));
+  std::memcpy(st + plan->off_fast, plan->fast.data(), plan->fast.size() * sizeof(FastAc));
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (cudaMemcpyAsync(sc, st, plan->desc_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return IIC_ERR_CUDA;
   const JpegImage* d_imgs = reinterpret_cast<const JpegImage*>(sc);
-  jpeg_huffman_kernel<<<m_out, 32, 0, s>>>(d_imgs, reinterpret_cast<const int*>(sc + plan->off_order), dev_blob, sc);
+  jpeg_huffman_kernel<<<(m_out + kHuffWarps - 1) / kHuffWarps, 32 * kHuffWarps, 0, s>>>(
+                                           d_imgs, reinterpret_cast<const int*>(sc + plan->off_order), m_out,
+                                           reinterpret_cast<const HuffTable*>(sc + plan->off_tables),
+                                           reinterpret_cast<const FastAc*>(sc + plan->off_fast), dev_blob, sc);
   jpeg_idct_kernel<<<ic, 256, 0, s>>>(d_imgs, reinterpret_cast<const int2*>(sc + plan->off_units),
                                       reinterpret_cast<const int*>(sc + plan->off_idct_start), u, sc);
   jpeg_color_kernel<<<cc, 256, 0, s>>>(d_imgs, reinterpret_cast<const int*>(sc + plan->off_color_img),

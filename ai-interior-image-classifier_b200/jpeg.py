@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from collections import deque
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -24,13 +23,65 @@ from . import _lib as L
 
 JPEG_OK, JPEG_UNSUPPORTED, JPEG_CORRUPT = 0, 1, 2
 _PAD = 64          # the device blob must be readable 8 bytes past its end (include/iic.h); keeps the next buffer aligned too
-_inflight: deque = deque()   # (event, tensors kept alive until the stream has consumed them)
+_READ_THREADS = 8
 
 
-def _retire(keep: int = 4) -> None:
-    while len(_inflight) > keep:
-        ev, _ = _inflight.popleft()
-        ev.synchronize()
+class _Slot:
+    """Grow-only buffers of one in-flight batch: pinned host (file bytes, descriptors) and device (file bytes, scratch).  Two
+    slots per device alternate, so batch i+1 is read and parsed on the host while batch i is still being decoded; a slot is
+    reused only after the event recorded behind its last decode has completed (cudaHostAlloc / cudaMalloc happen only when
+    a buffer grows)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.blob = torch.empty(0, dtype=torch.uint8)
+        self.staging = torch.empty(0, dtype=torch.uint8)
+        self.dev_blob = torch.empty(0, dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(0, dtype=torch.uint8, device=device)
+        self.event: Optional[torch.cuda.Event] = None
+
+    def wait(self) -> None:
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+
+    @staticmethod
+    def _grow(t: torch.Tensor, nbytes: int, **kw) -> torch.Tensor:
+        if t.numel() >= nbytes:
+            return t
+        return torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, **kw)
+
+    def host_blob(self, nbytes: int) -> torch.Tensor:
+        self.blob = self._grow(self.blob, nbytes + _PAD, pin_memory=True)
+        return self.blob
+
+    def reserve(self, blob_bytes: int, staging_bytes: int, scratch_bytes: int) -> None:
+        self.staging = self._grow(self.staging, max(staging_bytes, 16), pin_memory=True)
+        self.dev_blob = self._grow(self.dev_blob, blob_bytes + _PAD, device=self.device)
+        self.scratch = self._grow(self.scratch, scratch_bytes, device=self.device)
+
+
+_slots: dict = {}
+_turn: dict = {}
+
+
+def _next_slot(device: torch.device) -> _Slot:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ring = _slots.setdefault(key, [_Slot(device), _Slot(device)])
+    k = _turn.get(key, 0)
+    _turn[key] = (k + 1) % len(ring)
+    slot = ring[k]
+    slot.wait()
+    return slot
+
+
+def release_buffers() -> None:
+    """drops the cached pinned / device buffers (they are grow-only otherwise)"""
+    for ring in _slots.values():
+        for s in ring:
+            s.wait()
+    _slots.clear()
+    _turn.clear()
 
 
 class JpegPlan:
@@ -45,15 +96,13 @@ class JpegPlan:
         if rc != L.IIC_OK:
             raise RuntimeError(f"iic_jpeg_plan_create failed (code {rc})")
         self.h = h
-        w, hh, st = C.c_int(), C.c_int(), C.c_int()
-        self.sizes: List[Tuple[int, int]] = []       # (height, width), (0, 0) outside the envelope
-        self.status: List[int] = []
-        self.reasons: List[str] = []
-        for i in range(self.n):
-            self.lib.iic_jpeg_plan_info(h, i, C.byref(w), C.byref(hh), C.byref(st))
-            self.sizes.append((hh.value, w.value))
-            self.status.append(st.value)
-            self.reasons.append("" if st.value == JPEG_OK else (self.lib.iic_jpeg_plan_reason(h, i) or b"").decode())
+        whs = np.zeros((max(self.n, 1), 3), dtype=np.int32)
+        self.lib.iic_jpeg_plan_infos(h, whs.ctypes.data)
+        self.whs = whs[:self.n]
+        self.sizes: List[Tuple[int, int]] = [(int(r[1]), int(r[0])) for r in self.whs]       # (height, width); (0, 0) outside the envelope
+        self.status: List[int] = [int(r[2]) for r in self.whs]
+        self.reasons: List[str] = ["" if st == JPEG_OK else (self.lib.iic_jpeg_plan_reason(h, i) or b"").decode()
+                                   for i, st in enumerate(self.status)]
         self.staging_bytes = int(self.lib.iic_jpeg_plan_staging_bytes(h))
         self.scratch_bytes = int(self.lib.iic_jpeg_plan_scratch_bytes(h))
 
@@ -69,63 +118,62 @@ class JpegPlan:
             pass
 
 
-def _decode(blob: torch.Tensor, offsets: np.ndarray, device) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
-    """blob: pinned uint8 host tensor holding the files back to back (+ _PAD spare bytes)."""
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("the JPEG decoder runs on a CUDA device only (no CPU path)")
-    plan = JpegPlan(blob, offsets)
+def _decode(slot: _Slot, nbytes: int, offsets: np.ndarray) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
+    """slot.blob[:nbytes]: the files back to back in pinned memory."""
+    device = slot.device
+    plan = JpegPlan(slot.blob, offsets)
     try:
-        ok = [i for i in range(plan.n) if plan.status[i] == JPEG_OK]
         out: List[Optional[torch.Tensor]] = [None] * plan.n
-        if not ok:
+        ok = np.nonzero(plan.whs[:, 2] == JPEG_OK)[0]
+        if ok.size == 0:
             return out, plan.reasons
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device)
-            dev_blob = blob.to(device, non_blocking=True)
+            slot.reserve(nbytes, plan.staging_bytes, plan.scratch_bytes)
+            slot.dev_blob[:nbytes + _PAD].copy_(slot.blob[:nbytes + _PAD], non_blocking=True)
             # one allocation for all decoded images of the batch (256-byte aligned slices)
-            starts, total = [], 0
-            for i in ok:
-                starts.append(total)
-                total += (plan.sizes[i][0] * plan.sizes[i][1] * 3 + 255) // 256 * 256
-            pixels = torch.empty(total, dtype=torch.uint8, device=device)
-            ptrs = (C.c_void_p * plan.n)()
-            for i, s0 in zip(ok, starts):
-                h, w = plan.sizes[i]
-                out[i] = pixels[s0:s0 + h * w * 3].view(h, w, 3)
-                ptrs[i] = pixels.data_ptr() + s0
-            staging = torch.empty(max(plan.staging_bytes, 16), dtype=torch.uint8, pin_memory=True)
-            scratch = torch.empty(plan.scratch_bytes, dtype=torch.uint8, device=device)
-            rc = plan.lib.iic_jpeg_decode(plan.h, dev_blob.data_ptr(), ptrs, staging.data_ptr(), scratch.data_ptr(), stream.cuda_stream)
+            npix = plan.whs[ok, 0].astype(np.int64) * plan.whs[ok, 1].astype(np.int64) * 3
+            sizes = (npix + 255) // 256 * 256
+            starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            pixels = torch.empty(int(sizes.sum()), dtype=torch.uint8, device=device)
+            ptrs = np.zeros(plan.n, dtype=np.uint64)
+            ptrs[ok] = np.uint64(pixels.data_ptr()) + starts.astype(np.uint64)
+            for i, s0, nb in zip(ok.tolist(), starts.tolist(), npix.tolist()):
+                out[i] = pixels[s0:s0 + nb].view(int(plan.whs[i, 1]), int(plan.whs[i, 0]), 3)
+            rc = plan.lib.iic_jpeg_decode(plan.h, slot.dev_blob.data_ptr(), ptrs.ctypes.data_as(C.POINTER(C.c_void_p)),
+                                          slot.staging.data_ptr(), slot.scratch.data_ptr(), stream.cuda_stream)
             if rc != L.IIC_OK:
                 raise RuntimeError(f"iic_jpeg_decode failed (code {rc})")
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            _inflight.append((ev, (blob, staging, dev_blob, scratch)))   # stream-ordered consumers: keep alive until done
-            _retire()
+            slot.event = torch.cuda.Event()
+            slot.event.record(stream)
         return out, plan.reasons
     finally:
         plan.close()
 
 
-def _pinned(nbytes: int) -> torch.Tensor:
-    return torch.empty(nbytes + _PAD, dtype=torch.uint8, pin_memory=True)
+def _device(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("the JPEG decoder runs on a CUDA device only (no CPU path)")
+    return device
 
 
 def decode_jpeg_bytes(files: Sequence[bytes], device) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
+    slot = _next_slot(_device(device))
     offsets = np.zeros(len(files) + 1, dtype=np.int64)
     np.cumsum([len(b) for b in files], out=offsets[1:])
-    blob = _pinned(int(offsets[-1]))
-    view = blob.numpy()
+    nbytes = int(offsets[-1])
+    view = slot.host_blob(nbytes).numpy()
     for b, lo, hi in zip(files, offsets[:-1], offsets[1:]):
         view[lo:hi] = np.frombuffer(b, dtype=np.uint8)
-    view[offsets[-1]:] = 0
-    return _decode(blob, offsets, device)
+    view[nbytes:nbytes + _PAD] = 0
+    return _decode(slot, nbytes, offsets)
 
 
 def decode_jpeg_files(paths: Sequence[str], device) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
-    """Reads the files straight into ONE pinned buffer (no per-file bytes objects) and decodes them on `device`.
-    An unreadable file gets (None, "<error>") like a file outside the envelope."""
+    """Reads the files straight into ONE pinned buffer (a few reader threads, no per-file bytes objects) and decodes them on
+    `device`.  An unreadable file gets (None, "<error>") like a file outside the envelope."""
+    slot = _next_slot(_device(device))
     sizes, errs = [], [""] * len(paths)
     for i, p in enumerate(paths):
         try:
@@ -135,19 +183,29 @@ def decode_jpeg_files(paths: Sequence[str], device) -> Tuple[List[Optional[torch
             errs[i] = f"unreadable: {e}"
     offsets = np.zeros(len(paths) + 1, dtype=np.int64)
     np.cumsum(sizes, out=offsets[1:])
-    blob = _pinned(int(offsets[-1]))
-    view = memoryview(blob.numpy())
-    for i, p in enumerate(paths):
+    nbytes = int(offsets[-1])
+    view = memoryview(slot.host_blob(nbytes).numpy())
+
+    def read(i: int) -> None:
         if errs[i]:
-            continue
+            return
         try:
-            with open(p, "rb", buffering=0) as f:
+            with open(paths[i], "rb", buffering=0) as f:
                 got = f.readinto(view[offsets[i]:offsets[i + 1]])
             if got != sizes[i]:
                 errs[i] = "short read"
-                view[offsets[i]:offsets[i] + 2] = b"\0\0"
         except OSError as e:
             errs[i] = f"unreadable: {e}"
-    view[offsets[-1]:] = bytes(_PAD)
-    imgs, reasons = _decode(blob, offsets, device)
+        if errs[i] and sizes[i] >= 2:
+            view[offsets[i]:offsets[i] + 2] = b"\0\0"       # no SOI: the plan reports the file as corrupt
+
+    if len(paths) >= 4 * _READ_THREADS:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=_READ_THREADS) as ex:   # readinto releases the GIL
+            list(ex.map(read, range(len(paths)), chunksize=16))
+    else:
+        for i in range(len(paths)):
+            read(i)
+    view[nbytes:nbytes + _PAD] = bytes(_PAD)
+    imgs, reasons = _decode(slot, nbytes, offsets)
     return imgs, [e or r for e, r in zip(errs, reasons)]

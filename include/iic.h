@@ -166,6 +166,7 @@ typedef struct iic_jpeg_plan iic_jpeg_plan;
 int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic_jpeg_plan** out);
 void iic_jpeg_plan_destroy(iic_jpeg_plan* plan);
 int iic_jpeg_plan_info(const iic_jpeg_plan* plan, int i, int* width, int* height, int* status);
+int iic_jpeg_plan_infos(const iic_jpeg_plan* plan, int* whs); /* host int [n][3] = (width, height, status) of every file */
 const char* iic_jpeg_plan_reason(const iic_jpeg_plan* plan, int i); /* why file i is outside the envelope ("" if it is not) */
 size_t iic_jpeg_plan_staging_bytes(const iic_jpeg_plan* plan);
 size_t iic_jpeg_plan_scratch_bytes(const iic_jpeg_plan* plan);
