@@ -13,6 +13,7 @@ c_proj GEMM (+LoRA)) -> fused head over 437 labels in 6 groups.  Prints ONE JSON
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -193,9 +194,10 @@ def main():
     ap.add_argument("--lora-rank", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--legs", default=os.environ.get("IIC_BENCH_LEGS", "train,l14,latency,bf16"),
+    ap.add_argument("--legs", default=os.environ.get("IIC_BENCH_LEGS", "train,l14,latency,bf16,ingest"),
                     help="extra sub-records beside the headline: train (configs[3]), l14 (configs[4]), latency (configs[0]), "
-                         "bf16 (the non-default dtype arm); '' = headline only")
+                         "bf16 (the non-default dtype arm), ingest (SURVEY 8(f) N2: JPEG files -> pixels on the device -> top-k); "
+                         "'' = headline only")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -438,6 +440,20 @@ def main():
         lat["what"] = "host wall clock per call, one 224x224 image resident on the device -> top-k on the host (one sync per call)"
         extra["latency_b1"] = lat
         del eng, vis
+    # ---- image ingest - 1024 JPEG files (1024x768) -> pixels resident on the device, and on to top-k ----
+    if "ingest" in legs and rank == 0:
+        try:
+            spec = importlib.util.spec_from_file_location("bench_ingest", os.path.join(ROOT, "tools", "bench_ingest.py"))
+            bi = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bi)
+            vis = build_tower(clipc, lora, "ViT-B/16", args.lora_rank, dev, args.operand_dtype)
+            eng = vis.sync_engine()
+            eng.set_labels(torch.nn.functional.normalize(torch.randn(sum(GROUPS), 512, device=dev), dim=-1), GROUPS, SPLIT, topk=5, logit_scale=100.0)
+            extra["ingest"] = bi.measure(n=1024, reps=3, dev=dev, with_nvjpeg=False, engine=eng, pipeline_batches=3)
+            del eng, vis
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down
+            extra["ingest"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world > 1:
         dist.barrier()
 

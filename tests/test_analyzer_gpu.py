@@ -207,33 +207,30 @@ def test_style_worker_shape(iic, analyzer):
 
 
 def test_gpu_jpeg_ingest(analyzer, tmp_path):
-    """local JPEGs decoded by nvJPEG on the GPU feed the preprocess kernel directly.  nvJPEG and libjpeg
-    (PIL) differ by a grey level here and there (IDCT / chroma upsampling), so the bar is the image-path bar: same labels,
-    probabilities within the analyzer tolerance, and pixels within a few levels."""
+    """local JPEG files decoded on the GPU by the engine's own decoder (csrc/jpeg.cu) feed the preprocess kernel
+    directly.  The decoder is bit-identical to Pillow, so the analyzer's result dict must be EQUAL to the host-decode one."""
     from importlib import import_module
     from PIL import Image
     an = import_module("ai-interior-image-classifier_b200.analyzer")
-    crops = golden_npz("crops_u8.npz")["crops"][:24]
+    crops = golden_npz("crops_u8.npz")["crops"][:40]
     paths = []
     for i, c in enumerate(crops):
         p = str(tmp_path / f"img{i}.jpg")
-        Image.fromarray(c).save(p, quality=92)
+        Image.fromarray(c).save(p, quality=(92, 75, 60)[i % 3], subsampling=(2, 0, 1)[i % 3], optimize=(i % 5 == 0))
         paths.append(p)
-    paths.append(str(tmp_path / "missing.jpg"))
+    prog = str(tmp_path / "progressive.jpg")
+    Image.fromarray(crops[0]).save(prog, quality=85, progressive=True)     # outside the envelope: host path inside the same call
+    paths += [prog, str(tmp_path / "missing.jpg")]
     host = an.load_images(paths, "cuda", gpu_decode=False)
     dev = an.load_images(paths, "cuda", gpu_decode=True)
     assert host[-1] is None and dev[-1] is None
-    assert all(isinstance(d, an.DeviceImage) for d in dev[:-1]) and all(not isinstance(h, an.DeviceImage) for h in host[:-1])
-    diffs = []
-    for h, d in zip(host[:-1], dev[:-1]):
-        a = torch.from_numpy(np.array(h)).int()
-        b = d.tensor.cpu().int()
-        assert a.shape == b.shape and d.size == h.size
-        diffs.append((a - b).abs())
-    diff = torch.stack(diffs).float()
-    print(f"\n[nvJPEG vs PIL] mean |d| {diff.mean():.3f} levels, max {diff.max():.0f}, share > 2 levels {(diff > 2).float().mean():.5f}")
-    # measured: mean 1.5 levels (4:2:0 chroma upsampling differs between nvJPEG and libjpeg's fancy upsampling)
-    assert diff.mean().item() < 2.5 and (diff > 24).float().mean().item() < 1e-3
+    assert all(isinstance(d, an.DeviceImage) for d in dev[:-2]) and all(not isinstance(h, an.DeviceImage) for h in host[:-1])
+    assert not isinstance(dev[-2], an.DeviceImage) and dev[-2] is not None
+    for h, d in zip(host[:-2], dev[:-2]):
+        assert d.size == h.size and torch.equal(torch.from_numpy(np.array(h)), d.tensor.cpu())
+    # below the batch threshold the files stay on the host path (one image = one serial Huffman chain on the GPU)
+    few = an.load_images(paths[:3], "cuda", gpu_decode=True)
+    assert all(not isinstance(f, an.DeviceImage) for f in few)
     saved = analyzer.gpu_decode
     try:
         analyzer.gpu_decode = False
@@ -244,12 +241,8 @@ def test_gpu_jpeg_ingest(analyzer, tmp_path):
         analyzer.gpu_decode = saved
     assert set(r_host) == set(r_dev) == set(paths)
     assert r_dev[paths[-1]]["is_interior"] is False
-    same_style = 0
-    for p in paths[:-1]:
-        hs, ds = r_host[p]["analysis"]["styles"], r_dev[p]["analysis"]["styles"]
-        same_style += hs[0][0] == ds[0][0]
-        assert abs(hs[0][1] - ds[0][1]) < 2e-2
-    assert same_style >= len(paths) - 2
+    for p in paths:
+        assert r_host[p] == r_dev[p], p
 
 
 def test_analyze_images_batch_data_parallel(analyzer):
