@@ -120,7 +120,7 @@ def test_truncated_and_corrupt_streams_do_not_hang(jp):
     assert np.array_equal(imgs[3].cpu().numpy(), _pil(good))
 
 
-def test_load_images_gpu_decode_feeds_the_analyzer_path(jp, tmp_path):
+def test_load_images_gpu_decode_feeds_the_analyzer_path(jp, tmp_path, monkeypatch):
     """analyzer.load_images(gpu_decode=True): baseline files come back as device images with Pillow's pixels, a progressive file
     and a PNG go through the host path (PIL objects), order preserved"""
     from importlib import import_module
@@ -135,6 +135,7 @@ def test_load_images_gpu_decode_feeds_the_analyzer_path(jp, tmp_path):
     png = str(tmp_path / "g.png")
     Image.fromarray(_photo(rng, 50, 60)).save(png)
     paths.append(png)
+    monkeypatch.setattr(an, "GPU_DECODE_MIN_FILES", 1)     # (calls with a handful of files stay on the host pool by default)
     out = an.load_images(paths, device="cuda:0", gpu_decode=True)
     assert isinstance(out[0], an.DeviceImage) and isinstance(out[2], an.DeviceImage)
     assert not isinstance(out[1], an.DeviceImage) and not isinstance(out[3], an.DeviceImage)
