@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -58,14 +59,23 @@ struct FastAc {
 
 struct alignas(16) JpegComp {
   uint16_t qt[64];            // quantisation table, natural order
-  unsigned long long coef_off;    // byte offsets into the scratch buffer
-  unsigned long long plane_off;
+  unsigned long long plane_off;   // byte offset of the sample plane in the scratch buffer
+  int blk0, pad0_;            // index of the component's first block inside an MCU
   int h, v;                   // sampling factors (1 x 1 for a lone component)
   int bw, bh;                 // block grid (padded to whole MCUs)
   int dw, dh;                 // real samples of the component (downsampled_width / height)
   int pitch;                  // bytes per plane row = 8 bw
   int td, ta;                 // Huffman table slots (0 / 1)
   int pad_[3];
+};
+// Coefficient blocks are stored in DECODING order - [MCU][block of the MCU][64] - once per CHAIN of the image (see
+// jpeg_huffman_kernel): a chain that starts in the middle of the entropy-coded segment cannot know its MCU index.
+constexpr int kMaxChains = 8;
+constexpr int kChainWindow = 32;   // MCUs a speculative chain decodes (and discards) before it publishes a boundary
+struct ChainInfo {                 // written by the Huffman kernel, read by the IDCT kernel
+  int start_mcu[kMaxChains];       // first MCU of the image the chain's stored blocks belong to
+  int n_mcu[kMaxChains];           // stored MCUs that are valid (0: the chain never synchronised / is not used)
+  int dc_off[kMaxChains][3];       // DC predictor of every component at the chain's first stored MCU
 };
 static_assert(sizeof(JpegComp) == 192, "layout shared by host and device");
 
@@ -75,10 +85,15 @@ struct alignas(16) JpegImage {
   unsigned int data_len;          // bytes from data_off to the end of the file
   int width, height, ncomp, hmax, vmax, mcux, mcuy, restart_interval;
   short tab[4];                   // DC0, DC1, AC0, AC1: index into the batch's table array (identical tables are stored once)
+  int nchains;                    // decoding chains of this image (1 or the batch's chain count)
+  unsigned long long coef_off;    // coefficient blocks of chain 0; chain c at coef_off + c * chain_stride
+  unsigned long long chain_stride;
+  unsigned long long info_off;    // ChainInfo
+  int bpm;                        // blocks per MCU
   int pad_;
   JpegComp comp[3];
 };
-static_assert(sizeof(JpegImage) == 64 + 3 * 192, "layout shared by host and device");
+static_assert(sizeof(JpegImage) == 96 + 3 * 192, "layout shared by host and device");
 
 __constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
@@ -91,6 +106,7 @@ struct BitReader {
   uint64_t acc;         // MSB-aligned bit accumulator
   int n;                // valid bits in acc
   int marker;           // a marker has been reached: zeros are fed from here on (jdhuff.c jpeg_fill_bit_buffer)
+  int fake;             // zero bits fed so far (they sit below the real bits of the accumulator)
 };
 
 __device__ __forceinline__ uint32_t load_be32(const uint8_t* p) {
@@ -126,9 +142,26 @@ __device__ __forceinline__ void refill(BitReader& br) {
         else { br.marker = int(b2); b = 0; }
       }
     }
+    else br.fake += 8;
     br.acc |= uint64_t(b) << (56 - br.n);
     br.n += 8;
   }
+}
+
+// Canonical form of a reader state: whole buffered bytes go back to the stream, at most 7 bits of the last data byte stay
+// (a data byte 0xFF occupies two raw bytes, FF 00).  Two readers that have consumed the same bits of the same stream end
+// up with the same (p, n): the position below identifies a point of the stream.
+__device__ __forceinline__ void normalize(BitReader& br, const uint8_t* lo) {
+  while (br.n >= 8) {
+    const uint8_t* q = br.p - 1;
+    if (q > lo && q[0] == 0x00 && q[-1] == 0xFF) --q;
+    br.p = q;
+    br.n -= 8;
+  }
+  br.acc = br.n ? (br.acc & ~(~0ull >> br.n)) : 0ull;
+}
+__device__ __forceinline__ unsigned long long stream_pos(const BitReader& br, const uint8_t* base) {
+  return (unsigned long long)(br.p - base) * 8ull - (unsigned long long)br.n;
 }
 
 // byte-align and step over the RSTn marker (jdhuff.c process_restart / jdmarker.c read_restart_marker)
@@ -215,74 +248,181 @@ __device__ __forceinline__ void decode_block(BitReader& br, const HuffTable* __r
   }
 }
 
-// kHuffWarps images per CTA, one warp each.  The one-look-up tables of the CTA's FIRST image sit in shared memory; the host orders
-// the images by AC table pair, so the other warps nearly always use the same pair and read them there too (a warp whose image
-// has different tables reads its own from global memory / L1 instead).
-constexpr int kHuffWarps = 4;
+// Entropy decoding is serial inside a scan, so the parallelism comes from two places:
+//   ACROSS the images of the batch: a CTA of kHuffWarps warps serves kHuffWarps / chains images, one warp per CHAIN.  The
+//       one-look-up tables of the CTA's first image sit in shared memory; the host orders the images by AC table pair, so the
+//       other warps nearly always read them there too (else from global memory / L1).
+//   INSIDE an image (chains > 1: batches too small to fill the GPU with one chain per image): chain c starts at byte
+//       c * len / chains of the entropy-coded segment in a guessed state.  Huffman streams self-synchronise: after `window` MCUs
+//       (decoded and discarded) chain c brings its reader into canonical form, PUBLISHES that stream position, zeroes its DC
+//       predictors and from there on stores blocks under its own MCU count.  Chain c - 1 (whose state is true by induction
+//       from chain 0) compares its canonical position at every MCU boundary behind the successor's start byte: equal -> both
+//       are in the same state from there on, so it stops and the successor's blocks are the image's; past it without a match
+//       -> the successor never synchronised in its window, is told to stop, and the chain carries on towards the next one.
+//       Every outcome yields Pillow's pixels; what varies is who decoded them.
+// lane 0 of a warp walks the bit stream; the whole warp writes each finished block (zig-zag order) as one 128-byte store.
+constexpr int kHuffWarps = 8;
+static_assert(kHuffWarps == kMaxChains, "one warp per chain");
+
+struct ChainShared {
+  unsigned long long pub[kMaxChains];   // published position of the chain's first stored MCU; ~0: not yet; 0: never
+  int dead[kMaxChains];
+  int n_mcu[kMaxChains], matched[kMaxChains], end_pred[kMaxChains][3];
+};
+
 __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ order,
                                                                        int n_images, const HuffTable* __restrict__ tables,
                                                                        const FastAc* __restrict__ fast_tables,
-                                                                       const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch) {
+                                                                       const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch,
+                                                                       int chains, int window) {
   __shared__ __align__(16) int16_t blk_s[kHuffWarps][64];
   __shared__ __align__(16) int32_t fast_s[2][kFastSize];
+  __shared__ ChainShared sh_all[kHuffWarps];               // one per image of the CTA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int first = blockIdx.x * kHuffWarps;
-  {
-    const JpegImage& im0 = imgs[order[first]];
-    for (int t = 0; t < 2; ++t) {
-      const uint4* src = reinterpret_cast<const uint4*>(fast_tables[im0.tab[2 + t]].e);
-      uint4* dst = reinterpret_cast<uint4*>(fast_s[t]);
-      for (int i = threadIdx.x; i < kFastSize / 4; i += 32 * kHuffWarps) dst[i] = __ldg(src + i);
-    }
+  const int ipc = kHuffWarps / chains;                     // images per CTA
+  const int first = int(blockIdx.x) * ipc;
+  const JpegImage& im0 = imgs[order[first]];
+  for (int t = 0; t < 2; ++t) {
+    const uint4* src = reinterpret_cast<const uint4*>(fast_tables[im0.tab[2 + t]].e);
+    uint4* dst = reinterpret_cast<uint4*>(fast_s[t]);
+    for (int i = threadIdx.x; i < kFastSize / 4; i += 32 * kHuffWarps) dst[i] = __ldg(src + i);
+  }
+  if (threadIdx.x < kHuffWarps * kMaxChains) {
+    ChainShared& z = sh_all[threadIdx.x / kMaxChains];
+    const int c = threadIdx.x % kMaxChains;
+    z.pub[c] = ~0ull;
+    z.dead[c] = 0;
+    z.n_mcu[c] = 0;
+    z.matched[c] = -1;
+    z.end_pred[c][0] = z.end_pred[c][1] = z.end_pred[c][2] = 0;
   }
   __syncthreads();
-  if (first + warp >= n_images) return;
-  const JpegImage& im = imgs[order[first + warp]];
-  int16_t* blk = blk_s[warp];
-  const int32_t* fast[2];
-  {
-    const JpegImage& im0 = imgs[order[first]];
-    for (int t = 0; t < 2; ++t)
-      fast[t] = im.tab[2 + t] == im0.tab[2 + t] ? fast_s[t] : fast_tables[im.tab[2 + t]].e;
-  }
-  reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
-  __syncwarp();
-  BitReader br;
-  br.p = blob + im.data_off;
-  br.end = br.p + im.data_len;
-  br.acc = 0;
-  br.n = 0;
-  br.marker = 0;
-  const HuffTable* dc_tab[2] = {tables + im.tab[0], tables + im.tab[1]};
-  const HuffTable* ac_tab[2] = {tables + im.tab[2], tables + im.tab[3]};
-  int pred[3] = {0, 0, 0};
-  int todo = im.restart_interval;
-  const int ncomp = im.ncomp;
-  for (int my = 0; my < im.mcuy; ++my) {
-    for (int mx = 0; mx < im.mcux; ++mx) {
-      if (lane == 0 && im.restart_interval) {
-        if (todo == 0) {
-          restart(br);
-          pred[0] = pred[1] = pred[2] = 0;
-          todo = im.restart_interval;
+  const int img_slot = first + warp / chains;
+  const int chain = warp % chains;
+  ChainShared& sh = sh_all[warp / chains];
+  const bool active = img_slot < n_images && chain < imgs[order[img_slot < n_images ? img_slot : first]].nchains;
+  if (active) {
+    const JpegImage& im = imgs[order[img_slot]];
+    const int nchains = im.nchains;
+    int16_t* blk = blk_s[warp];
+    const int32_t* fast[2];
+    for (int t = 0; t < 2; ++t) fast[t] = im.tab[2 + t] == im0.tab[2 + t] ? fast_s[t] : fast_tables[im.tab[2 + t]].e;
+    reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
+    __syncwarp();
+    const uint8_t* seg = blob + im.data_off;
+    BitReader br;
+    br.p = seg + (size_t(im.data_len) * size_t(chain)) / size_t(nchains);
+    br.end = seg + im.data_len;
+    if (chain > 0 && br.p[-1] == 0xFF && br.p[0] == 0x00) ++br.p;      // not on the stuffing byte of an FF 00 pair
+    br.acc = 0;
+    br.n = 0;
+    br.marker = 0;
+    br.fake = 0;
+    const HuffTable* dc_tab[2] = {tables + im.tab[0], tables + im.tab[1]};
+    const HuffTable* ac_tab[2] = {tables + im.tab[2], tables + im.tab[3]};
+    int pred[3] = {0, 0, 0};
+    int todo = im.restart_interval;
+    const int ncomp = im.ncomp, total = im.mcux * im.mcuy, bpm = im.bpm;
+    int16_t* region = reinterpret_cast<int16_t*>(scratch + im.coef_off + im.chain_stride * size_t(chain));
+    int spec = chain > 0 ? window : 0;             // MCUs still to decode before this chain's blocks count
+    int stored = 0, decoded = 0;
+    int cand = chain + 1;                          // the successor this chain expects to meet
+    const uint8_t* cand_start = seg + (size_t(im.data_len) * size_t(cand)) / size_t(nchains);
+    int matched = -1;
+#pragma unroll 1
+    for (;;) {
+      int stop = 0;
+      if (lane == 0) {
+        if (decoded >= total) stop = 1;
+        if (nchains > 1 && !stop) {
+          if (chain > 0 && spec == 0 && stored == 0) {                  // end of the window: first trusted boundary
+            if (br.marker) {
+              stop = 1;                                                  // ran into the end of the data inside the window
+            } else {
+              normalize(br, seg);
+              pred[0] = pred[1] = pred[2] = 0;
+              sh.pub[chain] = stream_pos(br, seg);
+              __threadfence_block();
+            }
+          }
+          if (!stop && *reinterpret_cast<volatile int*>(&sh.dead[chain])) stop = 1;
+          while (!stop && cand < nchains && br.p >= cand_start && !br.marker) {
+            normalize(br, seg);
+            const unsigned long long pos = stream_pos(br, seg);
+            unsigned long long pb;
+            while ((pb = *reinterpret_cast<volatile unsigned long long*>(&sh.pub[cand])) == ~0ull) __nanosleep(200);
+            if (spec == 0 && pos == pb) {
+              matched = cand;
+              stop = 1;
+            } else if (pos > pb) {                                       // behind its first boundary without meeting it
+              *reinterpret_cast<volatile int*>(&sh.dead[cand]) = 1;
+              ++cand;
+              cand_start = seg + (size_t(im.data_len) * size_t(cand)) / size_t(nchains);
+            } else {
+              break;                                                     // not there yet
+            }
+          }
+          if (!stop && chain > 0 && br.fake > 0 && br.n - br.fake < 8) stop = 1;   // all real bits consumed
         }
-        --todo;
+        if (!stop && im.restart_interval) {
+          if (todo == 0) {
+            restart(br);
+            pred[0] = pred[1] = pred[2] = 0;
+            todo = im.restart_interval;
+          }
+          --todo;
+        }
       }
+      stop = __shfl_sync(0xffffffffu, stop, 0);
+      if (stop) break;
+      const bool keep = __shfl_sync(0xffffffffu, spec, 0) == 0;
+      const int slot = __shfl_sync(0xffffffffu, stored, 0);
+      int bi = 0;
 #pragma unroll 1
       for (int ci = 0; ci < ncomp; ++ci) {
         const JpegComp& cp = im.comp[ci];
-        int16_t* coef = reinterpret_cast<int16_t*>(scratch + cp.coef_off);
-        for (int by = 0; by < cp.v; ++by) {
-          for (int bx = 0; bx < cp.h; ++bx) {
-            if (lane == 0) decode_block(br, dc_tab[cp.td], ac_tab[cp.ta], fast[cp.ta], pred[ci], blk);
-            __syncwarp();
-            const size_t b = size_t(my * cp.v + by) * cp.bw + size_t(mx * cp.h + bx);
-            reinterpret_cast<uint32_t*>(coef + b * 64)[lane] = reinterpret_cast<uint32_t*>(blk)[lane];
-            reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
-            __syncwarp();
-          }
+        const int nb = cp.h * cp.v;
+        for (int b = 0; b < nb; ++b, ++bi) {
+          if (lane == 0) decode_block(br, dc_tab[cp.td], ac_tab[cp.ta], fast[cp.ta], pred[ci], blk);
+          __syncwarp();
+          if (keep) reinterpret_cast<uint32_t*>(region + (size_t(slot) * bpm + bi) * 64)[lane] = reinterpret_cast<uint32_t*>(blk)[lane];
+          reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
+          __syncwarp();
         }
       }
+      if (lane == 0) {
+        ++decoded;
+        if (spec > 0) --spec; else ++stored;
+      }
+    }
+    if (lane == 0) {
+      if (chain > 0 && *reinterpret_cast<volatile unsigned long long*>(&sh.pub[chain]) == ~0ull) sh.pub[chain] = 0ull;   // never got there
+      sh.n_mcu[chain] = stored;
+      sh.matched[chain] = matched;
+      for (int c = 0; c < 3; ++c) sh.end_pred[chain][c] = pred[c];
+      __threadfence_block();
+    }
+  }
+  __syncthreads();
+  if (int(threadIdx.x) < ipc && first + int(threadIdx.x) < n_images) {   // who decoded which MCUs: follow the matches from chain 0
+    const JpegImage& im = imgs[order[first + threadIdx.x]];
+    const ChainShared& z = sh_all[threadIdx.x];
+    ChainInfo* info = reinterpret_cast<ChainInfo*>(scratch + im.info_off);
+    const int total = im.mcux * im.mcuy;
+    for (int c = 0; c < kMaxChains; ++c) {
+      info->start_mcu[c] = 0;
+      info->n_mcu[c] = 0;
+      info->dc_off[c][0] = info->dc_off[c][1] = info->dc_off[c][2] = 0;
+    }
+    int start = 0, dc[3] = {0, 0, 0};
+    for (int c = 0; c >= 0 && c < kMaxChains && start < total;) {
+      const int n = min(z.n_mcu[c], total - start);
+      info->start_mcu[c] = start;
+      info->n_mcu[c] = n;
+      for (int k = 0; k < 3; ++k) info->dc_off[c][k] = dc[k];
+      for (int k = 0; k < 3; ++k) dc[k] += z.end_pred[c][k];
+      start += n;
+      c = z.matched[c];
     }
   }
 }
@@ -356,14 +496,35 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restr
   if (threadIdx.x < 64) unzig[c_zigzag[threadIdx.x]] = uint8_t(threadIdx.x);
   const int u = find_unit(cta_start, n_units, int(blockIdx.x));
   const int2 un = units[u];
-  const JpegComp& cp = imgs[un.x].comp[un.y];
+  const JpegImage& im = imgs[un.x];
+  const JpegComp& cp = im.comp[un.y];
   const int lb = threadIdx.x >> 3, r = threadIdx.x & 7;
   const long long nblocks = (long long)cp.bw * cp.bh;
   const long long b = (long long)(int(blockIdx.x) - __ldg(&cta_start[u])) * 32 + lb;
   const bool valid = b < nblocks;
   {
     int4 in = make_int4(0, 0, 0, 0);
-    if (valid) in = *reinterpret_cast<const int4*>(scratch + cp.coef_off + size_t(b) * 128 + r * 16);
+    int dc_off = 0;
+    if (valid) {
+      // the block's place in decoding order: MCU m, block `bi` of the MCU; then the chain that decoded MCU m
+      const int gy = int(b / cp.bw), gx = int(b - (long long)gy * cp.bw);
+      const int m = (gy / cp.v) * im.mcux + gx / cp.h;
+      const int bi = cp.blk0 + (gy % cp.v) * cp.h + gx % cp.h;
+      const ChainInfo* info = reinterpret_cast<const ChainInfo*>(scratch + im.info_off);
+      for (int c = 0; c < kMaxChains; ++c) {
+        const int s0 = info->start_mcu[c], n = info->n_mcu[c];
+        if (m >= s0 && m < s0 + n) {
+          in = *reinterpret_cast<const int4*>(scratch + im.coef_off + im.chain_stride * size_t(c) +
+                                              (size_t(m - s0) * im.bpm + bi) * 128 + r * 16);
+          dc_off = info->dc_off[c][un.y];
+          break;
+        }
+      }
+    }
+    if (r == 0) {                                         // DC: stored relative to the chain's first MCU
+      int16_t* h16 = reinterpret_cast<int16_t*>(&in);
+      h16[0] = int16_t(int(h16[0]) + dc_off);
+    }
     *reinterpret_cast<int4*>(&raw[lb][r * 8]) = in;
     __syncthreads();
     const uint4 q = *reinterpret_cast<const uint4*>(cp.qt + r * 8);
@@ -666,6 +827,8 @@ struct iic_jpeg_plan {
   std::vector<iic::HuffTable> tables;  // the distinct Huffman tables of the batch, built once
   std::vector<iic::FastAc> fast;       // one-look-up companion of every table (only those of AC tables are read)
   size_t off_fast = 0;
+  int chains = 1;                      // decoding chains per image (jpeg_huffman_kernel): 1 = one warp per image
+  int window = iic::kChainWindow;      // MCUs a speculative chain discards before it publishes (IIC_JPEG_CHAIN_WINDOW: tests)
   std::vector<int> ok;                 // indices of the files inside the envelope, longest entropy segment first
   size_t desc_bytes = 0;               // descriptor region = staging size: images, tables, unit tables
   size_t off_tables = 0, off_order = 0, off_units = 0, off_idct_start = 0, off_color_img = 0, off_color_start = 0;
@@ -694,6 +857,26 @@ int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic
     }
   }
 
+  // Small batches cannot fill the GPU with one serial chain per image (a chain is latency-bound: ~0.15 instructions per clock
+  // on a scheduler that could issue 1): split every image into 8 / 4 / 2 chains until the batch alone provides a few thousand of them.
+  {
+    const char* e = getenv("IIC_JPEG_CHAINS");
+    const int want = e ? atoi(e) : 0;
+    // ... as long as the per-chain coefficient regions stay within a budget (12 GB unless IIC_JPEG_SCRATCH_GB says otherwise)
+    const size_t nimg = pl->ok.size();
+    double coef_bytes = 0.0;
+    for (size_t j = 0; j < nimg; ++j) {
+      const JpegImage& im = pl->files[size_t(pl->ok[j])].img;
+      for (int c = 0; c < im.ncomp; ++c) coef_bytes += 128.0 * double(im.comp[c].bw) * double(im.comp[c].bh);
+    }
+    const char* g = getenv("IIC_JPEG_SCRATCH_GB");
+    const double budget = (g && atof(g) > 0.0 ? atof(g) : 12.0) * 1e9;
+    int k = 8;
+    while (k > 1 && (double(k) * coef_bytes > budget || nimg * size_t(k) > 8192)) k /= 2;
+    pl->chains = (want == 1 || want == 2 || want == 4 || want == 8) ? want : k;
+    const char* w = getenv("IIC_JPEG_CHAIN_WINDOW");
+    if (w && atoi(w) >= 0 && atoi(w) <= 4096) pl->window = atoi(w);
+  }
   // the distinct Huffman tables of the batch (most encoders emit the Annex K tables: a handful per batch, L1-resident on the device)
   const size_t m = pl->ok.size();
   {
@@ -757,16 +940,31 @@ int iic_jpeg_plan_create(const uint8_t* blob, const int64_t* offsets, int n, iic
   int units = 0;
   for (size_t j = 0; j < m; ++j) {
     Parsed& p = pl->files[size_t(pl->ok[j])];
+    size_t all_blocks = 0;
+    int bpm = 0;
     for (int c = 0; c < p.img.ncomp; ++c) {
       JpegComp& cp = p.img.comp[c];
       const size_t blocks = size_t(cp.bw) * size_t(cp.bh);
-      cp.coef_off = off;
-      off += align_up(blocks * 128, 256);
+      cp.blk0 = bpm;
+      bpm += cp.h * cp.v;
+      all_blocks += blocks;
       cp.plane_off = off;
       off += align_up(blocks * 64, 256);
       idct_ctas += (long long)((blocks + 31) / 32);
       ++units;
     }
+    const int mcus = p.img.mcux * p.img.mcuy;
+    p.img.bpm = bpm;
+    // chains inside the image only where each gets a segment several windows long, and never across restart markers
+    p.img.nchains = 1;
+    if (p.img.restart_interval == 0)
+      for (int k = pl->chains; k > 1; k /= 2)
+        if (mcus >= k * 4 * kChainWindow) { p.img.nchains = k; break; }
+    p.img.info_off = off;
+    off += align_up(sizeof(ChainInfo), 256);
+    p.img.chain_stride = align_up(all_blocks * 128, 256);
+    p.img.coef_off = off;
+    off += p.img.chain_stride * size_t(p.img.nchains);
     color_ctas += ((long long)((p.img.width + 3) / 4) * p.img.height + 255) / 256;
   }
   if (idct_ctas > 0x7fffffffLL || color_ctas > 0x7fffffffLL) {
@@ -854,10 +1052,12 @@ int iic_jpeg_decode(const iic_jpeg_plan* plan, const uint8_t* dev_blob, uint8_t*
   uint8_t* sc = static_cast<uint8_t*>(scratch);
   if (cudaMemcpyAsync(sc, st, plan->desc_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return IIC_ERR_CUDA;
   const JpegImage* d_imgs = reinterpret_cast<const JpegImage*>(sc);
-  jpeg_huffman_kernel<<<(m_out + kHuffWarps - 1) / kHuffWarps, 32 * kHuffWarps, 0, s>>>(
-                                           d_imgs, reinterpret_cast<const int*>(sc + plan->off_order), m_out,
-                                           reinterpret_cast<const HuffTable*>(sc + plan->off_tables),
-                                           reinterpret_cast<const FastAc*>(sc + plan->off_fast), dev_blob, sc);
+  {
+    const int ipc = kHuffWarps / plan->chains;
+    jpeg_huffman_kernel<<<(m_out + ipc - 1) / ipc, 32 * kHuffWarps, 0, s>>>(
+        d_imgs, reinterpret_cast<const int*>(sc + plan->off_order), m_out, reinterpret_cast<const HuffTable*>(sc + plan->off_tables),
+        reinterpret_cast<const FastAc*>(sc + plan->off_fast), dev_blob, sc, plan->chains, plan->window);
+  }
   jpeg_idct_kernel<<<ic, 256, 0, s>>>(d_imgs, reinterpret_cast<const int2*>(sc + plan->off_units),
                                       reinterpret_cast<const int*>(sc + plan->off_idct_start), u, sc);
   jpeg_color_kernel<<<cc, 256, 0, s>>>(d_imgs, reinterpret_cast<const int*>(sc + plan->off_color_img),

@@ -28,7 +28,8 @@ def _pil(data):
 
 
 def _encode(arr, **kw):
-    from PIL import Image
+    from PIL import Image, ImageFile
+    ImageFile.MAXBLOCK = max(ImageFile.MAXBLOCK, 4 * arr.size)     # optimize=True writes the whole scan in one piece
     buf = io.BytesIO()
     Image.fromarray(arr).save(buf, "JPEG", **kw)
     return buf.getvalue()
@@ -143,3 +144,45 @@ def test_load_images_gpu_decode_feeds_the_analyzer_path(jp, tmp_path, monkeypatc
         assert np.array_equal(out[i].tensor.cpu().numpy(), np.asarray(Image.open(paths[i]).convert("RGB")))
     for i in (1, 3):
         assert np.array_equal(np.asarray(out[i]), np.asarray(Image.open(paths[i]).convert("RGB")))
+
+
+@pytest.mark.parametrize("chains,window", [("1", "32"), ("2", "32"), ("4", "32"), ("8", "32"), ("4", "0"), ("8", "1"), ("4", "300"), ("8", "100")])
+def test_chains_inside_an_image(jp, monkeypatch, chains, window):
+    """Small batches split every image into several decoding chains that start in the middle of the entropy-coded segment in a
+    guessed state and hand over where their stream positions meet (jpeg_huffman_kernel<true>).  Whatever the chain count, and
+    whether the speculative chains synchronise in their window (32 MCUs), cannot (window 0 / 1: they publish an untrusted
+    boundary, are told to stop and the predecessor decodes on) or never get to publish (window longer than their segment):
+    Pillow's pixels, bit for bit."""
+    monkeypatch.setenv("IIC_JPEG_CHAINS", chains)
+    monkeypatch.setenv("IIC_JPEG_CHAIN_WINDOW", window)
+    rng = np.random.default_rng(21)
+    files = []
+    for (h, w, sub, q) in ((768, 1024, 2, 85), (600, 800, 0, 92), (1500, 2000, 2, 75), (479, 640, 1, 60), (1024, 768, 2, 97),
+                           (512, 512, 2, 30), (333, 517, 2, 88), (64, 64, 2, 85)):
+        files.append(_encode(_photo(rng, h, w), quality=q, subsampling=sub, optimize=(q % 2 == 0)))
+    files.append(_encode(_photo(rng, 700, 900), quality=85, subsampling=2, restart_marker_blocks=7))     # restart markers: one chain
+    from PIL import Image
+    gray = io.BytesIO()
+    Image.fromarray(_photo(rng, 640, 960)).convert("L").save(gray, "JPEG", quality=80)
+    files.append(gray.getvalue())
+    imgs, reasons = jp.decode_jpeg_bytes(files, "cuda:0")
+    torch.cuda.synchronize()
+    for i, (data, im) in enumerate(zip(files, imgs)):
+        ref = _pil(data)
+        assert im is not None, (i, reasons[i])
+        got = im.cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), (i, ref.shape, int((got != ref).sum()))
+
+
+def test_chains_on_truncated_streams_do_not_hang(jp, monkeypatch):
+    monkeypatch.setenv("IIC_JPEG_CHAINS", "8")
+    rng = np.random.default_rng(23)
+    good = _encode(_photo(rng, 768, 1024), quality=85, subsampling=2)
+    bad = bytearray(good)
+    for k in range(len(bad) // 3, len(bad) - 2, 997):
+        bad[k] = (bad[k] * 31 + 7) & 0xFF if bad[k] != 0xFF else 0xFE
+    files = [good[: len(good) // 2], bytes(bad), good[: len(good) * 7 // 8], good]
+    imgs, _ = jp.decode_jpeg_bytes(files, "cuda:0")
+    torch.cuda.synchronize()
+    assert all(im is not None and tuple(im.shape) == (768, 1024, 3) for im in imgs)
+    assert np.array_equal(imgs[3].cpu().numpy(), _pil(good))
