@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restr
       const int m = (gy / cp.v) * im.mcux + gx / cp.h;
       const int bi = cp.blk0 + (gy % cp.v) * cp.h + gx % cp.h;
       const ChainInfo* info = reinterpret_cast<const ChainInfo*>(scratch + im.info_off);
-      for (int c = 0; c < kMaxChains; ++c) {
-        const int s0 = info->start_mcu[c], n = info->n_mcu[c];
+      for (int c = 0; c < im.nchains; ++c) {
+        const int s0 = __ldg(&info->start_mcu[c]), n = __ldg(&info->n_mcu[c]);
         if (m >= s0 && m < s0 + n) {
           in = *reinterpret_cast<const int4*>(scratch + im.coef_off + im.chain_stride * size_t(c) +
                                               (size_t(m - s0) * im.bpm + bi) * 128 + r * 16);
@@ -579,6 +579,41 @@ __device__ __forceinline__ int upsample(const uint8_t* __restrict__ plane, const
 
 __device__ __forceinline__ uint8_t clamp255(int v) { return uint8_t(min(max(v, 0), 255)); }
 
+// the same for 4 horizontally adjacent pixels x0 .. x0 + 3 (x0 % 4 == 0): the two chroma samples they share and their two
+// neighbours are read once.  Pixels beyond the image width come out as garbage and are not stored by the caller.
+__device__ __forceinline__ void upsample4(const uint8_t* __restrict__ plane, const JpegComp& cp, int hmax, int vmax, int x0, int y, int w,
+                                          int (&out)[4]) {
+  if (cp.h == hmax && cp.v == vmax) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(plane + size_t(y) * cp.pitch + x0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = int((v >> (8 * i)) & 255u);
+    return;
+  }
+  if (cp.dw <= 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = upsample(plane, cp, hmax, vmax, min(x0 + i, w - 1), y);
+    return;
+  }
+  const int c0 = x0 >> 1, cm = max(c0 - 1, 0), c1 = min(c0 + 1, cp.dw - 1), c2 = min(c0 + 2, cp.dw - 1);
+  if (cp.v == vmax) {                                   // h2v1
+    const uint8_t* row = plane + size_t(y) * cp.pitch;
+    const int pm = row[cm], p0 = row[c0], p1 = row[c1], p2 = row[c2];
+    out[0] = (3 * p0 + pm + 1) >> 2;
+    out[1] = (3 * p0 + p1 + 2) >> 2;
+    out[2] = (3 * p1 + p0 + 1) >> 2;
+    out[3] = (3 * p1 + p2 + 2) >> 2;
+    return;
+  }
+  const int cy = y >> 1, oy = (y & 1) ? min(cy + 1, cp.dh - 1) : max(cy - 1, 0);
+  const uint8_t* r0 = plane + size_t(cy) * cp.pitch;
+  const uint8_t* r1 = plane + size_t(oy) * cp.pitch;
+  const int sm = 3 * r0[cm] + r1[cm], s0 = 3 * r0[c0] + r1[c0], s1 = 3 * r0[c1] + r1[c1], s2 = 3 * r0[c2] + r1[c2];
+  out[0] = (3 * s0 + sm + 8) >> 4;
+  out[1] = (3 * s0 + s1 + 7) >> 4;
+  out[2] = (3 * s1 + s0 + 8) >> 4;
+  out[3] = (3 * s1 + s2 + 7) >> 4;
+}
+
 // cta_start[i] = first CTA of image i; a thread converts 4 horizontally adjacent pixels (a CTA: 1024 pixel slots, rows padded to 4)
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImage* __restrict__ imgs, const int* __restrict__ image_of,
                                                          const int* __restrict__ cta_start, int n,
@@ -597,14 +632,13 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImage* __rest
 #pragma unroll
     for (int i = 0; i < 4; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = uint8_t(y4 >> (8 * i));
   } else {
-    const uint8_t* pcb = scratch + im.comp[1].plane_off;
-    const uint8_t* pcr = scratch + im.comp[2].plane_off;
+    int cb4[4], cr4[4];
+    upsample4(scratch + im.comp[1].plane_off, im.comp[1], im.hmax, im.vmax, x0, y, im.width, cb4);
+    upsample4(scratch + im.comp[2].plane_off, im.comp[2], im.hmax, im.vmax, x0, y, im.width, cr4);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int x = min(x0 + i, im.width - 1);
       const int Y = int((y4 >> (8 * i)) & 255u);
-      const int cb = upsample(pcb, im.comp[1], im.hmax, im.vmax, x, y) - 128;
-      const int cr = upsample(pcr, im.comp[2], im.hmax, im.vmax, x, y) - 128;
+      const int cb = cb4[i] - 128, cr = cr4[i] - 128;
       // jdcolor.c build_ycc_rgb_table: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554
       rgb[3 * i] = clamp255(Y + ((91881 * cr + 32768) >> 16));
       rgb[3 * i + 1] = clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
