@@ -113,6 +113,46 @@ def load_images(paths: Sequence[str], device=None, gpu_decode: bool = False, tim
     return out
 
 
+INGEST_CHUNK = int(os.environ.get("IIC_INGEST_CHUNK", "1024"))
+
+
+def iter_loaded(paths: Sequence[str], device=None, gpu_decode: bool = False, chunk: int = 0):
+    """`load_images` over a long list, `chunk` paths at a time: yields (chunk_paths, images).  While the caller works on chunk i
+    (preprocess + encoder + head on the current stream), a worker thread reads, parses and decodes chunk i + 1 on a side stream
+    (file reads, header parsing and the ctypes calls all release the GIL), so ingest and encoder overlap instead of alternating.
+    Results do not depend on the chunking: every image is decoded and scored on its own."""
+    chunk = chunk or INGEST_CHUNK
+    paths = list(paths)
+    on_gpu = gpu_decode and device is not None and torch.device(device).type == "cuda"
+    if len(paths) <= chunk or not on_gpu:
+        if paths:
+            yield paths, load_images(paths, device, gpu_decode)
+        return
+    dev = torch.device(device)
+    side = torch.cuda.Stream(device=dev)
+
+    def work(lo: int):
+        part = paths[lo:lo + chunk]
+        with torch.cuda.device(dev), torch.cuda.stream(side):
+            imgs = load_images(part, dev, True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return part, imgs, ev
+
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(work, 0)
+        for lo in range(0, len(paths), chunk):
+            part, imgs, ev = fut.result()
+            if lo + chunk < len(paths):
+                fut = ex.submit(work, lo + chunk)
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(ev)
+            for im in imgs:                      # decoded on the side stream, consumed on this one
+                if isinstance(im, DeviceImage):
+                    im.tensor.record_stream(main)
+            yield part, imgs
+
+
 def _encode_labels(model, texts: Sequence[str], device) -> torch.Tensor:
     with torch.no_grad():
         tok = clip.tokenize(list(texts)).to(device)
@@ -313,8 +353,12 @@ class CachedInteriorAnalyzer:
 
     def _analyze_shared(self, image_paths, batch_size: int, confidence_threshold: float):
         """filter + analyse in ONE encode per image (valid while the vision LoRA delta is zero)."""
-        imgs = load_images(image_paths, self.device, self.gpu_decode)
         results = {}
+        for part, imgs in iter_loaded(image_paths, self.device, self.gpu_decode):
+            self._analyze_shared_chunk(part, imgs, results, batch_size, confidence_threshold)
+        return {p: results[p] for p in image_paths if p in results}      # the reference's order: that of image_paths
+
+    def _analyze_shared_chunk(self, image_paths, imgs, results, batch_size: int, confidence_threshold: float):
         ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
         for p, im in zip(image_paths, imgs):
             if im is None:
@@ -322,7 +366,9 @@ class CachedInteriorAnalyzer:
                               "analysis": {}, "reason": "Nie wnętrze: load error (confidence: 0.000)"}
         if not ok:
             return results
-        tv, ti, ss, non, names = self._classify_pil([im for _, im in ok], True, max(batch_size, 64))
+        # GPU batch: results do not depend on it; long lists of device-decoded images run at the encoder's efficient batch sizes
+        gpu_batch = max(batch_size, 256 if len(ok) >= 256 else 64)
+        tv, ti, ss, non, names = self._classify_pil([im for _, im in ok], True, gpu_batch)
         for r, (p, _) in enumerate(ok):
             interior, top_conf = float(ss[r, 0]), float(tv[r, 0, 0])
             category = self.detector.categories[int(ti[r, 0, 0])]
@@ -415,6 +461,10 @@ class CachedInteriorAnalyzer:
                 image_metadata.append({"path": path, "interior_confidence": confidence, "is_interior": True})
         else:
             print("  Pomijam filtrowanie wnętrz - przetwarzam wszystkie obrazy")
+            if len(image_paths) > INGEST_CHUNK and self.gpu_decode:      # long list: ingest of chunk i + 1 under the encode of chunk i
+                for part, imgs in iter_loaded(image_paths, self.device, self.gpu_decode):
+                    results.update(self._analyze_no_filter_chunk(part, imgs, batch_size))
+                return {p: results[p] for p in image_paths if p in results}
             for path, img in zip(image_paths, load_images(image_paths, self.device, self.gpu_decode)):
                 if img is not None:
                     valid_images.append(img)
@@ -433,6 +483,21 @@ class CachedInteriorAnalyzer:
                                      "analysis": self._analysis_from_head(tv, ti, idx, names, 0),
                                      "reason": "Success - interior image analyzed"}
         return results
+
+    def _analyze_no_filter_chunk(self, image_paths, imgs, batch_size: int):
+        """the filter_interiors=False body of analyze_images_batch (main.py:404-467) for one chunk of a long list"""
+        out = {}
+        ok = [(p, im) for p, im in zip(image_paths, imgs) if im is not None]
+        for p, im in zip(image_paths, imgs):
+            if im is None:
+                out[p] = {"is_interior": False, "interior_confidence": 0.0, "detected_category": "load error",
+                          "analysis": {}, "reason": "Błąd ładowania"}
+        if ok:
+            tv, ti, _, _, names = self._classify_pil([im for _, im in ok], False, max(batch_size, 256 if len(ok) >= 256 else 1))
+            for idx, (p, _) in enumerate(ok):
+                out[p] = {"is_interior": True, "interior_confidence": 1.0, "detected_category": "interior",
+                          "analysis": self._analysis_from_head(tv, ti, idx, names, 0), "reason": "Success - interior image analyzed"}
+        return out
 
     def analyze_image_from_url(self, url, filter_interiors: bool = True):
         img = load_image(url)

@@ -243,6 +243,24 @@ def test_gpu_jpeg_ingest(analyzer, tmp_path):
     assert r_dev[paths[-1]]["is_interior"] is False
     for p in paths:
         assert r_host[p] == r_dev[p], p
+    # long lists are ingested chunk by chunk, chunk i + 1 decoded on a side stream under the encode of chunk i: same dicts
+    try:
+        analyzer.gpu_decode = True
+        old_chunk, old_min = an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES
+        an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES = 9, 1
+        for flt in (False, True):
+            whole = r_dev if not flt else None
+            chunked = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=flt)
+            an.INGEST_CHUNK = 10 ** 6
+            if whole is None:
+                whole = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=flt)
+            an.INGEST_CHUNK = 9
+            assert list(chunked) == [p for p in paths if p in chunked] and set(chunked) == set(paths)
+            for p in paths:
+                assert chunked[p] == whole[p], (flt, p)
+    finally:
+        analyzer.gpu_decode = saved
+        an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES = old_chunk, old_min
 
 
 def test_analyze_images_batch_data_parallel(analyzer):
