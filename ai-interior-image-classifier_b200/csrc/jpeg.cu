@@ -763,6 +763,8 @@ void parse_one(const uint8_t* d, size_t n, Parsed& p) {
       p.img.width = (seg[3] << 8) | seg[4];
       p.img.ncomp = seg[5];
       if (p.img.width <= 0 || p.img.height <= 0) return unsupported("zero image dimension (DNL)");
+      // Pillow refuses files beyond 2 x MAX_IMAGE_PIXELS (179 MP) as decompression bombs; the host path keeps that decision
+      if ((long long)p.img.width * p.img.height > 178956970LL) return unsupported("image larger than 178 MP");
       if (p.img.ncomp != 1 && p.img.ncomp != 3) return unsupported("component count other than 1 or 3 (CMYK / YCCK)");
       if (sl < size_t(6 + 3 * p.img.ncomp)) return corrupt("bad SOF");
       for (int c = 0; c < p.img.ncomp; ++c) {

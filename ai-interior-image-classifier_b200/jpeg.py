@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -39,6 +40,7 @@ class _Slot:
         self.dev_blob = torch.empty(0, dtype=torch.uint8, device=device)
         self.scratch = torch.empty(0, dtype=torch.uint8, device=device)
         self.event: Optional[torch.cuda.Event] = None
+        self.lock = threading.Lock()     # held from _next_slot() until the decode has been enqueued (several feeder threads)
 
     def wait(self) -> None:
         if self.event is not None:
@@ -63,25 +65,29 @@ class _Slot:
 
 _slots: dict = {}
 _turn: dict = {}
+_slots_lock = threading.Lock()      # feeder threads of several devices (analyze_images_batch(devices=...)) share this module
 
 
 def _next_slot(device: torch.device) -> _Slot:
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    ring = _slots.setdefault(key, [_Slot(device), _Slot(device)])
-    k = _turn.get(key, 0)
-    _turn[key] = (k + 1) % len(ring)
-    slot = ring[k]
+    with _slots_lock:
+        ring = _slots.setdefault(key, [_Slot(device), _Slot(device)])
+        k = _turn.get(key, 0)
+        _turn[key] = (k + 1) % len(ring)
+        slot = ring[k]
+    slot.lock.acquire()
     slot.wait()
     return slot
 
 
 def release_buffers() -> None:
     """drops the cached pinned / device buffers (they are grow-only otherwise)"""
-    for ring in _slots.values():
-        for s in ring:
-            s.wait()
-    _slots.clear()
-    _turn.clear()
+    with _slots_lock:
+        for ring in _slots.values():
+            for s in ring:
+                s.wait()
+        _slots.clear()
+        _turn.clear()
 
 
 class JpegPlan:
@@ -160,20 +166,30 @@ def _device(device) -> torch.device:
 
 def decode_jpeg_bytes(files: Sequence[bytes], device) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
     slot = _next_slot(_device(device))
-    offsets = np.zeros(len(files) + 1, dtype=np.int64)
-    np.cumsum([len(b) for b in files], out=offsets[1:])
-    nbytes = int(offsets[-1])
-    view = slot.host_blob(nbytes).numpy()
-    for b, lo, hi in zip(files, offsets[:-1], offsets[1:]):
-        view[lo:hi] = np.frombuffer(b, dtype=np.uint8)
-    view[nbytes:nbytes + _PAD] = 0
-    return _decode(slot, nbytes, offsets)
+    try:
+        offsets = np.zeros(len(files) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in files], out=offsets[1:])
+        nbytes = int(offsets[-1])
+        view = slot.host_blob(nbytes).numpy()
+        for b, lo, hi in zip(files, offsets[:-1], offsets[1:]):
+            view[lo:hi] = np.frombuffer(b, dtype=np.uint8)
+        view[nbytes:nbytes + _PAD] = 0
+        return _decode(slot, nbytes, offsets)
+    finally:
+        slot.lock.release()
 
 
 def decode_jpeg_files(paths: Sequence[str], device) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
     """Reads the files straight into ONE pinned buffer (a few reader threads, no per-file bytes objects) and decodes them on
     `device`.  An unreadable file gets (None, "<error>") like a file outside the envelope."""
     slot = _next_slot(_device(device))
+    try:
+        return _decode_files(slot, paths)
+    finally:
+        slot.lock.release()
+
+
+def _decode_files(slot: _Slot, paths: Sequence[str]) -> Tuple[List[Optional[torch.Tensor]], List[str]]:
     sizes, errs = [], [""] * len(paths)
     for i, p in enumerate(paths):
         try:

@@ -258,6 +258,12 @@ def test_gpu_jpeg_ingest(analyzer, tmp_path):
             assert list(chunked) == [p for p in paths if p in chunked] and set(chunked) == set(paths)
             for p in paths:
                 assert chunked[p] == whole[p], (flt, p)
+        # data parallel over three replicas (two of them on one device: their feeder threads share that device's decoder slots)
+        an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES = 10 ** 6, 1
+        ndev = torch.cuda.device_count()
+        dp = analyzer.analyze_images_batch(paths, batch_size=16, filter_interiors=False, devices=[0, 1 % ndev, 0])
+        for p in paths:
+            assert dp[p] == r_dev[p], p
     finally:
         analyzer.gpu_decode = saved
         an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES = old_chunk, old_min
