@@ -186,3 +186,27 @@ def test_chains_on_truncated_streams_do_not_hang(jp, monkeypatch):
     torch.cuda.synchronize()
     assert all(im is not None and tuple(im.shape) == (768, 1024, 3) for im in imgs)
     assert np.array_equal(imgs[3].cpu().numpy(), _pil(good))
+
+
+@pytest.mark.parametrize("chains", ["1", "8"])
+def test_crafted_streams_bit_exact(jp, monkeypatch, chains):
+    """tests/jpeg_craft.py: valid files with what third-party encoders emit and Pillow's encoder does not - Huffman codes up to 16
+    bits (the canonical-code walk behind the look-up tables), restart intervals of 1 / 3 / 7 MCUs with fill bytes before RSTn, 16-bit
+    quantisation tables, tables redefined before the scan, luma on table id 1, component ids 0-2 / 'RGB' under JFIF, Adobe markers,
+    ZRL runs, blocks filled to coefficient 63, large magnitudes; also big enough to be cut into 8 chains"""
+    import jpeg_craft as C
+    from test_oracle import CRAFTED
+    monkeypatch.setenv("IIC_JPEG_CHAINS", chains)
+    rng = np.random.default_rng(3)
+    files = [C.random_case(rng, **kw) for kw in CRAFTED]
+    files += [C.random_case(rng, width=512, height=512), C.random_case(rng, width=640, height=400, sampling=(1, 1)),
+              C.random_case(rng, width=700, height=520, sampling=(2, 1), deep=False), C.random_case(rng, width=512, height=384, restart=5)]
+    rgb = [C.random_case(rng, width=32, height=32, jfif=False, adobe=0), C.random_case(rng, width=32, height=32, jfif=False, comp_ids=(82, 71, 66))]
+    imgs, reasons = jp.decode_jpeg_bytes(files + rgb, "cuda:0")
+    torch.cuda.synchronize()
+    for i, data in enumerate(files):
+        assert imgs[i] is not None, (i, reasons[i])
+        ref = _pil(data)
+        got = imgs[i].cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), (i, ref.shape, int((got != ref).sum()))
+    assert imgs[-1] is None and imgs[-2] is None and "RGB" in reasons[-1] and "RGB" in reasons[-2]

@@ -238,3 +238,29 @@ def test_jpeg_plan_parses_headers_without_a_gpu():
     assert plan.status[-3:] == [jp.JPEG_CORRUPT] * 3
     assert plan.scratch_bytes > plan.staging_bytes > 8 * 640 + 2448     # 8 image descriptors + at least one Huffman table
     plan.close()
+
+
+CRAFTED = [dict(width=64, height=48), dict(width=97, height=61, sampling=(2, 1)), dict(width=40, height=40, sampling=(1, 1)),
+           dict(width=80, height=72, restart=3, fill_before_rst=2), dict(width=80, height=72, restart=1), dict(width=50, height=30, dqt16=True),
+           dict(width=33, height=17, comp_ids=(0, 1, 2)), dict(width=48, height=48, comp_ids=(82, 71, 66)), dict(width=48, height=48, adobe=1),
+           dict(width=48, height=48, jfif=False, adobe=1), dict(width=64, height=64, table_ids=((1, 1), (0, 0), (0, 0))),
+           dict(width=64, height=64, redefine=True), dict(width=72, height=40, gray=True), dict(width=64, height=48, deep=False)]
+
+
+def test_jpeg_oracle_matches_pillow_on_crafted_streams():
+    """files written by tests/jpeg_craft.py with the features third-party encoders use and Pillow's encoder does not (16-bit Huffman
+    codes, restart intervals + fill bytes, 16-bit DQT, redefined tables, unusual ids, Adobe / JFIF combinations, ZRL, blocks filled
+    to coefficient 63): Pillow decodes them, the oracle agrees bit for bit; RGB-coded files are outside the envelope"""
+    import io
+    import numpy as np
+    from PIL import Image
+    import jpeg_craft as C
+    from oracle import jpeg_ref as J
+    rng = np.random.default_rng(0)
+    for kw in CRAFTED:
+        data = C.random_case(rng, **kw)
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        assert np.array_equal(J.decode_rgb(data), ref), kw
+    for kw in (dict(jfif=False, adobe=0), dict(jfif=False, comp_ids=(82, 71, 66))):
+        with pytest.raises(J.Unsupported):
+            J.decode_rgb(C.random_case(rng, width=32, height=32, **kw))
