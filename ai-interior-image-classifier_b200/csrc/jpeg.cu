@@ -278,6 +278,13 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
   __shared__ __align__(16) int16_t blk_s[kHuffWarps][64];
   __shared__ __align__(16) int32_t fast_s[2][kFastSize];
   __shared__ ChainShared sh_all[kHuffWarps];               // one per image of the CTA
+  struct BlockDesc {                                       // what block `bi` of an MCU decodes with (per warp: images differ)
+    const HuffTable* dc;
+    const HuffTable* ac;
+    const int32_t* fast;
+    int comp, pad_;
+  };
+  __shared__ BlockDesc bd_s[kHuffWarps][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ipc = kHuffWarps / chains;                     // images per CTA
   const int first = int(blockIdx.x) * ipc;
@@ -318,14 +325,25 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
     br.n = 0;
     br.marker = 0;
     br.fake = 0;
-    const HuffTable* dc_tab[2] = {tables + im.tab[0], tables + im.tab[1]};
-    const HuffTable* ac_tab[2] = {tables + im.tab[2], tables + im.tab[3]};
-    int pred[3] = {0, 0, 0};
+    BlockDesc* bd = bd_s[warp];
+    if (lane == 0) {
+      int bi = 0;
+      for (int ci = 0; ci < im.ncomp; ++ci)
+        for (int b = 0; b < im.comp[ci].h * im.comp[ci].v && bi < 12; ++b, ++bi) {
+          bd[bi].dc = tables + im.tab[im.comp[ci].td];
+          bd[bi].ac = tables + im.tab[2 + im.comp[ci].ta];
+          bd[bi].fast = fast[im.comp[ci].ta];
+          bd[bi].comp = ci;
+        }
+    }
+    __syncwarp();
+    int pred0 = 0, pred1 = 0, pred2 = 0;
     int todo = im.restart_interval;
     const int ncomp = im.ncomp, total = im.mcux * im.mcuy, bpm = im.bpm;
     int16_t* region = reinterpret_cast<int16_t*>(scratch + im.coef_off + im.chain_stride * size_t(chain));
-    int spec = chain > 0 ? window : 0;             // MCUs still to decode before this chain's blocks count
+    int spec = chain > 0 ? window : 0;             // MCUs still to decode before this chain's blocks count (every lane counts)
     int stored = 0, decoded = 0;
+    uint32_t* out_blk = reinterpret_cast<uint32_t*>(region) + lane;      // this lane's word of the next stored block
     int cand = chain + 1;                          // the successor this chain expects to meet
     const uint8_t* cand_start = seg + (size_t(im.data_len) * size_t(cand)) / size_t(nchains);
     int matched = -1;
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
               stop = 1;                                                  // ran into the end of the data inside the window
             } else {
               normalize(br, seg);
-              pred[0] = pred[1] = pred[2] = 0;
+              pred0 = pred1 = pred2 = 0;
               sh.pub[chain] = stream_pos(br, seg);
               __threadfence_block();
             }
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
         if (!stop && im.restart_interval) {
           if (todo == 0) {
             restart(br);
-            pred[0] = pred[1] = pred[2] = 0;
+            pred0 = pred1 = pred2 = 0;
             todo = im.restart_interval;
           }
           --todo;
@@ -375,31 +393,33 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
       }
       stop = __shfl_sync(0xffffffffu, stop, 0);
       if (stop) break;
-      const bool keep = __shfl_sync(0xffffffffu, spec, 0) == 0;
-      const int slot = __shfl_sync(0xffffffffu, stored, 0);
-      int bi = 0;
+      const bool keep = spec == 0;
 #pragma unroll 1
-      for (int ci = 0; ci < ncomp; ++ci) {
-        const JpegComp& cp = im.comp[ci];
-        const int nb = cp.h * cp.v;
-        for (int b = 0; b < nb; ++b, ++bi) {
-          if (lane == 0) decode_block(br, dc_tab[cp.td], ac_tab[cp.ta], fast[cp.ta], pred[ci], blk);
-          __syncwarp();
-          if (keep) reinterpret_cast<uint32_t*>(region + (size_t(slot) * bpm + bi) * 64)[lane] = reinterpret_cast<uint32_t*>(blk)[lane];
-          reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
-          __syncwarp();
+      for (int bi = 0; bi < bpm; ++bi) {
+        if (lane == 0) {
+          const BlockDesc d = bd[bi];
+          int pr = d.comp == 0 ? pred0 : (d.comp == 1 ? pred1 : pred2);
+          decode_block(br, d.dc, d.ac, d.fast, pr, blk);
+          if (d.comp == 0) pred0 = pr; else if (d.comp == 1) pred1 = pr; else pred2 = pr;
         }
+        __syncwarp();
+        if (keep) {
+          *out_blk = reinterpret_cast<uint32_t*>(blk)[lane];
+          out_blk += 32;
+        }
+        reinterpret_cast<uint32_t*>(blk)[lane] = 0u;
+        __syncwarp();
       }
-      if (lane == 0) {
-        ++decoded;
-        if (spec > 0) --spec; else ++stored;
-      }
+      ++decoded;
+      if (spec > 0) --spec; else ++stored;
     }
     if (lane == 0) {
       if (chain > 0 && *reinterpret_cast<volatile unsigned long long*>(&sh.pub[chain]) == ~0ull) sh.pub[chain] = 0ull;   // never got there
       sh.n_mcu[chain] = stored;
       sh.matched[chain] = matched;
-      for (int c = 0; c < 3; ++c) sh.end_pred[chain][c] = pred[c];
+      sh.end_pred[chain][0] = pred0;
+      sh.end_pred[chain][1] = pred1;
+      sh.end_pred[chain][2] = pred2;
       __threadfence_block();
     }
   }
