@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
   struct BlockDesc {                                       // what block `bi` of an MCU decodes with (per warp: images differ)
     const HuffTable* dc;
     const HuffTable* ac;
-    const int32_t* fast;
-    int comp, pad_;
+    const int32_t* fast;                                   // the image's own table in global memory ...
+    int comp, ta;                                          // ... or fast_s[ta] when it equals the CTA's shared copy
   };
   __shared__ BlockDesc bd_s[kHuffWarps][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -334,12 +334,13 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
           bd[bi].ac = tables + im.tab[2 + im.comp[ci].ta];
           bd[bi].fast = fast[im.comp[ci].ta];
           bd[bi].comp = ci;
+          bd[bi].ta = im.comp[ci].ta;
         }
     }
     __syncwarp();
     int pred0 = 0, pred1 = 0, pred2 = 0;
     int todo = im.restart_interval;
-    const int ncomp = im.ncomp, total = im.mcux * im.mcuy, bpm = im.bpm;
+    const int total = im.mcux * im.mcuy, bpm = im.bpm;
     int16_t* region = reinterpret_cast<int16_t*>(scratch + im.coef_off + im.chain_stride * size_t(chain));
     int spec = chain > 0 ? window : 0;             // MCUs still to decode before this chain's blocks count (every lane counts)
     int stored = 0, decoded = 0;
@@ -399,7 +400,9 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
         if (lane == 0) {
           const BlockDesc d = bd[bi];
           int pr = d.comp == 0 ? pred0 : (d.comp == 1 ? pred1 : pred2);
-          decode_block(br, d.dc, d.ac, d.fast, pr, blk);
+          // the shared-memory copy is addressed as such (LDS with a 32-bit address instead of a generic load)
+          if (d.fast == fast_s[d.ta]) decode_block(br, d.dc, d.ac, fast_s[d.ta], pr, blk);
+          else decode_block(br, d.dc, d.ac, d.fast, pr, blk);
           if (d.comp == 0) pred0 = pr; else if (d.comp == 1) pred1 = pr; else pred2 = pr;
         }
         __syncwarp();
