@@ -219,8 +219,8 @@ __device__ __forceinline__ void decode_block(BitReader& br, const HuffTable* __r
     const int len = e & 255, pos = k + ((e >> 8) & 255) - 1;
     br.acc <<= len;
     br.n -= len;
-    if (pos < 64) blk[pos] = int16_t(e >> 16);          // ZRL writes a zero into a still-zero slot; EOB lands beyond the block
-    k = pos + 1;
+    blk[pos] = int16_t(e >> 16);     // ZRL writes a zero into a still-zero slot; EOB (and a corrupt run) lands in the 64 spare
+    k = pos + 1;                     // slots behind the block, which nobody reads: no store predicate, one exit test per symbol
   };
 #pragma unroll 1
   while (k < 64) {
@@ -232,7 +232,7 @@ __device__ __forceinline__ void decode_block(BitReader& br, const HuffTable* __r
       int v = 0;
       if (s) v = receive_extend(br, s);
       const int pos = k + (s ? (rs >> 4) + 1 : ((rs >> 4) == 15 ? 16 : 64)) - 1;
-      if (pos < 64) blk[pos] = int16_t(v);
+      blk[pos] = int16_t(v);
       k = pos + 1;
       continue;
     }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const Jpe
                                                                        const FastAc* __restrict__ fast_tables,
                                                                        const uint8_t* __restrict__ blob, uint8_t* __restrict__ scratch,
                                                                        int chains, int window) {
-  __shared__ __align__(16) int16_t blk_s[kHuffWarps][64];
+  __shared__ __align__(16) int16_t blk_s[kHuffWarps][128];   // a block + 64 spare slots (decode_block: positions up to 126)
   __shared__ __align__(16) int32_t fast_s[2][kFastSize];
   __shared__ ChainShared sh_all[kHuffWarps];               // one per image of the CTA
   struct BlockDesc {                                       // what block `bi` of an MCU decodes with (per warp: images differ)
