@@ -202,26 +202,35 @@ def _decode_files(slot: _Slot, paths: Sequence[str]) -> Tuple[List[Optional[torc
     nbytes = int(offsets[-1])
     view = memoryview(slot.host_blob(nbytes).numpy())
 
-    def read(i: int) -> None:
-        if errs[i]:
-            return
-        try:
-            with open(paths[i], "rb", buffering=0) as f:
-                got = f.readinto(view[offsets[i]:offsets[i + 1]])
-            if got != sizes[i]:
-                errs[i] = "short read"
-        except OSError as e:
-            errs[i] = f"unreadable: {e}"
-        if errs[i] and sizes[i] >= 2:
-            view[offsets[i]:offsets[i] + 2] = b"\0\0"       # no SOI: the plan reports the file as corrupt
+    def read_some(first: int, step: int) -> None:
+        # plain file descriptors (os.open / os.readv): the io module's wrappers cost more than the read of a 300 KB file
+        for i in range(first, len(paths), step):
+            if errs[i]:
+                continue
+            try:
+                fd = os.open(paths[i], os.O_RDONLY)
+                try:
+                    got, want = 0, sizes[i]
+                    while got < want:
+                        n = os.readv(fd, [view[offsets[i] + got:offsets[i + 1]]])
+                        if n <= 0:
+                            break
+                        got += n
+                finally:
+                    os.close(fd)
+                if got != sizes[i]:
+                    errs[i] = "short read"
+            except OSError as e:
+                errs[i] = f"unreadable: {e}"
+            if errs[i] and sizes[i] >= 2:
+                view[offsets[i]:offsets[i] + 2] = b"\0\0"       # no SOI: the plan reports the file as corrupt
 
     if len(paths) >= 4 * _READ_THREADS:
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=_READ_THREADS) as ex:   # readinto releases the GIL
-            list(ex.map(read, range(len(paths)), chunksize=16))
+        with ThreadPoolExecutor(max_workers=_READ_THREADS) as ex:   # one strided share per thread; readv releases the GIL
+            list(ex.map(lambda t: read_some(t, _READ_THREADS), range(_READ_THREADS)))
     else:
-        for i in range(len(paths)):
-            read(i)
+        read_some(0, 1)
     view[nbytes:nbytes + _PAD] = bytes(_PAD)
     imgs, reasons = _decode(slot, nbytes, offsets)
     return imgs, [e or r for e, r in zip(errs, reasons)]
