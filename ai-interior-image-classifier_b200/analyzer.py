@@ -118,9 +118,11 @@ INGEST_CHUNK = int(os.environ.get("IIC_INGEST_CHUNK", "1024"))
 
 def iter_loaded(paths: Sequence[str], device=None, gpu_decode: bool = False, chunk: int = 0):
     """`load_images` over a long list, `chunk` paths at a time: yields (chunk_paths, images).  While the caller works on chunk i
-    (preprocess + encoder + head on the current stream), a worker thread reads, parses and decodes chunk i + 1 on a side stream
-    (file reads, header parsing and the ctypes calls all release the GIL), so ingest and encoder overlap instead of alternating.
-    Results do not depend on the chunking: every image is decoded and scored on its own."""
+    (preprocess + encoder + head), a worker thread already reads and parses the files of chunk i + 1 and enqueues their decode
+    (file reads, header parsing and the ctypes calls release the GIL): the HOST side of the ingest disappears behind the encoder.
+    The decode is enqueued on the caller's own stream - a side stream was measured and gains nothing: the encoder's GEMM CTAs
+    hold the whole register file of an SM, so decode and encoder kernels cannot share one, and cross-stream allocation only
+    makes the caching allocator's life hard.  Results do not depend on the chunking: every image is decoded and scored alone."""
     chunk = chunk or INGEST_CHUNK
     paths = list(paths)
     on_gpu = gpu_decode and device is not None and torch.device(device).type == "cuda"
@@ -129,27 +131,19 @@ def iter_loaded(paths: Sequence[str], device=None, gpu_decode: bool = False, chu
             yield paths, load_images(paths, device, gpu_decode)
         return
     dev = torch.device(device)
-    side = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.current_stream(dev)
 
     def work(lo: int):
         part = paths[lo:lo + chunk]
-        with torch.cuda.device(dev), torch.cuda.stream(side):
-            imgs = load_images(part, dev, True)
-            ev = torch.cuda.Event()
-            ev.record(side)
-        return part, imgs, ev
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            return part, load_images(part, dev, True)
 
     with ThreadPoolExecutor(max_workers=1) as ex:
         fut = ex.submit(work, 0)
         for lo in range(0, len(paths), chunk):
-            part, imgs, ev = fut.result()
+            part, imgs = fut.result()
             if lo + chunk < len(paths):
                 fut = ex.submit(work, lo + chunk)
-            main = torch.cuda.current_stream(dev)
-            main.wait_event(ev)
-            for im in imgs:                      # decoded on the side stream, consumed on this one
-                if isinstance(im, DeviceImage):
-                    im.tensor.record_stream(main)
             yield part, imgs
 
 

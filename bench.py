@@ -449,7 +449,7 @@ def main():
             vis = build_tower(clipc, lora, "ViT-B/16", args.lora_rank, dev, args.operand_dtype)
             eng = vis.sync_engine()
             eng.set_labels(torch.nn.functional.normalize(torch.randn(sum(GROUPS), 512, device=dev), dim=-1), GROUPS, SPLIT, topk=5, logit_scale=100.0)
-            extra["ingest"] = bi.measure(n=1024, reps=3, dev=dev, with_nvjpeg=False, engine=eng, pipeline_batches=3)
+            extra["ingest"] = bi.measure(n=1024, reps=3, dev=dev, with_nvjpeg=False, engine=eng, pipeline_batches=4)
             del eng, vis
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001 - a sub-record must not take the headline down

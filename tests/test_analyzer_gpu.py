@@ -243,7 +243,7 @@ def test_gpu_jpeg_ingest(analyzer, tmp_path):
     assert r_dev[paths[-1]]["is_interior"] is False
     for p in paths:
         assert r_host[p] == r_dev[p], p
-    # long lists are ingested chunk by chunk, chunk i + 1 decoded on a side stream under the encode of chunk i: same dicts
+    # long lists are ingested chunk by chunk, chunk i + 1 read, parsed and enqueued by a worker thread under the encode of chunk i: same dicts
     try:
         analyzer.gpu_decode = True
         old_chunk, old_min = an.INGEST_CHUNK, an.GPU_DECODE_MIN_FILES

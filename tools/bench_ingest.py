@@ -129,8 +129,8 @@ def measure(n=1024, uniq=32, size="1024x768", quality=85, reps=5, dev=None, with
             # serial Huffman chains lose issue slots to the GEMM warps they share the SMs with)
             res["files_to_topk"] = {"images_s": to_topk(), "batches": pipeline_batches,
                                     "what": "decode_jpeg_files -> Engine.classify (Pillow-exact resize to 224, encoder, head) -> top-k on the host"}
-            # the analyzer's way for long lists (analyzer.iter_loaded): chunk i + 1 is read, parsed and decoded by a worker thread on a
-            # side stream while chunk i is preprocessed, encoded and scored
+            # the analyzer's way for long lists (analyzer.iter_loaded): chunk i + 1 is read, parsed and enqueued by a worker thread
+            # while chunk i is preprocessed, encoded and scored
             an = import_module("ai-interior-image-classifier_b200.analyzer")
             many = paths * pipeline_batches
 
@@ -146,7 +146,7 @@ def measure(n=1024, uniq=32, size="1024x768", quality=85, reps=5, dev=None, with
                 return len(many) / (time.perf_counter() - t0)
             chunked()
             res["files_to_topk_overlapped"] = {"images_s": chunked(), "files": len(many), "chunk": n,
-                                               "what": "analyzer.iter_loaded (next chunk decoded on a side stream by a worker thread) -> Engine.classify -> top-k on the host"}
+                                               "what": "analyzer.iter_loaded (the next chunk is read, parsed and enqueued by a worker thread) -> Engine.classify -> top-k on the host"}
             sub = paths[: min(n, 256)]
 
             def host_decoder():
