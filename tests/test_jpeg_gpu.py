@@ -210,3 +210,30 @@ def test_crafted_streams_bit_exact(jp, monkeypatch, chains):
         got = imgs[i].cpu().numpy()
         assert got.shape == ref.shape and np.array_equal(got, ref), (i, ref.shape, int((got != ref).sum()))
     assert imgs[-1] is None and imgs[-2] is None and "RGB" in reasons[-1] and "RGB" in reasons[-2]
+
+
+def test_random_crafted_batch(jp):
+    """48 random valid streams (tests/jpeg_craft.py) in ONE batch: random sizes from 1x1 to 300x300, every sampling layout and
+    grayscale, random restart intervals and fill bytes, deep or flat Huffman tables, 8 / 16-bit quantisation tables, random ids"""
+    import jpeg_craft as C
+    rng = np.random.default_rng(2024)
+    files = []
+    for i in range(48):
+        w, h = int(rng.integers(1, 301)), int(rng.integers(1, 301))
+        gray = bool(rng.integers(0, 6) == 0)
+        kw = dict(width=w, height=h, gray=gray, deep=bool(rng.integers(0, 2)), dqt16=bool(rng.integers(0, 4) == 0))
+        if not gray:
+            kw["sampling"] = [(1, 1), (2, 1), (2, 2)][int(rng.integers(0, 3))]
+            kw["comp_ids"] = [(1, 2, 3), (0, 1, 2), (10, 20, 30)][int(rng.integers(0, 3))]
+            kw["table_ids"] = [((0, 0), (1, 1), (1, 1)), ((1, 1), (0, 0), (0, 0)), ((0, 1), (1, 0), (0, 0))][int(rng.integers(0, 3))]
+        if rng.integers(0, 3) == 0:
+            kw["restart"] = int(rng.integers(1, 9))
+            kw["fill_before_rst"] = int(rng.integers(0, 3))
+        files.append(C.random_case(rng, **kw))
+    imgs, reasons = jp.decode_jpeg_bytes(files, "cuda:0")
+    torch.cuda.synchronize()
+    for i, data in enumerate(files):
+        assert imgs[i] is not None, (i, reasons[i])
+        ref = _pil(data)
+        got = imgs[i].cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), (i, ref.shape, int((got != ref).sum()))
