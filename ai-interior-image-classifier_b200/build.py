@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libiic_b200.so")
-SOURCES = ["gemm_sm100.cu", "rowwise.cu", "attention.cu", "attention_sm100.cu", "attention_row_sm100.cu", "attention_bwd.cu", "attention_bwd_sm100.cu", "train_ops.cu", "head.cu", "preprocess.cu", "jpeg.cu",
+SOURCES = ["gemm_sm100.cu", "rowwise.cu", "attention.cu", "attention_sm100.cu", "attention_row_sm100.cu", "attention_bwd.cu", "attention_bwd_sm100.cu", "attention_bwd_fused_sm100.cu", "train_ops.cu", "head.cu", "preprocess.cu", "jpeg.cu",
            "iic_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

@@ -478,6 +478,17 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 }
 }  // namespace
 
+int launch_attention_bwd_dsum(const void* d_out, const void* out, float* dsum, int B, int T, int H, int f16, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  const long long total = (long long)B * T * H * 8;
+  const int blocks = int((total + 255) / 256);
+  if (f16)
+    attention_bwd_dsum_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(d_out), static_cast<const uint16_t*>(out), dsum, B, T, H);
+  else
+    attention_bwd_dsum_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(d_out), static_cast<const uint16_t*>(out), dsum, B, T, H);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 // returns -3 when the shape is outside this kernel's envelope (caller falls back to the mma.sync kernel)
 int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum_scratch,
                                void* dqkv, int B, int T, int H, int head_dim, int f16, int causal, int num_sms,
@@ -515,15 +526,7 @@ int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_o
   p.scale = 1.0f / sqrtf(float(head_dim));
   p.scale_log2e = 1.4426950408889634f * p.scale;
   const int d = H * kHd;
-  {
-    const long long total = (long long)B * T * H * 8;
-    const int blocks = int((total + 255) / 256);
-    if (f16)
-      attention_bwd_dsum_kernel<true><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(d_out), static_cast<const uint16_t*>(out), dsum_scratch, B, T, H);
-    else
-      attention_bwd_dsum_kernel<false><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(d_out), static_cast<const uint16_t*>(out), dsum_scratch, B, T, H);
-    if (cudaGetLastError() != cudaSuccess) return -2;
-  }
+  if (int rc = launch_attention_bwd_dsum(d_out, out, dsum_scratch, B, T, H, f16, stream)) return rc;
   CUtensorMap tqf, tqt, tdf, tdt;
   const uint64_t rows = uint64_t(B) * T;
   const bool h16 = f16 != 0;

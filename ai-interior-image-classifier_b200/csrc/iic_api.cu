@@ -110,7 +110,7 @@ struct iic_handle {
                           // applies act'(u) in its epilogue; 0 (IIC_TRAIN_FUSED=0): recompute u in the backward + act_bwd kernel
   int lora_bwd_fused = 1; // 1: dB and dP of a LoRA pair from one pass over the output gradient (IIC_LORA_BWD_FUSED=0: GEMM + reduction)
   int pdl_max_batch = 16;  // batches up to this size launch their kernels with programmatic dependent launch (IIC_PDL_MAX_BATCH; 0 = off)
-  int attn_bwd_impl = 0;  // 0 auto (tcgen05 backward for T <= 592), 1 mma.sync backward (IIC_ATTN_BWD_IMPL)
+  int attn_bwd_impl = 0;  // 0 auto (tcgen05: one-pass kernel for T <= 256, two-pass kernel up to 592), 1 mma.sync, 2 two-pass tcgen05 (IIC_ATTN_BWD_IMPL)
   float grad_unscale = 1.f;  // 1 / loss scale: folded into the LoRA gradient reductions (iic_train_set_loss_scale)
   const float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr,
               *lnpost_b = nullptr, *proj = nullptr;
@@ -204,6 +204,11 @@ int run_attention(iic_handle* h, const void* qkv, void* out, float* lse, int B, 
 // attention backward: tcgen05 kernel for T <= 592 (needs a [B*H*T] f32 scratch for D), mma.sync kernel otherwise
 int run_attention_bwd(iic_handle* h, const void* qkv, const void* out, const void* d_out, const float* lse, float* dsum,
                       void* dqkv, int B, int T, int H, int hd, cudaStream_t s) {
+  if ((h->attn_bwd_impl == 0 || h->attn_bwd_impl == 3) && dsum != nullptr && T <= 256) {   // one pass per key tile (attention_bwd_fused_sm100.cu)
+    int rc = launch_attention_bwd_dsum(d_out, out, dsum, B, T, H, h->f16, s);
+    if (rc == 0) rc = launch_attention_bwd_fused_sm100(qkv, d_out, lse, dsum, dqkv, B, T, H, hd, h->f16, h->cfg.causal, h->num_sms, s);
+    if (rc != -3) return rc;
+  }
   if (h->attn_bwd_impl != 1 && dsum != nullptr) {
     int rc = launch_attention_bwd_sm100(qkv, out, d_out, lse, dsum, dqkv, B, T, H, hd, h->f16, h->cfg.causal, h->num_sms, s);
     if (rc != -3) return rc;

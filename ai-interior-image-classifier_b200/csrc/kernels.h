@@ -80,6 +80,12 @@ int launch_attention_bwd_sm100(const void* qkv, const void* out, const void* d_o
                                void* dqkv, int B, int T, int H, int head_dim, int f16, int causal, int num_sms,
                                cudaStream_t stream);
 
+// D[bh, q] = rowsum(dO o O), f32 [B*H*T] (attention_bwd_sm100.cu): the pre-kernel of the tcgen05 backward kernels
+int launch_attention_bwd_dsum(const void* d_out, const void* out, float* dsum, int B, int T, int H, int f16, cudaStream_t stream);
+// one pass per key tile (attention_bwd_fused_sm100.cu), T <= 256; dsum already computed; -3 outside its envelope
+int launch_attention_bwd_fused_sm100(const void* qkv, const void* d_out, const float* lse, const float* dsum, void* dqkv, int B, int T,
+                                     int H, int head_dim, int f16, int causal, int num_sms, cudaStream_t stream);
+
 // ---- train_ops.cu ----
 int launch_layernorm_bwd(const void* dy, const float* x, const float* gamma, float* dx, void* dx16, int rows, int D,
                          float eps, int f16, cudaStream_t stream);
