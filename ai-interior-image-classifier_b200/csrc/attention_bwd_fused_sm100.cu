@@ -326,6 +326,7 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, cons
       for (int t = 0; t < n_tiles; ++t, ++tile_cnt) {
         const int row = t * 128 + r;                       // the key this thread owns
         const bool row_ok = row < T;
+        const bool warp_live = t * 128 + quad * 32 < T;    // warps whose 32 keys are all padding only zero their dS^T rows
         for (int j = 0; j < nblk; ++j, ++blk_cnt) {
           const int u = blk_units(j), u0 = blk_start(j), ua = (u + 1) / 2;
           const int v_lo = grp == 0 ? 0 : ua, v_hi = grp == 0 ? ua : u;
@@ -334,7 +335,12 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, cons
 #pragma unroll
           for (int vv = 0; vv < 4; ++vv) {
             const int v = v_lo + vv;                       // unit inside the block
-            if (v < v_hi) {
+            if (v < v_hi && !warp_live) {
+              uint8_t* rowp = my_stage_row + (v >> 2) * kTileBytes;
+              const int ch = (v & 3) * 2;
+              *reinterpret_cast<uint4*>(rowp + (((ch) ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            } else if (v < v_hi) {
               uint32_t sv[16], dv[16];
               ld16(lane_addr + kColS + uint32_t(16 * v), sv);
               ld16(lane_addr + kColDp + uint32_t(16 * v), dv);
