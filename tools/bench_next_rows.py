@@ -5,6 +5,8 @@
       measured up to "uint8 pixels resident on the GPU".
 Prints one JSON line."""
 import io, json, os, sys, tempfile, time
+os.environ.setdefault("IIC_ALLOW_RANDOM_INIT", "1")       # synthetic benchmark: seeded weights by design
+os.environ.setdefault("IIC_ALLOW_STANDIN_TOKENIZER", "1")
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import iic_b200

@@ -5,6 +5,8 @@ Each step = frozen vision encode of the image batch (engine inference path) + te
 (causal attention, LoRA r=16 on the text MLPs: train_lora.py:62-100, 184) + clip_grad_norm_ + AdamW + NCCL all-reduce of the
 LoRA gradients.  Prints one JSON line (rank 0)."""
 import json, os, sys
+os.environ.setdefault("IIC_ALLOW_RANDOM_INIT", "1")       # synthetic benchmark: seeded weights by design
+os.environ.setdefault("IIC_ALLOW_STANDIN_TOKENIZER", "1")
 import torch
 import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
